@@ -1,0 +1,88 @@
+/*
+ * maggie_b200.h - C ABI of libmaggie_b200.so: hand-written sm_100a CUDA kernels for the MaGGIe
+ * forward/backward hot path (encoder/ASPP convs, mask-guided attention decoder, sparse refinement).
+ *
+ * The reference (hmchuong/MaGGIe) has NO FFI: its native work is library calls made from Python
+ * (cuDNN/ATen through torch, spconv, cv2.dilate).  Each entry point below therefore replaces a Python
+ * call site of the reference; the citation after "replaces:" is relative to /root/reference/maggie.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; all buffers (inputs, outputs,
+ *     workspaces) are owned and allocated by the caller (PyTorch) and only borrowed for the call;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no internal synchronisation,
+ *     no allocation: safe for CUDA-graph capture;
+ *   - return value 0 = OK, non-zero = error (message via mg_last_error(), thread local); the library never
+ *     exits or throws across the ABI;
+ *   - activations are NHWC fp16 unless stated, statistics / logits / alphas fp32, index data int32.
+ */
+#ifndef MAGGIE_B200_H
+#define MAGGIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_OK 0
+#define MG_ERR_ARG 1
+#define MG_ERR_CUDA 2
+#define MG_ERR_UNSUPPORTED 3
+
+/* ---- library ---- */
+int mg_version(void);
+const char* mg_last_error(void);
+/* number of kernels this library has launched since load / last reset (bench.py's "gpu_launches") */
+unsigned long long mg_launch_count(void);
+void mg_reset_launch_count(void);
+
+/* ---- K8a: uncertainty ("unknown") mask -------------------------------------------------------------
+ * replaces: utils/utils.py:28-55 compute_unknown (threshold 1/255 < a < 254/255, then per-slice
+ *           cv2.dilate with MORPH_ELLIPSE(width) on the CPU, incl. the D2H/H2D round trip).
+ * alpha     [slices,H,W] fp32.          widths [slices] int32, ellipse size 1..29 per slice.
+ * and_mask  optional [slices,H,W] uint8: result is AND-ed with (and_mask != 0)   (fuse(): "* detail_mask",
+ *           decoder/resnet_inst_matt_spconv.py:279,285,335-336).
+ * out_u8    optional [slices,H,W] uint8 in {0,1}.   out_bits optional [slices,H,ceil(W/32)] uint32, bit x%32
+ *           of word x/32.  At least one output must be given.  Bit-exact.                              */
+int mg_unknown_mask(const float* alpha, int slices, int H, int W, const int32_t* widths,
+                    const uint8_t* and_mask, uint8_t* out_u8, uint32_t* out_bits, void* stream);
+
+/* ---- K8b: active-site lists for the sparse refinement ---------------------------------------------
+ * replaces: decoder/resnet_inst_matt_spconv.py:203-218 (torch.nonzero + spconv `dummy_downscale`, whose only
+ *           live product is the OS1/OS2/OS4/OS8 index sets and the (in,out,tap) pair tables).
+ * Level l (0..3) has spatial size (H>>l, W>>l) (H, W multiples of 8).  Level l+1 site q is active iff any
+ * level-l site lies in rows/cols 2q-1..2q+1 (SparseConv2d k3 s2 p1).  Sites of a level are numbered in
+ * lexicographic (slot,y,x) order == torch.nonzero order.
+ *
+ * mg_sites_workspace : bytes needed for `ws`.
+ * mg_sites_count     : builds the bit pyramids + rank structure in `ws`, writes counts[4] (device int32).
+ * mg_sites_tables    : after the caller has read counts[] (one 16-byte D2H) and allocated exact-size outputs:
+ *   coords[l]  [N_l,3] int32 (slot,y,x)                                     (l = 0..3, any may be NULL)
+ *   nbr[l]     [N_l,9] int32  row of the active neighbour at tap (ky,kx) = (y+ky-1, x+kx-1), else -1
+ *              (SubMConv2d 3x3 rulebook; requested for l = 0 and l = 2)
+ *   parent[l]  [N_l,9] int32  for l = 0..2: row (at level l+1) of q with p = 2q-1+k for tap k, else -1
+ *              (SparseInverseConv2d rulebook, forward)
+ *   child[l]   [N_l,9] int32  for l = 1..3: row (at level l-1) of p = 2q-1+k if active, else -1
+ *              (SparseInverseConv2d backward / SparseConv2d forward rulebook)                            */
+size_t mg_sites_workspace(int slots, int H, int W);
+int mg_sites_count(const uint8_t* roi, int slots, int H, int W, void* ws, int32_t* counts, void* stream);
+int mg_sites_tables(const void* ws, int slots, int H, int W, const int32_t* counts_host,
+                    int32_t* const* coords, int32_t* const* nbr, int32_t* const* parent,
+                    int32_t* const* child, void* stream);
+
+/* ---- K1: mask-id embedding + NHWC pack -------------------------------------------------------------
+ * replaces: arch/maggie.py:200-235 (zero-padded 10-slot mask tensor + cat) and
+ *           encoder/resnet.py:211-229 (Embedding gather, masked mean over instances, permute, cat).
+ * image [B,3,H,W] fp32 NCHW; masks [B,M,H,W] fp32 {0,1}; slot_ids_host[M] = slot (0..9) of each given mask;
+ * table [11,3] fp32; out [B,H,W,C] fp16 NHWC, C >= 6: ch 0-2 image, 3-5 mean embedding, rest zero.     */
+int mg_mask_embed_fwd(const float* image, const float* masks, const int32_t* slot_ids_host, int M,
+                      const float* table, void* out_f16, int B, int H, int W, int C, void* stream);
+/* grad_table [11,3] fp32 += d(out[...,3:6]) / d(table)   (caller zeroes grad_table)                     */
+int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, const int32_t* slot_ids_host, int M,
+                      float* grad_table, int B, int H, int W, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGGIE_B200_H */

@@ -1,0 +1,65 @@
+"""ctypes binding of libmaggie_b200.so (the C ABI declared in include/maggie_b200.h).
+
+No fallback: if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int, c_int32, c_size_t, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmaggie_b200.so")
+_lib = None
+
+_I32P = POINTER(c_int32)
+_PP = POINTER(c_void_p)
+
+# name -> (restype, argtypes); must list every symbol in include/maggie_b200.h
+SIGNATURES = {
+    "mg_version": (c_int, []),
+    "mg_last_error": (c_char_p, []),
+    "mg_launch_count": (c_ulonglong, []),
+    "mg_reset_launch_count": (None, []),
+    "mg_unknown_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mg_sites_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "mg_sites_count": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mg_sites_tables": (c_int, [c_void_p, c_int, c_int, c_int, _I32P, _PP, _PP, _PP, _PP, c_void_p]),
+    "mg_mask_embed_fwd": (c_int, [c_void_p, c_void_p, _I32P, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mg_mask_embed_bwd": (c_int, [c_void_p, c_void_p, _I32P, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+}
+
+
+def lib():
+    """The loaded library; raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m maggie_b200._build` (or __graft_entry__.build()). "
+                "maggie_b200 has no fallback path.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        raise RuntimeError(f"{what} failed ({code}): {lib().mg_last_error().decode()}")
+
+
+def launch_count():
+    return int(lib().mg_launch_count())
+
+
+def reset_launch_count():
+    lib().mg_reset_launch_count()
+
+
+def i32_array(values):
+    return (c_int32 * len(values))(*[int(v) for v in values])
+
+
+def ptr_array(ptrs):
+    return (c_void_p * len(ptrs))(*[c_void_p(p) if p else None for p in ptrs])

@@ -1,0 +1,308 @@
+"""MaGGIe decoder: OS32->OS8 dense blocks, mask-guided attention at OS8 (InstanceMatteDecoder), uncertainty
+mask, sparse OS8->OS4->OS2->OS1 refinement on the active sites only, progressive fusion.
+
+Reference: decoder/resnet.py:9-45 (BasicBlock), decoder/resnet_inst_matt_spconv.py:14-388,
+module/instance_matte_decoder.py:9-306, module/mask_attention.py:9-206.  Attribute paths equal the
+reference's (state-dict compatible).  No spconv, no cv2, no nonzero/boolean-index host syncs except the one
+16-byte read of the site counts.
+"""
+import random
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from .layers import PlainConv, Slot, SNConv, SparseConvParams, seq
+
+
+# ------------------------------------------------------------------------------------------- dense blocks
+class DecBlock(nn.Module):
+    """conv1 (ConvT 4x4 s2 when upsampling else 3x3) - BN - LReLU - conv2 3x3 - BN - (+skip) - LReLU."""
+
+    def __init__(self, inplanes, planes, up=False):
+        super().__init__()
+        self.up = up
+        self.conv1 = SNConv(inplanes, inplanes, 4 if up else 3, transposed=up)
+        self.bn1 = nn.BatchNorm2d(inplanes)
+        self.conv2 = SNConv(inplanes, planes, 3)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.upsample = None
+        if up:
+            # [UpsamplingNearest2d(2), SN conv1x1, BN]  (resnet_inst_matt_spconv.py:141-146)
+            self.upsample = seq(Slot(), SNConv(inplanes, planes, 1), nn.BatchNorm2d(planes))
+
+    def forward(self, x):
+        t = self.training
+        out = ops.conv_bn_act(x, self.conv1.weight(), self.bn1, t, act="lrelu", transposed=self.up)
+        idt = x
+        if self.up:
+            # nearest x2 commutes with a 1x1 conv and leaves BN batch statistics unchanged, so the skip path runs
+            # at the low resolution and is replicated afterwards
+            idt = ops.conv_bn_act(x, self.upsample[1].weight(), self.upsample[2], t, padding=0, act=None)
+            idt = F.interpolate(idt, scale_factor=2, mode="nearest")
+        return ops.conv_bn_act(out, self.conv2.weight(), self.bn2, t, act="lrelu", residual=idt)
+
+
+# ------------------------------------------------------------------------------------------- attention
+class _FFN(nn.Module):
+    def __init__(self, d, hidden, dropout=0.0):
+        super().__init__()
+        self.linear1, self.linear2 = nn.Linear(d, hidden), nn.Linear(hidden, d)
+        self.dropout = nn.Dropout(dropout)  # p is read by the forward below
+        self.norm = nn.LayerNorm(d)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def forward(self, x):
+        p, t = self.dropout.p, self.training
+        h = F.relu(ops.linear(x, self.linear1.weight, self.linear1.bias))
+        h = F.dropout(h, p, t)
+        h = F.dropout(ops.linear(h, self.linear2.weight, self.linear2.bias), p, t)
+        return ops.layer_norm(x + h, self.norm)
+
+
+class _Attn(nn.Module):
+    """Post-norm attention layer; `attn_name` is `multihead_attn` (cross) or `self_attn` (self)."""
+
+    def __init__(self, d, attn_name):
+        super().__init__()
+        self.attn_name = attn_name
+        setattr(self, attn_name, nn.MultiheadAttention(d, 1, dropout=0.0))
+        self.norm = nn.LayerNorm(d)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def forward(self, tgt, mem, tgt_pos, mem_pos, key_padding=None, guidance=None):
+        """tgt [B,L,E] (queries, residual stream), mem [B,S,E]; positional terms are added to Q and K only."""
+        mha = getattr(self, self.attn_name)
+        E = tgt.shape[-1]
+        w, b = mha.in_proj_weight, mha.in_proj_bias
+        q = ops.linear(tgt if tgt_pos is None else tgt + tgt_pos, w[:E], b[:E])
+        k = ops.linear(mem if mem_pos is None else mem + mem_pos, w[E:2 * E], b[E:2 * E])
+        v = ops.linear(mem, w[2 * E:], b[2 * E:])
+        o, stat = ops.attention(q, k, v, key_padding, guidance)
+        o = ops.linear(o, mha.out_proj.weight, mha.out_proj.bias)
+        return ops.layer_norm(tgt + o, self.norm), stat
+
+
+class _MLP1(nn.Module):
+    def __init__(self, din, dout):
+        super().__init__()
+        self.layers = nn.ModuleList([nn.Linear(din, dout)])
+
+
+class InstanceMatteDecoder(nn.Module):
+    def __init__(self, input_dim=128, attention_dim=128, n_block=2, output_dim=64, max_inst=10, use_id_pe=True, **_):
+        super().__init__()
+        d = attention_dim
+        self.n_block, self.max_inst, self.use_id_pe = n_block, max_inst, use_id_pe
+        self.feat_proj = _MLP1(input_dim, d)
+        self.sa_layers = nn.ModuleList(_Attn(d, "self_attn") for _ in range(n_block))
+        self.token_feat_ca_layers = nn.ModuleList(_Attn(d, "multihead_attn") for _ in range(n_block))
+        self.mlp_layers = nn.ModuleList(_FFN(d, d) for _ in range(n_block))
+        self.feat_token_ca_layers = nn.ModuleList(_Attn(d, "multihead_attn") for _ in range(n_block))
+        self.final_token_feat_ca = _Attn(d, "multihead_attn")
+        self.final_mlp = _MLP1(d, output_dim)
+        self.decoder_norm = nn.LayerNorm(output_dim)
+        self.query_feat = nn.Embedding(max_inst, d)
+        self.id_embedding = nn.Embedding(max_inst + 1, d)
+        nn.init.xavier_uniform_(self.id_embedding.weight)
+        nn.init.xavier_uniform_(self.query_feat.weight)
+        self.conv = seq(PlainConv(d, d, 3), nn.BatchNorm2d(d), Slot(), PlainConv(d, output_dim, 1),
+                        nn.BatchNorm2d(output_dim), Slot())
+
+    def forward(self, feat, mask_os8, gt_mask_os8=None):
+        """feat [b*n_f, C, h, w] channels-last; mask_os8 [b, n_f, n_i, h, w] bool (avg-pool>0 of the input masks);
+        gt_mask_os8 (training) [b, n_f, n_i, h, w] bool (max-pool of gt alpha > 0).
+        Returns logits [b*n_f, 10, h, w] fp32, out_feat [b*n_f, 64, h, w], tokens [b, 10, 64] fp32, loss."""
+        b, n_f, n_i, h, w = mask_os8.shape
+        hw, nq, t = h * w, self.max_inst, self.training
+        dt = feat.dtype
+        # key index = pixel * n_f + frame (instance_matte_decoder.py:177)
+        x = feat.permute(0, 2, 3, 1).reshape(b, n_f, hw, -1).permute(0, 2, 1, 3).reshape(b, hw * n_f, -1)
+        ids = torch.arange(1, n_i + 1, device=feat.device).view(1, 1, n_i, 1, 1)
+        id_pos = (mask_os8 * ids).amax(2)                                                   # [b,n_f,h,w]
+        emb = self.id_embedding.weight
+        x_pos = emb[id_pos.reshape(b, n_f, hw).permute(0, 2, 1).reshape(b, hw * n_f)].to(dt)  # [b,S,E]
+        x = ops.linear(x, self.feat_proj.layers[0].weight, self.feat_proj.layers[0].bias)
+        tok = self.query_feat.weight.to(dt)[None].expand(b, -1, -1)
+        tok_pos = emb[1:nq + 1].to(dt)[None].expand(b, -1, -1)
+
+        valid = mask_os8.flatten(3).any(3).any(1)                                           # [b,n_i]
+        if n_i < nq:
+            valid = torch.cat([valid, valid.new_zeros(b, nq - n_i)], 1)
+        tok_pad = ~valid
+        guidance = target = None
+        if t:
+            g = gt_mask_os8.reshape(b, n_f, n_i, hw).permute(0, 2, 3, 1).reshape(b, n_i, hw * n_f)
+            if n_i < nq:
+                g = torch.cat([g, g.new_zeros(b, nq - n_i, hw * n_f)], 1)
+            guidance = g
+            target = g.any(2).float()
+
+        loss = 0.0
+        pe = self.use_id_pe
+        for i in range(self.n_block):
+            tok, st = self.token_feat_ca_layers[i](tok, x, tok_pos if pe else None, x_pos if pe else None, None, guidance)
+            if t:
+                loss = loss + (target - st).sum() / (n_f * b)
+            tok = self.mlp_layers[i](tok)
+            tok, _ = self.sa_layers[i](tok, tok, tok_pos, tok_pos, tok_pad)
+            x, _ = self.feat_token_ca_layers[i](x, tok, x_pos if pe else None, tok_pos if pe else None, tok_pad)
+        tok, st = self.final_token_feat_ca(tok, x, tok_pos, x_pos, None, guidance)
+        if t:
+            loss = loss + (target - st).sum() / (n_f * b)
+        loss = loss / (self.n_block + 1)
+
+        x = x.reshape(b, hw, n_f, -1).permute(0, 2, 3, 1).reshape(b * n_f, -1, h, w)
+        x = x.contiguous(memory_format=torch.channels_last)
+        x = ops.conv_bn_act(x, self.conv[0].weight, self.conv[1], t, act="lrelu")
+        x = ops.conv_bn_act(x, self.conv[3].weight, self.conv[4], t, padding=0, act="lrelu")
+        tok = ops.linear(tok, self.final_mlp.layers[0].weight, self.final_mlp.layers[0].bias)
+        tok = F.layer_norm(tok.float(), (tok.shape[-1],), self.decoder_norm.weight, self.decoder_norm.bias,
+                           self.decoder_norm.eps)                                           # [b,10,64] fp32
+        logits = torch.einsum("bqc,btchw->btqhw", tok, x.float().reshape(b, n_f, -1, h, w)).flatten(0, 1)
+        return logits, x, tok, loss
+
+
+# ------------------------------------------------------------------------------------------- full decoder
+def _draw_widths(n, k_size, is_train):
+    """Ellipse sizes for compute_unknown: same numpy draws, in the same order, as utils/utils.py:45-50."""
+    return [int(np.random.randint(1, k_size)) for _ in range(n)] if is_train else [k_size // 2] * n
+
+
+class MaGGIeDecoder(nn.Module):
+    """`res_shortcut_inst_matt_spconv_22`."""
+
+    def __init__(self, atten_dim=128, atten_block=2, atten_head=1, final_channel=64, max_inst=10, use_id_pe=True,
+                 warmup_mask_atten_iter=0, warmup_detail_iter=3000, detail_mask_dropout=0.2, **_):
+        super().__init__()
+        assert atten_head == 1, "the reference configs use one attention head"
+        fc = final_channel
+        self.max_inst = max_inst
+        self.warmup_mask_atten_iter, self.warmup_detail_iter = warmup_mask_atten_iter, warmup_detail_iter
+        self.inst_spec_layer = _FFN(fc, fc, 0.1)
+        self.layer1 = seq(DecBlock(512, 256, up=True), DecBlock(256, 256))
+        self.layer2 = seq(DecBlock(256, 128, up=True), DecBlock(128, 128), DecBlock(128, 128))
+        self.refine_OS8 = InstanceMatteDecoder(128, atten_dim, atten_block, fc, max_inst, use_id_pe)
+        S, BN = SparseConvParams, nn.BatchNorm1d
+        # index-only path of the reference (weights exist, never train, features are discarded)
+        self.dummy_downscale = seq(S(3, 32, 3), S(32, 32, 3), S(32, 64, 3), S(64, 64, 3))
+        self.layer3 = seq(S(fc, 64, 3), BN(64), Slot(), S(64, 64, 3))
+        self.guidance_layer = seq(S(128, 64, 1), BN(64), Slot(), S(64, 64, 3, bias=True), Slot())
+        self.layer3_smooth = seq(S(64, 64, 1, bias=True), Slot(), BN(64))
+        self.layer4 = seq(S(64, 32, 3), BN(32), Slot(), S(32, 32, 1))
+        self.layer4_smooth = seq(S(64, 32, 1, bias=True), Slot(), BN(32))
+        self.layer5 = seq(S(32, 32, 3), BN(32), Slot(), S(32, 32, 3))
+        self.layer5_smooth = seq(S(64, 32, 1, bias=True), Slot(), BN(32))
+        self.refine_OS4 = seq(S(64, 32, 3), BN(32), Slot(), S(32, 1, 3, bias=True))
+        self.refine_OS1 = seq(S(32, 32, 3), BN(32), Slot(), S(32, 1, 3, bias=True))
+        for p in self.dummy_downscale.parameters():
+            p.requires_grad_(True)  # as in the reference: trainable flag set, but they never receive a gradient
+
+    # -- sparse refinement ---------------------------------------------------------------------------
+    def _bn1d(self, x, bn):
+        return x if x.shape[0] == 0 else ops.batch_norm(x.float(), bn, self.training).to(x.dtype)
+
+    def predict_details(self, os8_feat, roi, queries, fea1, fea2, fea3):
+        """roi uint8 [B, n_i, H, W]; queries [B, 10, 64] fp32.  Returns fp32 logit maps
+        [B*n_i,1,H/4,W/4], [B*n_i,1,H,W] (-99 where inactive) and the site counts."""
+        B, n_i, H, W = roi.shape
+        slots = B * n_i
+        T = ops.build_sites(roi.reshape(slots, H, W))
+        c1, c2, c4, c8 = T.coords
+        lre = lambda v: F.leaky_relu(v, 0.2)
+        dt = os8_feat.dtype
+
+        x = ops.gather_dense(os8_feat, c8, n_i)
+        g = queries[torch.div(c8[:, 0].long(), n_i, rounding_mode="floor"), (c8[:, 0] % n_i).long()]
+        x = self.inst_spec_layer(x * g.to(dt))
+        # OS8 -> OS4
+        x = ops.gather_conv(x, T.parent[2], self.layer3[0].weight)
+        x = ops.gather_conv(lre(self._bn1d(x, self.layer3[1])), T.nbr[2], self.layer3[3].weight)
+        det = ops.gather_dense(fea3, c4, n_i)
+        gd = ops.pointwise_conv(torch.cat([det, x], 1), self.guidance_layer[0].weight)
+        gd = ops.gather_conv(lre(self._bn1d(gd, self.guidance_layer[1])), T.nbr[2], self.guidance_layer[3].weight,
+                             self.guidance_layer[3].bias)
+        x = det * torch.sigmoid(gd.float()).to(dt)
+        x = self._bn1d(F.relu(ops.pointwise_conv(x, self.layer3_smooth[0].weight, self.layer3_smooth[0].bias)),
+                       self.layer3_smooth[2])
+        y = ops.gather_conv(x, T.nbr[2], self.refine_OS4[0].weight)
+        y = ops.gather_conv(lre(self._bn1d(y, self.refine_OS4[1])), T.nbr[2], self.refine_OS4[3].weight,
+                            self.refine_OS4[3].bias)
+        os4 = ops.scatter_logits(y, c4, slots, H // 4, W // 4)
+        # OS4 -> OS2
+        x = ops.gather_conv(x, T.parent[1], self.layer4[0].weight)
+        x = ops.pointwise_conv(lre(self._bn1d(x, self.layer4[1])), self.layer4[3].weight)
+        x = torch.cat([ops.gather_dense(fea2, c2, n_i), x], 1)
+        x = self._bn1d(F.relu(ops.pointwise_conv(x, self.layer4_smooth[0].weight, self.layer4_smooth[0].bias)),
+                       self.layer4_smooth[2])
+        # OS2 -> OS1
+        x = ops.gather_conv(x, T.parent[0], self.layer5[0].weight)
+        x = ops.gather_conv(lre(self._bn1d(x, self.layer5[1])), T.nbr[0], self.layer5[3].weight)
+        x = torch.cat([ops.gather_dense(fea1, c1, n_i), x], 1)
+        x = self._bn1d(F.relu(ops.pointwise_conv(x, self.layer5_smooth[0].weight, self.layer5_smooth[0].bias)),
+                       self.layer5_smooth[2])
+        y = ops.gather_conv(x, T.nbr[0], self.refine_OS1[0].weight)
+        y = ops.gather_conv(lre(self._bn1d(y, self.refine_OS1[1])), T.nbr[0], self.refine_OS1[3].weight,
+                            self.refine_OS1[3].bias)
+        os1 = ops.scatter_logits(y, c1, slots, H, W)
+        return os4, os1, T.counts
+
+    # -- forward --------------------------------------------------------------------------------------
+    def forward(self, x, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, **_):
+        """x: ASPP output; fea: (fea1..fea5); masks [b*n_f, n_i, H, W] fp32 {0,1}; gt_alphas [b*n_f, n_i, H, W]."""
+        t = self.training
+        fea1, fea2, fea3, fea4, fea5 = fea
+        H, W = image_hw
+        valid = masks.flatten(2).sum(2)[:, :, None, None] > 0
+        x = self.layer1(x) + fea5
+        x = self.layer2(x) + fea4
+
+        m5 = masks.reshape(b, n_f, n_i, H, W)
+        mask_os8 = F.avg_pool2d(m5.flatten(0, 1), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0
+        gt_os8 = None
+        if t:
+            gt_os8 = F.max_pool2d((gt_alphas > 0).float(), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0
+        os8_logits, x, queries, loss_atten = self.refine_OS8(x, mask_os8, gt_os8)
+        a8 = ops.upsample_tanh(os8_logits, size=(H, W))
+        a8 = a8 * valid if t else a8[:, :n_i]
+
+        guided, use_gt = a8, False
+        wd = self.warmup_detail_iter
+        if t and (iter < wd or float(a8.sum()) == 0 or (iter < wd * 3 and random.random() < 0.5)):
+            guided, use_gt = gt_alphas, True
+        n_sl = guided.shape[0] * guided.shape[1]
+        unk = ops.unknown_mask(guided, _draw_widths(n_sl, 30, False))
+        if t and int(unk.max()) == 0:
+            unk[:, :, 200:250, 200:250] = 1
+        counts = [0, 0, 0, 0]
+        if t or int(unk.max()) > 0:
+            q = queries[:, None].expand(-1, n_f, -1, -1).reshape(b * n_f, *queries.shape[1:])
+            os4, os1, counts = self.predict_details(x, unk, q, fea1, fea2, fea3)
+            os4 = os4.reshape(b * n_f, guided.shape[1], H // 4, W // 4)
+            os1 = os1.reshape(b * n_f, guided.shape[1], H, W)
+            a4 = ops.upsample_tanh(os4, scale=4.0)
+            a1 = ops.upsample_tanh(os1)
+        else:
+            a4 = torch.zeros_like(a8)
+            a1 = torch.zeros_like(a8)
+        ret = dict(alpha_os1=a1, alpha_os4=a4, alpha_os8=a8)
+        # progressive fusion (resnet_inst_matt_spconv.py:272-290)
+        w4 = ops.unknown_mask(a8, _draw_widths(n_sl, 27, t), and_mask=unk).to(a8.dtype)
+        a = a4 * w4 + a8 * (1 - w4)
+        w1 = ops.unknown_mask(a, _draw_widths(n_sl, 15, t), and_mask=unk).to(a8.dtype)
+        a = a1 * w1 + a * (1 - w1)
+        ret["refined_masks"] = a
+        if use_gt:
+            w4 = ops.unknown_mask(gt_alphas, _draw_widths(n_sl, 30, t), and_mask=unk)
+            w1 = ops.unknown_mask(gt_alphas, _draw_widths(n_sl, 15, t), and_mask=unk)
+        ret["weight_os4"], ret["weight_os1"], ret["detail_mask"] = w4, w1, unk
+        ret["site_counts"] = counts
+        if t and iter >= self.warmup_mask_atten_iter:
+            ret["loss_max_atten"] = loss_atten
+        return ret

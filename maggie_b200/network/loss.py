@@ -1,0 +1,90 @@
+"""Training losses evaluated inside forward(): weighted L1, 3-level Laplacian pyramid, Sobel gradient.
+
+Reference: arch/maggie.py:237-368 (regression_loss, compute_loss), loss.py:67-191 (GradientLoss, LapLoss).
+INTERIM: composed from torch ops in fp32 (a fused stencil-reduction kernel is the SURVEY §8f rank-1 "next" row).
+"""
+import torch
+import torch.nn.functional as F
+
+_GAUSS = torch.tensor([1.0, 4.0, 6.0, 4.0, 1.0])
+_GAUSS2D = (_GAUSS[:, None] * _GAUSS[None, :]) / 256.0
+_SOBEL = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]]) / 8.0
+
+
+def weighted_l1(pred, target, weight):
+    return (pred * weight - target * weight).abs().sum() / (weight.sum() + 1e-8)
+
+
+def _blur(x, k):
+    return F.conv2d(F.pad(x, (2, 2, 2, 2), mode="reflect"), k)
+
+
+def _pyramid(x, levels):
+    k = _GAUSS2D.to(x.device, x.dtype)[None, None]
+    out = []
+    for _ in range(levels):
+        down = _blur(x, k)[:, :, ::2, ::2]
+        up = x.new_zeros(x.shape)
+        up[:, :, ::2, ::2] = down
+        out.append(x - _blur(up, 4.0 * k))
+        x = down
+    return out
+
+
+def lap_loss(pred, target, weight, levels=3):
+    """pred/target/weight [N,1,H,W].  The reference's LapLoss() is built for 3 channels and fed 1-channel images,
+    which triples every level's weighted sum (loss.py:170-173 with groups=1) - reproduced by the factor 3."""
+    pp, pt = _pyramid(pred, levels), _pyramid(target, levels)
+    total = 0.0
+    for i in range(levels):
+        total = total + 3.0 * ((pp[i] - pt[i]).abs() * weight).sum() / (weight.sum() + 1e-6)
+        weight = weight[:, :, ::2, ::2]
+    return total
+
+
+def _sobel_mag(x, eps=1e-6):
+    n, c, h, w = x.shape
+    xp = F.pad(x.reshape(n * c, 1, h, w), (1, 1, 1, 1), mode="replicate")
+    kx = _SOBEL.to(x.device, x.dtype)
+    gx, gy = F.conv2d(xp, kx[None, None]), F.conv2d(xp, kx.t()[None, None])
+    return torch.sqrt(gx * gx + gy * gy + eps).reshape(n, c, h, w)
+
+
+def grad_loss(pred, target, weight, eps=1e-6):
+    return (_sobel_mag(pred * weight) - _sobel_mag(target * weight)).abs().sum() / (weight.sum() + eps)
+
+
+def compute_loss(pred, w4, w1, alphas, cfg):
+    """Image-model loss dictionary (dtSSD handled by the video subclass)."""
+    a1, a4, a8 = pred["alpha_os1"], pred["alpha_os4"], pred["alpha_os8"]
+    w8 = (alphas.sum((2, 3), keepdim=True) > 0).to(a8.dtype).expand_as(a8)
+    if cfg.loss_reweight_os8:
+        lo, hi = 1.0 / 255.0, 254.0 / 255.0
+        unk = ((alphas <= hi) & (alphas >= lo)) | ((a8 <= hi) & (a8 >= lo))
+        w8 = unk.to(a8.dtype) + w8
+    w4, w1 = w4.to(a8.dtype), w1.to(a8.dtype)
+    L = {}
+    total = 0.0
+    if cfg.loss_alpha_w > 0:
+        r1, r4, r8 = weighted_l1(a1, alphas, w1), weighted_l1(a4, alphas, w4), weighted_l1(a8, alphas, w8)
+        L.update(loss_rec_os1=r1, loss_rec_os4=r4, loss_rec_os8=r8, loss_rec=r1 * 2 + r4 + r8)
+        total = total + L["loss_rec"] * cfg.loss_alpha_w
+    h, w = a8.shape[-2:]
+    v = lambda z: z.reshape(-1, 1, h, w)
+    if cfg.loss_alpha_lap_w > 0:
+        tp = _pyramid(v(alphas), 3)  # target pyramid is shared by the three scales
+        def lap(p, wt):
+            pp, tot, wt = _pyramid(v(p), 3), 0.0, v(wt)
+            for i in range(3):
+                tot = tot + 3.0 * ((pp[i] - tp[i]).abs() * wt).sum() / (wt.sum() + 1e-6)
+                wt = wt[:, :, ::2, ::2]
+            return tot
+        l1_, l4_, l8_ = lap(a1, w1), lap(a4, w4), lap(a8, w8)
+        L.update(loss_lap_os1=l1_, loss_lap_os4=l4_, loss_lap_os8=l8_, loss_lap=l1_ * 2 + l4_ + l8_)
+        total = total + L["loss_lap"] * cfg.loss_alpha_lap_w
+    if cfg.loss_alpha_grad_w > 0:
+        g1, g4, g8 = grad_loss(a1, alphas, w1), grad_loss(a4, alphas, w4), grad_loss(a8, alphas, w8)
+        L.update(loss_grad_os1=g1, loss_grad_os4=g4, loss_grad_os8=g8, loss_grad=g1 * 2 + g4 + g8)
+        total = total + L["loss_grad"] * cfg.loss_alpha_grad_w
+    L["total"] = total
+    return L

@@ -1,0 +1,248 @@
+"""Operator layer between `maggie_b200.network` and the C ABI (include/maggie_b200.h).
+
+Two kinds of ops live here:
+  * NATIVE ops - `torch.autograd.Function`s / plain functions that hand raw device pointers to
+    libmaggie_b200.so (hand-written sm_100a kernels).  No fallback: they raise if the tensors are not CUDA
+    tensors or the library is missing.
+  * INTERIM ops - the parts of the path whose kernels are not written yet are composed from torch CUDA ops
+    (cuDNN/cuBLAS/ATen).  They are listed in DESIGN.md ("native coverage") and are replaced one by one; the
+    model code above this layer does not change when that happens.
+Activations are fp16, channels-last in memory (NHWC) and NCHW-shaped for torch; statistics, logits and
+alphas are fp32.
+"""
+import ctypes
+from collections import namedtuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+COMPUTE_DTYPE = torch.float16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("maggie_b200 native op called with a non-CUDA tensor; there is no CPU fallback")
+
+
+# =============================================================================================== native: K8a
+def unknown_mask(alpha, widths, and_mask=None):
+    """uint8 {0,1} mask of the dilated uncertain region (reference: utils/utils.py:28-55 compute_unknown).
+    alpha [..., H, W] fp32; widths: one ellipse size (1..29) per [H, W] slice; and_mask optional uint8."""
+    _need_cuda(alpha, and_mask)
+    a = alpha.detach().to(torch.float32).contiguous()
+    H, W = a.shape[-2:]
+    slices = a.numel() // (H * W) if a.numel() else 0
+    out = torch.empty(a.shape, dtype=torch.uint8, device=a.device)
+    if slices == 0:
+        return out
+    if len(widths) != slices:
+        raise ValueError(f"unknown_mask: {len(widths)} widths for {slices} slices")
+    w = torch.tensor(list(widths), dtype=torch.int32).pin_memory().to(a.device, non_blocking=True)
+    if and_mask is not None:
+        and_mask = and_mask.to(torch.uint8).contiguous()
+        assert and_mask.shape == a.shape
+    _lib.check(_lib.lib().mg_unknown_mask(_ptr(a), slices, H, W, _ptr(w), _ptr(and_mask), _ptr(out), None, _stream()),
+               "mg_unknown_mask")
+    return out
+
+
+# =============================================================================================== native: K8b
+SiteTables = namedtuple("SiteTables", "counts coords nbr parent child shapes")
+
+
+def build_sites(roi):
+    """Active-site lists and rulebook tables of the 4 sparse levels (reference:
+    decoder/resnet_inst_matt_spconv.py:203-218: nonzero + spconv dummy_downscale index generation).
+    roi uint8 [slots, H, W].  One 16-byte D2H read of the four counts."""
+    _need_cuda(roi)
+    roi = roi.to(torch.uint8).contiguous()
+    S, H, W = roi.shape
+    L = _lib.lib()
+    ws = torch.empty(L.mg_sites_workspace(S, H, W), dtype=torch.uint8, device=roi.device)
+    counts_d = torch.zeros(4, dtype=torch.int32, device=roi.device)
+    _lib.check(L.mg_sites_count(_ptr(roi), S, H, W, _ptr(ws), _ptr(counts_d), _stream()), "mg_sites_count")
+    counts = [int(c) for c in counts_d.cpu()]
+    mk = lambda n, k: torch.empty((n, k), dtype=torch.int32, device=roi.device)
+    coords = [mk(n, 3) for n in counts]
+    nbr = [mk(counts[0], 9), None, mk(counts[2], 9), None]
+    parent = [mk(counts[l], 9) for l in range(3)] + [None]
+    child = [None] + [mk(counts[l], 9) for l in range(1, 4)]
+    pa = lambda ts: _lib.ptr_array([t.data_ptr() if (t is not None and t.numel()) else 0 for t in ts])
+    _lib.check(L.mg_sites_tables(_ptr(ws), S, H, W, _lib.i32_array(counts), pa(coords), pa(nbr), pa(parent), pa(child),
+                                 _stream()), "mg_sites_tables")
+    shapes = [(H >> l, W >> l) for l in range(4)]
+    return SiteTables(counts, coords, nbr, parent, child, shapes)
+
+
+# =============================================================================================== native: K1
+class _MaskEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, masks, table, slot_ids, C):
+        _need_cuda(image, masks, table)
+        image = image.to(torch.float32).contiguous()
+        masks = masks.to(torch.float32).contiguous()
+        B, _, H, W = image.shape
+        M = masks.shape[1]
+        out = torch.empty((B, H, W, C), dtype=torch.float16, device=image.device)
+        ids = _lib.i32_array(slot_ids)
+        tab = table.detach().to(torch.float32).contiguous()
+        _lib.check(_lib.lib().mg_mask_embed_fwd(_ptr(image), _ptr(masks), ids, M, _ptr(tab), _ptr(out), B, H, W, C,
+                                               _stream()), "mg_mask_embed_fwd")
+        ctx.save_for_backward(masks)
+        ctx.meta = (tuple(slot_ids), C, table.shape, table.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (masks,) = ctx.saved_tensors
+        slot_ids, C, tshape, tdtype = ctx.meta
+        B, H, W, _ = gout.shape
+        g = gout.to(torch.float16).contiguous()
+        gtab = torch.zeros(tshape, dtype=torch.float32, device=gout.device)
+        _lib.check(_lib.lib().mg_mask_embed_bwd(_ptr(g), _ptr(masks), _lib.i32_array(slot_ids), masks.shape[1],
+                                               _ptr(gtab), B, H, W, C, _stream()), "mg_mask_embed_bwd")
+        return None, None, gtab.to(tdtype), None, None
+
+
+def mask_embed(image, masks, table, slot_ids, C=8):
+    """image [B,3,H,W] fp32, masks [B,M,H,W] {0,1}, table [11,3] -> packed encoder input, NCHW-shaped
+    channels-last fp16 [B,C,H,W] (ch 0-2 image, 3-5 mean id embedding, rest 0).
+    Reference: arch/maggie.py:200-235 + encoder/resnet.py:211-229."""
+    return _MaskEmbed.apply(image, masks, table, list(slot_ids), C).permute(0, 3, 1, 2)
+
+
+# =============================================================================================== interim ops
+def _act(x, act):
+    if act == "relu":
+        return F.relu(x)
+    if act == "lrelu":
+        return F.leaky_relu(x, 0.2)
+    assert act is None
+    return x
+
+
+def spectral_weight(w_bar, u, v):
+    """One power iteration (updates u, v in place, no grad) and W = W_bar / sigma
+    (reference: module/spectral_norm.py:22-35).  INTERIM (torch)."""
+    h = w_bar.shape[0]
+    with torch.no_grad():
+        wm = w_bar.detach().reshape(h, -1)
+        vn = torch.mv(wm.t(), u)
+        vn = vn / (vn.norm() + 1e-12)
+        un = torch.mv(wm, vn)
+        un = un / (un.norm() + 1e-12)
+        v.copy_(vn)
+        u.copy_(un)
+    sigma = torch.dot(u.detach(), torch.mv(w_bar.reshape(h, -1), v.detach()))
+    return w_bar / sigma
+
+
+def batch_norm(x, bn, training):
+    """Training-mode (batch statistics, running-stat update) or eval-mode BatchNorm from a container's
+    tensors.  INTERIM (torch)."""
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum, bn.eps)
+
+
+def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="relu", act_first=False,
+                residual=None, transposed=False):
+    """conv (or 4x4 s2 transposed conv) -> BN -> (+residual) -> act, or conv -> act -> BN when act_first.
+    x NCHW-shaped channels-last; w in the reference's layout ([Cout,Cin,k,k]; [Cin,Cout,4,4] transposed).
+    INTERIM (cuDNN via torch)."""
+    w = w.to(x.dtype)
+    if w.shape[0 if transposed else 1] < x.shape[1]:  # input was channel-padded by mask_embed
+        pad = x.shape[1] - w.shape[0 if transposed else 1]
+        w = F.pad(w, (0, 0, 0, 0, 0, pad)) if not transposed else F.pad(w, (0, 0, 0, 0, 0, 0, 0, pad))
+    if transposed:
+        y = F.conv_transpose2d(x, w, stride=2, padding=1)
+    else:
+        y = F.conv2d(x, w, stride=stride, padding=padding, dilation=dilation)
+    if act_first:
+        y = _act(y, act)
+    if bn is not None:
+        y = batch_norm(y, bn, training)
+    if residual is not None:
+        y = y + residual
+    if not act_first:
+        y = _act(y, act)
+    return y
+
+
+def linear(x, w, b=None):
+    return F.linear(x, w.to(x.dtype), None if b is None else b.to(x.dtype))
+
+
+def layer_norm(x, ln):
+    return F.layer_norm(x.float(), (x.shape[-1],), ln.weight, ln.bias, ln.eps).to(x.dtype)
+
+
+def attention(q, k, v, key_padding=None, need_stat=None):
+    """Single-head attention, batch-first: q [B,L,E], k/v [B,S,E] (already projected).  Softmax in fp32.
+    key_padding [B,S] bool (True = ignore).  need_stat: optional [B,L,S] bool guidance mask; if given also
+    returns stat[b,l] = sum_s guidance * A (the only thing the attention-max loss needs,
+    module/instance_matte_decoder.py:101-109).  INTERIM (torch)."""
+    s = torch.bmm(q, k.transpose(1, 2)).float() * (q.shape[-1] ** -0.5)
+    if key_padding is not None:
+        s = s.masked_fill(key_padding[:, None, :], float("-inf"))
+    a = torch.softmax(s, dim=-1)
+    o = torch.bmm(a.to(v.dtype), v)
+    if need_stat is not None:
+        return o, (a * need_stat).sum(-1)
+    return o, None
+
+
+def gather_conv(src, table, weight, bias=None):
+    """Rulebook convolution: out[p] = sum_t W[t] . src[table[p,t]] (table entry -1 = no contribution).
+    src [Ns,Cin]; table [No,T] int32; weight in spconv layout [Cout,kh,kw,Cin] with kh*kw == T.
+    Covers SubMConv2d (nbr table) and SparseInverseConv2d (parent table).  INTERIM (torch gather + GEMM)."""
+    No, T = table.shape
+    Cout, Cin = weight.shape[0], weight.shape[-1]
+    if No == 0:
+        return src.new_zeros((0, Cout))
+    padded = torch.cat([src, src.new_zeros((1, Cin))], dim=0)
+    idx = torch.where(table < 0, src.shape[0], table.long()).reshape(-1)
+    g = padded.index_select(0, idx).reshape(No, T * Cin)
+    w = weight.reshape(Cout, T * Cin).to(src.dtype)
+    out = g @ w.t()
+    return out if bias is None else out + bias.to(out.dtype)
+
+
+def pointwise_conv(src, weight, bias=None):
+    """SubMConv2d with k=1 == per-site linear map. weight [Cout,1,1,Cin]. INTERIM."""
+    return linear(src, weight.reshape(weight.shape[0], -1), bias)
+
+
+def gather_dense(dense, coords, n_i):
+    """dense NCHW-shaped channels-last [B,C,H,W] -> rows [N,C] at coords (frame = slot // n_i). INTERIM."""
+    nhwc = dense.permute(0, 2, 3, 1)
+    c = coords.long()
+    return nhwc[torch.div(c[:, 0], n_i, rounding_mode="floor"), c[:, 1], c[:, 2]]
+
+
+def scatter_logits(vals, coords, slots, H, W):
+    """fp32 logit map [slots,1,H,W]: -99 everywhere, value at active sites computed as ((v - 99) + 99) like the
+    reference's dense()/-99/+=99 sequence (decoder/resnet_inst_matt_spconv.py:248-251). INTERIM."""
+    out = torch.full((slots, 1, H, W), -99.0, dtype=torch.float32, device=vals.device)
+    c = coords.long()
+    v = (vals.float().reshape(-1) - 99.0) + 99.0
+    return out.index_put((c[:, 0], torch.zeros_like(c[:, 0]), c[:, 1], c[:, 2]), v)
+
+
+def upsample_tanh(logits, size=None, scale=None):
+    """bilinear (align_corners=False) -> (tanh+1)/2 in fp32. INTERIM."""
+    x = logits.float()
+    if size is not None or scale is not None:
+        x = F.interpolate(x, size=size, scale_factor=scale, mode="bilinear", align_corners=False)
+    return (torch.tanh(x) + 1.0) / 2.0

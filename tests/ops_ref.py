@@ -1,0 +1,91 @@
+"""Reference (oracle-backed, CPU) implementations of the NATIVE ops' contracts.  Test-only: used (a) to check
+the CUDA kernels against on the GPU box and (b) injected into `maggie_b200.ops` so the host-side model logic
+can be exercised on the CPU container."""
+import contextlib
+
+import numpy as np
+import torch
+
+from maggie_b200 import ops
+from oracle import unknown as U
+
+
+def unknown_mask(alpha, widths, and_mask=None):
+    out = U.compute_unknown(alpha.detach().cpu().float().numpy(), list(widths))
+    if and_mask is not None:
+        out = out * (and_mask.cpu().numpy() != 0)
+    return torch.from_numpy(out.astype(np.uint8)).to(alpha.device)
+
+
+def _imap(coords, slots, H, W):
+    m = np.full((slots, H, W), -1, np.int64)
+    if len(coords):
+        m[coords[:, 0], coords[:, 1], coords[:, 2]] = np.arange(len(coords))
+    return m
+
+
+def _lookup(imap, s, y, x):
+    S, H, W = imap.shape
+    ok = (y >= 0) & (y < H) & (x >= 0) & (x < W)
+    out = np.full(len(s), -1, np.int64)
+    out[ok] = imap[s[ok], y[ok], x[ok]]
+    return out
+
+
+def sites_tables_ref(roi):
+    """numpy restatement of mg_sites_count + mg_sites_tables. roi uint8 [S,H,W] (numpy)."""
+    S, H, W = roi.shape
+    coords = [U.active_sites(roi)]
+    shapes = [(H, W)]
+    for _ in range(3):
+        c, shp = U.downscale_sites(coords[-1], *shapes[-1])
+        coords.append(c), shapes.append(shp)
+    imaps = [_imap(c, S, *shp) for c, shp in zip(coords, shapes)]
+    nbr, parent, child = [None] * 4, [None] * 4, [None] * 4
+    for l in range(4):
+        c = coords[l].astype(np.int64)
+        s, y, x = c[:, 0], c[:, 1], c[:, 2]
+        if l in (0, 2):
+            nbr[l] = np.stack([_lookup(imaps[l], s, y + ky - 1, x + kx - 1) for ky in range(3) for kx in range(3)], 1)
+        if l < 3:
+            cols = []
+            for ky in range(3):
+                for kx in range(3):
+                    ty, tx = y + 1 - ky, x + 1 - kx
+                    r = _lookup(imaps[l + 1], s, ty // 2, tx // 2)
+                    r[(ty % 2 != 0) | (tx % 2 != 0) | (ty < 0) | (tx < 0)] = -1
+                    cols.append(r)
+            parent[l] = np.stack(cols, 1)
+        if l >= 1:
+            child[l] = np.stack([_lookup(imaps[l - 1], s, 2 * y - 1 + ky, 2 * x - 1 + kx) for ky in range(3) for kx in range(3)], 1)
+    return coords, nbr, parent, child, shapes
+
+
+def build_sites(roi):
+    dev = roi.device
+    coords, nbr, parent, child, shapes = sites_tables_ref(roi.cpu().numpy().astype(np.uint8))
+    tt = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a).astype(np.int32).reshape(len(a), -1)).to(dev)
+    return ops.SiteTables([len(c) for c in coords], [tt(c) for c in coords], [tt(a) for a in nbr],
+                          [tt(a) for a in parent], [tt(a) for a in child], shapes)
+
+
+def mask_embed(image, masks, table, slot_ids, C=8):
+    """Differentiable torch restatement of K1 (encoder/resnet.py:211-229); NCHW-shaped [B,C,H,W]."""
+    B, _, H, W = image.shape
+    ids = torch.tensor([s + 1 for s in slot_ids], device=image.device).view(1, -1, 1, 1)
+    m = (masks * ids).long()
+    on = (m > 0).float().unsqueeze(-1)
+    emb = (table[m] * on).sum(1) / (on.sum(1) + 1e-6)
+    out = torch.cat([image, emb.permute(0, 3, 1, 2), image.new_zeros(B, C - 6, H, W)], 1)
+    return out.to(ops.COMPUTE_DTYPE).contiguous(memory_format=torch.channels_last)
+
+
+@contextlib.contextmanager
+def injected(dtype=torch.float32):
+    """Swap the native ops for the references above (CPU container only)."""
+    saved = (ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.COMPUTE_DTYPE)
+    ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.COMPUTE_DTYPE = unknown_mask, build_sites, mask_embed, dtype
+    try:
+        yield
+    finally:
+        ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.COMPUTE_DTYPE = saved

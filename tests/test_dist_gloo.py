@@ -1,0 +1,39 @@
+"""world_size-2 gloo test of the flat gradient all-reduce used by the N>1 path."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from maggie_b200.dp import FlatGradAllReduce, shard_frames
+
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    fr = FlatGradAllReduce(lin.parameters())
+    x = torch.arange(16.0).view(4, 4)
+    lo, hi = shard_frames(4, rank, world)
+    fr.zero()
+    lin(x[lo:hi]).sum().backward()
+    fr.allreduce(average=False)
+    got = fr.flat.clone()
+    # single-process reference over the full batch
+    ref = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    ref.load_state_dict(lin.state_dict())
+    ref(x).sum().backward()
+    want = torch.cat([p.grad.flatten() for p in ref.parameters()])
+    assert torch.allclose(got, want, atol=1e-5), (got, want)
+    assert all(p.grad.data_ptr() >= fr.flat.data_ptr() for p in lin.parameters())
+    dist.destroy_process_group()
+
+
+def test_flat_allreduce_matches_full_batch_gradient():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
