@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py - frames/s (fwd+bwd) of the MaGGIe hot path on N B200s (BASELINE.json metric, config C2/C3).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (one rank per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A step = model(batch) + (loss * scale).backward() (+ one flat gradient all-reduce when N>1) on a synthetic
+batch of 8 frames x 512x512 x 3 instances per GPU (weak scaling), training mode, iter=1.
+`value`  : inputs already resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : the same step through the public API with the batch in pinned HOST memory: H2D copies and the D2H
+           read of the loss are inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU, H, W, N_INST, EDGE_PX = 8, 512, 512, 3, 6.0
+LOSS_SCALE = 128.0
+F_DENSE_PER_FRAME = 69.23e9 * (H * W) / (512 * 512)
+
+
+def f_sparse(counts):
+    n1, n2, n4, n8 = counts
+    return 2.0 * (23072 * n1 + 7680 * n2 + 113952 * n4 + 8192 * n8)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        z = json.load(open(p))
+        return dict(hbm=z["hbm_gbs"], tf_burst=z["bf16_tflops"], tf_sustained=z["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_fn(frames=2):
+    """Oracle port (CPU fp32 restatement of the reference path) fwd+bwd on a `frames`-frame sample of C2."""
+    import torch
+
+    from oracle import maggie_oracle as O
+    from oracle import make_golden as G
+    from oracle import synth
+
+    torch.set_num_threads(os.cpu_count())
+    import numpy as np
+    z = np.load(os.path.join(G.GOLDEN_DIR, "state_shapes.npz"))
+    tmpl = {k: torch.zeros(tuple(z[k]), dtype=torch.long if k.endswith("num_batches_tracked") else torch.float32)
+            for k in z.files}
+    P = synth.synth_state_dict(tmpl)
+    for k, v in P.items():
+        if v.is_floating_point() and not k.endswith(("weight_u", "weight_v", "running_mean", "running_var")) \
+                and "dummy_downscale" not in k:
+            v.requires_grad_(True)
+    batch = synth.make_batch(b=frames, n_f=1, n_i=N_INST, H=H, W=W, edge_px=EDGE_PX, train=True, it=1)
+    cfg = synth.model_cfg()
+
+    def step():
+        G.seed_all()
+        for v in P.values():
+            v.grad = None
+        _, loss = O.forward(P, batch, True, cfg)
+        loss["total"].backward()
+        return float(loss["total"])
+
+    return step, frames
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, frames = cpu_step_fn(2)
+    warm = min(args.warmup, 1)  # one warm-up is what a ~15 s CPU step affords; stated in `sample`
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = frames / dt
+    sample = f"{frames} frames x {H}x{W} x {N_INST} inst per step (BatchNorm needs >=2), fp32, {warm} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": "frames_per_sec_fwd_bwd", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd (CPU sample: {frames} frames/step)"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def kernel_probes(torch, dev, peaks):
+    """Live CUDA-event timing of this repo's own kernels at the C2 shapes (L2 flushed between launches)."""
+    from maggie_b200 import ops
+    from oracle import synth
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    al = torch.stack([synth.soft_ellipse_alphas(1, 10, H, W, EDGE_PX, seed=s)[0] for s in range(FRAMES_PER_GPU)]).to(dev)
+    widths = [15] * (FRAMES_PER_GPU * 10)
+    img = torch.randn(FRAMES_PER_GPU, 3, H, W, device=dev)
+    msk = (al[:, :3] > 0.5).float().contiguous()
+    tab = torch.randn(11, 3, device=dev)
+    probes = {
+        "unknown_mask_kernel": (lambda: ops.unknown_mask(al, widths), al.numel() * 5.0),
+        "mask_embed_fwd_kernel": (lambda: ops.mask_embed(img, msk, tab, [0, 1, 2], 8), img.shape[0] * H * W * (6 * 4 + 16.0)),
+    }
+    out = {}
+    for name, (fn, nbytes) in probes.items():
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        t = sorted(ts)[len(ts) // 2]
+        out[name] = dict(bound="hbm", achieved=nbytes / t / 1e9, peak=peaks["hbm"], unit="GB/s",
+                         frac=nbytes / t / 1e9 / peaks["hbm"], traffic=None, us=t * 1e6, algorithmic_bytes=nbytes)
+    return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from maggie_b200 import _lib
+    from maggie_b200.config import CfgNode
+    from maggie_b200.dp import FlatGradAllReduce
+    from maggie_b200.network import build_model
+    from oracle import synth  # synthetic inputs only (test infrastructure used as a data generator)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234)  # identical initial weights on every rank
+    model, _ = build_model(CfgNode(synth.model_cfg()))
+    model.to(dev).train()
+    flat = FlatGradAllReduce(model.parameters())
+
+    host = synth.make_batch(b=FRAMES_PER_GPU, n_f=1, n_i=N_INST, H=H, W=W, edge_px=EDGE_PX, seed=1234 + rank, train=True, it=1)
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items() if k not in ("fg", "bg")}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    to_dev = lambda: {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+    resident = to_dev()
+
+    import numpy as np
+    import random
+
+    def step(batch):
+        np.random.seed(7), random.seed(7)
+        flat.zero()
+        _, loss = model(batch, mem_feat=None)
+        (loss["total"] * LOSS_SCALE).backward()
+        flat.allreduce()
+        return loss["total"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    ms = timed(lambda: step(resident), args.steps)
+    launches = _lib.launch_count()
+
+    def e2e_step():
+        return float(step(to_dev()))  # float() = D2H read of the loss
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    counts = model.last_site_counts
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    frames = FRAMES_PER_GPU * world
+    value, e2e = frames / (ms * 1e-3), frames / (ms_e2e * 1e-3)
+    f_step = 3.0 * (F_DENSE_PER_FRAME * FRAMES_PER_GPU + f_sparse(counts))  # per GPU per step
+    probes = kernel_probes(torch, dev, peaks)
+    top = max(probes, key=lambda k: probes[k]["us"])
+    roof = dict(probes[top], kernel=top, peak_source=peaks["src"])
+    line = {
+        "metric": "frames_per_sec_fwd_bwd", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd per GPU (iter=1, edge {EDGE_PX}px)",
+                   "frames_per_gpu": FRAMES_PER_GPU, "active_sites_os1_os2_os4_os8": counts,
+                   "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
+                   "loss_scale": LOSS_SCALE, "sync_bn": False},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels": probes,
+        "flop_roofline": {"flop_per_step_per_gpu": f_step, "achieved_tflops": f_step / (ms * 1e-3) / 1e12,
+                          "peak_tflops_sustained": peaks["tf_sustained"],
+                          "frac": f_step / (ms * 1e-3) / 1e12 / peaks["tf_sustained"], "peak_source": peaks["src"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cstep, cframes = cpu_step_fn(2)
+        cstep()
+        t0 = time.perf_counter()
+        cstep()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": cframes / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"1 timed step (after 1 warm-up) of {cframes} frames x {H}x{W} x {N_INST} inst, fp32 oracle port"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,34 @@ int mg_mask_embed_fwd(const float* image, const float* masks, const int32_t* slo
 int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, const int32_t* slot_ids_host, int M,
                       float* grad_table, int B, int H, int W, int C, void* stream);
 
+
+/* ---- K2: dense convolution, implicit GEMM on tcgen05 tensor cores with TMA-staged operands ---------
+ * replaces: every nn.Conv2d / nn.ConvTranspose2d call of the hot path (cuDNN via ATen): encoder
+ *           encoder/resnet.py:177-200, ASPP module/aspp.py:35-56, decoder decoder/resnet.py:33-45,
+ *           module/instance_matte_decoder.py:81-88; and, with the transposed weight pack, their data gradients.
+ * x    NHWC fp16 [N,Hi,Wi,Ci], Ci % 16 == 0.      w  packed fp16 [Co][Ktot] (K contiguous), Co % 16 == 0.
+ * The op computes, for every image n and logical grid point (y,x), 0<=y<Hg, 0<=x<Wg:
+ *     acc[c] = sum_t sum_ci  x[n, y*sy + tap_dy[t], x*sx + tap_dx[t], ci] * w[c][tap_koff[t] + ci]   (zero outside x)
+ *     out[n, y*oys + oy0, x*oxs + ox0, c_off + c] = fp16( relu?(acc[c] + bias[c]) )
+ * out is NHWC fp16 [N,Ho,Wo,Cs].  3x3 pad 1: taps (ky-1,kx-1); dilation d: d*(k-1); stride 2: sy=sx=2;
+ * 4x4 stride-2 transposed conv: four launches (one per output parity) with oys=oxs=2.
+ * stats (optional): float [MG_CONV_STAT_COPIES][2][Co], must be zeroed by the caller; the kernel accumulates
+ * per-channel sum (row 0) and sum of squares (row 1) of the stored values' fp32 pre-images, spread over the
+ * copies to keep atomics uncontended (mg_bn_finalize adds the copies up).                                  */
+#define MG_CONV_MAX_TAPS 16
+#define MG_CONV_STAT_COPIES 64
+typedef struct mg_conv_desc {
+    const void* x; int32_t N, Hi, Wi, Ci;
+    const void* w; int32_t Co, Ktot;
+    int32_t n_taps; int32_t tap_dy[MG_CONV_MAX_TAPS], tap_dx[MG_CONV_MAX_TAPS], tap_koff[MG_CONV_MAX_TAPS];
+    int32_t sy, sx, Hg, Wg;
+    void* out; int32_t Ho, Wo, Cs, c_off, oys, oy0, oxs, ox0;
+    int32_t epi_relu;
+    float* stats;
+    const float* bias;
+} mg_conv_desc;
+int mg_conv_fprop(const mg_conv_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,294 @@
+// K2: dense convolution as an implicit GEMM on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in
+// TMEM), operands staged by TMA.
+//
+//   D[128 pixels x BN channels] = sum over (tap, Cin chunk)  A_tap[128 x BK] * W_tap[BN x BK]^T
+//
+// * A tile: a th x tw rectangle of output pixels (th*tw = 128).  For tap (dy,dx) the operand is simply the input
+//   box shifted by (dy,dx): ONE 4-D TMA load {BK channels, tw, th, 1 image} of the NHWC tensor, with the
+//   hardware zero-filling out-of-bounds coordinates (= the conv's zero padding) and `elementStrides` doing the
+//   stride-2 subsampling.  The box lands in shared memory as 128 rows of BK*2 bytes with 32/64/128-byte
+//   swizzle = the canonical K-major UMMA operand layout.  No im2col buffer ever exists.
+// * W tile: 2-D TMA box {BK, BN} of the packed weight matrix [Cout][taps*Cin] (K contiguous).
+// * 4-stage mbarrier pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator), warps 2..5 =
+//   epilogue (tcgen05.ld -> optional ReLU -> fp16 NHWC store, + per-channel sum / sum-of-squares partials for
+//   training-mode BatchNorm).
+// The same kernel serves 3x3/1x1/dilated/strided forward convs, the four sub-pixel phases of the 4x4 stride-2
+// transposed conv, the 2x2 stride-2 "avg-pool + 1x1" skip conv, and every data-gradient (dgrad) by passing the
+// transposed/flipped weight pack and tap table.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+
+namespace {
+
+using namespace mg::ptx;
+
+constexpr int BM = 128;            // pixels per tile (UMMA M)
+constexpr int THREADS = 192;       // 6 warps
+constexpr int MAX_TAPS = MG_CONV_MAX_TAPS;
+constexpr int STAT_COPIES = MG_CONV_STAT_COPIES;
+
+struct KArgs {
+    int n_taps;
+    int tap_dy[MAX_TAPS], tap_dx[MAX_TAPS], tap_koff[MAX_TAPS];
+    int sy, sx, Hg, Wg, th, tw, tiles_y, tiles_x;
+    int BK, kchunks, BN, Co, stages, swizzle;
+    __half* out;
+    int Ho, Wo, Cs, c_off, oys, oy0, oxs, ox0;
+    int epi_relu;
+    float* stats;
+    const float* bias;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = BM * a.BK * 2, b_bytes = a.BN * a.BK * 2;
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + a.stages * a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + a.stages * b_bytes);  // full[stages], empty[stages], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
+    float* s_stage = reinterpret_cast<float*>(tmem_slot + 4);               // [4 warps][32][17]
+    float* s_part = s_stage + 4 * 32 * 17;                                  // [4 warps][2][BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * a.stages, tfull = empty0 + 8 * a.stages;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tx = t % a.tiles_x;
+    t /= a.tiles_x;
+    const int ty = t % a.tiles_y, img = t / a.tiles_y;
+    const int y0 = ty * a.th, x0 = tx * a.tw, n0 = blockIdx.y * a.BN;
+    const int nkb = a.n_taps * a.kchunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), a.BN < 32 ? 32 : a.BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % a.stages, ph = (kb / a.stages) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                mbar_expect_tx(full0 + 8 * s, a_bytes + b_bytes);
+                const int tap = kb / a.kchunks, c = kb - tap * a.kchunks;
+                tma_load_4d(smem_u32(sA + s * a_bytes), &tmA, full0 + 8 * s, c * a.BK, x0 * a.sx + a.tap_dx[tap],
+                            y0 * a.sy + a.tap_dy[tap], img);
+                tma_load_2d(smem_u32(sB + s * b_bytes), &tmB, full0 + 8 * s, a.tap_koff[tap] + c * a.BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = instr_desc_f16(BM, a.BN, 0, 0);
+            const uint32_t layout = swizzle_layout(a.swizzle), sbo = 8 * a.swizzle;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % a.stages, ph = (kb / a.stages) & 1;
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t abase = smem_u32(sA + s * a_bytes), bbase = smem_u32(sB + s * b_bytes);
+                for (int k = 0; k < a.BK / 16; ++k) {
+                    const uint64_t da = smem_desc(abase + k * 32, 0, sbo, layout);
+                    const uint64_t db = smem_desc(bbase + k * 32, 0, sbo, layout);
+                    mma_f16(tmem_base, da, db, idesc, (kb | k) != 0);
+                }
+                mma_commit(empty0 + 8 * s);  // frees the smem slot when these MMAs retire
+            }
+            mma_commit(tfull);               // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;                  // accumulator row = pixel within the tile
+        const int py = y0 + m / a.tw, px = x0 + m % a.tw;
+        const bool valid = (py < a.Hg) && (px < a.Wg);
+        __half* orow = a.out + (((size_t)img * a.Ho + (size_t)py * a.oys + a.oy0) * a.Wo + (size_t)px * a.oxs + a.ox0) * a.Cs +
+                       a.c_off + n0;
+        float* stg = s_stage + q * 32 * 17;
+        float* part = s_part + q * 2 * a.BN;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        for (int c0 = 0; c0 < a.BN; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] = __uint_as_float(r[i]);
+                if (a.bias) v[i] += __ldg(a.bias + n0 + c0 + i);
+                if (a.epi_relu) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (valid && n0 + c0 < a.Co) {
+                uint4 o0, o1;
+                __half2 h;
+                h = __floats2half2_rn(v[0], v[1]);   o0.x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[2], v[3]);   o0.y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[4], v[5]);   o0.z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[6], v[7]);   o0.w = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[8], v[9]);   o1.x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[10], v[11]); o1.y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[12], v[13]); o1.z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[14], v[15]); o1.w = *reinterpret_cast<uint32_t*>(&h);
+                reinterpret_cast<uint4*>(orow + c0)[0] = o0;
+                reinterpret_cast<uint4*>(orow + c0)[1] = o1;
+            }
+            if (a.stats) {
+                // per-channel sum / sum of squares over this warp's 32 rows (invalid rows hold exact zeros unless
+                // a bias / relu made them non-zero -> mask them)
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) stg[lane * 17 + i] = valid ? v[i] : 0.f;
+                __syncwarp();
+                const int col = lane & 15;
+                float acc = 0.f;
+                if (lane < 16) {
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) acc += stg[rr * 17 + col];
+                } else {
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) { const float z = stg[rr * 17 + col]; acc += z * z; }
+                }
+                part[(lane >> 4) * a.BN + c0 + col] = acc;
+            }
+        }
+        if (a.stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+            const int et = threadIdx.x - 64;                 // 0..127
+            float* dst = a.stats + (size_t)(blockIdx.x % STAT_COPIES) * 2 * a.Co;
+            for (int i = et; i < 2 * a.BN; i += 128) {
+                const int kind = i / a.BN, c = i - kind * a.BN;
+                if (n0 + c < a.Co) {
+                    const float tot = s_part[0 * 2 * a.BN + i] + s_part[1 * 2 * a.BN + i] + s_part[2 * 2 * a.BN + i] +
+                                      s_part[3 * 2 * a.BN + i];
+                    atomicAdd(dst + kind * a.Co + n0 + c, tot);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.BN < 32 ? 32 : a.BN);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+
+EncodeTiledFn get_encode() {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    });
+    return g_encode;
+}
+
+CUtensorMapSwizzle swz_enum(int bytes) {
+    return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+}  // namespace
+
+extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
+    MG_REQUIRE(d && d->x && d->w && d->out, "mg_conv_fprop: null pointer");
+    MG_REQUIRE(d->n_taps >= 1 && d->n_taps <= MAX_TAPS, "mg_conv_fprop: n_taps %d out of range", d->n_taps);
+    MG_REQUIRE(d->Ci % 16 == 0 && d->Co % 16 == 0, "mg_conv_fprop: Ci (%d) and Co (%d) must be multiples of 16", d->Ci, d->Co);
+    MG_REQUIRE(d->Ktot % 8 == 0 && d->Cs % 8 == 0 && d->c_off % 8 == 0, "mg_conv_fprop: Ktot/Cs/c_off must be multiples of 8");
+    MG_REQUIRE(d->sy >= 1 && d->sx >= 1 && d->sy <= 2 && d->sx <= 2, "mg_conv_fprop: stride must be 1 or 2");
+    MG_REQUIRE(d->N > 0 && d->Hg > 0 && d->Wg > 0, "mg_conv_fprop: empty problem");
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        mg::set_error("mg_conv_fprop: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+        return MG_ERR_CUDA;
+    }
+    KArgs a;
+    a.n_taps = d->n_taps;
+    for (int t = 0; t < d->n_taps; ++t) a.tap_dy[t] = d->tap_dy[t], a.tap_dx[t] = d->tap_dx[t], a.tap_koff[t] = d->tap_koff[t];
+    a.sy = d->sy, a.sx = d->sx, a.Hg = d->Hg, a.Wg = d->Wg;
+    if (d->Wg > 8) a.th = 8, a.tw = 16; else a.th = 16, a.tw = 8;
+    a.tiles_y = mg::ceil_div(d->Hg, a.th), a.tiles_x = mg::ceil_div(d->Wg, a.tw);
+    a.BK = (d->Ci % 64 == 0) ? 64 : ((d->Ci % 32 == 0) ? 32 : 16);
+    a.kchunks = d->Ci / a.BK;
+    a.swizzle = a.BK * 2;
+    a.Co = d->Co;
+    a.BN = d->Co >= 128 ? 128 : (d->Co >= 64 ? 64 : 32);
+    MG_REQUIRE(d->Co % a.BN == 0 || d->Co < a.BN, "mg_conv_fprop: Co=%d not a multiple of the N tile %d", d->Co, a.BN);
+    if (d->Co < a.BN) a.BN = d->Co;  // 16 (TMEM allocation is rounded up to 32 columns)
+    a.out = static_cast<__half*>(d->out);
+    a.Ho = d->Ho, a.Wo = d->Wo, a.Cs = d->Cs, a.c_off = d->c_off;
+    a.oys = d->oys, a.oy0 = d->oy0, a.oxs = d->oxs, a.ox0 = d->ox0;
+    a.epi_relu = d->epi_relu, a.stats = d->stats, a.bias = d->bias;
+
+    const int a_bytes = BM * a.BK * 2, b_bytes = a.BN * a.BK * 2;
+    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 17 * 4 + 4 * 2 * a.BN * 4;
+    a.stages = std::min(6, (200 * 1024 - fixed) / (a_bytes + b_bytes));
+    a.stages = std::max(2, std::min(a.stages, d->n_taps * a.kchunks < 2 ? 2 : a.stages));
+    const size_t smem = (size_t)fixed + (size_t)a.stages * (a_bytes + b_bytes);
+
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d->Ci, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->N};
+        cuuint64_t strides[3] = {(cuuint64_t)d->Ci * 2, (cuuint64_t)d->Wi * d->Ci * 2, (cuuint64_t)d->Hi * d->Wi * d->Ci * 2};
+        cuuint32_t box[4] = {(cuuint32_t)a.BK, (cuuint32_t)(a.tw * a.sx), (cuuint32_t)(a.th * a.sy), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)a.sx, (cuuint32_t)a.sy, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(a.swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            mg::set_error("mg_conv_fprop: cuTensorMapEncodeTiled(A) failed (%d): x=%p N=%d H=%d W=%d C=%d box=%u,%u,%u", (int)r,
+                          d->x, d->N, d->Hi, d->Wi, d->Ci, box[0], box[1], box[2]);
+            return MG_ERR_CUDA;
+        }
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)d->Ktot, (cuuint64_t)d->Co};
+        cuuint64_t strides[1] = {(cuuint64_t)d->Ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)a.BK, (cuuint32_t)a.BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(a.swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            mg::set_error("mg_conv_fprop: cuTensorMapEncodeTiled(W) failed (%d): Ktot=%d Co=%d", (int)r, d->Ktot, d->Co);
+            return MG_ERR_CUDA;
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+            mg::set_error("mg_conv_fprop: cannot raise dynamic shared memory limit");
+            return MG_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid(d->N * a.tiles_y * a.tiles_x, mg::ceil_div(d->Co, a.BN));
+    MG_LAUNCH(conv_tcgen05_kernel, grid, THREADS, smem, stream, tmA, tmB, a);
+    MG_CHECK_LAUNCH("mg_conv_fprop");
+    return MG_OK;
+}

@@ -36,6 +36,22 @@ def _need_cuda(*tensors):
 
 
 # =============================================================================================== native: K8a
+_WIDTHS_CACHE = {}
+
+
+def _widths_tensor(widths, device):
+    """Device int32 copy of the per-slice ellipse sizes; constant (eval) width lists are cached."""
+    key = (widths, device)
+    t = _WIDTHS_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(widths, dtype=torch.int32, device=device)
+        if len(set(widths)) == 1:
+            if len(_WIDTHS_CACHE) > 64:
+                _WIDTHS_CACHE.clear()
+            _WIDTHS_CACHE[key] = t
+    return t
+
+
 def unknown_mask(alpha, widths, and_mask=None):
     """uint8 {0,1} mask of the dilated uncertain region (reference: utils/utils.py:28-55 compute_unknown).
     alpha [..., H, W] fp32; widths: one ellipse size (1..29) per [H, W] slice; and_mask optional uint8."""
@@ -48,7 +64,7 @@ def unknown_mask(alpha, widths, and_mask=None):
         return out
     if len(widths) != slices:
         raise ValueError(f"unknown_mask: {len(widths)} widths for {slices} slices")
-    w = torch.tensor(list(widths), dtype=torch.int32).pin_memory().to(a.device, non_blocking=True)
+    w = _widths_tensor(tuple(int(v) for v in widths), a.device)
     if and_mask is not None:
         and_mask = and_mask.to(torch.uint8).contiguous()
         assert and_mask.shape == a.shape
