@@ -90,7 +90,8 @@ int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, const int32_
  * x    NHWC fp16 [N,Hi,Wi,Ci], Ci % 16 == 0.      w  packed fp16 [Co][Ktot] (K contiguous), Co % 16 == 0.
  * The op computes, for every image n and logical grid point (y,x), 0<=y<Hg, 0<=x<Wg:
  *     acc[c] = sum_t sum_ci  x[n, y*sy + tap_dy[t], x*sx + tap_dx[t], ci] * w[c][tap_koff[t] + ci]   (zero outside x)
- *     out[n, y*oys + oy0, x*oxs + ox0, c_off + c] = fp16( relu?(acc[c] + bias[c]) )
+ *     v = pre_act(acc[c] + bias[c]);  [stats see v];  v = v*scale[c] + shift[c];  v += res[...];  v = post_act(v)
+ *     out[n, y*oys + oy0, x*oxs + ox0, c_off + c] = fp16(v)
  * out is NHWC fp16 [N,Ho,Wo,Cs].  3x3 pad 1: taps (ky-1,kx-1); dilation d: d*(k-1); stride 2: sy=sx=2;
  * 4x4 stride-2 transposed conv: four launches (one per output parity) with oys=oxs=2.
  * stats (optional): float [MG_CONV_STAT_COPIES][2][Co], must be zeroed by the caller; the kernel accumulates
@@ -104,11 +105,49 @@ typedef struct mg_conv_desc {
     int32_t n_taps; int32_t tap_dy[MG_CONV_MAX_TAPS], tap_dx[MG_CONV_MAX_TAPS], tap_koff[MG_CONV_MAX_TAPS];
     int32_t sy, sx, Hg, Wg;
     void* out; int32_t Ho, Wo, Cs, c_off, oys, oy0, oxs, ox0;
-    int32_t epi_relu;
+    int32_t pre_act, post_act;   /* 0 none, 1 ReLU, 2 LeakyReLU(0.2) */
     float* stats;
     const float* bias;
+    const float* scale; const float* shift;   /* optional per-channel affine (eval-mode BN folded in) */
+    const void* res; int32_t res_up;          /* optional fp16 residual [N,Ho,Wo,Co] ([N,Ho/2,Wo/2,Co] if res_up) */
 } mg_conv_desc;
 int mg_conv_fprop(const mg_conv_desc* desc, void* stream);
+
+/* ---- K4: convolution weight gradient (tcgen05, split-K over pixels) ---------------------------------
+ * replaces: cuDNN's wgrad behind `loss.backward()` for every conv above (engine/train.py:266).
+ * dw[co][tap_koff[t] + ci] += sum_{n,y,x} dy[n, y*ays + ay0, x*axs + ax0, co] * x[n, y*sy + tap_dy[t], x*sx + tap_dx[t], ci]
+ * over the logical grid 0<=y<Hg, 0<=x<Wg (zero outside either tensor).  dy NHWC fp16 [N,Hy,Wy,Co]; x NHWC fp16
+ * [N,Hi,Wi,Ci] (Ci % 16 == 0, Co % 8 == 0); dw fp32 [Co][Ktot], accumulated with atomics (caller zeroes it).  */
+typedef struct mg_wgrad_desc {
+    const void* dy; int32_t N, Hy, Wy, Co;
+    const void* x; int32_t Hi, Wi, Ci;
+    float* dw; int32_t Ktot;
+    int32_t n_taps; int32_t tap_dy[MG_CONV_MAX_TAPS], tap_dx[MG_CONV_MAX_TAPS], tap_koff[MG_CONV_MAX_TAPS];
+    int32_t sy, sx, ays, ay0, axs, ax0, Hg, Wg;
+} mg_wgrad_desc;
+int mg_conv_wgrad(const mg_wgrad_desc* desc, void* stream);
+
+/* ---- K3: BatchNorm pieces around the conv kernel (NHWC fp16 activations, fp32 statistics) ----------
+ * replaces: nn.BatchNorm2d forward/backward (cuDNN via ATen) + the separate ReLU/LeakyReLU/add passes of
+ *           encoder/resnet.py:23-39, decoder/resnet.py:29-45, module/aspp.py:35-56.
+ * mg_bn_finalize : stats = conv-epilogue copies [MG_CONV_STAT_COPIES][2][C] (training; also updates the running
+ *                  statistics with `momentum`, unbiased variance) or NULL (eval: use running statistics);
+ *                  writes scale = gamma*invstd, shift = beta - mean*scale, and (optionally) mean / invstd.
+ * mg_bn_apply    : y = act(x*scale + shift + res)      act: 0 none, 1 ReLU, 2 LeakyReLU(0.2); res optional,
+ *                  res_up: residual is [N,H/2,W/2,C] and replicated 2x2 (nearest upsampling).
+ * mg_bn_bwd_reduce / mg_bn_bwd_apply : dz = dy*act'(y); sums = [sum dz ; sum dz*xhat] (caller zeroes sums [2][C]);
+ *                  dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (* pre_act'(conv_out) if pre_act),
+ *                  dres = dz (optional).  dgamma = sums[1], dbeta = sums[0].                                  */
+int mg_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
+                   float* save_invstd, int C, void* stream);
+int mg_bn_apply(const void* x, const float* scale, const float* shift, const void* res, int res_up, void* y, int N,
+                int H, int W, int C, int act, void* stream);
+int mg_bn_bwd_reduce(const void* dy, const void* y, const void* conv_out, const float* mean, const float* invstd,
+                     float* sums, int N, int H, int W, int C, int act, void* stream);
+int mg_bn_bwd_apply(const void* dy, const void* y, const void* conv_out, const float* mean, const float* invstd,
+                    const float* gamma, const float* sums, void* dx, void* dres, int N, int H, int W, int C, int act,
+                    int pre_act, void* stream);
 
 #ifdef __cplusplus
 }

@@ -4,7 +4,7 @@ No fallback: if the shared object is missing or a call fails, a RuntimeError is 
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_int, c_int32, c_size_t, c_ulonglong, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmaggie_b200.so")
@@ -25,6 +25,14 @@ SIGNATURES = {
     "mg_sites_tables": (c_int, [c_void_p, c_int, c_int, c_int, _I32P, _PP, _PP, _PP, _PP, c_void_p]),
     "mg_mask_embed_fwd": (c_int, [c_void_p, c_void_p, _I32P, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_conv_fprop": (c_int, [c_void_p, c_void_p]),
+    "mg_conv_wgrad": (c_int, [c_void_p, c_void_p]),
+    "mg_bn_finalize": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_int, c_void_p]),
+    "mg_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mg_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
+    "mg_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_mask_embed_bwd": (c_int, [c_void_p, c_void_p, _I32P, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
@@ -64,3 +72,19 @@ def i32_array(values):
 
 def ptr_array(ptrs):
     return (c_void_p * len(ptrs))(*[c_void_p(p) if p else None for p in ptrs])
+
+
+def stream_ptr():
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def tensor_ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("maggie_b200 native op called with a non-CUDA tensor; there is no CPU fallback")

@@ -17,6 +17,7 @@
 // transposed/flipped weight pack and tap table.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tma_host.cuh"
 
 #include <mutex>
 
@@ -36,10 +37,18 @@ struct KArgs {
     int BK, kchunks, BN, Co, stages, swizzle;
     __half* out;
     int Ho, Wo, Cs, c_off, oys, oy0, oxs, ox0;
-    int epi_relu;
+    int pre_act, post_act;           // 0 none, 1 relu, 2 leaky-relu(0.2); pre: before the affine, post: after residual
     float* stats;
     const float* bias;
+    const float* scale;              // optional per-channel affine (eval-mode BatchNorm folded into the epilogue)
+    const float* shift;
+    const __half* res;               // optional residual, NHWC [N,Ho,Wo,Co] or [N,Ho/2,Wo/2,Co] when res_up
+    int res_up;
 };
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    return act == 1 ? fmaxf(v, 0.f) : (act == 2 ? (v > 0.f ? v : 0.2f * v) : v);
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs a) {
@@ -119,8 +128,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m = q * 32 + lane;                  // accumulator row = pixel within the tile
         const int py = y0 + m / a.tw, px = x0 + m % a.tw;
         const bool valid = (py < a.Hg) && (px < a.Wg);
-        __half* orow = a.out + (((size_t)img * a.Ho + (size_t)py * a.oys + a.oy0) * a.Wo + (size_t)px * a.oxs + a.ox0) * a.Cs +
-                       a.c_off + n0;
+        const int oy = py * a.oys + a.oy0, ox = px * a.oxs + a.ox0;
+        __half* orow = a.out + (((size_t)img * a.Ho + oy) * a.Wo + ox) * a.Cs + a.c_off + n0;
+        const __half* rrow = nullptr;
+        if (a.res)
+            rrow = a.res + (a.res_up ? (((size_t)img * (a.Ho >> 1) + (oy >> 1)) * (a.Wo >> 1) + (ox >> 1))
+                                     : (((size_t)img * a.Ho + oy) * a.Wo + ox)) * a.Co + n0;
         float* stg = s_stage + q * 32 * 17;
         float* part = s_part + q * 2 * a.BN;
         mbar_wait(tfull, 0);
@@ -134,25 +147,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int i = 0; i < 16; ++i) {
                 v[i] = __uint_as_float(r[i]);
                 if (a.bias) v[i] += __ldg(a.bias + n0 + c0 + i);
-                if (a.epi_relu) v[i] = fmaxf(v[i], 0.f);
-            }
-            if (valid && n0 + c0 < a.Co) {
-                uint4 o0, o1;
-                __half2 h;
-                h = __floats2half2_rn(v[0], v[1]);   o0.x = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(v[2], v[3]);   o0.y = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(v[4], v[5]);   o0.z = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(v[6], v[7]);   o0.w = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(v[8], v[9]);   o1.x = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(v[10], v[11]); o1.y = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(v[12], v[13]); o1.z = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(v[14], v[15]); o1.w = *reinterpret_cast<uint32_t*>(&h);
-                reinterpret_cast<uint4*>(orow + c0)[0] = o0;
-                reinterpret_cast<uint4*>(orow + c0)[1] = o1;
+                v[i] = apply_act(v[i], a.pre_act);
             }
             if (a.stats) {
-                // per-channel sum / sum of squares over this warp's 32 rows (invalid rows hold exact zeros unless
-                // a bias / relu made them non-zero -> mask them)
+                // per-channel sum / sum of squares over this warp's 32 rows (rows outside the image are masked: a bias
+                // would make them non-zero)
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) stg[lane * 17 + i] = valid ? v[i] : 0.f;
@@ -167,6 +166,37 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int rr = 0; rr < 32; ++rr) { const float z = stg[rr * 17 + col]; acc += z * z; }
                 }
                 part[(lane >> 4) * a.BN + c0 + col] = acc;
+            }
+            if (valid && n0 + c0 < a.Co) {
+                if (a.scale) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(a.scale + n0 + c0 + i), __ldg(a.shift + n0 + c0 + i));
+                }
+                if (rrow) {
+                    const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rrow + c0)), r1 = __ldg(reinterpret_cast<const uint4*>(rrow + c0) + 1);
+                    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
+                        v[2 * i] += f.x, v[2 * i + 1] += f.y;
+                    }
+                }
+                if (a.post_act) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.post_act);
+                }
+                uint4 o0, o1;
+                __half2 h;
+                h = __floats2half2_rn(v[0], v[1]);   o0.x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[2], v[3]);   o0.y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[4], v[5]);   o0.z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[6], v[7]);   o0.w = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[8], v[9]);   o1.x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[10], v[11]); o1.y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[12], v[13]); o1.z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[14], v[15]); o1.w = *reinterpret_cast<uint32_t*>(&h);
+                reinterpret_cast<uint4*>(orow + c0)[0] = o0;
+                reinterpret_cast<uint4*>(orow + c0)[1] = o1;
             }
         }
         if (a.stats) {
@@ -191,28 +221,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
-// ---- host side ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-std::once_flag g_encode_once;
-
-EncodeTiledFn get_encode() {
-    std::call_once(g_encode_once, [] {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-    });
-    return g_encode;
-}
-
-CUtensorMapSwizzle swz_enum(int bytes) {
-    return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-}
-
 }  // namespace
 
 extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
@@ -222,7 +230,7 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
     MG_REQUIRE(d->Ktot % 8 == 0 && d->Cs % 8 == 0 && d->c_off % 8 == 0, "mg_conv_fprop: Ktot/Cs/c_off must be multiples of 8");
     MG_REQUIRE(d->sy >= 1 && d->sx >= 1 && d->sy <= 2 && d->sx <= 2, "mg_conv_fprop: stride must be 1 or 2");
     MG_REQUIRE(d->N > 0 && d->Hg > 0 && d->Wg > 0, "mg_conv_fprop: empty problem");
-    EncodeTiledFn enc = get_encode();
+    mg::EncodeTiledFn enc = mg::get_encode();
     if (!enc) {
         mg::set_error("mg_conv_fprop: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
         return MG_ERR_CUDA;
@@ -243,7 +251,10 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
     a.out = static_cast<__half*>(d->out);
     a.Ho = d->Ho, a.Wo = d->Wo, a.Cs = d->Cs, a.c_off = d->c_off;
     a.oys = d->oys, a.oy0 = d->oy0, a.oxs = d->oxs, a.ox0 = d->ox0;
-    a.epi_relu = d->epi_relu, a.stats = d->stats, a.bias = d->bias;
+    a.pre_act = d->pre_act, a.post_act = d->post_act, a.stats = d->stats, a.bias = d->bias;
+    a.scale = d->scale, a.shift = d->shift, a.res = static_cast<const __half*>(d->res), a.res_up = d->res_up;
+    MG_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "mg_conv_fprop: scale and shift go together");
+    MG_REQUIRE(!d->res || (d->c_off == 0 && d->Cs == d->Co), "mg_conv_fprop: residual needs a dense [N,Ho,Wo,Co] output");
 
     const int a_bytes = BM * a.BK * 2, b_bytes = a.BN * a.BK * 2;
     const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 17 * 4 + 4 * 2 * a.BN * 4;
@@ -258,7 +269,7 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
         cuuint32_t box[4] = {(cuuint32_t)a.BK, (cuuint32_t)(a.tw * a.sx), (cuuint32_t)(a.th * a.sy), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)a.sx, (cuuint32_t)a.sy, 1};
         CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(a.swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, mg::swz_enum(a.swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             mg::set_error("mg_conv_fprop: cuTensorMapEncodeTiled(A) failed (%d): x=%p N=%d H=%d W=%d C=%d box=%u,%u,%u", (int)r,
@@ -272,7 +283,7 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
         cuuint32_t box[2] = {(cuuint32_t)a.BK, (cuuint32_t)a.BN};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(a.swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, mg::swz_enum(a.swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             mg::set_error("mg_conv_fprop: cuTensorMapEncodeTiled(W) failed (%d): Ktot=%d Co=%d", (int)r, d->Ktot, d->Co);

@@ -1,0 +1,253 @@
+// K3: BatchNorm around the conv kernel, NHWC fp16 activations, fp32 statistics.  All HBM-bound streaming
+// kernels (one 16-byte vector = 8 channels per thread access).
+//   forward (train): conv epilogue -> per-channel sum/sumsq copies -> mg_bn_finalize -> mg_bn_apply
+//   forward (eval) : mg_bn_finalize (running stats) -> scale/shift folded into the conv epilogue (no extra pass)
+//   backward       : mg_bn_bwd_reduce (sum dz, sum dz*xhat) -> mg_bn_bwd_apply (dx, optional d-residual)
+#include "common.cuh"
+
+namespace {
+
+constexpr int STAT_COPIES = MG_CONV_STAT_COPIES;
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mean, var;
+    if (stats) {
+        float s = 0.f, q = 0.f;
+        for (int k = 0; k < STAT_COPIES; ++k) {
+            s += stats[(size_t)k * 2 * C + c];
+            q += stats[(size_t)k * 2 * C + C + c];
+        }
+        mean = s / count;
+        var = fmaxf(q / count - mean * mean, 0.f);
+        if (rmean) {
+            rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+            rvar[c] = (1.f - momentum) * rvar[c] + momentum * var * (count > 1.f ? count / (count - 1.f) : 1.f);
+        }
+    } else {
+        mean = rmean[c], var = rvar[c];
+    }
+    const float invstd = rsqrtf(var + eps);
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    scale[c] = g * invstd;
+    shift[c] = b - mean * g * invstd;
+    if (save_mean) save_mean[c] = mean, save_invstd[c] = invstd;
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+    return act == 1 ? fmaxf(v, 0.f) : (act == 2 ? (v > 0.f ? v : 0.2f * v) : v);
+}
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+    return act == 1 ? (y > 0.f ? 1.f : 0.f) : (act == 2 ? (y > 0.f ? 1.f : 0.2f) : 1.f);
+}
+
+struct H8 {
+    uint4 u;
+    __device__ __forceinline__ void to_float(float (&f)[8]) const {
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 t = __half22float2(h[i]);
+            f[2 * i] = t.x, f[2 * i + 1] = t.y;
+        }
+    }
+    __device__ __forceinline__ void from_float(const float (&f)[8]) {
+        __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    }
+};
+
+// y = act(x*scale + shift (+ res)), vectorised over 8 channels.
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                const __half* __restrict__ res, int res_up, __half* __restrict__ y, size_t npix, int C, int H, int W, int act) {
+    extern __shared__ float s_ss[];  // [2][C]
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_ss[i] = scale[i], s_ss[C + i] = shift[i];
+    __syncthreads();
+    const int G = C >> 3;
+    const size_t total = npix * G;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = v / G;
+        const int g = (int)(v - p * G), c0 = g << 3;
+        H8 in;
+        in.u = __ldg(reinterpret_cast<const uint4*>(x + p * C + c0));
+        float f[8];
+        in.to_float(f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], s_ss[c0 + i], s_ss[C + c0 + i]);
+        if (res) {
+            size_t rp = p;
+            if (res_up) {
+                const int xx = (int)(p % W), yy = (int)((p / W) % H);
+                const size_t n = p / ((size_t)W * H);
+                rp = (n * (H >> 1) + (yy >> 1)) * (W >> 1) + (xx >> 1);
+            }
+            H8 r;
+            r.u = __ldg(reinterpret_cast<const uint4*>(res + rp * C + c0));
+            float rf[8];
+            r.to_float(rf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += rf[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = act_fwd(f[i], act);
+        H8 o;
+        o.from_float(f);
+        *reinterpret_cast<uint4*>(y + p * C + c0) = o.u;
+    }
+}
+
+// sums[0][c] = sum dz, sums[1][c] = sum dz * xhat   with dz = dy * act'(y) (act after BN) or dy (act_first)
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __half* __restrict__ dy, const __half* __restrict__ yout, const __half* __restrict__ r,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ sums,
+                     size_t npix, int C, int act) {
+    __shared__ float s_red[256 * 16];
+    const int G = C >> 3, lanes_per_g = 256 / G;  // G in {4..64} divides 256
+    const int g = threadIdx.x % G, sub = threadIdx.x / G, c0 = g << 3;
+    float m[8], is[8], a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = mean[c0 + i], is[i] = invstd[c0 + i], a0[i] = 0.f, a1[i] = 0.f;
+    for (size_t p = (size_t)blockIdx.x * lanes_per_g + sub; p < npix; p += (size_t)gridDim.x * lanes_per_g) {
+        H8 d, rr;
+        d.u = __ldg(reinterpret_cast<const uint4*>(dy + p * C + c0));
+        rr.u = __ldg(reinterpret_cast<const uint4*>(r + p * C + c0));
+        float df[8], rf[8];
+        d.to_float(df), rr.to_float(rf);
+        if (act) {
+            H8 yy;
+            yy.u = __ldg(reinterpret_cast<const uint4*>(yout + p * C + c0));
+            float yf[8];
+            yy.to_float(yf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) df[i] *= act_grad_from_out(yf[i], act);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a0[i] += df[i], a1[i] += df[i] * (rf[i] - m[i]) * is[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_red[threadIdx.x * 16 + i] = a0[i], s_red[threadIdx.x * 16 + 8 + i] = a1[i];
+    __syncthreads();
+    // thread t < 16*G: channel group t/16, quantity t%16 -> sum over the lanes_per_g sub-rows
+    for (int t = threadIdx.x; t < 16 * G; t += 256) {
+        const int gg = t >> 4, k = t & 15;
+        float acc = 0.f;
+        for (int s = 0; s < lanes_per_g; ++s) acc += s_red[(s * G + gg) * 16 + k];
+        atomicAdd(sums + (k >> 3) * C + (gg << 3) + (k & 7), acc);
+    }
+}
+
+// dx = scale * (dz - mean_dz - xhat * mean_dzx) [* relu'(r) when act_first]; dres = dz (optional)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ yout, const __half* __restrict__ r,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ sums, float inv_count, __half* __restrict__ dx, __half* __restrict__ dres,
+                    size_t npix, int C, int act, int pre_act) {
+    extern __shared__ float s_p[];  // [4][C]: mean, scale=gamma*invstd, mean_dz, invstd*mean_dzx
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        const float is = invstd[i];
+        s_p[i] = mean[i];
+        s_p[C + i] = (gamma ? gamma[i] : 1.f) * is;
+        s_p[2 * C + i] = sums[i] * inv_count;
+        s_p[3 * C + i] = sums[C + i] * inv_count * is;
+    }
+    __syncthreads();
+    const int G = C >> 3;
+    const size_t total = npix * G;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = v / G;
+        const int c0 = (int)(v - p * G) << 3;
+        H8 d, rr;
+        d.u = __ldg(reinterpret_cast<const uint4*>(dy + p * C + c0));
+        rr.u = __ldg(reinterpret_cast<const uint4*>(r + p * C + c0));
+        float df[8], rf[8], o[8];
+        d.to_float(df), rr.to_float(rf);
+        if (act) {
+            H8 yy;
+            yy.u = __ldg(reinterpret_cast<const uint4*>(yout + p * C + c0));
+            float yf[8];
+            yy.to_float(yf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) df[i] *= act_grad_from_out(yf[i], act);
+        }
+        if (dres) {
+            H8 z;
+            z.from_float(df);
+            *reinterpret_cast<uint4*>(dres + p * C + c0) = z.u;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = c0 + i;
+            o[i] = s_p[C + c] * (df[i] - s_p[2 * C + c] - (rf[i] - s_p[c]) * s_p[3 * C + c]);
+            if (pre_act) o[i] *= act_grad_from_out(rf[i], pre_act);
+        }
+        H8 w;
+        w.from_float(o);
+        *reinterpret_cast<uint4*>(dx + p * C + c0) = w.u;
+    }
+}
+
+int stream_grid(size_t work_items) {
+    return (int)std::min<size_t>((work_items + 255) / 256, (size_t)mg::kNumSMs * 8);
+}
+
+}  // namespace
+
+extern "C" int mg_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, float momentum, float eps, float* scale, float* shift,
+                              float* save_mean, float* save_invstd, int C, void* stream) {
+    MG_REQUIRE(scale && shift && C > 0, "mg_bn_finalize: null pointer");
+    MG_REQUIRE(stats || (running_mean && running_var), "mg_bn_finalize: need batch statistics or running statistics");
+    MG_REQUIRE((save_mean == nullptr) == (save_invstd == nullptr), "mg_bn_finalize: save_mean/save_invstd go together");
+    MG_LAUNCH(bn_finalize_kernel, mg::ceil_div(C, 128), 128, 0, stream, stats, count, gamma, beta, running_mean, running_var,
+              momentum, eps, scale, shift, save_mean, save_invstd, C);
+    MG_CHECK_LAUNCH("mg_bn_finalize");
+    return MG_OK;
+}
+
+extern "C" int mg_bn_apply(const void* x, const float* scale, const float* shift, const void* res, int res_up, void* y,
+                           int N, int H, int W, int C, int act, void* stream) {
+    MG_REQUIRE(x && scale && shift && y, "mg_bn_apply: null pointer");
+    MG_REQUIRE(C % 8 == 0 && C <= 4096, "mg_bn_apply: C must be a multiple of 8 (got %d)", C);
+    const size_t npix = (size_t)N * H * W;
+    if (npix == 0) return MG_OK;
+    MG_LAUNCH(bn_apply_kernel, stream_grid(npix * (C / 8)), 256, 2 * C * sizeof(float), stream,
+              static_cast<const __half*>(x), scale, shift, static_cast<const __half*>(res), res_up,
+              static_cast<__half*>(y), npix, C, H, W, act);
+    MG_CHECK_LAUNCH("mg_bn_apply");
+    return MG_OK;
+}
+
+extern "C" int mg_bn_bwd_reduce(const void* dy, const void* y, const void* conv_out, const float* mean, const float* invstd,
+                                float* sums, int N, int H, int W, int C, int act, void* stream) {
+    MG_REQUIRE(dy && conv_out && mean && invstd && sums && (y || !act), "mg_bn_bwd_reduce: null pointer");
+    MG_REQUIRE(C >= 32 && C <= 512 && (C & (C - 1)) == 0, "mg_bn_bwd_reduce: C must be a power of two in 32..512 (got %d)", C);
+    const size_t npix = (size_t)N * H * W;
+    if (npix == 0) return MG_OK;
+    const int rows_per_block = 256 / (C / 8);
+    const int grid = (int)std::min<size_t>((npix + rows_per_block - 1) / rows_per_block, (size_t)mg::kNumSMs * 4);
+    MG_LAUNCH(bn_bwd_reduce_kernel, grid, 256, 0, stream, static_cast<const __half*>(dy), static_cast<const __half*>(y),
+              static_cast<const __half*>(conv_out), mean, invstd, sums, npix, C, act);
+    MG_CHECK_LAUNCH("mg_bn_bwd_reduce");
+    return MG_OK;
+}
+
+extern "C" int mg_bn_bwd_apply(const void* dy, const void* y, const void* conv_out, const float* mean, const float* invstd,
+                               const float* gamma, const float* sums, void* dx, void* dres, int N, int H, int W, int C,
+                               int act, int pre_act, void* stream) {
+    MG_REQUIRE(dy && conv_out && mean && invstd && sums && dx && (y || !act), "mg_bn_bwd_apply: null pointer");
+    MG_REQUIRE(C % 8 == 0 && C <= 2048, "mg_bn_bwd_apply: C must be a multiple of 8 (got %d)", C);
+    const size_t npix = (size_t)N * H * W;
+    if (npix == 0) return MG_OK;
+    MG_LAUNCH(bn_bwd_apply_kernel, stream_grid(npix * (C / 8)), 256, 4 * C * sizeof(float), stream,
+              static_cast<const __half*>(dy), static_cast<const __half*>(y), static_cast<const __half*>(conv_out), mean,
+              invstd, gamma, sums, 1.0f / (float)npix, static_cast<__half*>(dx), static_cast<__half*>(dres), npix, C, act,
+              pre_act);
+    MG_CHECK_LAUNCH("mg_bn_bwd_apply");
+    return MG_OK;
+}

@@ -1,0 +1,188 @@
+// K4: convolution weight gradient on tcgen05 tensor cores.
+//
+//   dW[co][tap][ci] = sum over pixels p   dY[p][co] * X[p shifted by tap][ci]
+//
+// GEMM with K = pixels.  Both operands are NHWC, i.e. channel-contiguous = "MN-major" UMMA operands: a TMA box
+// {64 channels, tw, th} of a 128-pixel tile lands in shared memory as 128 rows of 128 bytes (one row per pixel =
+// one K index) with the 128-byte swizzle, which is exactly the canonical MN-major SWIZZLE_128B atom stack
+// (SBO = 8 rows = 1024 B between K groups, LBO = 128 rows = 16 KB between 64-channel atoms).  The shifted X box
+// uses the same hardware zero fill / element strides as the forward kernel.  M = 128 output channels (rows of a
+// narrower layer are zero-filled by TMA), N = up to 256 input channels, accumulators [128 x N] fp32 in TMEM.
+// Split-K over pixel tiles across CTAs; partial results are added to the fp32 dW pack with red.global.add.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
+
+namespace {
+
+using namespace mg::ptx;
+
+constexpr int THREADS = 192;
+constexpr int MAX_TAPS = MG_CONV_MAX_TAPS;
+
+struct WArgs {
+    int tap_dy[MAX_TAPS], tap_dx[MAX_TAPS], tap_koff[MAX_TAPS];
+    int sy, sx, ays, ay0, axs, ax0;
+    int th, tw, tiles_y, tiles_x, n_tiles, tiles_per_cta;
+    int Co, Ci, Ktot, BN, atomw_b, swz_b, n_atoms_b, co_tiles, stages;
+    float* dw;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = 2 * 128 * 128;                       // two 64-channel atoms x 128 pixels
+    const int b_atom_bytes = 128 * a.swz_b, b_bytes = a.n_atoms_b * b_atom_bytes;
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + a.stages * a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + a.stages * b_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * a.stages, tfull = empty0 + 8 * a.stages;
+    const int tap = blockIdx.y;
+    const int co0 = (blockIdx.z % a.co_tiles) * 128, ci0 = (blockIdx.z / a.co_tiles) * a.BN;
+    const int t_begin = blockIdx.x * a.tiles_per_cta, t_end = min(t_begin + a.tiles_per_cta, a.n_tiles);
+    const int nk = t_end - t_begin;
+    const uint32_t tmem_cols = a.BN < 32 ? 32 : a.BN;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmDY);
+        prefetch_tmap(&tmX);
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (nk > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int i = 0; i < nk; ++i) {
+                    const int s = i % a.stages, ph = (i / a.stages) & 1;
+                    int t = t_begin + i;
+                    const int tx = t % a.tiles_x;
+                    t /= a.tiles_x;
+                    const int ty = t % a.tiles_y, img = t / a.tiles_y;
+                    const int y0 = ty * a.th, x0 = tx * a.tw;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    mbar_expect_tx(full0 + 8 * s, a_bytes + b_bytes);
+                    const uint32_t dstA = smem_u32(sA + s * a_bytes), dstB = smem_u32(sB + s * b_bytes);
+                    for (int j = 0; j < 2; ++j)
+                        tma_load_4d(dstA + j * 128 * 128, &tmDY, full0 + 8 * s, co0 + 64 * j, x0 * a.axs + a.ax0,
+                                    y0 * a.ays + a.ay0, img);
+                    for (int j = 0; j < a.n_atoms_b; ++j)
+                        tma_load_4d(dstB + j * b_atom_bytes, &tmX, full0 + 8 * s, ci0 + a.atomw_b * j,
+                                    x0 * a.sx + a.tap_dx[tap], y0 * a.sy + a.tap_dy[tap], img);
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = instr_desc_f16(128, a.BN, 1, 1);  // both operands MN-major
+                const uint32_t layB = swizzle_layout(a.swz_b);
+                for (int i = 0; i < nk; ++i) {
+                    const int s = i % a.stages, ph = (i / a.stages) & 1;
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(sA + s * a_bytes), bbase = smem_u32(sB + s * b_bytes);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {  // 128 pixels = 8 x UMMA_K(16)
+                        const uint64_t da = smem_desc(abase + k * 16 * 128, 128 * 128, 8 * 128, 2);
+                        const uint64_t db = smem_desc(bbase + k * 16 * a.swz_b, b_atom_bytes, 8 * a.swz_b, layB);
+                        mma_f16(tmem_base, da, db, idesc, (i | k) != 0);
+                    }
+                    mma_commit(empty0 + 8 * s);
+                }
+                mma_commit(tfull);
+            }
+        } else {
+            const int q = warp & 3;
+            const int co = co0 + q * 32 + lane;
+            float* drow = a.dw + (size_t)co * a.Ktot + a.tap_koff[tap] + ci0;
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+            for (int c0 = 0; c0 < a.BN; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+                tmem_ld_wait();
+                if (co < a.Co) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (ci0 + c0 + i < a.Ci) atomicAdd(drow + c0 + i, __uint_as_float(r[i]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+}  // namespace
+
+extern "C" int mg_conv_wgrad(const mg_wgrad_desc* d, void* stream) {
+    MG_REQUIRE(d && d->dy && d->x && d->dw, "mg_conv_wgrad: null pointer");
+    MG_REQUIRE(d->n_taps >= 1 && d->n_taps <= MAX_TAPS, "mg_conv_wgrad: n_taps %d out of range", d->n_taps);
+    MG_REQUIRE(d->Ci % 16 == 0 && d->Co % 8 == 0, "mg_conv_wgrad: Ci %% 16 and Co %% 8 required (Ci=%d Co=%d)", d->Ci, d->Co);
+    MG_REQUIRE(d->sy >= 1 && d->sy <= 2 && d->ays >= 1 && d->ays <= 2, "mg_conv_wgrad: strides must be 1 or 2");
+    if (!mg::get_encode()) {
+        mg::set_error("mg_conv_wgrad: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+        return MG_ERR_CUDA;
+    }
+    WArgs a;
+    for (int t = 0; t < d->n_taps; ++t) a.tap_dy[t] = d->tap_dy[t], a.tap_dx[t] = d->tap_dx[t], a.tap_koff[t] = d->tap_koff[t];
+    a.sy = d->sy, a.sx = d->sx, a.ays = d->ays, a.ay0 = d->ay0, a.axs = d->axs, a.ax0 = d->ax0;
+    if (d->Wg > 8) a.th = 8, a.tw = 16; else a.th = 16, a.tw = 8;
+    a.tiles_y = mg::ceil_div(d->Hg, a.th), a.tiles_x = mg::ceil_div(d->Wg, a.tw);
+    a.n_tiles = d->N * a.tiles_y * a.tiles_x;
+    a.Co = d->Co, a.Ci = d->Ci, a.Ktot = d->Ktot, a.dw = d->dw;
+    a.BN = d->Ci >= 256 ? 256 : d->Ci;       // Ci in {16,32,64,128,256,512,1280}
+    MG_REQUIRE(d->Ci % a.BN == 0 && (a.BN % 64 == 0 || a.BN == 32 || a.BN == 16), "mg_conv_wgrad: unsupported Ci=%d", d->Ci);
+    a.atomw_b = a.BN >= 64 ? 64 : a.BN;
+    a.swz_b = a.atomw_b * 2;
+    a.n_atoms_b = a.BN / a.atomw_b;
+    a.co_tiles = mg::ceil_div(d->Co, 128);
+    const int ci_tiles = d->Ci / a.BN;
+    const int a_bytes = 2 * 128 * 128, b_bytes = a.n_atoms_b * 128 * a.swz_b;
+    a.stages = std::max(2, std::min(4, (200 * 1024) / (a_bytes + b_bytes)));
+    const size_t smem = 1024 + 256 + (size_t)a.stages * (a_bytes + b_bytes);
+    const int base_ctas = d->n_taps * a.co_tiles * ci_tiles;
+    int splits = std::max(1, std::min(a.n_tiles, mg::ceil_div(2 * mg::kNumSMs, base_ctas)));
+    a.tiles_per_cta = mg::ceil_div(a.n_tiles, splits);
+    splits = mg::ceil_div(a.n_tiles, a.tiles_per_cta);
+
+    CUtensorMap tmDY, tmX;
+    CUresult r = mg::encode_nhwc(&tmDY, d->dy, d->N, d->Hy, d->Wy, d->Co, 64, a.tw * a.axs, a.th * a.ays, a.axs, a.ays, 128);
+    if (r != CUDA_SUCCESS) {
+        mg::set_error("mg_conv_wgrad: cuTensorMapEncodeTiled(dY) failed (%d)", (int)r);
+        return MG_ERR_CUDA;
+    }
+    r = mg::encode_nhwc(&tmX, d->x, d->N, d->Hi, d->Wi, d->Ci, a.atomw_b, a.tw * a.sx, a.th * a.sy, a.sx, a.sy, a.swz_b);
+    if (r != CUDA_SUCCESS) {
+        mg::set_error("mg_conv_wgrad: cuTensorMapEncodeTiled(X) failed (%d)", (int)r);
+        return MG_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+            mg::set_error("mg_conv_wgrad: cannot raise dynamic shared memory limit");
+            return MG_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid(splits, d->n_taps, a.co_tiles * ci_tiles);
+    MG_LAUNCH(wgrad_tcgen05_kernel, grid, THREADS, smem, stream, tmDY, tmX, a);
+    MG_CHECK_LAUNCH("mg_conv_wgrad");
+    return MG_OK;
+}

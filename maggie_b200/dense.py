@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .ops import _need_cuda, _ptr, _stream
+_need_cuda, _ptr, _stream = _lib.need_cuda, _lib.tensor_ptr, _lib.stream_ptr
 
 MAX_TAPS = 16
 STAT_COPIES = 64
@@ -22,8 +22,11 @@ class ConvDesc(ctypes.Structure):
         ("sy", c_int32), ("sx", c_int32), ("Hg", c_int32), ("Wg", c_int32),
         ("out", c_void_p), ("Ho", c_int32), ("Wo", c_int32), ("Cs", c_int32), ("c_off", c_int32),
         ("oys", c_int32), ("oy0", c_int32), ("oxs", c_int32), ("ox0", c_int32),
-        ("epi_relu", c_int32), ("stats", c_void_p), ("bias", c_void_p),
+        ("pre_act", c_int32), ("post_act", c_int32), ("stats", c_void_p), ("bias", c_void_p),
+        ("scale", c_void_p), ("shift", c_void_p), ("res", c_void_p), ("res_up", c_int32),
     ]
+
+ACT = {None: 0, "relu": 1, "lrelu": 2}
 
 
 def pad_channels(c):
@@ -46,7 +49,8 @@ def conv_taps(kh, kw, pad, dil, ci_pad):
 
 
 def conv_launch(x, w_packed, taps, *, stride=1, grid_hw=None, out=None, out_hw=None, out_map=(1, 0, 1, 0), c_off=0,
-                relu=False, stats=None, bias=None):
+                relu=False, stats=None, bias=None, pre_act=None, post_act=None, scale=None, shift=None, res=None,
+                res_up=False):
     """Generic launch of mg_conv_fprop.  x [N,Hi,Wi,Ci] fp16 NHWC; w_packed [Co,Ktot] fp16; taps [(dy,dx,koff)].
     grid_hw: logical output grid (defaults to ceil(Hi/stride)); out: preallocated NHWC fp16 (or None);
     out_map = (oys, oy0, oxs, ox0)."""
@@ -69,14 +73,19 @@ def conv_launch(x, w_packed, taps, *, stride=1, grid_hw=None, out=None, out_hw=N
     d.Hg, d.Wg = Hg, Wg
     d.out, d.Ho, d.Wo, d.Cs, d.c_off = out.data_ptr(), out.shape[1], out.shape[2], out.shape[3], c_off
     d.oys, d.oy0, d.oxs, d.ox0 = out_map
-    d.epi_relu = int(relu)
+    d.pre_act = ACT["relu" if relu else pre_act]
+    d.post_act = ACT[post_act]
     d.stats = stats.data_ptr() if stats is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.shift = shift.data_ptr() if shift is not None else None
+    d.res = res.data_ptr() if res is not None else None
+    d.res_up = int(res_up)
     _lib.check(_lib.lib().mg_conv_fprop(ctypes.byref(d), _stream()), "mg_conv_fprop")
     return out
 
 
-def conv2d_nhwc(x, w, *, stride=1, padding=1, dilation=1, relu=False, stats=None, bias=None, out=None, c_off=0):
+def conv2d_nhwc(x, w, *, stride=1, padding=1, dilation=1, relu=False, stats=None, bias=None, out=None, c_off=0, **epi):
     """Forward conv: x NHWC fp16 (channels already padded to a multiple of 16), w torch layout [Co,Ci,kh,kw]."""
     Co, Ci, kh, kw = w.shape
     ci_pad = x.shape[-1]
@@ -85,7 +94,7 @@ def conv2d_nhwc(x, w, *, stride=1, padding=1, dilation=1, relu=False, stats=None
     Ho = (Hi + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
     Wo = (Wi + 2 * padding - dilation * (kw - 1) - 1) // stride + 1
     return conv_launch(x, wp, conv_taps(kh, kw, padding, dilation, ci_pad), stride=stride, grid_hw=(Ho, Wo), relu=relu,
-                       stats=stats, bias=bias, out=out, c_off=c_off)
+                       stats=stats, bias=bias, out=out, c_off=c_off, **epi)
 
 
 def conv_transpose4x4s2_nhwc(x, w, *, stats=None):
@@ -112,3 +121,214 @@ def conv_transpose4x4s2_nhwc(x, w, *, stats=None):
 
 def new_stats(co, device):
     return torch.zeros((STAT_COPIES, 2, co), dtype=torch.float32, device=device)
+
+
+# ================================================================================================ wgrad (K4)
+class WgradDesc(ctypes.Structure):
+    """Mirror of `mg_wgrad_desc`."""
+    _fields_ = [
+        ("dy", c_void_p), ("N", c_int32), ("Hy", c_int32), ("Wy", c_int32), ("Co", c_int32),
+        ("x", c_void_p), ("Hi", c_int32), ("Wi", c_int32), ("Ci", c_int32),
+        ("dw", c_void_p), ("Ktot", c_int32),
+        ("n_taps", c_int32), ("tap_dy", c_int32 * MAX_TAPS), ("tap_dx", c_int32 * MAX_TAPS), ("tap_koff", c_int32 * MAX_TAPS),
+        ("sy", c_int32), ("sx", c_int32), ("ays", c_int32), ("ay0", c_int32), ("axs", c_int32), ("ax0", c_int32),
+        ("Hg", c_int32), ("Wg", c_int32),
+    ]
+
+
+def wgrad_launch(dy, x, taps, dw, *, stride=1, dy_map=(1, 0, 1, 0), grid_hw):
+    """dw fp32 [Co, Ktot] += sum_p dy[p mapped by dy_map] (x) x[p*stride + tap]  (see mg_conv_wgrad)."""
+    _need_cuda(dy, x, dw)
+    assert dy.dtype == torch.float16 and dy.is_contiguous() and x.dtype == torch.float16 and x.is_contiguous()
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    d = WgradDesc()
+    d.dy, d.N, d.Hy, d.Wy, d.Co = dy.data_ptr(), dy.shape[0], dy.shape[1], dy.shape[2], dy.shape[3]
+    d.x, d.Hi, d.Wi, d.Ci = x.data_ptr(), x.shape[1], x.shape[2], x.shape[3]
+    d.dw, d.Ktot = dw.data_ptr(), dw.shape[1]
+    d.n_taps = len(taps)
+    for i, (ty, tx, ko) in enumerate(taps):
+        d.tap_dy[i], d.tap_dx[i], d.tap_koff[i] = ty, tx, ko
+    d.sy = d.sx = stride
+    d.ays, d.ay0, d.axs, d.ax0 = dy_map
+    d.Hg, d.Wg = grid_hw
+    _lib.check(_lib.lib().mg_conv_wgrad(ctypes.byref(d), _stream()), "mg_conv_wgrad")
+    return dw
+
+
+# ================================================================================================ geometry
+class ConvGeom:
+    """Forward / dgrad / wgrad launch recipes of one conv layer.  kind 'conv': k x k, stride 1|2, pad, dilation
+    (torch weight [Co,Ci,k,k]); kind 'convT': ConvTranspose2d(4, 2, 1) (torch weight [Ci,Co,4,4])."""
+
+    def __init__(self, kind="conv", k=3, stride=1, pad=1, dil=1):
+        self.kind, self.k, self.stride, self.pad, self.dil = kind, k, stride, pad, dil
+        assert kind in ("conv", "convT") and stride in (1, 2)
+        assert not (stride == 2 and dil != 1)
+
+    # ---- forward
+    def out_hw(self, Hi, Wi):
+        if self.kind == "convT":
+            return 2 * Hi, 2 * Wi
+        f = lambda n: (n + 2 * self.pad - self.dil * (self.k - 1) - 1) // self.stride + 1
+        return f(Hi), f(Wi)
+
+    def fwd(self, x, w, **epi):
+        if self.kind == "convT":
+            assert not epi or set(epi) <= {"stats"}
+            return conv_transpose4x4s2_nhwc(x, w, **epi)
+        return conv2d_nhwc(x, w, stride=self.stride, padding=self.pad, dilation=self.dil, **epi)
+
+    # ---- data gradient: dx [N,Hi,Wi,Ci_pad] from dy [N,Ho,Wo,Co]
+    def dgrad(self, dy, w, x_shape):
+        N, Hi, Wi, ci_pad = x_shape
+        k, p, dl = self.k, self.pad, self.dil
+        if self.kind == "convT":
+            Ci, Co = w.shape[:2]
+            wp = pack_weight(w, Co) if ci_pad == Ci else pack_weight(F.pad(w, (0, 0, 0, 0, 0, 0, 0, ci_pad - Ci)), Co)
+            taps = [(ky - 1, kx - 1, (ky * 4 + kx) * Co) for ky in range(4) for kx in range(4)]
+            return conv_launch(dy, wp, taps, stride=2, grid_hw=(Hi, Wi))
+        Co, Ci = w.shape[:2]
+        wt = w.permute(1, 0, 2, 3)  # [Ci,Co,k,k]
+        if ci_pad != Ci:
+            wt = F.pad(wt, (0, 0, 0, 0, 0, 0, 0, ci_pad - Ci))
+        wp = pack_weight(wt, Co)      # [Ci_pad][k*k][Co]
+        if self.stride == 1:
+            taps = [(p - ky * dl, p - kx * dl, (ky * k + kx) * Co) for ky in range(k) for kx in range(k)]
+            return conv_launch(dy, wp, taps, grid_hw=(Hi, Wi))
+        assert Hi % 2 == 0 and Wi % 2 == 0
+        dx = torch.empty((N, Hi, Wi, ci_pad), dtype=torch.float16, device=dy.device)
+        for py in range(2):
+            for px in range(2):
+                taps = [((py + p - ky) // 2, (px + p - kx) // 2, (ky * k + kx) * Co)
+                        for ky in range(k) if (py + p - ky) % 2 == 0 for kx in range(k) if (px + p - kx) % 2 == 0]
+                if not taps:
+                    dx[:, py::2, px::2] = 0
+                    continue
+                conv_launch(dy, wp, taps, grid_hw=(Hi // 2, Wi // 2), out=dx, out_map=(2, py, 2, px))
+        return dx
+
+    # ---- weight gradient in the torch layout, fp32
+    def wgrad(self, dy, x, w_shape):
+        ci_pad = x.shape[-1]
+        k = self.k
+        if self.kind == "convT":
+            Ci, Co = w_shape[:2]
+            dwp = torch.zeros((Co, 16 * ci_pad), dtype=torch.float32, device=x.device)
+            for py in range(2):
+                for px in range(2):
+                    taps = [((py + 1 - ky) // 2, (px + 1 - kx) // 2, (ky * 4 + kx) * ci_pad)
+                            for ky in range(4) if (py + 1 - ky) % 2 == 0 for kx in range(4) if (px + 1 - kx) % 2 == 0]
+                    wgrad_launch(dy, x, taps, dwp, dy_map=(2, py, 2, px), grid_hw=x.shape[1:3])
+            return dwp.view(Co, 4, 4, ci_pad)[..., :Ci].permute(3, 0, 1, 2)
+        Co, Ci = w_shape[:2]
+        dwp = torch.zeros((Co, k * k * ci_pad), dtype=torch.float32, device=x.device)
+        wgrad_launch(dy, x, conv_taps(k, k, self.pad, self.dil, ci_pad), dwp, stride=self.stride, grid_hw=dy.shape[1:3])
+        return dwp.view(Co, k, k, ci_pad)[..., :Ci].permute(0, 3, 1, 2)
+
+
+# ================================================================================================ BN pieces (K3)
+def bn_finalize(stats, count, bn, training):
+    """-> scale, shift, mean, invstd (fp32 [C]).  Training: batch statistics from the conv epilogue + running-stat
+    update; eval: running statistics."""
+    C = bn.weight.shape[0]
+    dev = bn.weight.device
+    out = torch.empty((4, C), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    if training:
+        bn.num_batches_tracked.add_(1)
+        _lib.check(L.mg_bn_finalize(_ptr(stats), float(count), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean),
+                                    _ptr(bn.running_var), float(bn.momentum), float(bn.eps), _ptr(out[0]), _ptr(out[1]),
+                                    _ptr(out[2]), _ptr(out[3]), C, _stream()), "mg_bn_finalize")
+    else:
+        _lib.check(L.mg_bn_finalize(None, 1.0, _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean), _ptr(bn.running_var),
+                                    0.0, float(bn.eps), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), C,
+                                    _stream()), "mg_bn_finalize")
+    return out[0], out[1], out[2], out[3]
+
+
+class _ConvBNAct(torch.autograd.Function):
+    """conv -> BN(batch stats) -> (+res) -> act   |   conv -> act -> BN   (act_first), training mode, all native."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, res, geom, bn, act, act_first, res_up):
+        xn = x.permute(0, 2, 3, 1)
+        assert xn.is_contiguous() and xn.dtype == torch.float16
+        Co = w.shape[1] if geom.kind == "convT" else w.shape[0]
+        stats = new_stats(Co, x.device)
+        wd = w.detach()
+        r = geom.fwd(xn, wd, stats=stats) if not act_first else geom.fwd(xn, wd, stats=stats, pre_act=act)
+        N, Ho, Wo, _ = r.shape
+        scale, shift, mean, invstd = bn_finalize(stats, N * Ho * Wo, bn, True)
+        y = torch.empty_like(r)
+        rn = None
+        if res is not None:
+            rn = res.permute(0, 2, 3, 1)
+            assert rn.is_contiguous() and rn.dtype == torch.float16
+        _lib.check(_lib.lib().mg_bn_apply(_ptr(r), _ptr(scale), _ptr(shift), _ptr(rn), int(res_up), _ptr(y), N, Ho, Wo, Co,
+                                          0 if act_first else ACT[act], _stream()), "mg_bn_apply")
+        ctx.save_for_backward(xn, wd, r, y, mean, invstd, gamma.detach())
+        ctx.cfg = (geom, act, act_first, res_up, res is not None, tuple(w.shape))
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xn, w, r, y, mean, invstd, gamma = ctx.saved_tensors
+        geom, act, act_first, res_up, has_res, w_shape = ctx.cfg
+        dy = gy.permute(0, 2, 3, 1)
+        if not dy.is_contiguous() or dy.dtype != torch.float16:
+            dy = dy.contiguous().to(torch.float16)
+        N, Ho, Wo, Co = r.shape
+        L = _lib.lib()
+        sums = torch.zeros((2, Co), dtype=torch.float32, device=r.device)
+        a_post = 0 if act_first else ACT[act]
+        _lib.check(L.mg_bn_bwd_reduce(_ptr(dy), _ptr(y), _ptr(r), _ptr(mean), _ptr(invstd), _ptr(sums), N, Ho, Wo, Co, a_post,
+                                      _stream()), "mg_bn_bwd_reduce")
+        dr = torch.empty_like(r)
+        dres = torch.empty_like(r) if has_res else None
+        _lib.check(L.mg_bn_bwd_apply(_ptr(dy), _ptr(y), _ptr(r), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(sums), _ptr(dr),
+                                     _ptr(dres), N, Ho, Wo, Co, a_post, ACT[act] if act_first else 0, _stream()),
+                   "mg_bn_bwd_apply")
+        dx = geom.dgrad(dr, w, xn.shape).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
+        dw = geom.wgrad(dr, xn, w_shape) if ctx.needs_input_grad[1] else None
+        if dres is not None:
+            dres = dres.permute(0, 3, 1, 2)
+            if res_up:
+                dres = F.avg_pool2d(dres.float(), 2).mul_(4.0).to(torch.float16)
+        return dx, dw, sums[1], sums[0], dres, None, None, None, None, None
+
+
+def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="relu", act_first=False, residual=None,
+                transposed=False, res_up=False):
+    """x NCHW-shaped channels-last fp16 (channels padded to a multiple of 16); w in the reference layout, fp32.
+    Training: conv(stats epilogue) + finalize + apply kernels with a native backward.  Eval: BatchNorm is folded
+    into the conv epilogue (one kernel)."""
+    _need_cuda(x, w)
+    geom = ConvGeom("convT", 4, 2, 1, 1) if transposed else ConvGeom("conv", w.shape[-1], stride, padding, dilation)
+    if x.dtype != torch.float16 or not x.permute(0, 2, 3, 1).is_contiguous():
+        x = x.to(torch.float16).contiguous(memory_format=torch.channels_last)
+    if residual is not None and (residual.dtype != torch.float16 or not residual.permute(0, 2, 3, 1).is_contiguous()):
+        residual = residual.to(torch.float16).contiguous(memory_format=torch.channels_last)
+    if training:
+        assert bn is not None
+        return _ConvBNAct.apply(x, w, bn.weight, bn.bias, residual, geom, bn, act, act_first, res_up)
+    xn = x.permute(0, 2, 3, 1)
+    scale = shift = None
+    if bn is not None:
+        scale, shift, _, _ = bn_finalize(None, 1, bn, False)
+    rn = residual.permute(0, 2, 3, 1) if residual is not None else None
+    if geom.kind == "convT":
+        # four phase launches write disjoint output pixels; epilogue fusion applies per launch
+        N, Hi, Wi, ci_pad = xn.shape
+        Ci, Co = w.shape[:2]
+        y = torch.empty((N, 2 * Hi, 2 * Wi, Co), dtype=torch.float16, device=x.device)
+        wp = pack_weight(w.detach().permute(1, 0, 2, 3), ci_pad)
+        for py in range(2):
+            for px in range(2):
+                taps = [((py + 1 - ky) // 2, (px + 1 - kx) // 2, (ky * 4 + kx) * ci_pad)
+                        for ky in range(4) if (py + 1 - ky) % 2 == 0 for kx in range(4) if (px + 1 - kx) % 2 == 0]
+                conv_launch(xn, wp, taps, grid_hw=(Hi, Wi), out=y, out_map=(2, py, 2, px), scale=scale, shift=shift,
+                            pre_act=act if act_first else None, post_act=None if act_first else act)
+    else:
+        y = conv2d_nhwc(xn, w.detach(), stride=stride, padding=padding, dilation=dilation, scale=scale, shift=shift, res=rn,
+                        res_up=res_up, pre_act=act if act_first else None, post_act=None if act_first else act)
+    return y.permute(0, 3, 1, 2)

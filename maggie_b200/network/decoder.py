@@ -41,8 +41,7 @@ class DecBlock(nn.Module):
             # nearest x2 commutes with a 1x1 conv and leaves BN batch statistics unchanged, so the skip path runs
             # at the low resolution and is replicated afterwards
             idt = ops.conv_bn_act(x, self.upsample[1].weight(), self.upsample[2], t, padding=0, act=None)
-            idt = F.interpolate(idt, scale_factor=2, mode="nearest")
-        return ops.conv_bn_act(out, self.conv2.weight(), self.bn2, t, act="lrelu", residual=idt)
+        return ops.conv_bn_act(out, self.conv2.weight(), self.bn2, t, act="lrelu", residual=idt, res_up=self.up)
 
 
 # ------------------------------------------------------------------------------------------- attention

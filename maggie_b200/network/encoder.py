@@ -21,7 +21,7 @@ class EncBlock(nn.Module):
         self.bn2 = nn.BatchNorm2d(planes)
         nn.init.constant_(self.bn2.weight, 0)  # resnet.py:97-99
         self.downsample = None
-        if stride != 1 or inplanes != planes:
+        if stride != 1:
             # [AvgPool2d(2, stride), SN conv1x1, BN]  (resnet.py:111-116)
             self.downsample = seq(Slot(), SNConv(inplanes, planes, 1), nn.BatchNorm2d(planes))
 
@@ -30,8 +30,9 @@ class EncBlock(nn.Module):
         out = ops.conv_bn_act(x, self.conv1.weight(), self.bn1, t, stride=self.stride, act="relu")
         idt = x
         if self.downsample is not None:
-            idt = torch.nn.functional.avg_pool2d(x, 2, self.stride)
-            idt = ops.conv_bn_act(idt, self.downsample[1].weight(), self.downsample[2], t, padding=0, act=None)
+            # AvgPool2d(2,2) followed by a 1x1 conv == one 2x2 stride-2 conv with the 1x1 weight / 4 on every tap
+            w2 = self.downsample[1].weight().expand(-1, -1, 2, 2) * 0.25
+            idt = ops.conv_bn_act(x, w2, self.downsample[2], t, stride=2, padding=0, act=None)
         # conv2 -> bn2 -> (+identity) -> relu
         return ops.conv_bn_act(out, self.conv2.weight(), self.bn2, t, act="relu", residual=idt)
 
@@ -51,7 +52,7 @@ def _make_shortcut(inplane, planes):
 class ResMaskEmbedShortCutEncoder(nn.Module):
     """`res_shortcut_embed_29`: blocks [3,4,4,2], num_embed mask-embedding channels."""
 
-    IN_PAD = 8  # packed input channels: 3 image + num_embed + zero padding
+    IN_PAD = 16  # packed input channels: 3 image + num_embed + zero padding (tcgen05 K granularity)
 
     def __init__(self, num_mask=10, num_embed=3, **_):
         super().__init__()

@@ -21,18 +21,7 @@ from . import _lib
 COMPUTE_DTYPE = torch.float16
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
-def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
-
-
-def _need_cuda(*tensors):
-    for t in tensors:
-        if t is not None and not t.is_cuda:
-            raise RuntimeError("maggie_b200 native op called with a non-CUDA tensor; there is no CPU fallback")
+_stream, _ptr, _need_cuda = _lib.stream_ptr, _lib.tensor_ptr, _lib.need_cuda
 
 
 # =============================================================================================== native: K8a
@@ -173,27 +162,14 @@ def batch_norm(x, bn, training):
 
 
 def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="relu", act_first=False,
-                residual=None, transposed=False):
+                residual=None, transposed=False, res_up=False):
     """conv (or 4x4 s2 transposed conv) -> BN -> (+residual) -> act, or conv -> act -> BN when act_first.
-    x NCHW-shaped channels-last; w in the reference's layout ([Cout,Cin,k,k]; [Cin,Cout,4,4] transposed).
-    INTERIM (cuDNN via torch)."""
-    w = w.to(x.dtype)
-    if w.shape[0 if transposed else 1] < x.shape[1]:  # input was channel-padded by mask_embed
-        pad = x.shape[1] - w.shape[0 if transposed else 1]
-        w = F.pad(w, (0, 0, 0, 0, 0, pad)) if not transposed else F.pad(w, (0, 0, 0, 0, 0, 0, 0, pad))
-    if transposed:
-        y = F.conv_transpose2d(x, w, stride=2, padding=1)
-    else:
-        y = F.conv2d(x, w, stride=stride, padding=padding, dilation=dilation)
-    if act_first:
-        y = _act(y, act)
-    if bn is not None:
-        y = batch_norm(y, bn, training)
-    if residual is not None:
-        y = y + residual
-    if not act_first:
-        y = _act(y, act)
-    return y
+    NATIVE: tcgen05/TMA implicit-GEMM conv (K2) with BN-statistics epilogue, K3 BatchNorm kernels, native dgrad
+    (K2 with the transposed pack) and wgrad (K4).  See maggie_b200/dense.py."""
+    from . import dense
+
+    return dense.conv_bn_act(x, w, bn, training, stride=stride, padding=padding, dilation=dilation, act=act,
+                             act_first=act_first, residual=residual, transposed=transposed, res_up=res_up)
 
 
 def linear(x, w, b=None):

@@ -80,12 +80,35 @@ def mask_embed(image, masks, table, slot_ids, C=8):
     return out.to(ops.COMPUTE_DTYPE).contiguous(memory_format=torch.channels_last)
 
 
+def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="relu", act_first=False,
+                residual=None, transposed=False, res_up=False):
+    """torch restatement of the conv+BN+act contract (cuDNN/ATen or CPU)."""
+    import torch.nn.functional as F
+    a = lambda t: F.relu(t) if act == "relu" else (F.leaky_relu(t, 0.2) if act == "lrelu" else t)
+    w = w.to(x.dtype)
+    cin_w = w.shape[0 if transposed else 1]
+    if cin_w < x.shape[1]:  # input was channel-padded by mask_embed
+        pad = x.shape[1] - cin_w
+        w = F.pad(w, (0, 0, 0, 0, 0, pad)) if not transposed else F.pad(w, (0, 0, 0, 0, 0, 0, 0, pad))
+    y = F.conv_transpose2d(x, w, stride=2, padding=1) if transposed else F.conv2d(x, w, stride=stride, padding=padding, dilation=dilation)
+    if act_first:
+        y = a(y)
+    if bn is not None:
+        y = ops.batch_norm(y, bn, training)
+    if residual is not None:
+        y = y + (F.interpolate(residual, scale_factor=2, mode="nearest") if res_up else residual)
+    return y if act_first else a(y)
+
+
 @contextlib.contextmanager
 def injected(dtype=torch.float32):
     """Swap the native ops for the references above (CPU container only)."""
-    saved = (ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.COMPUTE_DTYPE)
-    ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.COMPUTE_DTYPE = unknown_mask, build_sites, mask_embed, dtype
+    names = ("unknown_mask", "build_sites", "mask_embed", "conv_bn_act", "COMPUTE_DTYPE")
+    saved = {n: getattr(ops, n) for n in names}
+    ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.conv_bn_act, ops.COMPUTE_DTYPE = \
+        unknown_mask, build_sites, mask_embed, conv_bn_act, dtype
     try:
         yield
     finally:
-        ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.COMPUTE_DTYPE = saved
+        for n, v in saved.items():
+            setattr(ops, n, v)
