@@ -372,7 +372,7 @@ def unknown(alpha, k_size, is_train=False):
     return torch.from_numpy(U.compute_unknown(alpha.detach().cpu().numpy(), widths))
 
 
-def decoder(P, emb, fea, image, b, n_f, n_i, masks, it, gt_alphas, training, cfg):
+def decoder(P, emb, fea, image, b, n_f, n_i, masks, it, gt_alphas, training, cfg, p_drop=0.1):
     """resnet_inst_matt_spconv.py:292-388."""
     d = "decoder."
     da = cfg["decoder_args"]
@@ -405,7 +405,7 @@ def decoder(P, emb, fea, image, b, n_f, n_i, masks, it, gt_alphas, training, cfg
         unk[:, :, 200:250, 200:250] = 1
     if unk.sum() > 0 or training:
         q = queries[:, None].expand(-1, n_f, -1, -1).reshape(b * n_f, *queries.shape[1:])
-        os4, os1, counts = predict_details(P, x, unk, q, fea1, fea2, fea3, training)
+        os4, os1, counts = predict_details(P, x, unk, q, fea1, fea2, fea3, training, p_drop)
         stages.update(counts)
         os4 = os4.reshape(b * n_f, guided.shape[1], *os4.shape[-2:])
         os1 = os1.reshape(b * n_f, guided.shape[1], *os1.shape[-2:])
@@ -512,7 +512,7 @@ def compute_loss(pred, w4, w1, alphas, cfg):
 
 
 # ----------------------------------------------------------------------------- top level
-def forward(P, batch, training, cfg, return_stages=False):
+def forward(P, batch, training, cfg, return_stages=False, p_drop=0.1):
     """MaGGIe.forward (arch/maggie.py:63-139). Returns eval: output dict; train: (output, loss_dict)."""
     num_masks = cfg["encoder_args"]["num_mask"]
     x, masks = batch["image"], batch["mask"]
@@ -550,7 +550,7 @@ def forward(P, batch, training, cfg, return_stages=False):
         trans = trans.view(-1, n_i, h, w)
     emb, fea, image = encoder(P, inp, training)
     emb = aspp(P, emb, training)
-    pred, stages = decoder(P, emb, fea, image, b, n_f, n_i, masks, batch.get("iter", 0), alphas, training, cfg)
+    pred, stages = decoder(P, emb, fea, image, b, n_f, n_i, masks, batch.get("iter", 0), alphas, training, cfg, p_drop)
     stages["aspp"] = emb
 
     alpha_pred = pred.pop("refined_masks")
