@@ -149,6 +149,37 @@ int mg_bn_bwd_apply(const void* dy, const void* y, const void* conv_out, const f
                     const float* gamma, const float* sums, void* dx, void* dres, int N, int H, int W, int C, int act,
                     int pre_act, void* stream);
 
+/* ---- K9: sparse refinement on the active-site lists (no spconv) -------------------------------------
+ * replaces: spconv SubMConv2d / SparseInverseConv2d / SparseConvTensor.dense() and the dense<->sparse gathers of
+ *           decoder/resnet_inst_matt_spconv.py:161-270, plus their backward passes.
+ * mg_gather_rows      : out[r, c_off:c_off+C] = dense[coords[r].slot / n_i, y, x, :]   (dense NHWC fp16 [B,H,W,C])
+ * mg_scatter_rows_add : ddense[slot / n_i, y, x, :] += g[r, c_off:c_off+C]              (backward of the gather)
+ * mg_sparse_conv      : rulebook convolution  out[p][co] = sum_t sum_ci src[table[p][t]][ci] * w[co][t*Cin + ci] + bias
+ *     src fp16 rows (row stride src_stride); table int32 [No][T] with -1 = none, or NULL with T = 1 (1x1 / Linear);
+ *     w fp16 [ceil16(Cout)][T*Cin] (rows beyond Cout zero); pre_act 1 = ReLU on the result;
+ *     out fp16 rows written at column c_off (row stride out_stride), or, when `map` is given (the 32->1 heads), the
+ *     fp32 logit map[slot][mapH][mapW] (pre-filled with -99 by the caller) gets ((v - 99) + 99) at coords[p];
+ *     stats optional [MG_CONV_STAT_COPIES][2][Cout] as in mg_conv_fprop (BatchNorm1d batch statistics).
+ *     SubMConv2d: table = nbr;  SparseInverseConv2d: table = parent;  their data gradients: the same call with the
+ *     mirrored nbr taps / the child table and the transposed weight pack.
+ * mg_sparse_wgrad     : dw[co][t*Cin + ci] += sum_p dout[p][co] * src[table[p][t]][ci]   (fp32, atomics; caller zeroes) */
+typedef struct mg_sparse_conv_desc {
+    const void* src; int32_t src_stride;
+    const int32_t* table; int32_t T, No, Cin, Cout;
+    const void* w; const float* bias;
+    void* out; int32_t out_stride, c_off;
+    float* stats;
+    float* map; const int32_t* coords; int32_t mapH, mapW;
+    int32_t pre_act;
+} mg_sparse_conv_desc;
+int mg_gather_rows(const void* dense, const int32_t* coords, int n, int n_i, int H, int W, int C, void* out, int out_stride,
+                   int c_off, void* stream);
+int mg_scatter_rows_add(const void* g, int g_stride, int c_off, const int32_t* coords, int n, int n_i, int H, int W, int C,
+                        void* ddense, void* stream);
+int mg_sparse_conv(const mg_sparse_conv_desc* desc, void* stream);
+int mg_sparse_wgrad(const void* dout, int dout_stride, int Cout, const void* src, int src_stride, int Cin,
+                    const int32_t* table, int T, int No, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

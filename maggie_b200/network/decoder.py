@@ -204,9 +204,6 @@ class MaGGIeDecoder(nn.Module):
             p.requires_grad_(True)  # as in the reference: trainable flag set, but they never receive a gradient
 
     # -- sparse refinement ---------------------------------------------------------------------------
-    def _bn1d(self, x, bn):
-        return x if x.shape[0] == 0 else ops.batch_norm(x.float(), bn, self.training).to(x.dtype)
-
     def predict_details(self, os8_feat, roi, queries, fea1, fea2, fea3):
         """roi uint8 [B, n_i, H, W]; queries [B, 10, 64] fp32.  Returns fp32 logit maps
         [B*n_i,1,H/4,W/4], [B*n_i,1,H,W] (-99 where inactive) and the site counts."""
@@ -214,42 +211,39 @@ class MaGGIeDecoder(nn.Module):
         slots = B * n_i
         T = ops.build_sites(roi.reshape(slots, H, W))
         c1, c2, c4, c8 = T.coords
-        lre = lambda v: F.leaky_relu(v, 0.2)
         dt = os8_feat.dtype
+        t = self.training
+
+        nb4, nb1 = T.nbr[2], T.nbr[0]
+        conv = lambda src, m, **kw: ops.rows_conv(src, m.weight, m.bias, training=t, **kw)
+        subm = lambda src, m, nb, **kw: conv(src, m, table=nb, table_t=nb, mirror=True, **kw)
 
         x = ops.gather_dense(os8_feat, c8, n_i)
         g = queries[torch.div(c8[:, 0].long(), n_i, rounding_mode="floor"), (c8[:, 0] % n_i).long()]
         x = self.inst_spec_layer(x * g.to(dt))
-        # OS8 -> OS4
-        x = ops.gather_conv(x, T.parent[2], self.layer3[0].weight)
-        x = ops.gather_conv(lre(self._bn1d(x, self.layer3[1])), T.nbr[2], self.layer3[3].weight)
+        # OS8 -> OS4: inverse conv + BN + LReLU, SubM 3x3
+        x = conv(x, self.layer3[0], table=T.parent[2], table_t=T.child[3], bn=self.layer3[1], mode="bn_act", act="lrelu")
+        x = subm(x, self.layer3[3], nb4)
+        # instance-specific guidance: gate the dense detail features with sigma(conv(cat[detail, instance]))
         det = ops.gather_dense(fea3, c4, n_i)
-        gd = ops.pointwise_conv(torch.cat([det, x], 1), self.guidance_layer[0].weight)
-        gd = ops.gather_conv(lre(self._bn1d(gd, self.guidance_layer[1])), T.nbr[2], self.guidance_layer[3].weight,
-                             self.guidance_layer[3].bias)
+        gd = conv(torch.cat([det, x], 1), self.guidance_layer[0], bn=self.guidance_layer[1], mode="bn_act", act="lrelu")
+        gd = subm(gd, self.guidance_layer[3], nb4)
         x = det * torch.sigmoid(gd.float()).to(dt)
-        x = self._bn1d(F.relu(ops.pointwise_conv(x, self.layer3_smooth[0].weight, self.layer3_smooth[0].bias)),
-                       self.layer3_smooth[2])
-        y = ops.gather_conv(x, T.nbr[2], self.refine_OS4[0].weight)
-        y = ops.gather_conv(lre(self._bn1d(y, self.refine_OS4[1])), T.nbr[2], self.refine_OS4[3].weight,
-                            self.refine_OS4[3].bias)
-        os4 = ops.scatter_logits(y, c4, slots, H // 4, W // 4)
+        x = conv(x, self.layer3_smooth[0], bn=self.layer3_smooth[2], mode="act_bn", act="relu")
+        y = subm(x, self.refine_OS4[0], nb4, bn=self.refine_OS4[1], mode="bn_act", act="lrelu")
+        os4 = ops.rows_head(y, self.refine_OS4[3].weight, self.refine_OS4[3].bias, nb4, c4, slots, H // 4, W // 4)
         # OS4 -> OS2
-        x = ops.gather_conv(x, T.parent[1], self.layer4[0].weight)
-        x = ops.pointwise_conv(lre(self._bn1d(x, self.layer4[1])), self.layer4[3].weight)
+        x = conv(x, self.layer4[0], table=T.parent[1], table_t=T.child[2], bn=self.layer4[1], mode="bn_act", act="lrelu")
+        x = conv(x, self.layer4[3])
         x = torch.cat([ops.gather_dense(fea2, c2, n_i), x], 1)
-        x = self._bn1d(F.relu(ops.pointwise_conv(x, self.layer4_smooth[0].weight, self.layer4_smooth[0].bias)),
-                       self.layer4_smooth[2])
+        x = conv(x, self.layer4_smooth[0], bn=self.layer4_smooth[2], mode="act_bn", act="relu")
         # OS2 -> OS1
-        x = ops.gather_conv(x, T.parent[0], self.layer5[0].weight)
-        x = ops.gather_conv(lre(self._bn1d(x, self.layer5[1])), T.nbr[0], self.layer5[3].weight)
+        x = conv(x, self.layer5[0], table=T.parent[0], table_t=T.child[1], bn=self.layer5[1], mode="bn_act", act="lrelu")
+        x = subm(x, self.layer5[3], nb1)
         x = torch.cat([ops.gather_dense(fea1, c1, n_i), x], 1)
-        x = self._bn1d(F.relu(ops.pointwise_conv(x, self.layer5_smooth[0].weight, self.layer5_smooth[0].bias)),
-                       self.layer5_smooth[2])
-        y = ops.gather_conv(x, T.nbr[0], self.refine_OS1[0].weight)
-        y = ops.gather_conv(lre(self._bn1d(y, self.refine_OS1[1])), T.nbr[0], self.refine_OS1[3].weight,
-                            self.refine_OS1[3].bias)
-        os1 = ops.scatter_logits(y, c1, slots, H, W)
+        x = conv(x, self.layer5_smooth[0], bn=self.layer5_smooth[2], mode="act_bn", act="relu")
+        y = subm(x, self.refine_OS1[0], nb1, bn=self.refine_OS1[1], mode="bn_act", act="lrelu")
+        os1 = ops.rows_head(y, self.refine_OS1[3].weight, self.refine_OS1[3].bias, nb1, c1, slots, H, W)
         return os4, os1, T.counts
 
     # -- forward --------------------------------------------------------------------------------------

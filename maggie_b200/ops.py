@@ -195,41 +195,28 @@ def attention(q, k, v, key_padding=None, need_stat=None):
     return o, None
 
 
-def gather_conv(src, table, weight, bias=None):
-    """Rulebook convolution: out[p] = sum_t W[t] . src[table[p,t]] (table entry -1 = no contribution).
-    src [Ns,Cin]; table [No,T] int32; weight in spconv layout [Cout,kh,kw,Cin] with kh*kw == T.
-    Covers SubMConv2d (nbr table) and SparseInverseConv2d (parent table).  INTERIM (torch gather + GEMM)."""
-    No, T = table.shape
-    Cout, Cin = weight.shape[0], weight.shape[-1]
-    if No == 0:
-        return src.new_zeros((0, Cout))
-    padded = torch.cat([src, src.new_zeros((1, Cin))], dim=0)
-    idx = torch.where(table < 0, src.shape[0], table.long()).reshape(-1)
-    g = padded.index_select(0, idx).reshape(No, T * Cin)
-    w = weight.reshape(Cout, T * Cin).to(src.dtype)
-    out = g @ w.t()
-    return out if bias is None else out + bias.to(out.dtype)
+def rows_conv(src, w, bias=None, *, table=None, table_t=None, mirror=False, bn=None, mode="plain", act=None,
+              training=False):
+    """Rulebook convolution on site rows (+ BatchNorm1d + activation), NATIVE (K9 gather -> tcgen05 tile -> rows;
+    K3 BatchNorm kernels; native data / weight gradients).  See maggie_b200/sparse.py."""
+    from . import sparse
+
+    return sparse.rows_conv(src, w, bias, table=table, table_t=table_t, mirror=mirror, bn=bn, mode=mode, act=act,
+                            training=training)
 
 
-def pointwise_conv(src, weight, bias=None):
-    """SubMConv2d with k=1 == per-site linear map. weight [Cout,1,1,Cin]. INTERIM."""
-    return linear(src, weight.reshape(weight.shape[0], -1), bias)
+def rows_head(src, w, bias, nbr, coords, slots, H, W):
+    """SubM 3x3 C->1 head written into the fp32 logit map (-99 where inactive), NATIVE (K9)."""
+    from . import sparse
+
+    return sparse.rows_head(src, w, bias, nbr, coords, slots, H, W)
 
 
 def gather_dense(dense, coords, n_i):
-    """dense NCHW-shaped channels-last [B,C,H,W] -> rows [N,C] at coords (frame = slot // n_i). INTERIM."""
-    nhwc = dense.permute(0, 2, 3, 1)
-    c = coords.long()
-    return nhwc[torch.div(c[:, 0], n_i, rounding_mode="floor"), c[:, 1], c[:, 2]]
+    """dense NCHW-shaped channels-last [B,C,H,W] -> rows [N,C] at coords (frame = slot // n_i), NATIVE (K9)."""
+    from . import sparse
 
-
-def scatter_logits(vals, coords, slots, H, W):
-    """fp32 logit map [slots,1,H,W]: -99 everywhere, value at active sites computed as ((v - 99) + 99) like the
-    reference's dense()/-99/+=99 sequence (decoder/resnet_inst_matt_spconv.py:248-251). INTERIM."""
-    out = torch.full((slots, 1, H, W), -99.0, dtype=torch.float32, device=vals.device)
-    c = coords.long()
-    v = (vals.float().reshape(-1) - 99.0) + 99.0
-    return out.index_put((c[:, 0], torch.zeros_like(c[:, 0]), c[:, 1], c[:, 2]), v)
+    return sparse.gather_dense(dense, coords, n_i)
 
 
 def upsample_tanh(logits, size=None, scale=None):

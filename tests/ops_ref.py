@@ -5,6 +5,7 @@ import contextlib
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from maggie_b200 import ops
 from oracle import unknown as U
@@ -100,13 +101,73 @@ def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="rel
     return y if act_first else a(y)
 
 
+# ---- torch restatements of the sparse (rulebook) ops -------------------------------------------------------
+def gather_conv(src, table, weight, bias=None):
+    """Rulebook convolution: out[p] = sum_t W[t] . src[table[p,t]] (table entry -1 = no contribution).
+    src [Ns,Cin]; table [No,T] int32; weight in spconv layout [Cout,kh,kw,Cin] with kh*kw == T.
+    Covers SubMConv2d (nbr table) and SparseInverseConv2d (parent table).  torch reference."""
+    No, T = table.shape
+    Cout, Cin = weight.shape[0], weight.shape[-1]
+    if No == 0:
+        return src.new_zeros((0, Cout))
+    padded = torch.cat([src, src.new_zeros((1, Cin))], dim=0)
+    idx = torch.where(table < 0, src.shape[0], table.long()).reshape(-1)
+    g = padded.index_select(0, idx).reshape(No, T * Cin)
+    w = weight.reshape(Cout, T * Cin).to(src.dtype)
+    out = g @ w.t()
+    return out if bias is None else out + bias.to(out.dtype)
+
+
+def pointwise_conv(src, weight, bias=None):
+    """SubMConv2d with k=1 == per-site linear map. weight [Cout,1,1,Cin]. torch reference."""
+    return ops.linear(src, weight.reshape(weight.shape[0], -1), bias)
+
+
+def gather_dense(dense, coords, n_i):
+    """dense NCHW-shaped channels-last [B,C,H,W] -> rows [N,C] at coords (frame = slot // n_i). torch reference."""
+    nhwc = dense.permute(0, 2, 3, 1)
+    c = coords.long()
+    return nhwc[torch.div(c[:, 0], n_i, rounding_mode="floor"), c[:, 1], c[:, 2]]
+
+
+def scatter_logits(vals, coords, slots, H, W):
+    """fp32 logit map [slots,1,H,W]: -99 everywhere, value at active sites computed as ((v - 99) + 99) like the
+    reference's dense()/-99/+=99 sequence (decoder/resnet_inst_matt_spconv.py:248-251). torch reference."""
+    out = torch.full((slots, 1, H, W), -99.0, dtype=torch.float32, device=vals.device)
+    c = coords.long()
+    v = (vals.float().reshape(-1) - 99.0) + 99.0
+    return out.index_put((c[:, 0], torch.zeros_like(c[:, 0]), c[:, 1], c[:, 2]), v)
+
+
+
+def rows_conv(src, w, bias=None, *, table=None, table_t=None, mirror=False, bn=None, mode="plain", act=None, training=False):
+    import torch.nn.functional as F
+    co, ci = w.shape[0], w.shape[-1]
+    y = gather_conv(src, table, w.reshape(co, -1, 1, ci), bias) if table is not None else pointwise_conv(src, w.reshape(co, 1, 1, ci), bias)
+    if mode == "plain":
+        return y
+    a = lambda t: F.relu(t) if act == "relu" else (F.leaky_relu(t, 0.2) if act == "lrelu" else t)
+    if mode == "act_bn":
+        y = F.relu(y)
+    if y.shape[0]:
+        y = ops.batch_norm(y.float(), bn, training).to(y.dtype)
+    return a(y) if mode == "bn_act" else y
+
+
+def rows_head(src, w, bias, nbr, coords, slots, H, W):
+    y = gather_conv(src, nbr, w.reshape(1, 9, 1, w.shape[-1]), bias)
+    return scatter_logits(y, coords, slots, H, W)
+
+
 @contextlib.contextmanager
 def injected(dtype=torch.float32):
     """Swap the native ops for the references above (CPU container only)."""
-    names = ("unknown_mask", "build_sites", "mask_embed", "conv_bn_act", "COMPUTE_DTYPE")
+    names = ("unknown_mask", "build_sites", "mask_embed", "conv_bn_act", "rows_conv", "rows_head", "gather_dense",
+             "COMPUTE_DTYPE")
     saved = {n: getattr(ops, n) for n in names}
     ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.conv_bn_act, ops.COMPUTE_DTYPE = \
         unknown_mask, build_sites, mask_embed, conv_bn_act, dtype
+    ops.rows_conv, ops.rows_head, ops.gather_dense = rows_conv, rows_head, gather_dense
     try:
         yield
     finally:
