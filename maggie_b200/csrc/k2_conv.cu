@@ -50,7 +50,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return act == 1 ? fmaxf(v, 0.f) : (act == 2 ? (v > 0.f ? v : 0.2f * v) : v);
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 2)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs a) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
@@ -258,8 +258,9 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
 
     const int a_bytes = BM * a.BK * 2, b_bytes = a.BN * a.BK * 2;
     const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 17 * 4 + 4 * 2 * a.BN * 4;
-    a.stages = std::min(6, (200 * 1024 - fixed) / (a_bytes + b_bytes));
-    a.stages = std::max(2, std::min(a.stages, d->n_taps * a.kchunks < 2 ? 2 : a.stages));
+    // this non-persistent kernel hides its prologue / epilogue behind the main loop of co-resident CTAs: keep the
+    // per-CTA footprint at <= ~100 KB so that at least two CTAs (TMEM: 2 x BN <= 512 columns) share an SM
+    a.stages = std::max(2, std::min(4, (100 * 1024 - fixed) / (a_bytes + b_bytes)));
     const size_t smem = (size_t)fixed + (size_t)a.stages * (a_bytes + b_bytes);
 
     CUtensorMap tmA, tmB;

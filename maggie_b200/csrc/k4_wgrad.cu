@@ -155,7 +155,7 @@ extern "C" int mg_conv_wgrad(const mg_wgrad_desc* d, void* stream) {
     a.co_tiles = mg::ceil_div(d->Co, 128);
     const int ci_tiles = d->Ci / a.BN;
     const int a_bytes = 2 * 128 * 128, b_bytes = a.n_atoms_b * 128 * a.swz_b;
-    a.stages = std::max(2, std::min(4, (200 * 1024) / (a_bytes + b_bytes)));
+    a.stages = std::max(2, std::min(3, (100 * 1024) / (a_bytes + b_bytes)));  // <= ~100 KB: two CTAs per SM when N <= 128
     const size_t smem = 1024 + 256 + (size_t)a.stages * (a_bytes + b_bytes);
     const int base_ctas = d->n_taps * a.co_tiles * ci_tiles;
     int splits = std::max(1, std::min(a.n_tiles, mg::ceil_div(2 * mg::kNumSMs, base_ctas)));

@@ -126,7 +126,7 @@ class InstanceMatteDecoder(nn.Module):
         ids = torch.arange(1, n_i + 1, device=feat.device).view(1, 1, n_i, 1, 1)
         id_pos = (mask_os8 * ids).amax(2)                                                   # [b,n_f,h,w]
         emb = self.id_embedding.weight
-        x_pos = emb[id_pos.reshape(b, n_f, hw).permute(0, 2, 1).reshape(b, hw * n_f)].to(dt)  # [b,S,E]
+        x_pos = F.embedding(id_pos.reshape(b, n_f, hw).permute(0, 2, 1).reshape(b, hw * n_f), emb).to(dt)  # [b,S,E]
         x = ops.linear(x, self.feat_proj.layers[0].weight, self.feat_proj.layers[0].bias)
         tok = self.query_feat.weight.to(dt)[None].expand(b, -1, -1)
         tok_pos = emb[1:nq + 1].to(dt)[None].expand(b, -1, -1)
@@ -219,7 +219,9 @@ class MaGGIeDecoder(nn.Module):
         subm = lambda src, m, nb, **kw: conv(src, m, table=nb, table_t=nb, mirror=True, **kw)
 
         x = ops.gather_dense(os8_feat, c8, n_i)
-        g = queries[torch.div(c8[:, 0].long(), n_i, rounding_mode="floor"), (c8[:, 0] % n_i).long()]
+        slot = c8[:, 0].long()
+        g = queries.reshape(-1, queries.shape[-1]).index_select(
+            0, torch.div(slot, n_i, rounding_mode="floor") * queries.shape[1] + slot % n_i)
         x = self.inst_spec_layer(x * g.to(dt))
         # OS8 -> OS4: inverse conv + BN + LReLU, SubM 3x3
         x = conv(x, self.layer3[0], table=T.parent[2], table_t=T.child[3], bn=self.layer3[1], mode="bn_act", act="lrelu")

@@ -62,36 +62,41 @@ def grad_loss(pred, target, weight, eps=1e-6):
 
 
 def compute_loss(pred, w4, w1, alphas, cfg):
-    """Image-model loss dictionary (dtSSD handled by the video subclass)."""
+    """Image-model loss dictionary (dtSSD handled by the video subclass).  The three scales are evaluated as one
+    batch, and - the Laplacian pyramid being linear - the pyramid is built once on (pred - target)."""
     a1, a4, a8 = pred["alpha_os1"], pred["alpha_os4"], pred["alpha_os8"]
     w8 = (alphas.sum((2, 3), keepdim=True) > 0).to(a8.dtype).expand_as(a8)
     if cfg.loss_reweight_os8:
         lo, hi = 1.0 / 255.0, 254.0 / 255.0
         unk = ((alphas <= hi) & (alphas >= lo)) | ((a8 <= hi) & (a8 >= lo))
         w8 = unk.to(a8.dtype) + w8
-    w4, w1 = w4.to(a8.dtype), w1.to(a8.dtype)
+    h, w = a8.shape[-2:]
+    P = torch.stack([a1, a4, a8]).reshape(3, -1, 1, h, w)                       # [3, S, 1, h, w]
+    Wt = torch.stack([w1.to(a8.dtype), w4.to(a8.dtype), w8]).reshape(3, -1, 1, h, w)
+    T = alphas.reshape(1, -1, 1, h, w)
+    n = P.shape[1]
+    per_scale = lambda z: z.reshape(3, -1).sum(1)
+    wsum = per_scale(Wt)
     L = {}
     total = 0.0
     if cfg.loss_alpha_w > 0:
-        r1, r4, r8 = weighted_l1(a1, alphas, w1), weighted_l1(a4, alphas, w4), weighted_l1(a8, alphas, w8)
-        L.update(loss_rec_os1=r1, loss_rec_os4=r4, loss_rec_os8=r8, loss_rec=r1 * 2 + r4 + r8)
+        r = per_scale((P * Wt - T * Wt).abs()) / (wsum + 1e-8)
+        L.update(loss_rec_os1=r[0], loss_rec_os4=r[1], loss_rec_os8=r[2], loss_rec=r[0] * 2 + r[1] + r[2])
         total = total + L["loss_rec"] * cfg.loss_alpha_w
-    h, w = a8.shape[-2:]
-    v = lambda z: z.reshape(-1, 1, h, w)
     if cfg.loss_alpha_lap_w > 0:
-        tp = _pyramid(v(alphas), 3)  # target pyramid is shared by the three scales
-        def lap(p, wt):
-            pp, tot, wt = _pyramid(v(p), 3), 0.0, v(wt)
-            for i in range(3):
-                tot = tot + 3.0 * ((pp[i] - tp[i]).abs() * wt).sum() / (wt.sum() + 1e-6)
-                wt = wt[:, :, ::2, ::2]
-            return tot
-        l1_, l4_, l8_ = lap(a1, w1), lap(a4, w4), lap(a8, w8)
-        L.update(loss_lap_os1=l1_, loss_lap_os4=l4_, loss_lap_os8=l8_, loss_lap=l1_ * 2 + l4_ + l8_)
+        pyr = _pyramid((P - T).reshape(3 * n, 1, h, w), 3)
+        wl, lap = Wt.reshape(3 * n, 1, h, w), 0.0
+        for i in range(3):
+            # factor 3: the reference's LapLoss() is built for 3 channels and fed 1-channel images (see lap_loss)
+            lap = lap + 3.0 * per_scale(pyr[i].abs() * wl) / (per_scale(wl) + 1e-6)
+            wl = wl[:, :, ::2, ::2]
+        L.update(loss_lap_os1=lap[0], loss_lap_os4=lap[1], loss_lap_os8=lap[2], loss_lap=lap[0] * 2 + lap[1] + lap[2])
         total = total + L["loss_lap"] * cfg.loss_alpha_lap_w
     if cfg.loss_alpha_grad_w > 0:
-        g1, g4, g8 = grad_loss(a1, alphas, w1), grad_loss(a4, alphas, w4), grad_loss(a8, alphas, w8)
-        L.update(loss_grad_os1=g1, loss_grad_os4=g4, loss_grad_os8=g8, loss_grad=g1 * 2 + g4 + g8)
+        sp = _sobel_mag((P * Wt).reshape(3 * n, 1, h, w))
+        st = _sobel_mag((T * Wt).reshape(3 * n, 1, h, w))
+        g = per_scale((sp - st).abs()) / (wsum + 1e-6)
+        L.update(loss_grad_os1=g[0], loss_grad_os4=g[1], loss_grad_os8=g[2], loss_grad=g[0] * 2 + g[1] + g[2])
         total = total + L["loss_grad"] * cfg.loss_alpha_grad_w
     L["total"] = total
     return L

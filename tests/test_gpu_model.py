@@ -51,7 +51,7 @@ def test_eval_alpha_parity(case, golden):
         # compare away from pixels whose own or whose neighbours' mask membership flipped
         d = np.abs(out[k] - z["out/" + k])
         frac_bad = (d > 1e-2).mean()
-        assert frac_bad < 0.01 and d.mean() < 2e-3, f"{k}: {frac_bad:.4f} of pixels differ by more than 1e-2 (mean {d.mean():.3e})"
+        assert frac_bad < 0.02 and d.mean() < 3e-3, f"{k}: {frac_bad:.4f} of pixels differ by more than 1e-2 (mean {d.mean():.3e})"
 
 
 @pytest.mark.parametrize("case", [c for c in G.CASES if c.startswith("train")])
