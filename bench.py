@@ -185,6 +185,7 @@ def run_gpu(args):
     torch.manual_seed(1234)  # identical initial weights on every rank
     model, _ = build_model(CfgNode(synth.model_cfg()))
     model.to(dev).train()
+    model.enable_cuda_graphs(not args.no_graphs)
     flat = FlatGradAllReduce(model.parameters())
 
     host = synth.make_batch(b=FRAMES_PER_GPU, n_f=1, n_i=N_INST, H=H, W=W, edge_px=EDGE_PX, seed=1234 + rank, train=True, it=1)
@@ -257,7 +258,7 @@ def run_gpu(args):
         "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd per GPU (iter=1, edge {EDGE_PX}px)",
                    "frames_per_gpu": FRAMES_PER_GPU, "active_sites_os1_os2_os4_os8": counts,
                    "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                   "loss_scale": LOSS_SCALE, "sync_bn": False},
+                   "loss_scale": LOSS_SCALE, "sync_bn": False, "cuda_graphs_dense_stage": not args.no_graphs},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
@@ -288,6 +289,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="run the dense stage eagerly instead of as CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -74,12 +74,12 @@ int mg_sites_tables(const void* ws, int slots, int H, int W, const int32_t* coun
 /* ---- K1: mask-id embedding + NHWC pack -------------------------------------------------------------
  * replaces: arch/maggie.py:200-235 (zero-padded 10-slot mask tensor + cat) and
  *           encoder/resnet.py:211-229 (Embedding gather, masked mean over instances, permute, cat).
- * image [B,3,H,W] fp32 NCHW; masks [B,M,H,W] fp32 {0,1}; slot_ids_host[M] = slot (0..9) of each given mask;
+ * image [B,3,H,W] fp32 NCHW; masks [B,M,H,W] fp32 {0,1}; slot_ids[M] (DEVICE int32) = slot (0..9) of each given mask;
  * table [11,3] fp32; out [B,H,W,C] fp16 NHWC, C >= 6: ch 0-2 image, 3-5 mean embedding, rest zero.     */
-int mg_mask_embed_fwd(const float* image, const float* masks, const int32_t* slot_ids_host, int M,
+int mg_mask_embed_fwd(const float* image, const float* masks, const int32_t* slot_ids, int M,
                       const float* table, void* out_f16, int B, int H, int W, int C, void* stream);
 /* grad_table [11,3] fp32 += d(out[...,3:6]) / d(table)   (caller zeroes grad_table)                     */
-int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, const int32_t* slot_ids_host, int M,
+int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, const int32_t* slot_ids, int M,
                       float* grad_table, int B, int H, int W, int C, void* stream);
 
 

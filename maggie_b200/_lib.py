@@ -23,7 +23,7 @@ SIGNATURES = {
     "mg_sites_workspace": (c_size_t, [c_int, c_int, c_int]),
     "mg_sites_count": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mg_sites_tables": (c_int, [c_void_p, c_int, c_int, c_int, _I32P, _PP, _PP, _PP, _PP, c_void_p]),
-    "mg_mask_embed_fwd": (c_int, [c_void_p, c_void_p, _I32P, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mg_mask_embed_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_conv_fprop": (c_int, [c_void_p, c_void_p]),
     "mg_conv_wgrad": (c_int, [c_void_p, c_void_p]),
     "mg_gather_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
@@ -37,7 +37,7 @@ SIGNATURES = {
                                  c_void_p]),
     "mg_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "mg_mask_embed_bwd": (c_int, [c_void_p, c_void_p, _I32P, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mg_mask_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 

@@ -13,10 +13,12 @@ struct SlotIds {
 
 template <int C>
 __global__ void __launch_bounds__(256)
-mask_embed_fwd_kernel(const float* __restrict__ image, const float* __restrict__ masks, SlotIds ids, int M,
-                      const float* __restrict__ table, __half* __restrict__ out, int B, int HW) {
+mask_embed_fwd_kernel(const float* __restrict__ image, const float* __restrict__ masks, const int32_t* __restrict__ slot_ids,
+                      int M, const float* __restrict__ table, __half* __restrict__ out, int B, int HW) {
     __shared__ float s_tab[33];
+    __shared__ SlotIds ids;
     if (threadIdx.x < 33) s_tab[threadIdx.x] = table[threadIdx.x];
+    if (threadIdx.x < MAX_M) ids.v[threadIdx.x] = threadIdx.x < M ? min(max(slot_ids[threadIdx.x], 0), 9) : 0;
     __syncthreads();
     const size_t total = (size_t)B * HW;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
@@ -57,10 +59,12 @@ mask_embed_fwd_kernel(const float* __restrict__ image, const float* __restrict__
 
 template <int C>
 __global__ void __launch_bounds__(256)
-mask_embed_bwd_kernel(const __half* __restrict__ gout, const float* __restrict__ masks, SlotIds ids, int M,
-                      float* __restrict__ gtable, int B, int HW) {
+mask_embed_bwd_kernel(const __half* __restrict__ gout, const float* __restrict__ masks, const int32_t* __restrict__ slot_ids,
+                      int M, float* __restrict__ gtable, int B, int HW) {
     __shared__ float s_acc[33];
+    __shared__ SlotIds ids;
     if (threadIdx.x < 33) s_acc[threadIdx.x] = 0.f;
+    if (threadIdx.x < MAX_M) ids.v[threadIdx.x] = threadIdx.x < M ? min(max(slot_ids[threadIdx.x], 0), 9) : 0;
     __syncthreads();
     float acc[MAX_M][3];
 #pragma unroll
@@ -98,44 +102,40 @@ mask_embed_bwd_kernel(const __half* __restrict__ gout, const float* __restrict__
     if (threadIdx.x < 33 && s_acc[threadIdx.x] != 0.f) atomicAdd(gtable + threadIdx.x, s_acc[threadIdx.x]);
 }
 
-int check(const int32_t* slot_ids_host, int M, int C, SlotIds& ids, const char* who) {
-    MG_REQUIRE(slot_ids_host && M >= 0 && M <= MAX_M, "%s: M must be 0..%d (got %d)", who, MAX_M, M);
+int check(const int32_t* slot_ids, int M, int C, const char* who) {
+    MG_REQUIRE((slot_ids || M == 0) && M >= 0 && M <= MAX_M, "%s: M must be 0..%d (got %d) with slot ids", who, MAX_M, M);
     MG_REQUIRE(C == 6 || C == 8 || C == 16, "%s: C must be 6, 8 or 16 (got %d)", who, C);
-    for (int m = 0; m < MAX_M; ++m) ids.v[m] = m < M ? slot_ids_host[m] : 0;
-    for (int m = 0; m < M; ++m) MG_REQUIRE(ids.v[m] >= 0 && ids.v[m] < 10, "%s: slot id %d out of range", who, ids.v[m]);
     return MG_OK;
 }
 
 }  // namespace
 
-extern "C" int mg_mask_embed_fwd(const float* image, const float* masks, const int32_t* slot_ids_host, int M,
+extern "C" int mg_mask_embed_fwd(const float* image, const float* masks, const int32_t* slot_ids, int M,
                                  const float* table, void* out_f16, int B, int H, int W, int C, void* stream) {
     MG_REQUIRE(image && table && out_f16 && (masks || M == 0), "mg_mask_embed_fwd: null pointer");
-    SlotIds ids;
-    if (int e = check(slot_ids_host, M, C, ids, "mg_mask_embed_fwd")) return e;
+    if (int e = check(slot_ids, M, C, "mg_mask_embed_fwd")) return e;
     if (B <= 0) return MG_OK;
     const int HW = H * W;
     const int grid = (int)std::min<size_t>(((size_t)B * HW + 255) / 256, (size_t)mg::kNumSMs * 16);
     __half* out = static_cast<__half*>(out_f16);
-    if (C == 6) MG_LAUNCH(mask_embed_fwd_kernel<6>, grid, 256, 0, stream, image, masks, ids, M, table, out, B, HW);
-    else if (C == 8) MG_LAUNCH(mask_embed_fwd_kernel<8>, grid, 256, 0, stream, image, masks, ids, M, table, out, B, HW);
-    else MG_LAUNCH(mask_embed_fwd_kernel<16>, grid, 256, 0, stream, image, masks, ids, M, table, out, B, HW);
+    if (C == 6) MG_LAUNCH(mask_embed_fwd_kernel<6>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
+    else if (C == 8) MG_LAUNCH(mask_embed_fwd_kernel<8>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
+    else MG_LAUNCH(mask_embed_fwd_kernel<16>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
     MG_CHECK_LAUNCH("mg_mask_embed_fwd");
     return MG_OK;
 }
 
-extern "C" int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, const int32_t* slot_ids_host, int M,
+extern "C" int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, const int32_t* slot_ids, int M,
                                  float* grad_table, int B, int H, int W, int C, void* stream) {
     MG_REQUIRE(grad_out_f16 && grad_table && (masks || M == 0), "mg_mask_embed_bwd: null pointer");
-    SlotIds ids;
-    if (int e = check(slot_ids_host, M, C, ids, "mg_mask_embed_bwd")) return e;
+    if (int e = check(slot_ids, M, C, "mg_mask_embed_bwd")) return e;
     if (B <= 0 || M == 0) return MG_OK;
     const int HW = H * W;
     const int grid = (int)std::min<size_t>(((size_t)B * HW + 255) / 256, (size_t)mg::kNumSMs * 8);
     const __half* g = static_cast<const __half*>(grad_out_f16);
-    if (C == 6) MG_LAUNCH(mask_embed_bwd_kernel<6>, grid, 256, 0, stream, g, masks, ids, M, grad_table, B, HW);
-    else if (C == 8) MG_LAUNCH(mask_embed_bwd_kernel<8>, grid, 256, 0, stream, g, masks, ids, M, grad_table, B, HW);
-    else MG_LAUNCH(mask_embed_bwd_kernel<16>, grid, 256, 0, stream, g, masks, ids, M, grad_table, B, HW);
+    if (C == 6) MG_LAUNCH(mask_embed_bwd_kernel<6>, grid, 256, 0, stream, g, masks, slot_ids, M, grad_table, B, HW);
+    else if (C == 8) MG_LAUNCH(mask_embed_bwd_kernel<8>, grid, 256, 0, stream, g, masks, slot_ids, M, grad_table, B, HW);
+    else MG_LAUNCH(mask_embed_bwd_kernel<16>, grid, 256, 0, stream, g, masks, slot_ids, M, grad_table, B, HW);
     MG_CHECK_LAUNCH("mg_mask_embed_bwd");
     return MG_OK;
 }

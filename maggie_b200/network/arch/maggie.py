@@ -19,12 +19,32 @@ except Exception:  # pragma: no cover
         pass
 
 from ...config import as_cfg
+from ... import ops
 from .. import loss as losses
 from ..decoder import MaGGIeDecoder
 from ..encoder import ASPP, ResMaskEmbedShortCutEncoder
 
 ENCODERS = {"res_shortcut_embed_29": ResMaskEmbedShortCutEncoder}
 DECODERS = {"res_shortcut_inst_matt_spconv_22": MaGGIeDecoder}
+
+
+class _DenseStage(nn.Module):
+    """encoder + ASPP + OS32->OS8 decoder blocks + mask-guided attention as ONE callable with static shapes and no
+    host synchronisation, so that forward and backward can each be replayed as a CUDA graph.  Holds references to
+    the model's sub-modules (it is deliberately not registered inside the model: the state dict is unchanged)."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.encoder, self.aspp, self.decoder = model.encoder, model.aspp, model.decoder
+
+    def forward(self, image, masks, slot_ids, mask_os8, gt_os8):
+        emb, fea = self.encoder(image, masks, slot_ids)
+        emb = self.aspp(emb)
+        logits, feat, queries, loss = self.decoder.dense_stage(emb, fea[3], fea[4], mask_os8 > 0,
+                                                               (gt_os8 > 0) if self.training else None)
+        if not torch.is_tensor(loss):
+            loss = logits.new_zeros(())
+        return fea[0], fea[1], fea[2], logits, feat, queries, loss
 
 
 class MaGGIe(nn.Module, PyTorchModelHubMixin):
@@ -39,6 +59,8 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         self.encoder = ENCODERS[cfg.encoder](**cfg.encoder_args)
         self.aspp = ASPP(cfg.aspp.in_channels, cfg.aspp.out_channels)
         self.decoder = DECODERS[cfg.decoder](**cfg.decoder_args)
+        self._stage = [_DenseStage(self)]          # in a list: not a registered sub-module
+        self._graphs, self._use_graphs = {}, False
         for module in (self.aspp, self.decoder):  # arch/maggie.py:41-49
             for _, p in module.named_parameters():
                 if p.dim() > 1:
@@ -74,12 +96,35 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
             trans = trans.reshape(b * n_f, n_i, h, w).float() if trans is not None else None
         return x, masks, slot_ids, dec_masks, alphas, trans, chosen, (b, n_f, n_i, h, w)
 
+    def enable_cuda_graphs(self, on=True):
+        """Replay the dense stage (encoder, ASPP, dense decoder blocks, attention; forward AND backward) as CUDA graphs.
+        Training mode only; one graph pair per input shape.  The sparse stage stays eager (its shapes follow the
+        number of active sites)."""
+        self._use_graphs = bool(on)
+        return self
+
+    def _dense(self, x, masks, slot_ids, mask_os8, gt_os8):
+        stage = self._stage[0]
+        stage.train(self.training)
+        ids = ops.slot_ids_tensor(slot_ids, x.device)
+        args = (x.float().contiguous(), masks.contiguous(), ids, mask_os8.float(),
+                gt_os8.float() if gt_os8 is not None else mask_os8.float())
+        if not (self._use_graphs and self.training and torch.is_grad_enabled()):
+            return stage(*args)
+        key = tuple((tuple(a.shape), a.dtype) for a in args)
+        fn = self._graphs.get(key)
+        if fn is None:
+            sample = tuple(a.clone() for a in args)
+            fn = torch.cuda.make_graphed_callables(stage, sample, num_warmup_iters=3, allow_unused_input=True)
+            self._graphs[key] = fn
+        return fn(*args)
+
     def forward(self, batch, **kwargs):
         x, masks, slot_ids, dec_masks, alphas, trans, chosen, (b, n_f, n_i, h, w) = self._prepare(batch)
-        emb, fea = self.encoder(x, masks, slot_ids)
-        emb = self.aspp(emb)
-        pred = self.decoder(emb, fea, (h, w), b=b, n_f=n_f, n_i=n_i, masks=dec_masks, iter=batch.get("iter", 0),
-                            gt_alphas=alphas, spar_gt=trans, **kwargs)
+        mask_os8, gt_os8 = self.decoder.pooled_masks(dec_masks, alphas, b, n_f, n_i, h, w, self.training)
+        fea1, fea2, fea3, logits, feat, queries, loss_atten = self._dense(x, masks, slot_ids, mask_os8, gt_os8)
+        pred = self.decoder((logits, feat, queries, loss_atten), (fea1, fea2, fea3), (h, w), b=b, n_f=n_f, n_i=n_i,
+                            masks=dec_masks, iter=batch.get("iter", 0), gt_alphas=alphas, spar_gt=trans, **kwargs)
         self.last_site_counts = pred.pop("site_counts", None)
 
         alpha_pred = pred.pop("refined_masks")

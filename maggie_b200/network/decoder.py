@@ -249,21 +249,30 @@ class MaGGIeDecoder(nn.Module):
         return os4, os1, T.counts
 
     # -- forward --------------------------------------------------------------------------------------
-    def forward(self, x, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, **_):
-        """x: ASPP output; fea: (fea1..fea5); masks [b*n_f, n_i, H, W] fp32 {0,1}; gt_alphas [b*n_f, n_i, H, W]."""
-        t = self.training
-        fea1, fea2, fea3, fea4, fea5 = fea
-        H, W = image_hw
-        valid = masks.flatten(2).sum(2)[:, :, None, None] > 0
+    def dense_stage(self, x, fea4, fea5, mask_os8, gt_os8):
+        """OS32 -> OS8 dense blocks + mask-guided attention (static shapes, no host sync: CUDA-graph capturable).
+        Returns OS8 logits [B,10,h,w] fp32, OS8 features [B,64,h,w], instance tokens [b,10,64], attention loss."""
         x = self.layer1(x) + fea5
         x = self.layer2(x) + fea4
+        return self.refine_OS8(x, mask_os8, gt_os8)
 
-        m5 = masks.reshape(b, n_f, n_i, H, W)
-        mask_os8 = F.avg_pool2d(m5.flatten(0, 1), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0
+    @staticmethod
+    def pooled_masks(masks, gt_alphas, b, n_f, n_i, H, W, training):
+        """mask -> OS8 by avg-pool > 0 (utils.py:16-21); GT alpha > 0 -> OS8 by max-pool (:11-15)."""
+        mask_os8 = F.avg_pool2d(masks.reshape(b * n_f, n_i, H, W), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0
         gt_os8 = None
-        if t:
+        if training:
             gt_os8 = F.max_pool2d((gt_alphas > 0).float(), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0
-        os8_logits, x, queries, loss_atten = self.refine_OS8(x, mask_os8, gt_os8)
+        return mask_os8, gt_os8
+
+    def forward(self, dense_out, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, **_):
+        """dense_out: (os8_logits, os8_feat, queries, loss_atten) from `dense_stage`; fea: (fea1, fea2, fea3);
+        masks [b*n_f, n_i, H, W] fp32 {0,1}; gt_alphas [b*n_f, n_i, H, W]."""
+        t = self.training
+        fea1, fea2, fea3 = fea
+        H, W = image_hw
+        valid = masks.flatten(2).sum(2)[:, :, None, None] > 0
+        os8_logits, x, queries, loss_atten = dense_out
         a8 = ops.upsample_tanh(os8_logits, size=(H, W))
         a8 = a8 * valid if t else a8[:, :n_i]
 

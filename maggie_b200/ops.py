@@ -34,7 +34,7 @@ def _widths_tensor(widths, device):
     t = _WIDTHS_CACHE.get(key)
     if t is None:
         t = torch.tensor(widths, dtype=torch.int32, device=device)
-        if len(set(widths)) == 1:
+        if len(set(widths)) == 1 or len(widths) <= 16:
             if len(_WIDTHS_CACHE) > 64:
                 _WIDTHS_CACHE.clear()
             _WIDTHS_CACHE[key] = t
@@ -94,37 +94,43 @@ def build_sites(roi):
 class _MaskEmbed(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, masks, table, slot_ids, C):
-        _need_cuda(image, masks, table)
+        _need_cuda(image, masks, table, slot_ids)
         image = image.to(torch.float32).contiguous()
         masks = masks.to(torch.float32).contiguous()
         B, _, H, W = image.shape
         M = masks.shape[1]
         out = torch.empty((B, H, W, C), dtype=torch.float16, device=image.device)
-        ids = _lib.i32_array(slot_ids)
         tab = table.detach().to(torch.float32).contiguous()
-        _lib.check(_lib.lib().mg_mask_embed_fwd(_ptr(image), _ptr(masks), ids, M, _ptr(tab), _ptr(out), B, H, W, C,
+        _lib.check(_lib.lib().mg_mask_embed_fwd(_ptr(image), _ptr(masks), _ptr(slot_ids), M, _ptr(tab), _ptr(out), B, H, W, C,
                                                _stream()), "mg_mask_embed_fwd")
-        ctx.save_for_backward(masks)
-        ctx.meta = (tuple(slot_ids), C, table.shape, table.dtype)
+        ctx.save_for_backward(masks, slot_ids)
+        ctx.meta = (C, table.shape, table.dtype)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        (masks,) = ctx.saved_tensors
-        slot_ids, C, tshape, tdtype = ctx.meta
+        masks, slot_ids = ctx.saved_tensors
+        C, tshape, tdtype = ctx.meta
         B, H, W, _ = gout.shape
         g = gout.to(torch.float16).contiguous()
         gtab = torch.zeros(tshape, dtype=torch.float32, device=gout.device)
-        _lib.check(_lib.lib().mg_mask_embed_bwd(_ptr(g), _ptr(masks), _lib.i32_array(slot_ids), masks.shape[1],
-                                               _ptr(gtab), B, H, W, C, _stream()), "mg_mask_embed_bwd")
+        _lib.check(_lib.lib().mg_mask_embed_bwd(_ptr(g), _ptr(masks), _ptr(slot_ids), masks.shape[1], _ptr(gtab), B, H, W, C,
+                                               _stream()), "mg_mask_embed_bwd")
         return None, None, gtab.to(tdtype), None, None
 
 
+def slot_ids_tensor(slot_ids, device):
+    """Device int32 tensor of the slot of each given mask (a tensor is passed through)."""
+    if torch.is_tensor(slot_ids):
+        return slot_ids.to(device=device, dtype=torch.int32)
+    return _widths_tensor(tuple(int(s) for s in slot_ids), device)
+
+
 def mask_embed(image, masks, table, slot_ids, C=8):
-    """image [B,3,H,W] fp32, masks [B,M,H,W] {0,1}, table [11,3] -> packed encoder input, NCHW-shaped
-    channels-last fp16 [B,C,H,W] (ch 0-2 image, 3-5 mean id embedding, rest 0).
+    """image [B,3,H,W] fp32, masks [B,M,H,W] {0,1}, table [11,3], slot_ids (list or device int32 tensor [M]) ->
+    packed encoder input, NCHW-shaped channels-last fp16 [B,C,H,W] (ch 0-2 image, 3-5 mean id embedding, rest 0).
     Reference: arch/maggie.py:200-235 + encoder/resnet.py:211-229."""
-    return _MaskEmbed.apply(image, masks, table, list(slot_ids), C).permute(0, 3, 1, 2)
+    return _MaskEmbed.apply(image, masks, table, slot_ids_tensor(slot_ids, image.device), C).permute(0, 3, 1, 2)
 
 
 # =============================================================================================== interim ops

@@ -73,6 +73,7 @@ def build_sites(roi):
 def mask_embed(image, masks, table, slot_ids, C=8):
     """Differentiable torch restatement of K1 (encoder/resnet.py:211-229); NCHW-shaped [B,C,H,W]."""
     B, _, H, W = image.shape
+    slot_ids = slot_ids.tolist() if torch.is_tensor(slot_ids) else slot_ids
     ids = torch.tensor([s + 1 for s in slot_ids], device=image.device).view(1, -1, 1, 1)
     m = (masks * ids).long()
     on = (m > 0).float().unsqueeze(-1)
