@@ -180,6 +180,23 @@ int mg_sparse_conv(const mg_sparse_conv_desc* desc, void* stream);
 int mg_sparse_wgrad(const void* dout, int dout_stride, int Cout, const void* src, int src_stride, int Cin,
                     const int32_t* table, int T, int No, float* dw, void* stream);
 
+/* ---- K12: fused training losses (weighted L1 + 3-level Laplacian pyramid + Sobel gradient, 3 alpha scales) ----
+ * replaces: arch/maggie.py:237-346 (regression_loss, compute_loss) + loss.py:67-191 (GradientLoss, LapLoss), ~9
+ *           pyramid / stencil passes of tiny cuDNN convolutions per scale, and their autograd backward.
+ * a1/a4/a8, target, w1/w4/w8: fp32 [S,H,W] (predictions per scale, GT alpha, per-scale weights).
+ * mg_loss_fwd : sums [MG_LOSS_COPIES][3 scales][8] (caller zeroes; add the copies up) with, per scale,
+ *               [0] sum|p*w - t*w|, [1..3] sum|L_k|*w_k for pyramid levels k=0..2 (w_k = w[::2^k, ::2^k]),
+ *               [4] sum|sobel(p*w) - sobel(t*w)|, [5..7] sum w_k.   ws: mg_loss_workspace_floats() floats;
+ *               sg: fp16 scratch of 3*S*H*W*(1 + 1/4 + 1/16) elements (sign(L_k)*w_k, kept for the backward).
+ * mg_loss_bwd : coef [3][5] (device) = upstream gradient of numerators [0..4]; writes d/d(a1), d/d(a4), d/d(a8).   */
+#define MG_LOSS_COPIES 32
+size_t mg_loss_workspace_floats(int S, int H, int W);
+int mg_loss_fwd(const float* a1, const float* a4, const float* a8, const float* target, const float* w1, const float* w4,
+                const float* w8, int S, int H, int W, float* ws, void* sg_f16, float* sums, void* stream);
+int mg_loss_bwd(const float* a1, const float* a4, const float* a8, const float* target, const float* w1, const float* w4,
+                const float* w8, int S, int H, int W, float* ws, const void* sg_f16, const float* coef, float* g1_out,
+                float* g4_out, float* g8_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,10 @@ SIGNATURES = {
     "mg_mask_embed_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_conv_fprop": (c_int, [c_void_p, c_void_p]),
     "mg_conv_wgrad": (c_int, [c_void_p, c_void_p]),
+    "mg_loss_workspace_floats": (c_size_t, [c_int, c_int, c_int]),
+    "mg_loss_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mg_loss_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p]),
     "mg_gather_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "mg_scatter_rows_add": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mg_sparse_conv": (c_int, [c_void_p, c_void_p]),

@@ -133,6 +133,44 @@ def mask_embed(image, masks, table, slot_ids, C=8):
     return _MaskEmbed.apply(image, masks, table, slot_ids_tensor(slot_ids, image.device), C).permute(0, 3, 1, 2)
 
 
+# =============================================================================================== native: K12
+class _MatteLossSums(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a1, a4, a8, target, w1, w4, w8):
+        _need_cuda(a1, a4, a8, target, w1, w4, w8)
+        f = lambda t: t.detach().to(torch.float32).contiguous()
+        a1d, a4d, a8d, td, w1d, w4d, w8d = (f(t) for t in (a1, a4, a8, target, w1, w4, w8))
+        H, W = a1d.shape[-2:]
+        S = a1d.numel() // (H * W)
+        L = _lib.lib()
+        ws = torch.empty(L.mg_loss_workspace_floats(S, H, W), dtype=torch.float32, device=a1.device)
+        n0 = 3 * S * H * W
+        sg = torch.empty(n0 + n0 // 4 + n0 // 16, dtype=torch.float16, device=a1.device)
+        sums = torch.zeros((32, 3, 8), dtype=torch.float32, device=a1.device)
+        _lib.check(L.mg_loss_fwd(_ptr(a1d), _ptr(a4d), _ptr(a8d), _ptr(td), _ptr(w1d), _ptr(w4d), _ptr(w8d), S, H, W, _ptr(ws),
+                                 _ptr(sg), _ptr(sums), _stream()), "mg_loss_fwd")
+        ctx.save_for_backward(a1d, a4d, a8d, td, w1d, w4d, w8d, ws, sg)
+        ctx.shape = (S, H, W, a1.shape)
+        return sums.sum(0)
+
+    @staticmethod
+    def backward(ctx, gs):
+        a1d, a4d, a8d, td, w1d, w4d, w8d, ws, sg = ctx.saved_tensors
+        S, H, W, shape = ctx.shape
+        coef = gs[:, :5].to(torch.float32).contiguous()
+        g = torch.empty((3,) + tuple(a1d.shape), dtype=torch.float32, device=a1d.device)
+        _lib.check(_lib.lib().mg_loss_bwd(_ptr(a1d), _ptr(a4d), _ptr(a8d), _ptr(td), _ptr(w1d), _ptr(w4d), _ptr(w8d), S, H, W,
+                                         _ptr(ws), _ptr(sg), _ptr(coef), _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _stream()),
+                   "mg_loss_bwd")
+        return g[0].view(shape), g[1].view(shape), g[2].view(shape), None, None, None, None
+
+
+def matte_loss_sums(a1, a4, a8, target, w1, w4, w8):
+    """Partial sums [3 scales, 8] of the matting losses (weighted L1, Laplacian pyramid levels, Sobel gradient, weight
+    sums) with a native backward to the three predictions.  NATIVE (K12).  Reference: arch/maggie.py:268-346."""
+    return _MatteLossSums.apply(a1, a4, a8, target, w1, w4, w8)
+
+
 # =============================================================================================== interim ops
 def _act(x, act):
     if act == "relu":

@@ -160,15 +160,62 @@ def rows_head(src, w, bias, nbr, coords, slots, H, W):
     return scatter_logits(y, coords, slots, H, W)
 
 
+# ---- torch restatement of the K12 partial sums (loss.py:67-191 semantics) -------------------------------------
+_G5 = torch.tensor([1.0, 4.0, 6.0, 4.0, 1.0])
+_GAUSS2D = (_G5[:, None] * _G5[None, :]) / 256.0
+_SOBEL = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]]) / 8.0
+
+
+def _blur(x, k):
+    return F.conv2d(F.pad(x, (2, 2, 2, 2), mode="reflect"), k)
+
+
+def _pyramid(x, levels=3):
+    k = _GAUSS2D.to(x.device, x.dtype)[None, None]
+    out = []
+    for _ in range(levels):
+        down = _blur(x, k)[:, :, ::2, ::2]
+        up = x.new_zeros(x.shape)
+        up[:, :, ::2, ::2] = down
+        out.append(x - _blur(up, 4.0 * k))
+        x = down
+    return out
+
+
+def _sobel_mag(x, eps=1e-6):
+    xp = F.pad(x, (1, 1, 1, 1), mode="replicate")
+    kx = _SOBEL.to(x.device, x.dtype)
+    gx, gy = F.conv2d(xp, kx[None, None]), F.conv2d(xp, kx.t()[None, None])
+    return torch.sqrt(gx * gx + gy * gy + eps)
+
+
+def matte_loss_sums(a1, a4, a8, target, w1, w4, w8):
+    h, w = a1.shape[-2:]
+    t = target.reshape(-1, 1, h, w).float()
+    rows = []
+    for p, wt in ((a1, w1), (a4, w4), (a8, w8)):
+        p, wt = p.reshape(-1, 1, h, w).float(), wt.reshape(-1, 1, h, w).float()
+        q = [(p * wt - t * wt).abs().sum()]
+        pyr, wl, ws = _pyramid(p - t), wt, []
+        for i in range(3):
+            q.append((pyr[i].abs() * wl).sum())
+            ws.append(wl.sum())
+            wl = wl[:, :, ::2, ::2]
+        q.append((_sobel_mag(p * wt) - _sobel_mag(t * wt)).abs().sum())
+        rows.append(torch.stack(q + ws))
+    return torch.stack(rows)
+
+
 @contextlib.contextmanager
 def injected(dtype=torch.float32):
     """Swap the native ops for the references above (CPU container only)."""
     names = ("unknown_mask", "build_sites", "mask_embed", "conv_bn_act", "rows_conv", "rows_head", "gather_dense",
-             "COMPUTE_DTYPE")
+             "matte_loss_sums", "COMPUTE_DTYPE")
     saved = {n: getattr(ops, n) for n in names}
     ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.conv_bn_act, ops.COMPUTE_DTYPE = \
         unknown_mask, build_sites, mask_embed, conv_bn_act, dtype
     ops.rows_conv, ops.rows_head, ops.gather_dense = rows_conv, rows_head, gather_dense
+    ops.matte_loss_sums = matte_loss_sums
     try:
         yield
     finally:
