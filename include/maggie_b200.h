@@ -197,6 +197,27 @@ int mg_loss_bwd(const float* a1, const float* a4, const float* a8, const float* 
                 const float* w8, int S, int H, int W, float* ws, const void* sg_f16, const float* coef, float* g1_out,
                 float* g4_out, float* g8_out, void* stream);
 
+/* ---- K6: mask-guided attention cores (single head, E = 128) ------------------------------------------
+ * replaces: nn.MultiheadAttention's QK^T / softmax / PV (unfused, weights materialised) inside
+ *           module/mask_attention.py:99-102 as used by module/instance_matte_decoder.py:219-267, and the
+ *           attention-max statistic of :101-109.  (The 128x128 in/out projections run on the K9 rows GEMM.)
+ * "tq": FEW queries (tokens, F <= 16, fp32 [B,F,E]) over MANY keys/values (fp16 rows [B,S,E]); key_pad [B,S] and
+ *       guidance [B,F,S] optional uint8; out fp32 [B,F,E], stat[b,f] = sum_k guidance*softmax; row_max/row_sum are
+ *       kept for the backward; ws: mg_attn_tq_workspace_floats().  Backward: dq fp32 (atomics, caller zeroes),
+ *       dk/dv fp16 rows.
+ * "fq": MANY queries (fp16 rows [B,S,E]) over FEW keys/values (fp32 [B,F,E], key_pad [B,F]); out fp16 rows.
+ *       Backward: dq fp16 rows, dk/dv fp32 (atomics, caller zeroes).                                           */
+size_t mg_attn_tq_workspace_floats(int B, int F, int S);
+int mg_attn_tq_fwd(const float* q, const void* k, const void* v, const uint8_t* key_pad, const uint8_t* guidance, int B, int F,
+                   int S, int E, float* out, float* stat, float* row_max, float* row_sum, float* ws, void* stream);
+int mg_attn_tq_bwd(const float* q, const void* k, const void* v, const uint8_t* key_pad, const uint8_t* guidance,
+                   const float* out, const float* stat, const float* row_max, const float* row_sum, const float* d_out,
+                   const float* d_stat, int B, int F, int S, int E, float* dq, void* dk, void* dv, void* stream);
+int mg_attn_fq_fwd(const void* q, const float* k, const float* v, const uint8_t* key_pad, int B, int F, int S, int E,
+                   void* out, void* stream);
+int mg_attn_fq_bwd(const void* q, const float* k, const float* v, const uint8_t* key_pad, const void* d_out, int B, int F,
+                   int S, int E, void* dq, float* dk, float* dv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -192,6 +192,46 @@ __device__ __forceinline__ float adjB(int y, int i, int n) {
     return a;
 }
 
+// Non-zero taps of the two 1-D adjoints for output index o.  Interior indices use the closed form (2-3 taps for
+// (DG)^T, 5 taps for U^T); the few indices whose 5-tap window crosses the image border fall back to the generic
+// "which taps reflect onto me" search.
+struct Taps {
+    int n, idx[5];
+    float wt[5];
+};
+__device__ __forceinline__ void taps_DGt(int y, int n_fine, Taps& t) {   // coarse i feeding fine y
+    t.n = 0;
+    const int nc = n_fine >> 1;
+    if (y >= 3 && y + 3 < n_fine) {   // no reflected tap lands on y (reflections reach 1, 2 and n-2 only)
+        if (y & 1) {
+            t.idx[0] = (y - 1) >> 1, t.wt[0] = 0.25f, t.idx[1] = (y + 1) >> 1, t.wt[1] = 0.25f, t.n = 2;
+        } else {
+            t.idx[0] = (y >> 1) - 1, t.wt[0] = 0.0625f, t.idx[1] = y >> 1, t.wt[1] = 0.375f, t.idx[2] = (y >> 1) + 1,
+            t.wt[2] = 0.0625f, t.n = 3;
+        }
+        return;
+    }
+    const int i0 = max(0, ((y - 2) >> 1) - 1), i1 = min(nc - 1, ((y + 2) >> 1) + 1);
+    for (int i = i0; i <= i1 && t.n < 5; ++i) {
+        const float a = adjA(i, y, n_fine);
+        if (a != 0.f) t.idx[t.n] = i, t.wt[t.n] = a, ++t.n;
+    }
+}
+__device__ __forceinline__ void taps_Ut(int i, int n_fine, Taps& t) {    // fine y feeding coarse i
+    t.n = 0;
+    if (i >= 2 && 2 * i + 2 < n_fine - 1) {   // reflections reach coarse 1 and n/2-1 only
+#pragma unroll
+        for (int k = 0; k < 5; ++k) t.idx[k] = 2 * i + 2 - k, t.wt[k] = 2.f * gk(k);
+        t.n = 5;
+        return;
+    }
+    const int y0 = max(0, 2 * i - 3), y1 = min(n_fine - 1, 2 * i + 3);
+    for (int y = y0; y <= y1 && t.n < 5; ++y) {
+        const float b = adjB(y, i, n_fine);
+        if (b != 0.f) t.idx[t.n] = y, t.wt[t.n] = b, ++t.n;
+    }
+}
+
 // g_k[y,x] = c_k s_k + sum_{i,j} A(i,y) A(j,x) g_{k+1}[i,j] - sum_{yy,xx} B(yy,y) B(xx,x) c_{k-1} s_{k-1}[yy,xx]
 // (level k has size h x w; k+1 is h/2 x w/2; k-1 is 2h x 2w).  Any of the three terms may be absent.
 __device__ __forceinline__ float bwd_level_value(const __half* __restrict__ sg_k, float c_k, const float* __restrict__ g_k1,
@@ -201,32 +241,25 @@ __device__ __forceinline__ float bwd_level_value(const __half* __restrict__ sg_k
     if (sg_k) v = c_k * __half2float(sg_k[(img * h + y) * w + x]);
     if (g_k1) {
         const int hc = h >> 1, wc = w >> 1;
-        const int i0 = max(0, ((y - 2) >> 1) - 1), i1 = min(hc - 1, ((y + 2) >> 1) + 1);
-        const int j0 = max(0, ((x - 2) >> 1) - 1), j1 = min(wc - 1, ((x + 2) >> 1) + 1);
-        for (int i = i0; i <= i1; ++i) {
-            const float ay = adjA(i, y, h);
-            if (ay == 0.f) continue;
+        Taps ty, tx;
+        taps_DGt(y, h, ty);
+        taps_DGt(x, w, tx);
+        for (int a = 0; a < ty.n; ++a) {
             float r = 0.f;
-            for (int j = j0; j <= j1; ++j) {
-                const float ax = adjA(j, x, w);
-                if (ax != 0.f) r += ax * __ldg(g_k1 + (img * hc + i) * wc + j);
-            }
-            v += ay * r;
+            for (int b = 0; b < tx.n; ++b) r += tx.wt[b] * __ldg(g_k1 + (img * hc + ty.idx[a]) * wc + tx.idx[b]);
+            v += ty.wt[a] * r;
         }
     }
     if (sg_km1) {
         const int hf = h << 1, wf = w << 1;
-        const int y0 = max(0, 2 * y - 3), y1 = min(hf - 1, 2 * y + 3), x0 = max(0, 2 * x - 3), x1 = min(wf - 1, 2 * x + 3);
+        Taps ty, tx;
+        taps_Ut(y, hf, ty);
+        taps_Ut(x, wf, tx);
         float u = 0.f;
-        for (int yy = y0; yy <= y1; ++yy) {
-            const float by = adjB(yy, y, hf);
-            if (by == 0.f) continue;
+        for (int a = 0; a < ty.n; ++a) {
             float r = 0.f;
-            for (int xx = x0; xx <= x1; ++xx) {
-                const float bx = adjB(xx, x, wf);
-                if (bx != 0.f) r += bx * __half2float(sg_km1[(img * hf + yy) * wf + xx]);
-            }
-            u += by * r;
+            for (int b = 0; b < tx.n; ++b) r += tx.wt[b] * __half2float(sg_km1[(img * hf + ty.idx[a]) * wf + tx.idx[b]]);
+            u += ty.wt[a] * r;
         }
         v -= c_km1 * u;
     }
@@ -304,6 +337,17 @@ loss_bwd_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const __hal
         g += c_rec * sgn(s_pw[row + 2][threadIdx.x + 2] - s_tw[row + 2][threadIdx.x + 2]) * ww;
         // Sobel adjoint (replicate padding: taps that were clamped onto this pixel come back to it)
         float sa = 0.f;
+        if (y >= 1 && y + 1 < H && x >= 1 && x + 1 < W) {
+            // interior: output (y+dy, x+dx) reaches (y,x) through exactly one tap (ky,kx) = (1-dy, 1-dx)
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const float ggx = s_gx[row + 1 + dy][threadIdx.x + 1 + dx], ggy = s_gy[row + 1 + dy][threadIdx.x + 1 + dx];
+                    const float a_y = dy == 0 ? 2.f : 1.f, a_x = dx == 0 ? 2.f : 1.f;
+                    sa += (a_y * (float)(-dx) * ggx + (float)(-dy) * a_x * ggy) * 0.125f;
+                }
+        } else
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll

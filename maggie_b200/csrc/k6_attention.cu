@@ -1,0 +1,341 @@
+// K6: mask-guided attention core of the InstanceMatteDecoder - single head, E = 128, between a FEW side
+// (<= 16 instance tokens) and a MANY side (h*w*n_f pixel features, 4096 per 512x512 frame).
+//
+//   tok <- feat ("tq"): queries = tokens, keys/values = pixels; softmax over the pixels; also emits the attention
+//                       statistic  stat[b,q] = sum_k guidance[b,q,k] * A[b,q,k]  that the attention-max loss needs
+//                       (the attention matrix itself is never written).  Keys are split over CTAs (flash-style
+//                       partial max / sum / output) and merged by a second tiny kernel.  Also used for the 10x10
+//                       token self-attention (with key padding).
+//   feat <- tok ("fq"): queries = pixels, keys/values = tokens (with key padding); softmax over <= 16 tokens is
+//                       local to each pixel.
+// The 128x128 projections around these cores dominate the FLOPs and run on tcgen05 (K9 rows GEMM); the cores
+// themselves have N = 10 and are HBM/latency bound, so they are CUDA-core kernels with the few side in shared
+// memory and the many side streamed once through a 128-row tile.  Softmax, statistics and gradients in fp32.
+#include "common.cuh"
+
+namespace {
+
+constexpr int E = 128;        // attention width (atten_dim of both live configs)
+constexpr int TM = 128;       // many-side rows per CTA
+constexpr int MAXF = 16;      // few-side rows
+constexpr int ROWP = E + 8;   // padded tile row (halfs) -> 2-way instead of 32-way bank conflicts
+
+__device__ __forceinline__ void load_tile(__half (*dst)[ROWP], const __half* __restrict__ src, int rows_valid) {
+    // 128 rows x 128 halfs, coalesced 16-byte pieces
+    for (int i = threadIdx.x; i < TM * (E / 8); i += blockDim.x) {
+        const int r = i / (E / 8), c = i - r * (E / 8);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * E) + c);
+        *reinterpret_cast<uint4*>(&dst[r][c * 8]) = v;
+    }
+}
+
+__device__ __forceinline__ float dot_row(const __half* row, const float* q) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < E; e += 2) {
+        const float2 k2 = __half22float2(*reinterpret_cast<const __half2*>(row + e));
+        acc = fmaf(k2.x, q[e], acc);
+        acc = fmaf(k2.y, q[e + 1], acc);
+    }
+    return acc;
+}
+
+// ================================================================================================ tq forward
+// grid (nsplit, B), 128 threads.  partial outputs: pm/pl [B][nsplit][F], po [B][nsplit][F][E], pstat [B][nsplit][F]
+__global__ void __launch_bounds__(128)
+attn_tq_partial_kernel(const float* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V,
+                       const uint8_t* __restrict__ key_pad, const uint8_t* __restrict__ guid, int F, int S, float scale,
+                       float* __restrict__ pm, float* __restrict__ pl, float* __restrict__ po, float* __restrict__ pstat) {
+    extern __shared__ uint8_t smem_raw[];
+    __half (*sK)[ROWP] = reinterpret_cast<__half (*)[ROWP]>(smem_raw);
+    __half (*sV)[ROWP] = sK + TM;
+    float* sQ = reinterpret_cast<float*>(sV + TM);   // [MAXF][E]
+    float* sP = sQ + MAXF * E;                        // [MAXF][TM]
+    float* sRed = sP + MAXF * TM;                     // [4]
+    const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x, t = threadIdx.x;
+    const int s0 = split * TM, rows = min(TM, S - s0);
+    load_tile(sK, K + ((size_t)b * S + s0) * E, rows);
+    load_tile(sV, V + ((size_t)b * S + s0) * E, rows);
+    for (int i = t; i < F * E; i += 128) sQ[i] = Q[(size_t)b * F * E + i];
+    __syncthreads();
+    const bool live = t < rows && !(key_pad && key_pad[(size_t)b * S + s0 + t]);
+    for (int f = 0; f < F; ++f) {
+        const float s = live ? dot_row(sK[t], sQ + f * E) * scale : -INFINITY;
+        // block max
+        float m = s;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if ((t & 31) == 0) sRed[t >> 5] = m;
+        __syncthreads();
+        m = fmaxf(fmaxf(sRed[0], sRed[1]), fmaxf(sRed[2], sRed[3]));
+        __syncthreads();
+        const float p = (live && m > -INFINITY) ? __expf(s - m) : 0.f;
+        sP[f * TM + t] = p;
+        float l = p, st = (guid && live && guid[((size_t)b * F + f) * S + s0 + t]) ? p : 0.f;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) l += __shfl_xor_sync(0xffffffffu, l, d), st += __shfl_xor_sync(0xffffffffu, st, d);
+        if ((t & 31) == 0) sRed[t >> 5] = l, sRed[4 + (t >> 5)] = st;
+        __syncthreads();
+        if (t == 0) {
+            const size_t o = ((size_t)b * nsplit + split) * F + f;
+            pm[o] = m, pl[o] = sRed[0] + sRed[1] + sRed[2] + sRed[3], pstat[o] = sRed[4] + sRed[5] + sRed[6] + sRed[7];
+        }
+        __syncthreads();
+    }
+    // partial output: thread = channel e
+    for (int f = 0; f < F; ++f) {
+        float acc = 0.f;
+        for (int k = 0; k < rows; ++k) acc = fmaf(sP[f * TM + k], __half2float(sV[k][t]), acc);
+        po[(((size_t)b * nsplit + split) * F + f) * E + t] = acc;
+    }
+}
+
+// grid (F, B), 128 threads: merge the key splits.
+__global__ void __launch_bounds__(128)
+attn_tq_merge_kernel(const float* __restrict__ pm, const float* __restrict__ pl, const float* __restrict__ po,
+                     const float* __restrict__ pstat, int F, int nsplit, float* __restrict__ O, float* __restrict__ stat,
+                     float* __restrict__ M, float* __restrict__ L) {
+    const int f = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+    float m = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) m = fmaxf(m, pm[((size_t)b * nsplit + s) * F + f]);
+    float l = 0.f, st = 0.f, acc = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        const size_t o = ((size_t)b * nsplit + s) * F + f;
+        const float w = pm[o] > -INFINITY ? __expf(pm[o] - m) : 0.f;
+        l += w * pl[o], st += w * pstat[o], acc += w * po[o * E + t];
+    }
+    // a fully masked row (l == 0) yields NaN exactly like softmax over an all -inf row in the reference
+    O[((size_t)b * F + f) * E + t] = acc / l;
+    if (t == 0) stat[(size_t)b * F + f] = st / l, M[(size_t)b * F + f] = m, L[(size_t)b * F + f] = l;
+}
+
+// ================================================================================================ tq backward
+// grid (nsplit, B), 128 threads.  dQ accumulated with atomics (fp32, caller zeroes); dK, dV fp16 rows.
+__global__ void __launch_bounds__(128)
+attn_tq_bwd_kernel(const float* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V,
+                   const uint8_t* __restrict__ key_pad, const uint8_t* __restrict__ guid, const float* __restrict__ O,
+                   const float* __restrict__ stat, const float* __restrict__ M, const float* __restrict__ L,
+                   const float* __restrict__ dO, const float* __restrict__ dstat, int F, int S, float scale,
+                   float* __restrict__ dQ, __half* __restrict__ dK, __half* __restrict__ dV) {
+    extern __shared__ uint8_t smem_raw[];
+    __half (*sK)[ROWP] = reinterpret_cast<__half (*)[ROWP]>(smem_raw);
+    __half (*sV)[ROWP] = sK + TM;
+    float* sQ = reinterpret_cast<float*>(sV + TM);   // [MAXF][E]
+    float* sdO = sQ + MAXF * E;                       // [MAXF][E]
+    float* sP = sdO + MAXF * E;                       // [MAXF][TM]
+    float* sdS = sP + MAXF * TM;                      // [MAXF][TM]
+    float* sD = sdS + MAXF * TM;                      // [MAXF]: sum_k P dP
+    const int b = blockIdx.y, split = blockIdx.x, t = threadIdx.x;
+    const int s0 = split * TM, rows = min(TM, S - s0);
+    load_tile(sK, K + ((size_t)b * S + s0) * E, rows);
+    load_tile(sV, V + ((size_t)b * S + s0) * E, rows);
+    for (int i = t; i < F * E; i += 128) sQ[i] = Q[(size_t)b * F * E + i], sdO[i] = dO[(size_t)b * F * E + i];
+    __syncthreads();
+    if (t < F) {
+        float d = 0.f;
+        for (int e = 0; e < E; ++e) d = fmaf(sdO[t * E + e], O[((size_t)b * F + t) * E + e], d);
+        sD[t] = d + (dstat ? dstat[(size_t)b * F + t] * stat[(size_t)b * F + t] : 0.f);
+    }
+    __syncthreads();
+    const bool live = t < rows && !(key_pad && key_pad[(size_t)b * S + s0 + t]);
+    for (int f = 0; f < F; ++f) {
+        float p = 0.f, ds = 0.f;
+        if (live) {
+            const float s = dot_row(sK[t], sQ + f * E) * scale;
+            p = __expf(s - M[(size_t)b * F + f]) / L[(size_t)b * F + f];
+            float dp = dot_row(sV[t], sdO + f * E);
+            if (dstat && guid && guid[((size_t)b * F + f) * S + s0 + t]) dp += dstat[(size_t)b * F + f];
+            ds = p * (dp - sD[f]);
+        }
+        sP[f * TM + t] = p, sdS[f * TM + t] = ds;
+    }
+    __syncthreads();
+    // thread = channel e: dV[k][e], dK[k][e] rows and dQ[f][e]
+    for (int k = 0; k < rows; ++k) {
+        float av = 0.f, ak = 0.f;
+        for (int f = 0; f < F; ++f) {
+            av = fmaf(sP[f * TM + k], sdO[f * E + t], av);
+            ak = fmaf(sdS[f * TM + k], sQ[f * E + t], ak);
+        }
+        dV[((size_t)b * S + s0 + k) * E + t] = __float2half(av);
+        dK[((size_t)b * S + s0 + k) * E + t] = __float2half(ak * scale);
+    }
+    for (int f = 0; f < F; ++f) {
+        float aq = 0.f;
+        for (int k = 0; k < rows; ++k) aq = fmaf(sdS[f * TM + k], __half2float(sK[k][t]), aq);
+        atomicAdd(dQ + ((size_t)b * F + f) * E + t, aq * scale);
+    }
+}
+
+// ================================================================================================ fq forward / backward
+// queries = many side.  grid (ceil(S/128), B), 128 threads.
+__global__ void __launch_bounds__(128)
+attn_fq_fwd_kernel(const __half* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                   const uint8_t* __restrict__ key_pad, int F, int S, float scale, __half* __restrict__ O) {
+    extern __shared__ uint8_t smem_raw[];
+    __half (*sQ)[ROWP] = reinterpret_cast<__half (*)[ROWP]>(smem_raw);
+    float* sK = reinterpret_cast<float*>(sQ + TM);   // [MAXF][E]
+    float* sV = sK + MAXF * E;
+    float* sP = sV + MAXF * E;                        // [TM][MAXF+1]
+    const int b = blockIdx.y, t = threadIdx.x, s0 = blockIdx.x * TM, rows = min(TM, S - s0);
+    load_tile(sQ, Q + ((size_t)b * S + s0) * E, rows);
+    for (int i = t; i < F * E; i += 128) sK[i] = K[(size_t)b * F * E + i], sV[i] = V[(size_t)b * F * E + i];
+    __syncthreads();
+    {
+        float s[MAXF], m = -INFINITY;
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) {
+            s[f] = -INFINITY;
+            if (f < F && !(key_pad && key_pad[(size_t)b * F + f])) s[f] = dot_row(sQ[t], sK + f * E) * scale;
+            m = fmaxf(m, s[f]);
+        }
+        float l = 0.f;
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) s[f] = (s[f] > -INFINITY) ? __expf(s[f] - m) : 0.f, l += s[f];
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) sP[t * (MAXF + 1) + f] = s[f] / l;   // l == 0 (all keys padded) -> NaN as in the reference
+    }
+    __syncthreads();
+    for (int r = 0; r < rows; ++r) {
+        float acc = 0.f;
+        for (int f = 0; f < F; ++f) acc = fmaf(sP[r * (MAXF + 1) + f], sV[f * E + t], acc);
+        O[((size_t)b * S + s0 + r) * E + t] = __float2half(acc);
+    }
+}
+
+// dQ fp16 rows; dK, dV [B][F][E] fp32 accumulated with atomics (caller zeroes).
+__global__ void __launch_bounds__(128)
+attn_fq_bwd_kernel(const __half* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                   const uint8_t* __restrict__ key_pad, const __half* __restrict__ dO, int F, int S, float scale,
+                   __half* __restrict__ dQ, float* __restrict__ dK, float* __restrict__ dV) {
+    extern __shared__ uint8_t smem_raw[];
+    __half (*sQ)[ROWP] = reinterpret_cast<__half (*)[ROWP]>(smem_raw);
+    __half (*sdO)[ROWP] = sQ + TM;
+    float* sK = reinterpret_cast<float*>(sdO + TM);
+    float* sV = sK + MAXF * E;
+    float* sP = sV + MAXF * E;                        // [TM][MAXF+1]
+    float* sdS = sP + TM * (MAXF + 1);                // [TM][MAXF+1]
+    const int b = blockIdx.y, t = threadIdx.x, s0 = blockIdx.x * TM, rows = min(TM, S - s0);
+    load_tile(sQ, Q + ((size_t)b * S + s0) * E, rows);
+    load_tile(sdO, dO + ((size_t)b * S + s0) * E, rows);
+    for (int i = t; i < F * E; i += 128) sK[i] = K[(size_t)b * F * E + i], sV[i] = V[(size_t)b * F * E + i];
+    __syncthreads();
+    {
+        float s[MAXF], dp[MAXF], m = -INFINITY;
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) {
+            s[f] = -INFINITY, dp[f] = 0.f;
+            if (f < F && !(key_pad && key_pad[(size_t)b * F + f])) {
+                s[f] = dot_row(sQ[t], sK + f * E) * scale;
+                dp[f] = dot_row(sdO[t], sV + f * E);
+            }
+            m = fmaxf(m, s[f]);
+        }
+        float l = 0.f, d = 0.f;
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) s[f] = (s[f] > -INFINITY) ? __expf(s[f] - m) : 0.f, l += s[f];
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) s[f] = (t < rows) ? s[f] / l : 0.f, d += s[f] * dp[f];
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) sP[t * (MAXF + 1) + f] = s[f], sdS[t * (MAXF + 1) + f] = s[f] * (dp[f] - d);
+    }
+    __syncthreads();
+    for (int r = 0; r < rows; ++r) {
+        float acc = 0.f;
+        for (int f = 0; f < F; ++f) acc = fmaf(sdS[r * (MAXF + 1) + f], sK[f * E + t], acc);
+        dQ[((size_t)b * S + s0 + r) * E + t] = __float2half(acc * scale);
+    }
+    for (int f = 0; f < F; ++f) {
+        float ak = 0.f, av = 0.f;
+        for (int r = 0; r < rows; ++r) {
+            ak = fmaf(sdS[r * (MAXF + 1) + f], __half2float(sQ[r][t]), ak);
+            av = fmaf(sP[r * (MAXF + 1) + f], __half2float(sdO[r][t]), av);
+        }
+        atomicAdd(dK + ((size_t)b * F + f) * E + t, ak * scale);
+        atomicAdd(dV + ((size_t)b * F + f) * E + t, av);
+    }
+}
+
+size_t tq_smem() { return 2 * TM * ROWP * 2 + (MAXF * E + MAXF * TM + 8) * 4; }
+size_t tq_bwd_smem() { return 2 * TM * ROWP * 2 + (2 * MAXF * E + 2 * MAXF * TM + MAXF) * 4; }
+size_t fq_smem() { return TM * ROWP * 2 + (2 * MAXF * E + TM * (MAXF + 1)) * 4; }
+size_t fq_bwd_smem() { return 2 * TM * ROWP * 2 + (2 * MAXF * E + 2 * TM * (MAXF + 1)) * 4; }
+
+template <typename Kern>
+int raise_smem(Kern k, size_t bytes, const char* who, bool& done) {
+    if (done) return MG_OK;
+    if (bytes > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        mg::set_error("%s: cannot raise dynamic shared memory limit", who);
+        return MG_ERR_CUDA;
+    }
+    done = true;
+    return MG_OK;
+}
+
+}  // namespace
+
+extern "C" size_t mg_attn_tq_workspace_floats(int B, int F, int S) {
+    const size_t ns = (size_t)mg::ceil_div(S, TM);
+    return (size_t)B * ns * F * (3 + E);
+}
+
+extern "C" int mg_attn_tq_fwd(const float* q, const void* k, const void* v, const uint8_t* key_pad, const uint8_t* guidance,
+                              int B, int F, int S, int Edim, float* out, float* stat, float* row_max, float* row_sum,
+                              float* ws, void* stream) {
+    MG_REQUIRE(q && k && v && out && stat && row_max && row_sum && ws, "mg_attn_tq_fwd: null pointer");
+    MG_REQUIRE(Edim == E && F >= 1 && F <= MAXF && S >= 1 && B >= 1 && B <= 65535, "mg_attn_tq_fwd: unsupported shape E=%d F=%d S=%d", Edim, F, S);
+    const int ns = mg::ceil_div(S, TM);
+    float* pm = ws;
+    float* pl = pm + (size_t)B * ns * F;
+    float* pstat = pl + (size_t)B * ns * F;
+    float* po = pstat + (size_t)B * ns * F;
+    static bool done = false;
+    if (int e = raise_smem(attn_tq_partial_kernel, tq_smem(), "mg_attn_tq_fwd", done)) return e;
+    const float scale = 1.0f / sqrtf((float)E);
+    MG_LAUNCH(attn_tq_partial_kernel, dim3(ns, B), 128, tq_smem(), stream, q, static_cast<const __half*>(k),
+              static_cast<const __half*>(v), key_pad, guidance, F, S, scale, pm, pl, po, pstat);
+    MG_LAUNCH(attn_tq_merge_kernel, dim3(F, B), 128, 0, stream, pm, pl, po, pstat, F, ns, out, stat, row_max, row_sum);
+    MG_CHECK_LAUNCH("mg_attn_tq_fwd");
+    return MG_OK;
+}
+
+extern "C" int mg_attn_tq_bwd(const float* q, const void* k, const void* v, const uint8_t* key_pad, const uint8_t* guidance,
+                              const float* out, const float* stat, const float* row_max, const float* row_sum,
+                              const float* d_out, const float* d_stat, int B, int F, int S, int Edim, float* dq, void* dk,
+                              void* dv, void* stream) {
+    MG_REQUIRE(q && k && v && out && stat && row_max && row_sum && d_out && dq && dk && dv, "mg_attn_tq_bwd: null pointer");
+    MG_REQUIRE(Edim == E && F >= 1 && F <= MAXF && S >= 1 && B >= 1 && B <= 65535, "mg_attn_tq_bwd: unsupported shape");
+    static bool done = false;
+    if (int e = raise_smem(attn_tq_bwd_kernel, tq_bwd_smem(), "mg_attn_tq_bwd", done)) return e;
+    const float scale = 1.0f / sqrtf((float)E);
+    MG_LAUNCH(attn_tq_bwd_kernel, dim3(mg::ceil_div(S, TM), B), 128, tq_bwd_smem(), stream, q, static_cast<const __half*>(k),
+              static_cast<const __half*>(v), key_pad, guidance, out, stat, row_max, row_sum, d_out, d_stat, F, S, scale, dq,
+              static_cast<__half*>(dk), static_cast<__half*>(dv));
+    MG_CHECK_LAUNCH("mg_attn_tq_bwd");
+    return MG_OK;
+}
+
+extern "C" int mg_attn_fq_fwd(const void* q, const float* k, const float* v, const uint8_t* key_pad, int B, int F, int S,
+                              int Edim, void* out, void* stream) {
+    MG_REQUIRE(q && k && v && out, "mg_attn_fq_fwd: null pointer");
+    MG_REQUIRE(Edim == E && F >= 1 && F <= MAXF && S >= 1 && B >= 1 && B <= 65535, "mg_attn_fq_fwd: unsupported shape");
+    static bool done = false;
+    if (int e = raise_smem(attn_fq_fwd_kernel, fq_smem(), "mg_attn_fq_fwd", done)) return e;
+    MG_LAUNCH(attn_fq_fwd_kernel, dim3(mg::ceil_div(S, TM), B), 128, fq_smem(), stream, static_cast<const __half*>(q), k, v,
+              key_pad, F, S, 1.0f / sqrtf((float)E), static_cast<__half*>(out));
+    MG_CHECK_LAUNCH("mg_attn_fq_fwd");
+    return MG_OK;
+}
+
+extern "C" int mg_attn_fq_bwd(const void* q, const float* k, const float* v, const uint8_t* key_pad, const void* d_out, int B,
+                              int F, int S, int Edim, void* dq, float* dk, float* dv, void* stream) {
+    MG_REQUIRE(q && k && v && d_out && dq && dk && dv, "mg_attn_fq_bwd: null pointer");
+    MG_REQUIRE(Edim == E && F >= 1 && F <= MAXF && S >= 1 && B >= 1 && B <= 65535, "mg_attn_fq_bwd: unsupported shape");
+    static bool done = false;
+    if (int e = raise_smem(attn_fq_bwd_kernel, fq_bwd_smem(), "mg_attn_fq_bwd", done)) return e;
+    MG_LAUNCH(attn_fq_bwd_kernel, dim3(mg::ceil_div(S, TM), B), 128, fq_bwd_smem(), stream, static_cast<const __half*>(q), k, v,
+              key_pad, static_cast<const __half*>(d_out), F, S, 1.0f / sqrtf((float)E), static_cast<__half*>(dq), dk, dv);
+    MG_CHECK_LAUNCH("mg_attn_fq_bwd");
+    return MG_OK;
+}

@@ -61,6 +61,7 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         self.decoder = DECODERS[cfg.decoder](**cfg.decoder_args)
         self._stage = [_DenseStage(self)]          # in a list: not a registered sub-module
         self._graphs, self._use_graphs = {}, False
+        self.replayed_native_launches = 0          # native kernels executed through graph replays (bench accounting)
         for module in (self.aspp, self.decoder):  # arch/maggie.py:41-49
             for _, p in module.named_parameters():
                 if p.dim() > 1:
@@ -112,12 +113,16 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         if not (self._use_graphs and self.training and torch.is_grad_enabled()):
             return stage(*args)
         key = tuple((tuple(a.shape), a.dtype) for a in args)
-        fn = self._graphs.get(key)
-        if fn is None:
+        entry = self._graphs.get(key)
+        if entry is None:
+            from ... import _lib
             sample = tuple(a.clone() for a in args)
+            before = _lib.launch_count()
             fn = torch.cuda.make_graphed_callables(stage, sample, num_warmup_iters=3, allow_unused_input=True)
-            self._graphs[key] = fn
-        return fn(*args)
+            # 3 warm-up iterations + 1 capture, each one forward + backward of the stage
+            entry = self._graphs[key] = (fn, (_lib.launch_count() - before) // 4)
+        self.replayed_native_launches += entry[1]
+        return entry[0](*args)
 
     def forward(self, batch, **kwargs):
         x, masks, slot_ids, dec_masks, alphas, trans, chosen, (b, n_f, n_i, h, w) = self._prepare(batch)

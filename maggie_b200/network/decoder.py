@@ -80,11 +80,11 @@ class _Attn(nn.Module):
         mha = getattr(self, self.attn_name)
         E = tgt.shape[-1]
         w, b = mha.in_proj_weight, mha.in_proj_bias
-        q = ops.linear(tgt if tgt_pos is None else tgt + tgt_pos, w[:E], b[:E])
-        k = ops.linear(mem if mem_pos is None else mem + mem_pos, w[E:2 * E], b[E:2 * E])
-        v = ops.linear(mem, w[2 * E:], b[2 * E:])
+        q = ops.linear_rows(tgt if tgt_pos is None else tgt + tgt_pos, w[:E], b[:E])
+        k = ops.linear_rows(mem if mem_pos is None else mem + mem_pos, w[E:2 * E], b[E:2 * E])
+        v = ops.linear_rows(mem, w[2 * E:], b[2 * E:])
         o, stat = ops.attention(q, k, v, key_padding, guidance)
-        o = ops.linear(o, mha.out_proj.weight, mha.out_proj.bias)
+        o = ops.linear_rows(o, mha.out_proj.weight, mha.out_proj.bias)
         return ops.layer_norm(tgt + o, self.norm), stat
 
 
@@ -127,7 +127,7 @@ class InstanceMatteDecoder(nn.Module):
         id_pos = (mask_os8 * ids).amax(2)                                                   # [b,n_f,h,w]
         emb = self.id_embedding.weight
         x_pos = F.embedding(id_pos.reshape(b, n_f, hw).permute(0, 2, 1).reshape(b, hw * n_f), emb).to(dt)  # [b,S,E]
-        x = ops.linear(x, self.feat_proj.layers[0].weight, self.feat_proj.layers[0].bias)
+        x = ops.linear_rows(x, self.feat_proj.layers[0].weight, self.feat_proj.layers[0].bias)
         tok = self.query_feat.weight.to(dt)[None].expand(b, -1, -1)
         tok_pos = emb[1:nq + 1].to(dt)[None].expand(b, -1, -1)
 

@@ -220,23 +220,101 @@ def linear(x, w, b=None):
     return F.linear(x, w.to(x.dtype), None if b is None else b.to(x.dtype))
 
 
+def linear_rows(x, w, b=None):
+    """Linear layer on [..., Cin] rows.  Large row counts (the pixel side of the attention: B*4096 rows) run on the
+    tcgen05 rows GEMM with native gradients (K9 with T = 1); the 10-token side stays a tiny torch matmul."""
+    rows = x.numel() // x.shape[-1]
+    if rows < 1024 or not x.is_cuda:
+        return linear(x, w, b)
+    y = rows_conv(x.reshape(rows, x.shape[-1]), w, b)
+    return y.reshape(*x.shape[:-1], w.shape[0]).to(x.dtype)
+
+
 def layer_norm(x, ln):
     return F.layer_norm(x.float(), (x.shape[-1],), ln.weight, ln.bias, ln.eps).to(x.dtype)
 
 
+class _AttnTQ(torch.autograd.Function):
+    """Few queries (tokens) over many keys, with the attention-max statistic (K6 "tq")."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_pad, guidance):
+        _need_cuda(q, k, v)
+        B, Fq, E = q.shape
+        S = k.shape[1]
+        qf = q.detach().to(torch.float32).contiguous()
+        kh, vh = k.detach().to(torch.float16).contiguous(), v.detach().to(torch.float16).contiguous()
+        kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
+        gd = guidance.to(torch.uint8).contiguous() if guidance is not None else None
+        L = _lib.lib()
+        dev = q.device
+        out = torch.empty((B, Fq, E), dtype=torch.float32, device=dev)
+        small = torch.empty((3, B, Fq), dtype=torch.float32, device=dev)   # stat, row max, row sum
+        ws = torch.empty(L.mg_attn_tq_workspace_floats(B, Fq, S), dtype=torch.float32, device=dev)
+        _lib.check(L.mg_attn_tq_fwd(_ptr(qf), _ptr(kh), _ptr(vh), _ptr(kp), _ptr(gd), B, Fq, S, E, _ptr(out), _ptr(small[0]),
+                                    _ptr(small[1]), _ptr(small[2]), _ptr(ws), _stream()), "mg_attn_tq_fwd")
+        ctx.save_for_backward(qf, kh, vh, kp, gd, out, small)
+        ctx.dt = (q.dtype, k.dtype, v.dtype)
+        return out.to(q.dtype), small[0]
+
+    @staticmethod
+    def backward(ctx, g_out, g_stat):
+        qf, kh, vh, kp, gd, out, small = ctx.saved_tensors
+        B, Fq, E = qf.shape
+        S = kh.shape[1]
+        go = g_out.to(torch.float32).contiguous()
+        gs = g_stat.to(torch.float32).contiguous() if (g_stat is not None and gd is not None) else None
+        dq = torch.zeros_like(qf)
+        dk, dv = torch.empty_like(kh), torch.empty_like(vh)
+        _lib.check(_lib.lib().mg_attn_tq_bwd(_ptr(qf), _ptr(kh), _ptr(vh), _ptr(kp), _ptr(gd), _ptr(out), _ptr(small[0]),
+                                            _ptr(small[1]), _ptr(small[2]), _ptr(go), _ptr(gs), B, Fq, S, E, _ptr(dq),
+                                            _ptr(dk), _ptr(dv), _stream()), "mg_attn_tq_bwd")
+        qd, kd, vd = ctx.dt
+        return dq.to(qd), dk.to(kd), dv.to(vd), None, None
+
+
+class _AttnFQ(torch.autograd.Function):
+    """Many queries (pixels) over few keys (tokens, with key padding) (K6 "fq")."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_pad):
+        _need_cuda(q, k, v)
+        B, S, E = q.shape
+        Fk = k.shape[1]
+        qh = q.detach().to(torch.float16).contiguous()
+        kf, vf = k.detach().to(torch.float32).contiguous(), v.detach().to(torch.float32).contiguous()
+        kp = key_pad.to(torch.uint8).contiguous() if key_pad is not None else None
+        out = torch.empty((B, S, E), dtype=torch.float16, device=q.device)
+        _lib.check(_lib.lib().mg_attn_fq_fwd(_ptr(qh), _ptr(kf), _ptr(vf), _ptr(kp), B, Fk, S, E, _ptr(out), _stream()),
+                   "mg_attn_fq_fwd")
+        ctx.save_for_backward(qh, kf, vf, kp)
+        ctx.dt = (q.dtype, k.dtype, v.dtype)
+        return out.to(q.dtype)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        qh, kf, vf, kp = ctx.saved_tensors
+        B, S, E = qh.shape
+        Fk = kf.shape[1]
+        go = g_out.to(torch.float16).contiguous()
+        dq = torch.empty_like(qh)
+        dk, dv = torch.zeros_like(kf), torch.zeros_like(vf)
+        _lib.check(_lib.lib().mg_attn_fq_bwd(_ptr(qh), _ptr(kf), _ptr(vf), _ptr(kp), _ptr(go), B, Fk, S, E, _ptr(dq), _ptr(dk),
+                                            _ptr(dv), _stream()), "mg_attn_fq_bwd")
+        qd, kd, vd = ctx.dt
+        return dq.to(qd), dk.to(kd), dv.to(vd), None
+
+
 def attention(q, k, v, key_padding=None, need_stat=None):
-    """Single-head attention, batch-first: q [B,L,E], k/v [B,S,E] (already projected).  Softmax in fp32.
-    key_padding [B,S] bool (True = ignore).  need_stat: optional [B,L,S] bool guidance mask; if given also
-    returns stat[b,l] = sum_s guidance * A (the only thing the attention-max loss needs,
-    module/instance_matte_decoder.py:101-109).  INTERIM (torch)."""
-    s = torch.bmm(q, k.transpose(1, 2)).float() * (q.shape[-1] ** -0.5)
-    if key_padding is not None:
-        s = s.masked_fill(key_padding[:, None, :], float("-inf"))
-    a = torch.softmax(s, dim=-1)
-    o = torch.bmm(a.to(v.dtype), v)
-    if need_stat is not None:
-        return o, (a * need_stat).sum(-1)
-    return o, None
+    """Single-head attention, batch-first: q [B,L,E], k/v [B,S,E] (already projected), softmax in fp32.
+    key_padding [B,S] bool (True = ignore).  need_stat: optional [B,L,S] bool guidance mask; if given also returns
+    stat[b,l] = sum_s guidance * A (the only thing the attention-max loss needs, instance_matte_decoder.py:101-109).
+    NATIVE (K6): few-query ("tq") kernel when L <= 16, many-query ("fq") kernel when S <= 16."""
+    if q.shape[1] <= 16:
+        o, stat = _AttnTQ.apply(q, k, v, key_padding, need_stat)
+        return o, (stat if need_stat is not None else None)
+    assert k.shape[1] <= 16 and need_stat is None, "attention: one side must have <= 16 rows"
+    return _AttnFQ.apply(q, k, v, key_padding), None
 
 
 def rows_conv(src, w, bias=None, *, table=None, table_t=None, mirror=False, bn=None, mode="plain", act=None,

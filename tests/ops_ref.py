@@ -160,6 +160,23 @@ def rows_head(src, w, bias, nbr, coords, slots, H, W):
     return scatter_logits(y, coords, slots, H, W)
 
 
+# ---- torch restatement of the attention core (K6) ----------------------------------------------------------
+def attention(q, k, v, key_padding=None, need_stat=None):
+    """Single-head attention, batch-first: q [B,L,E], k/v [B,S,E] (already projected).  Softmax in fp32.
+    key_padding [B,S] bool (True = ignore).  need_stat: optional [B,L,S] bool guidance mask; if given also
+    returns stat[b,l] = sum_s guidance * A (the only thing the attention-max loss needs,
+    module/instance_matte_decoder.py:101-109).  torch reference."""
+    s = torch.bmm(q, k.transpose(1, 2)).float() * (q.shape[-1] ** -0.5)
+    if key_padding is not None:
+        s = s.masked_fill(key_padding[:, None, :], float("-inf"))
+    a = torch.softmax(s, dim=-1)
+    o = torch.bmm(a.to(v.dtype), v)
+    if need_stat is not None:
+        return o, (a * need_stat).sum(-1)
+    return o, None
+
+
+
 # ---- torch restatement of the K12 partial sums (loss.py:67-191 semantics) -------------------------------------
 _G5 = torch.tensor([1.0, 4.0, 6.0, 4.0, 1.0])
 _GAUSS2D = (_G5[:, None] * _G5[None, :]) / 256.0
@@ -210,12 +227,12 @@ def matte_loss_sums(a1, a4, a8, target, w1, w4, w8):
 def injected(dtype=torch.float32):
     """Swap the native ops for the references above (CPU container only)."""
     names = ("unknown_mask", "build_sites", "mask_embed", "conv_bn_act", "rows_conv", "rows_head", "gather_dense",
-             "matte_loss_sums", "COMPUTE_DTYPE")
+             "matte_loss_sums", "attention", "COMPUTE_DTYPE")
     saved = {n: getattr(ops, n) for n in names}
     ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.conv_bn_act, ops.COMPUTE_DTYPE = \
         unknown_mask, build_sites, mask_embed, conv_bn_act, dtype
     ops.rows_conv, ops.rows_head, ops.gather_dense = rows_conv, rows_head, gather_dense
-    ops.matte_loss_sums = matte_loss_sums
+    ops.matte_loss_sums, ops.attention = matte_loss_sums, attention
     try:
         yield
     finally:
