@@ -125,14 +125,23 @@ sparse_conv_kernel(const SArgs a) {
             const int t = st / a.kblocks, kb = st - t * a.kblocks;
             mbar_wait(empty0 + 8 * s, ph ^ 1);
             uint8_t* tile = sA + (size_t)s * a_tile;
-            for (int r = rr; r < 128; r += rstep) {
-                const int p = tile0 + r;
-                int idx = -1;
-                if (p < a.No) idx = a.table ? __ldg(a.table + (size_t)p * a.T + t) : p;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (idx >= 0) v = __ldg(reinterpret_cast<const uint4*>(a.src + (size_t)idx * a.src_stride + kb * a.BK + sub * 8));
-                st_tile(tile, r, sub, a.rowb, v);
+            // all neighbour indices first, then all row loads, then the stores: 4-8 independent loads in flight per thread
+            int idx[8];
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rr + i * rstep, p = tile0 + r;
+                idx[i] = -1;
+                if (i < cpr && p < a.No) idx[i] = a.table ? __ldg(a.table + (size_t)p * a.T + t) : p;
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (idx[i] >= 0) v[i] = __ldg(reinterpret_cast<const uint4*>(a.src + (size_t)idx[i] * a.src_stride + kb * a.BK + sub * 8));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < cpr) st_tile(tile, rr + i * rstep, sub, a.rowb, v[i]);
             fence_async_smem();
             mbar_arrive(full0 + 8 * s);
         }
@@ -287,6 +296,7 @@ sparse_wgrad_kernel(const SWArgs a) {
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 // A: d_out rows (K index = site)
                 uint8_t* ta = sA + (size_t)s * a_tile;
+#pragma unroll 4
                 for (int e = tid; e < 128 * ca_chunks; e += 128) {
                     const int r = e / ca_chunks, c = e - r * ca_chunks;
                     const int p = row0 + r;
@@ -294,17 +304,28 @@ sparse_wgrad_kernel(const SWArgs a) {
                     if (p < a.No) v = __ldg(reinterpret_cast<const uint4*>(a.dout + (size_t)p * a.dout_stride + c * 8));
                     st_tile(ta + (size_t)(c / cpa) * a_atom, r, c % cpa, a.rowb_a, v);
                 }
-                // B: gathered source rows, one tile per tap
+                // B: gathered source rows, one tile per tap (indices, then loads, then stores: 4 gathers in flight)
                 for (int tt = 0; tt < nt; ++tt) {
                     uint8_t* tb = sB + (size_t)(s * a.taps_per_cta + tt) * b_tile;
-                    for (int e = tid; e < 128 * cb_chunks; e += 128) {
-                        const int r = e / cb_chunks, c = e - r * cb_chunks;
-                        const int p = row0 + r;
-                        int idx = -1;
-                        if (p < a.No) idx = a.table ? __ldg(a.table + (size_t)p * a.T + t0 + tt) : p;
-                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                        if (idx >= 0) v = __ldg(reinterpret_cast<const uint4*>(a.src + (size_t)idx * a.src_stride + c * 8));
-                        st_tile(tb + (size_t)(c / cpb) * b_atom, r, c % cpb, a.rowb_b, v);
+                    for (int e0 = tid; e0 < 128 * cb_chunks; e0 += 4 * 128) {
+                        int idx[4], rr4[4], cc4[4];
+                        uint4 v4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = e0 + u * 128;
+                            rr4[u] = e / cb_chunks, cc4[u] = e - rr4[u] * cb_chunks;
+                            const int p = row0 + rr4[u];
+                            idx[u] = -1;
+                            if (e < 128 * cb_chunks && p < a.No) idx[u] = a.table ? __ldg(a.table + (size_t)p * a.T + t0 + tt) : p;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            v4[u] = make_uint4(0u, 0u, 0u, 0u);
+                            if (idx[u] >= 0) v4[u] = __ldg(reinterpret_cast<const uint4*>(a.src + (size_t)idx[u] * a.src_stride + cc4[u] * 8));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (e0 + u * 128 < 128 * cb_chunks) st_tile(tb + (size_t)(cc4[u] / cpb) * b_atom, rr4[u], cc4[u] % cpb, a.rowb_b, v4[u]);
                     }
                 }
                 fence_async_smem();

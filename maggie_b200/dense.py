@@ -332,3 +332,38 @@ def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="rel
         y = conv2d_nhwc(xn, w.detach(), stride=stride, padding=padding, dilation=dilation, scale=scale, shift=shift, res=rn,
                         res_up=res_up, pre_act=act if act_first else None, post_act=None if act_first else act)
     return y.permute(0, 3, 1, 2)
+
+
+class _ConvBias(torch.autograd.Function):
+    """Plain conv (+ bias), no normalisation: ConvGRU gates, the 32->1 temporal-difference head."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, geom):
+        xn = x.permute(0, 2, 3, 1)
+        assert xn.is_contiguous() and xn.dtype == torch.float16
+        wd = w.detach()
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        y = geom.fwd(xn, wd, bias=b32)
+        ctx.save_for_backward(xn, wd)
+        ctx.cfg = (geom, tuple(w.shape), bias is not None)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xn, w = ctx.saved_tensors
+        geom, w_shape, has_bias = ctx.cfg
+        dy = gy.permute(0, 2, 3, 1)
+        if not dy.is_contiguous() or dy.dtype != torch.float16:
+            dy = dy.contiguous().to(torch.float16)
+        dx = geom.dgrad(dy, w, xn.shape).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
+        dw = geom.wgrad(dy, xn, w_shape) if ctx.needs_input_grad[1] else None
+        db = dy.float().sum((0, 1, 2)) if has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
+
+
+def conv_bias(x, w, bias=None, *, padding=1):
+    """x NCHW-shaped channels-last fp16; w [Co,Ci,k,k] fp32 (Co padded to a multiple of 16 by the caller)."""
+    _need_cuda(x, w)
+    if x.dtype != torch.float16 or not x.permute(0, 2, 3, 1).is_contiguous():
+        x = x.to(torch.float16).contiguous(memory_format=torch.channels_last)
+    return _ConvBias.apply(x, w, bias, ConvGeom("conv", w.shape[-1], 1, padding, 1))

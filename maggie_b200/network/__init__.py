@@ -2,7 +2,7 @@
 import logging
 import os
 
-from .arch import ARCHS, MaGGIe  # noqa: F401
+from .arch import ARCHS, MaGGIe, MaGGIe_Temp  # noqa: F401
 
 
 def build_model(cfg):

@@ -1,3 +1,3 @@
-from .maggie import MaGGIe  # noqa: F401
+from .maggie import MaGGIe, MaGGIe_Temp  # noqa: F401
 
-ARCHS = {"MaGGIe": MaGGIe}
+ARCHS = {"MaGGIe": MaGGIe, "MaGGIe_Temp": MaGGIe_Temp}

@@ -21,11 +21,11 @@ except Exception:  # pragma: no cover
 from ...config import as_cfg
 from ... import ops
 from .. import loss as losses
-from ..decoder import MaGGIeDecoder
+from ..decoder import MaGGIeDecoder, MaGGIeTempDecoder
 from ..encoder import ASPP, ResMaskEmbedShortCutEncoder
 
 ENCODERS = {"res_shortcut_embed_29": ResMaskEmbedShortCutEncoder}
-DECODERS = {"res_shortcut_inst_matt_spconv_22": MaGGIeDecoder}
+DECODERS = {"res_shortcut_inst_matt_spconv_22": MaGGIeDecoder, "res_shortcut_inst_matt_spconv_temp_22": MaGGIeTempDecoder}
 
 
 class _DenseStage(nn.Module):
@@ -37,14 +37,15 @@ class _DenseStage(nn.Module):
         super().__init__()
         self.encoder, self.aspp, self.decoder = model.encoder, model.aspp, model.decoder
 
-    def forward(self, image, masks, slot_ids, mask_os8, gt_os8):
+    def forward(self, image, masks, slot_ids, mask_os8, gt_os8, mem_feat=None):
         emb, fea = self.encoder(image, masks, slot_ids)
         emb = self.aspp(emb)
-        logits, feat, queries, loss = self.decoder.dense_stage(emb, fea[3], fea[4], mask_os8 > 0,
-                                                               (gt_os8 > 0) if self.training else None)
-        if not torch.is_tensor(loss):
-            loss = logits.new_zeros(())
-        return fea[0], fea[1], fea[2], logits, feat, queries, loss
+        extra = {} if mem_feat is None else {"mem_feat": mem_feat}
+        out = list(self.decoder.dense_stage(emb, fea[3], fea[4], mask_os8 > 0, (gt_os8 > 0) if self.training else None,
+                                            **extra))
+        if not torch.is_tensor(out[3]):
+            out[3] = out[0].new_zeros(())
+        return (fea[0], fea[1], fea[2], *out)
 
 
 class MaGGIe(nn.Module, PyTorchModelHubMixin):
@@ -104,12 +105,14 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         self._use_graphs = bool(on)
         return self
 
-    def _dense(self, x, masks, slot_ids, mask_os8, gt_os8):
+    def _dense(self, x, masks, slot_ids, mask_os8, gt_os8, mem_feat=None):
         stage = self._stage[0]
         stage.train(self.training)
         ids = ops.slot_ids_tensor(slot_ids, x.device)
         args = (x.float().contiguous(), masks.contiguous(), ids, mask_os8.float(),
                 gt_os8.float() if gt_os8 is not None else mask_os8.float())
+        if mem_feat is not None:
+            args = args + (mem_feat,)
         if not (self._use_graphs and self.training and torch.is_grad_enabled()):
             return stage(*args)
         key = tuple((tuple(a.shape), a.dtype) for a in args)
@@ -124,11 +127,23 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         self.replayed_native_launches += entry[1]
         return entry[0](*args)
 
+    # hooks overridden by the video model
+    def _extra_outputs(self, pred, output, n_i):
+        pass
+
+    def _extra_losses(self, pred, loss_dict, w4, w1, alphas, shape5):
+        pass
+
+    def _extra_decoder_losses(self, pred, loss_dict):
+        pass
+
     def forward(self, batch, **kwargs):
         x, masks, slot_ids, dec_masks, alphas, trans, chosen, (b, n_f, n_i, h, w) = self._prepare(batch)
         mask_os8, gt_os8 = self.decoder.pooled_masks(dec_masks, alphas, b, n_f, n_i, h, w, self.training)
-        fea1, fea2, fea3, logits, feat, queries, loss_atten = self._dense(x, masks, slot_ids, mask_os8, gt_os8)
-        pred = self.decoder((logits, feat, queries, loss_atten), (fea1, fea2, fea3), (h, w), b=b, n_f=n_f, n_i=n_i,
+        mem_feat = kwargs.pop("mem_feat", None)
+        fea1, fea2, fea3, *dense_out = self._dense(x, masks, slot_ids, mask_os8, gt_os8,
+                                                   mem_feat if torch.is_tensor(mem_feat) else None)
+        pred = self.decoder(tuple(dense_out), (fea1, fea2, fea3), (h, w), b=b, n_f=n_f, n_i=n_i,
                             masks=dec_masks, iter=batch.get("iter", 0), gt_alphas=alphas, spar_gt=trans, **kwargs)
         self.last_site_counts = pred.pop("site_counts", None)
 
@@ -141,6 +156,7 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         output = {k: view(pred[k]) for k in ("alpha_os1", "alpha_os4", "alpha_os8")}
         output["refined_masks"] = view(alpha_pred)
         output["detail_mask"] = view(pred["detail_mask"])
+        self._extra_outputs(pred, output, n_i)
 
         if self.training:
             valid = (trans.sum((2, 3), keepdim=True) > 0).float()
@@ -149,9 +165,11 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
                     continue
                 pred[k] = pred[k] * valid
             loss_dict = losses.compute_loss(pred, w4, w1, alphas, self.cfg)
+            self._extra_losses(pred, loss_dict, w4, w1, alphas, (b, n_f, self.num_masks, h, w))
             if "loss_max_atten" in pred and self.cfg.loss_atten_w > 0:
                 loss_dict["loss_max_atten"] = pred["loss_max_atten"]
                 loss_dict["total"] = loss_dict["total"] + loss_dict["loss_max_atten"] * self.cfg.loss_atten_w
+            self._extra_decoder_losses(pred, loss_dict)
             if chosen is not None:
                 output = {k: v[:, :, chosen] for k, v in output.items()}
             return output, loss_dict
@@ -160,4 +178,54 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         for k in pred:
             if k.startswith("mem_"):
                 output[k] = pred[k]
+        return output
+
+
+class MaGGIe_Temp(MaGGIe):
+    """Video model: temporal outputs / losses and the eval-time alpha-matte level aggregation over a 3-frame window.
+    Reference: arch/maggie_temp.py:5-77, arch/maggie.py:348-365 (dtSSD)."""
+
+    def _extra_outputs(self, pred, output, n_i):
+        db, df, ta = pred.pop("diff_backward", None), pred.pop("diff_forward", None), pred.pop("temp_alpha", None)
+        if db is not None:
+            output["diff_pred_backward"] = db.repeat(1, 1, n_i, 1, 1)
+            output["diff_pred_forward"] = df.repeat(1, 1, n_i, 1, 1)
+            output["temp_alpha"] = ta
+
+    def _extra_losses(self, pred, L, w4, w1, alphas, shape5):
+        if self.cfg.loss_dtSSD_w <= 0:
+            return
+        r = lambda t: t.reshape(*shape5).float()
+        a8 = pred["alpha_os8"]
+        w8 = (alphas.sum((2, 3), keepdim=True) > 0).to(a8.dtype).expand_as(a8)
+        if self.cfg.loss_reweight_os8:
+            lo, hi = 1.0 / 255.0, 254.0 / 255.0
+            w8 = (((alphas <= hi) & (alphas >= lo)) | ((a8 <= hi) & (a8 >= lo))).to(a8.dtype) + w8
+        dt = MaGGIeTempDecoder._loss_dtssd
+        d1 = dt(r(pred["alpha_os1"]), r(alphas), r(w1))
+        d4 = dt(r(pred["alpha_os4"]), r(alphas), r(w4))
+        d8 = dt(r(a8), r(alphas), r(w8))
+        L.update(loss_dtSSD_os1=d1, loss_dtSSD_os4=d4, loss_dtSSD_os8=d8, loss_dtSSD=d1 * 2 + d4 + d8)
+        L["total"] = L["total"] + L["loss_dtSSD"] * self.cfg.loss_dtSSD_w
+
+    def _extra_decoder_losses(self, pred, L):
+        if "loss_temp" in pred:
+            L.update(loss_temp_bce=pred["loss_temp_bce"], loss_temp=pred["loss_temp"], loss_temp_dtssd=pred["loss_temp_dtssd"])
+            L["total"] = L["total"] + pred["loss_temp"]
+
+    def forward(self, batch, **kwargs):
+        prev_pred = kwargs.pop("prev_pred", None)
+        output = super().forward(batch, **kwargs)
+        if self.training:
+            return output
+        al = output["refined_masks"]                                   # [1, 3, n_i, H, W]
+        prev = al[:, 0] if prev_pred is None else prev_pred.to(al.device)
+        nxt = al[:, -1]
+        dfw = (output["diff_pred_forward"] > 0.5).float()
+        dbw = (output["diff_pred_backward"] > 0.5).float()
+        p01 = prev * (1 - dfw[:, 1]) + al[:, 1] * dfw[:, 1]             # propagate t-1 -> t
+        p21 = nxt * (1 - dbw[:, 1]) + al[:, 1] * dbw[:, 1]              # propagate t+1 -> t
+        p01 = torch.where((p01 - p21).abs() > 0.0, al[:, 1], p01)       # disagreement -> the model's own frame t
+        al[:, 1] = p01
+        al[:, 2] = p01 * (1 - dfw[:, 2]) + nxt * dfw[:, 2]
         return output

@@ -114,10 +114,17 @@ class InstanceMatteDecoder(nn.Module):
         self.conv = seq(PlainConv(d, d, 3), nn.BatchNorm2d(d), Slot(), PlainConv(d, output_dim, 1),
                         nn.BatchNorm2d(output_dim), Slot())
 
-    def forward(self, feat, mask_os8, gt_mask_os8=None):
+    def _smooth(self, x):
+        t = self.training
+        x = ops.conv_bn_act(x, self.conv[0].weight, self.conv[1], t, act="lrelu")
+        return ops.conv_bn_act(x, self.conv[3].weight, self.conv[4], t, padding=0, act="lrelu")
+
+    def forward(self, feat, mask_os8, gt_mask_os8=None, temporal_fn=None):
         """feat [b*n_f, C, h, w] channels-last; mask_os8 [b, n_f, n_i, h, w] bool (avg-pool>0 of the input masks);
         gt_mask_os8 (training) [b, n_f, n_i, h, w] bool (max-pool of gt alpha > 0).
-        Returns logits [b*n_f, 10, h, w] fp32, out_feat [b*n_f, 64, h, w], tokens [b, 10, 64] fp32, loss."""
+        temporal_fn (video): [b, n_f, C, h, w] -> (propagated features, hidden states); the smoothing convs then run
+        on the un-propagated features (-> out_feat) and on the propagated ones (-> logits), as the reference does.
+        Returns logits [b*n_f, 10, h, w] fp32, out_feat [b*n_f, 64, h, w], tokens [b, 10, 64] fp32, loss (, hidden)."""
         b, n_f, n_i, h, w = mask_os8.shape
         hw, nq, t = h * w, self.max_inst, self.training
         dt = feat.dtype
@@ -159,13 +166,20 @@ class InstanceMatteDecoder(nn.Module):
 
         x = x.reshape(b, hw, n_f, -1).permute(0, 2, 3, 1).reshape(b * n_f, -1, h, w)
         x = x.contiguous(memory_format=torch.channels_last)
-        x = ops.conv_bn_act(x, self.conv[0].weight, self.conv[1], t, act="lrelu")
-        x = ops.conv_bn_act(x, self.conv[3].weight, self.conv[4], t, padding=0, act="lrelu")
+        hidden = out_feat = None
+        if temporal_fn is not None:
+            prop, hidden = temporal_fn(x.reshape(b, n_f, *x.shape[1:]))
+            out_feat = self._smooth(x)
+            x = self._smooth(prop.flatten(0, 1).contiguous(memory_format=torch.channels_last))
+        else:
+            x = out_feat = self._smooth(x)
         tok = ops.linear(tok, self.final_mlp.layers[0].weight, self.final_mlp.layers[0].bias)
         tok = F.layer_norm(tok.float(), (tok.shape[-1],), self.decoder_norm.weight, self.decoder_norm.bias,
                            self.decoder_norm.eps)                                           # [b,10,64] fp32
         logits = torch.einsum("bqc,btchw->btqhw", tok, x.float().reshape(b, n_f, -1, h, w)).flatten(0, 1)
-        return logits, x, tok, loss
+        if temporal_fn is not None:
+            return logits, out_feat, tok, loss, hidden
+        return logits, out_feat, tok, loss
 
 
 # ------------------------------------------------------------------------------------------- full decoder
@@ -265,38 +279,37 @@ class MaGGIeDecoder(nn.Module):
             gt_os8 = F.max_pool2d((gt_alphas > 0).float(), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0
         return mask_os8, gt_os8
 
-    def forward(self, dense_out, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, **_):
-        """dense_out: (os8_logits, os8_feat, queries, loss_atten) from `dense_stage`; fea: (fea1, fea2, fea3);
-        masks [b*n_f, n_i, H, W] fp32 {0,1}; gt_alphas [b*n_f, n_i, H, W]."""
+    def _os8_alpha(self, os8_logits, masks, n_i, H, W):
+        valid = masks.flatten(2).sum(2)[:, :, None, None] > 0
+        a8 = ops.upsample_tanh(os8_logits, size=(H, W))
+        return a8 * valid if self.training else a8[:, :n_i]
+
+    def _choose_guidance(self, a8, gt_alphas, iter):
+        """Warm-up switch of resnet_inst_matt_spconv.py:311-316 (same python RNG draw)."""
+        wd = self.warmup_detail_iter
+        if self.training and (iter < wd or float(a8.sum()) == 0 or (iter < wd * 3 and random.random() < 0.5)):
+            return gt_alphas, True
+        return a8, False
+
+    def _refine_and_fuse(self, x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W):
+        """process_os4_os1 + fuse (resnet_inst_matt_spconv.py:346-366, 272-290, 333-340)."""
         t = self.training
         fea1, fea2, fea3 = fea
-        H, W = image_hw
-        valid = masks.flatten(2).sum(2)[:, :, None, None] > 0
-        os8_logits, x, queries, loss_atten = dense_out
-        a8 = ops.upsample_tanh(os8_logits, size=(H, W))
-        a8 = a8 * valid if t else a8[:, :n_i]
-
-        guided, use_gt = a8, False
-        wd = self.warmup_detail_iter
-        if t and (iter < wd or float(a8.sum()) == 0 or (iter < wd * 3 and random.random() < 0.5)):
-            guided, use_gt = gt_alphas, True
-        n_sl = guided.shape[0] * guided.shape[1]
-        unk = ops.unknown_mask(guided, _draw_widths(n_sl, 30, False))
+        n_sl = a8.shape[0] * a8.shape[1]
         if t and int(unk.max()) == 0:
             unk[:, :, 200:250, 200:250] = 1
         counts = [0, 0, 0, 0]
         if t or int(unk.max()) > 0:
             q = queries[:, None].expand(-1, n_f, -1, -1).reshape(b * n_f, *queries.shape[1:])
             os4, os1, counts = self.predict_details(x, unk, q, fea1, fea2, fea3)
-            os4 = os4.reshape(b * n_f, guided.shape[1], H // 4, W // 4)
-            os1 = os1.reshape(b * n_f, guided.shape[1], H, W)
+            os4 = os4.reshape(b * n_f, a8.shape[1], H // 4, W // 4)
+            os1 = os1.reshape(b * n_f, a8.shape[1], H, W)
             a4 = ops.upsample_tanh(os4, scale=4.0)
             a1 = ops.upsample_tanh(os1)
         else:
             a4 = torch.zeros_like(a8)
             a1 = torch.zeros_like(a8)
         ret = dict(alpha_os1=a1, alpha_os4=a4, alpha_os8=a8)
-        # progressive fusion (resnet_inst_matt_spconv.py:272-290)
         w4 = ops.unknown_mask(a8, _draw_widths(n_sl, 27, t), and_mask=unk).to(a8.dtype)
         a = a4 * w4 + a8 * (1 - w4)
         w1 = ops.unknown_mask(a, _draw_widths(n_sl, 15, t), and_mask=unk).to(a8.dtype)
@@ -307,6 +320,157 @@ class MaGGIeDecoder(nn.Module):
             w1 = ops.unknown_mask(gt_alphas, _draw_widths(n_sl, 15, t), and_mask=unk)
         ret["weight_os4"], ret["weight_os1"], ret["detail_mask"] = w4, w1, unk
         ret["site_counts"] = counts
-        if t and iter >= self.warmup_mask_atten_iter:
+        return ret
+
+    def forward(self, dense_out, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, **_):
+        """dense_out: (os8_logits, os8_feat, queries, loss_atten) from `dense_stage`; fea: (fea1, fea2, fea3);
+        masks [b*n_f, n_i, H, W] fp32 {0,1}; gt_alphas [b*n_f, n_i, H, W]."""
+        H, W = image_hw
+        os8_logits, x, queries, loss_atten = dense_out
+        a8 = self._os8_alpha(os8_logits, masks, n_i, H, W)
+        guided, use_gt = self._choose_guidance(a8, gt_alphas, iter)
+        unk = ops.unknown_mask(guided, _draw_widths(guided.shape[0] * guided.shape[1], 30, False))
+        ret = self._refine_and_fuse(x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W)
+        if self.training and iter >= self.warmup_mask_atten_iter:
             ret["loss_max_atten"] = loss_atten
+        return ret
+
+
+# ------------------------------------------------------------------------------------------- video decoder
+class MaGGIeTempDecoder(MaGGIeDecoder):
+    """`res_shortcut_inst_matt_spconv_temp_22`: ConvGRU on the OS8 features (bidirectional), temporal-difference head,
+    bidirectional alpha fusion, eval-time box cropping.  Reference: decoder/resnet_inst_matt_spconv_temp.py:14-203,
+    module/conv_gru.py:4-70, utils/utils.py:61-84."""
+
+    def __init__(self, temp_method="bi", **kw):
+        super().__init__(**kw)
+        self.temp_method = temp_method.split("_")[0]
+        self.use_fusion = "fusion" in temp_method
+        assert self.temp_method == "bi", "only the live 'bi_fusion' configuration is implemented"
+        gru = nn.Module()
+        gru.ih = seq(nn.Conv2d(256, 256, 3, padding=1), Slot())
+        gru.hh = seq(nn.Conv2d(256, 128, 3, padding=1), Slot())
+        self.os8_temp_module = gru
+        self.diff_module = seq(SNConv(128, 64, 1), nn.BatchNorm2d(64), Slot(), SNConv(64, 32, 3), nn.BatchNorm2d(32), Slot(),
+                               PlainConv(32, 1, 3))
+
+    # -- ConvGRU -------------------------------------------------------------------------------------------
+    def _gru_step(self, x, h):
+        g = self.os8_temp_module
+        C = x.shape[1]
+        rz = torch.sigmoid(ops.conv_bias(torch.cat([x, h], 1), g.ih[0].weight, g.ih[0].bias).float())
+        r, z = rz[:, :C], rz[:, C:]
+        hf = h.float()
+        c = torch.tanh(ops.conv_bias(torch.cat([x, (r * hf).to(x.dtype)], 1), g.hh[0].weight, g.hh[0].bias).float())
+        return ((1 - z) * hf + z * c).to(x.dtype)
+
+    def propagate(self, feat, prev_h=None):
+        """feat [b, n_f, C, h, w] -> (bidirectionally propagated features, forward hidden states) (conv_gru.py:50-70)."""
+        n_f = feat.shape[1]
+        cl = lambda t: t.contiguous(memory_format=torch.channels_last)
+        h = cl(prev_h.to(feat.dtype)) if prev_h is not None else torch.zeros_like(cl(feat[:, 0]))
+        fw = []
+        for k in range(n_f):
+            h = self._gru_step(cl(feat[:, k]), h)
+            fw.append(h)
+        hb, bw = fw[-1], [None] * (n_f - 1)
+        for k in range(n_f - 2, -1, -1):
+            hb = self._gru_step(cl(feat[:, k]), hb)
+            bw[k] = hb
+        out = [((fw[k].float() + bw[k].float()) / 2).to(feat.dtype) for k in range(n_f - 1)] + [fw[-1]]
+        return torch.stack(out, 1), torch.stack(fw, 1)
+
+    def dense_stage(self, x, fea4, fea5, mask_os8, gt_os8, mem_feat=None):
+        x = self.layer1(x) + fea5
+        x = self.layer2(x) + fea4
+        return self.refine_OS8(x, mask_os8, gt_os8, temporal_fn=lambda f: self.propagate(f, mem_feat))
+
+    # -- temporal difference + fusion ----------------------------------------------------------------------
+    def _diff(self, x):
+        dm, t = self.diff_module, self.training
+        x = ops.conv_bn_act(x, dm[0].weight(), dm[1], t, padding=0, act="relu")
+        x = ops.conv_bn_act(x, dm[3].weight(), dm[4], t, act="relu")
+        d = ops.conv_bias(x, dm[6].weight, None).float()
+        return F.interpolate(d, scale_factor=8.0, mode="bilinear", align_corners=False)
+
+    def bidirectional_fusion(self, feat, preds):
+        n_f = feat.shape[1]
+        cat = lambda a, c: torch.cat([feat[:, a], feat[:, c]], 1).contiguous(memory_format=torch.channels_last)
+        fd, fp = [], [preds[:, 0]]
+        for i in range(1, n_f):
+            d = self._diff(cat(i - 1, i))
+            fd.append(d)
+            s = torch.sigmoid(d)
+            fp.append(fp[-1] * (1 - s) + preds[:, i] * s)
+        fd = torch.stack([torch.zeros_like(fd[0])] + fd, 1)
+        bd, bp = [], [preds[:, n_f - 1]]
+        for i in range(n_f - 1, 0, -1):
+            d = self._diff(cat(i, i - 1))
+            bd.append(d)
+            s = torch.sigmoid(d)
+            bp.append(bp[-1] * (1 - s) + preds[:, i - 1] * s)
+        bp, bd = bp[::-1], bd[::-1]
+        bd = torch.stack(bd + [torch.zeros_like(bd[-1])], 1)
+        fused = [fp[0]] + [(fp[i] + bp[i]) / 2 for i in range(1, n_f - 1)] + [bp[n_f - 1]]
+        return fd, bd, torch.stack(fused, 1)
+
+    @staticmethod
+    def _gaussian_smoothing(x, sigma=3):
+        """utils.py:61-84 (g*g broadcast kernel, un-normalised; crop; bilinear resize back)."""
+        ks, pad = sigma * 2 + 1, sigma
+        grid = torch.arange(ks, device=x.device).float() - ks // 2
+        g = torch.exp(-grid ** 2 / (2 * sigma ** 2))
+        g = g / g.sum()
+        k = (g * g).view(1, 1, 1, ks).expand(x.shape[1], 1, ks, ks).contiguous()
+        y = F.conv2d(F.pad(x, (pad, pad, pad, pad)), k, groups=x.shape[1])[:, :, pad:-pad, pad:-pad]
+        return F.interpolate(y, size=x.shape[-2:], mode="bilinear", align_corners=False)
+
+    @staticmethod
+    def _loss_dtssd(pred, gt, mask):
+        diff = ((pred[:, 1:] - pred[:, :-1]) - (gt[:, 1:] - gt[:, :-1])) ** 2 * mask[:, 1:]
+        return diff.sum() / torch.sum(mask[:, 1:] + 1e-6)
+
+    def forward(self, dense_out, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, spar_gt=None, **_):
+        H, W = image_hw
+        t = self.training
+        os8_logits, x, queries, loss_atten, hidden = dense_out
+        feat_os8 = x.reshape(b, n_f, *x.shape[1:]).detach()
+        a8 = self._os8_alpha(os8_logits, masks, n_i, H, W)
+        guided, use_gt = self._choose_guidance(a8, gt_alphas, iter)
+        if not t:
+            a8 = torch.where(a8 >= 0.95, torch.ones_like(a8), a8)
+            guided = a8
+        unk = ops.unknown_mask(guided, _draw_widths(guided.shape[0] * guided.shape[1], 30, False))
+        if not t:
+            # keep only a +-30 px box around each instance's smoothed coarse alpha (one D2H of the box table)
+            sm = self._gaussian_smoothing(a8, 3) > 0.1
+            ys, xs = sm.any(3), sm.any(2)                                           # [B, n_i, H], [B, n_i, W]
+            first = lambda m: m.float().argmax(-1)
+            last = lambda m: m.shape[-1] - 1 - m.flip(-1).float().argmax(-1)
+            box = torch.stack([first(ys), last(ys), first(xs), last(xs), ys.any(-1).long()], -1).cpu()
+            keep = torch.ones(a8.shape, dtype=torch.bool)
+            for i in range(a8.shape[0]):
+                for j in range(a8.shape[1]):
+                    y0, y1, x0, x1, ok = (int(v) for v in box[i, j])
+                    if not ok:
+                        continue
+                    keep[i, j] = False
+                    keep[i, j, max(0, y0 - 30):min(y1 + 30, H), max(0, x0 - 30):min(x1 + 30, W)] = True
+            keep = keep.to(a8.device)
+            unk = unk * keep
+            a8 = a8 * keep
+        ret = self._refine_and_fuse(x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W)
+        ret["mem_feat"] = hidden
+        a = ret["refined_masks"]
+        fd, bd, fused = self.bidirectional_fusion(feat_os8, a.reshape(b, n_f, *a.shape[1:]))
+        ret["temp_alpha"], ret["diff_forward"], ret["diff_backward"] = fused, torch.sigmoid(fd), torch.sigmoid(bd)
+        if t:
+            ret["loss_max_atten"] = loss_atten
+            sg = spar_gt.reshape(fd.shape[0], -1, *spar_gt.shape[1:])
+            bce = F.binary_cross_entropy_with_logits(fd[:, 1:, 0], sg[:, 1:, 0]) + \
+                F.binary_cross_entropy_with_logits(bd[:, :-1, 0], sg[:, 1:, 0])
+            ones = torch.ones_like(sg[:, 1:, 0:1])
+            dtf = self._loss_dtssd(torch.sigmoid(fd[:, 1:]), sg[:, 1:, 0:1], ones)
+            dtb = self._loss_dtssd(torch.sigmoid(bd[:, :-1]), sg[:, 1:, 0:1], ones)
+            ret.update(loss_temp_bce=bce, loss_temp_dtssd=dtf + dtb, loss_temp=(bce + dtf + dtb) * 0.25)
         return ret

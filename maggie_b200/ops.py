@@ -193,7 +193,8 @@ def spectral_weight(w_bar, u, v):
         un = un / (un.norm() + 1e-12)
         v.copy_(vn)
         u.copy_(un)
-    sigma = torch.dot(u.detach(), torch.mv(w_bar.reshape(h, -1), v.detach()))
+    # un / vn (fresh tensors) rather than the parameters: a layer may run several times per forward (video diff head)
+    sigma = torch.dot(un, torch.mv(w_bar.reshape(h, -1), vn))
     return w_bar / sigma
 
 
@@ -214,6 +215,20 @@ def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="rel
 
     return dense.conv_bn_act(x, w, bn, training, stride=stride, padding=padding, dilation=dilation, act=act,
                              act_first=act_first, residual=residual, transposed=transposed, res_up=res_up)
+
+
+def conv_bias(x, w, bias=None, *, padding=1):
+    """Plain conv + bias (ConvGRU gates, temporal-difference head).  Output channels are padded to the tensor-core
+    granularity (16) here and sliced back.  NATIVE (K2 forward / dgrad, K4 wgrad)."""
+    from . import dense
+
+    co = w.shape[0]
+    if co % 16:
+        pad = 16 - co % 16
+        w = F.pad(w, (0, 0, 0, 0, 0, 0, 0, pad))
+        bias = F.pad(bias, (0, pad)) if bias is not None else None
+    y = dense.conv_bias(x, w, bias, padding=padding)
+    return y[:, :co] if y.shape[1] != co else y
 
 
 def linear(x, w, b=None):

@@ -180,7 +180,7 @@ def pool_mask(x, stride, use_max):
     return x.view(*shp[:-2], *x.shape[-2:])
 
 
-def imd(P, feat, mask, gt_mask, training, n_block=2, max_inst=10, use_id_pe=True):
+def imd(P, feat, mask, gt_mask, training, n_block=2, max_inst=10, use_id_pe=True, temporal_hook=None, captured=None):
     """instance_matte_decoder.py:112-306 with use_mask_atten=False, atten_stride=1, no temporal PE.
     feat [b*n_f,128,h,w]; mask [b,n_f,n_i,H,W] {0,1}. Returns (logits [b*n_f,10,h,w], out_feat [b*n_f,64,h,w],
     tokens [b,10,64], max_loss)."""
@@ -241,14 +241,26 @@ def imd(P, feat, mask, gt_mask, training, n_block=2, max_inst=10, use_id_pe=True
     max_loss = max_loss / (n_block + 1)
 
     feat = feat.reshape(h, w, n_f, b, -1).permute(3, 2, 4, 0, 1).reshape(b * n_f, -1, h, w)
-    feat = F.conv2d(feat, P[pre + "conv.0.weight"], padding=1)
-    feat = lrelu(bn(P, pre + "conv.1", feat, training))
-    feat = F.conv2d(feat, P[pre + "conv.3.weight"])
-    feat = lrelu(bn(P, pre + "conv.4", feat, training))
+
+    def smooth(z):
+        z = F.conv2d(z, P[pre + "conv.0.weight"], padding=1)
+        z = lrelu(bn(P, pre + "conv.1", z, training))
+        z = F.conv2d(z, P[pre + "conv.3.weight"])
+        return lrelu(bn(P, pre + "conv.4", z, training))
+
+    out_feat = None
+    if temporal_hook is not None:            # instance_matte_decoder.py:280-288
+        temporal = temporal_hook(feat, b, n_f)
+        out_feat = smooth(feat)
+        feat = smooth(temporal)
+    else:
+        feat = smooth(feat)
 
     tokens = F.linear(tokens, P[pre + "final_mlp.layers.0.weight"], P[pre + "final_mlp.layers.0.bias"])
     tokens = layer_norm(P, pre + "decoder_norm", tokens.permute(1, 0, 2))      # [b,10,64]
     out = torch.einsum("bqc,btchw->btqhw", tokens, feat.reshape(b, n_f, -1, h, w)).flatten(0, 1)
+    if temporal_hook is not None:
+        return out, out_feat, tokens, max_loss, captured["hidden"]
     return out, feat, tokens, max_loss
 
 
@@ -576,3 +588,252 @@ def forward(P, batch, training, cfg, return_stages=False, p_drop=0.1):
         return (out, L, stages) if return_stages else (out, L)
     out = {k: v[:, :, :n_i] for k, v in out.items()}
     return (out, stages) if return_stages else out
+
+
+# ============================================================================================== video model
+# MaGGIe_Temp (arch/maggie_temp.py), ResShortCut_InstMattSpconv_BiTempSpar_Dec
+# (decoder/resnet_inst_matt_spconv_temp.py), ConvGRU (module/conv_gru.py), gaussian_smoothing (utils/utils.py:61-84),
+# loss_dtSSD (loss.py:7-16,41-44).
+def conv_gru_step(P, pre, x, h):
+    """conv_gru.py:23-28."""
+    C = x.shape[1]
+    rz = torch.sigmoid(F.conv2d(torch.cat([x, h], 1), P[pre + ".ih.0.weight"], P[pre + ".ih.0.bias"], padding=1))
+    r, z = rz.split(C, dim=1)
+    c = torch.tanh(F.conv2d(torch.cat([x, r * h], 1), P[pre + ".hh.0.weight"], P[pre + ".hh.0.bias"], padding=1))
+    return (1 - z) * h + z * c
+
+
+def propagate_bi(P, pre, feat, prev_h):
+    """conv_gru.py:50-70 with temp_method='bi'. feat [b,n_f,C,h,w] -> (feat', hidden states [b,n_f,C,h,w])."""
+    b, n_f = feat.shape[:2]
+    h = prev_h if prev_h is not None else torch.zeros_like(feat[:, 0])
+    fw = []
+    for t in range(n_f):
+        h = conv_gru_step(P, pre, feat[:, t], h)
+        fw.append(h)
+    hidden = torch.stack(fw, 1)
+    hb, bw = fw[-1], [None] * (n_f - 1)
+    for t in range(n_f - 2, -1, -1):
+        hb = conv_gru_step(P, pre, feat[:, t], hb)
+        bw[t] = hb
+    out = [(fw[t] + bw[t]) / 2 for t in range(n_f - 1)] + [fw[-1]]
+    return torch.stack(out, 1), hidden
+
+
+def imd_temp(P, feat, mask, gt_mask, training, mem_feat, **kw):
+    """instance_matte_decoder.py:112-306 with aggregate_mem_fn: the smoothing convs run twice (no-temporal features,
+    then ConvGRU-propagated features)."""
+    captured = {}
+
+    def hook(x, b, n_f):
+        captured["no_temp"] = x
+        f5, hidden = propagate_bi(P, "decoder.os8_temp_module", x.reshape(b, n_f, *x.shape[1:]), mem_feat)
+        captured["hidden"] = hidden
+        return f5.flatten(0, 1)
+
+    return imd(P, feat, mask, gt_mask, training, temporal_hook=hook, captured=captured, **kw)
+
+
+def gaussian_smoothing(x, sigma=3):
+    """utils.py:61-84 (not a true 2-D Gaussian: the kernel is g*g broadcast over rows, un-normalised; then the
+    result is cropped by the padding once more and bilinearly resized back)."""
+    ks = sigma * 2 + 1
+    pad = ks // 2
+    grid = torch.arange(ks).float() - ks // 2
+    g = torch.exp(-grid ** 2 / (2 * sigma ** 2))
+    g = g / g.sum()
+    k = (g.view(1, 1, -1) * g.view(1, 1, -1)).expand(x.shape[1], 1, ks, ks).type_as(x)
+    y = F.conv2d(F.pad(x, (pad, pad, pad, pad)), k, groups=x.shape[1])
+    y = y[:, :, pad:-pad, pad:-pad]
+    return F.interpolate(y, size=x.shape[-2:], mode="bilinear", align_corners=False)
+
+
+def diff_module(P, x, training):
+    d = "decoder.diff_module."
+    x = F.relu(bn(P, d + "1", F.conv2d(x, sn_weight(P, d + "0")), training))
+    x = F.relu(bn(P, d + "4", F.conv2d(x, sn_weight(P, d + "3"), padding=1), training))
+    return F.conv2d(x, P[d + "6.weight"], padding=1)
+
+
+def bidirectional_fusion(P, feat, preds, training):
+    """resnet_inst_matt_spconv_temp.py:35-79. feat [b,n_f,64,h,w] (detached), preds [b,n_f,n_i,H,W]."""
+    n_f = feat.shape[1]
+    up = lambda d: F.interpolate(d, scale_factor=8.0, mode="bilinear", align_corners=False)
+    fdiffs, fpreds = [], [preds[:, 0]]
+    for i in range(1, n_f):
+        d = up(diff_module(P, torch.cat([feat[:, i - 1], feat[:, i]], 1), training))
+        fdiffs.append(d)
+        fpreds.append(fpreds[-1] * (1 - d.sigmoid()) + preds[:, i] * d.sigmoid())
+    fdiffs = torch.stack([torch.zeros_like(fdiffs[0])] + fdiffs, 1)
+    bdiffs, bpreds = [], [preds[:, n_f - 1]]
+    for i in range(n_f - 1, 0, -1):
+        d = up(diff_module(P, torch.cat([feat[:, i], feat[:, i - 1]], 1), training))
+        bdiffs.append(d)
+        bpreds.append(bpreds[-1] * (1 - d.sigmoid()) + preds[:, i - 1] * d.sigmoid())
+    bpreds, bdiffs = bpreds[::-1], bdiffs[::-1]
+    bdiffs = torch.stack(bdiffs + [torch.zeros_like(bdiffs[-1])], 1)
+    fused = [fpreds[0]] + [(fpreds[i] + bpreds[i]) / 2 for i in range(1, n_f - 1)] + [bpreds[n_f - 1]]
+    return fdiffs, bdiffs, torch.stack(fused, 1)
+
+
+def loss_dtssd(pred, gt, mask):
+    """loss.py:7-16."""
+    diff = ((pred[:, 1:] - pred[:, :-1]) - (gt[:, 1:] - gt[:, :-1])) ** 2 * mask[:, 1:]
+    return diff.sum() / torch.sum(mask[:, 1:] + 1e-6)
+
+
+def decoder_temp(P, emb, fea, image, b, n_f, n_i, masks, it, gt_alphas, spar_gt, training, cfg, mem_feat=None, p_drop=0.1):
+    """resnet_inst_matt_spconv_temp.py:81-203."""
+    d = "decoder."
+    da = cfg["decoder_args"]
+    fea1, fea2, fea3, fea4, fea5 = fea
+    masks5 = masks.reshape(b, n_f, n_i, masks.shape[2], masks.shape[3])
+    valid = (masks5.flatten(0, 1).sum((2, 3), keepdim=True) > 0)
+    gt_masks = (gt_alphas > 0).reshape(b, n_f, n_i, *gt_alphas.shape[2:]) if training else None
+    x = dec_block(P, d + "layer1.0", emb, True, training)
+    x = dec_block(P, d + "layer1.1", x, False, training) + fea5
+    x = dec_block(P, d + "layer2.0", x, True, training)
+    x = dec_block(P, d + "layer2.1", x, False, training)
+    x = dec_block(P, d + "layer2.2", x, False, training) + fea4
+    h, w = image.shape[-2:]
+    x_os8, x, queries, loss_atten, hidden = imd_temp(P, x, masks5, gt_masks, training, mem_feat, n_block=da["atten_block"],
+                                                     max_inst=da["max_inst"], use_id_pe=da["use_id_pe"])
+    feat_os8 = x.view(b, n_f, *x.shape[1:]).detach()
+    x_os8 = (torch.tanh(F.interpolate(x_os8, scale_factor=8.0, mode="bilinear", align_corners=False)) + 1.0) / 2.0
+    x_os8 = x_os8 * valid if training else x_os8[:, :n_i]
+    guided, use_gt = x_os8, False
+    wd = da["warmup_detail_iter"]
+    if training and (it < wd or x_os8.sum() == 0 or (it < wd * 3 and random.random() < 0.5)):
+        guided, use_gt = gt_alphas.clone(), True
+    if not training:
+        x_os8[x_os8 >= 0.95] = 1.0
+    unk = unknown(guided, 30)
+    if not training:
+        smooth = gaussian_smoothing(x_os8, sigma=3)
+        for i in range(smooth.shape[0]):
+            for j in range(n_i):
+                ys, xs = torch.nonzero(smooth[i, j] > 0.1, as_tuple=True)
+                if len(ys) == 0:
+                    continue
+                y0, y1 = max(0, int(ys.min()) - 30), min(int(ys.max()) + 30, h)
+                x0, x1 = max(0, int(xs.min()) - 30), min(int(xs.max()) + 30, w)
+                tm = torch.zeros((h, w), dtype=torch.bool)
+                tm[y0:y1, x0:x1] = True
+                unk[i, j] = unk[i, j] * tm
+                x_os8[i, j] = x_os8[i, j] * tm
+    if unk.max() == 0 and training:
+        unk[:, :, 200:250, 200:250] = 1
+    if unk.sum() > 0 or training:
+        q = queries[:, None].expand(-1, n_f, -1, -1).reshape(b * n_f, *queries.shape[1:])
+        os4, os1, _ = predict_details(P, x, unk, q, fea1, fea2, fea3, training, p_drop)
+        os4 = os4.reshape(b * n_f, guided.shape[1], *os4.shape[-2:])
+        os1 = os1.reshape(b * n_f, guided.shape[1], *os1.shape[-2:])
+        os4 = (torch.tanh(F.interpolate(os4, scale_factor=4.0, mode="bilinear", align_corners=False)) + 1.0) / 2.0
+        os1 = (torch.tanh(os1) + 1.0) / 2.0
+    else:
+        os4 = torch.zeros((b * n_f, x_os8.shape[1], h, w))
+        os1 = torch.zeros_like(os4)
+    ret = dict(alpha_os1=os1, alpha_os4=os4, alpha_os8=x_os8)
+    a = x_os8
+    w4 = ((unknown(a, 27, training) * unk) > 0).type(a.dtype)
+    a = os4 * w4 + a * (1 - w4)
+    w1 = ((unknown(a, 15, training) * unk) > 0).type(a.dtype)
+    a = os1 * w1 + a * (1 - w1)
+    ret["refined_masks"], ret["detail_mask"], ret["mem_feat"] = a, unk, hidden
+    if use_gt:
+        w4 = unknown(gt_alphas, 30, training) * unk
+        w1 = unknown(gt_alphas, 15, training) * unk
+    ret["weight_os4"], ret["weight_os1"] = w4, w1
+    fd, bd, fused = bidirectional_fusion(P, feat_os8, a.view(b, n_f, *a.shape[1:]), training)
+    ret["temp_alpha"], ret["diff_forward"], ret["diff_backward"] = fused, fd.sigmoid(), bd.sigmoid()
+    if training:
+        ret["loss_max_atten"] = loss_atten
+        sg = spar_gt.view(fd.shape[0], -1, *spar_gt.shape[1:])
+        bce = F.binary_cross_entropy_with_logits(fd[:, 1:, 0], sg[:, 1:, 0]) + \
+            F.binary_cross_entropy_with_logits(bd[:, :-1, 0], sg[:, 1:, 0])
+        ones = torch.ones_like(sg[:, 1:, 0:1])
+        dtf = loss_dtssd(fd[:, 1:].sigmoid(), sg[:, 1:, 0:1], ones)
+        dtb = loss_dtssd(bd[:, :-1].sigmoid(), sg[:, 1:, 0:1], ones)
+        ret.update(loss_temp_bce=bce, loss_temp_dtssd=dtf + dtb, loss_temp=(bce + dtf + dtb) * 0.25)
+    return ret
+
+
+def forward_video(P, batch, training, cfg, mem_feat=None, prev_pred=None, p_drop=0.1):
+    """MaGGIe_Temp.forward (arch/maggie_temp.py:34-77 on top of arch/maggie.py:63-139)."""
+    num_masks = cfg["encoder_args"]["num_mask"]
+    x, masks = batch["image"], batch["mask"]
+    alphas, trans = batch.get("alpha"), batch.get("transition")
+    b, n_f, _, h, w = x.shape
+    n_i = masks.shape[2]
+    x = x.view(-1, 3, h, w)
+    masks = F.interpolate(masks.flatten(0, 1), size=(h, w), mode="nearest") if masks.shape[-1] != w else masks.view(-1, n_i, h, w)
+    chosen, inp_masks = None, masks
+    if num_masks - n_i > 0:
+        if not training:
+            inp_masks = torch.cat([masks, torch.zeros(b * n_f, num_masks - n_i, h, w)], 1)
+        else:
+            chosen = np.random.choice(num_masks, n_i, replace=False)
+            inp_masks = torch.zeros(b * n_f, num_masks, h, w)
+            inp_masks[:, chosen] = masks
+            masks = inp_masks
+            na, nt = torch.zeros(b, n_f, num_masks, h, w), torch.zeros(b, n_f, num_masks, h, w)
+            na[:, :, chosen], nt[:, :, chosen] = alphas, trans
+            alphas, trans, n_i = na, nt, num_masks
+    if alphas is not None:
+        alphas, trans = alphas.view(-1, n_i, h, w), trans.view(-1, n_i, h, w)
+    emb, fea, image = encoder(P, torch.cat([x, inp_masks], 1), training)
+    emb = aspp(P, emb, training)
+    pred = decoder_temp(P, emb, fea, image, b, n_f, n_i, masks, batch.get("iter", 0), alphas, trans, training, cfg, mem_feat, p_drop)
+    alpha_pred = pred.pop("refined_masks")
+    w4 = w1 = pred["detail_mask"].type(alpha_pred.dtype)
+    if training and np.random.rand() < 0.75:
+        w4, w1 = pred.pop("weight_os4"), pred.pop("weight_os1")
+    n_out = num_masks if (training and num_masks > 0) else n_i
+    v5 = lambda t: t[:, :n_out].view(b, n_f, n_out, h, w)
+    out = {k: v5(pred[k]) for k in ("alpha_os1", "alpha_os4", "alpha_os8")}
+    out["refined_masks"], out["detail_mask"] = v5(alpha_pred), v5(pred["detail_mask"])
+    db, df, ta = pred.pop("diff_backward"), pred.pop("diff_forward"), pred.pop("temp_alpha")
+    out["diff_pred_backward"], out["diff_pred_forward"], out["temp_alpha"] = db.repeat(1, 1, n_i, 1, 1), df.repeat(1, 1, n_i, 1, 1), ta
+    if training:
+        valid = (trans.sum((2, 3), keepdim=True) > 0).float()
+        for k, v in pred.items():
+            if "loss" in k or "mem_" in k:
+                continue
+            pred[k] = v * valid
+        L = compute_loss(pred, w4, w1, alphas, cfg)
+        if cfg["loss_dtSSD_w"] > 0:
+            shp = (b, n_f, num_masks, h, w)
+            r = lambda t: t.reshape(*shp)
+            d1 = loss_dtssd(r(pred["alpha_os1"]), r(alphas), r(w1))
+            d4 = loss_dtssd(r(pred["alpha_os4"]), r(alphas), r(w4))
+            w8 = torch.ones_like(pred["alpha_os8"]) * (alphas.sum((2, 3), keepdim=True) > 0)
+            if cfg["loss_reweight_os8"]:
+                ug = (alphas <= 254.0 / 255.0) & (alphas >= 1.0 / 255.0)
+                up = (pred["alpha_os8"] <= 254.0 / 255.0) & (pred["alpha_os8"] >= 1.0 / 255.0)
+                w8 = (ug | up).type(w8.dtype) + w8
+            d8 = loss_dtssd(r(pred["alpha_os8"]), r(alphas), r(w8))
+            L.update(loss_dtSSD_os1=d1, loss_dtSSD_os4=d4, loss_dtSSD_os8=d8, loss_dtSSD=d1 * 2 + d4 + d8)
+            L["total"] = L["total"] + L["loss_dtSSD"] * cfg["loss_dtSSD_w"]
+        if cfg["loss_atten_w"] > 0:
+            L["loss_max_atten"] = pred["loss_max_atten"]
+            L["total"] = L["total"] + L["loss_max_atten"] * cfg["loss_atten_w"]
+        L.update(loss_temp_bce=pred["loss_temp_bce"], loss_temp=pred["loss_temp"], loss_temp_dtssd=pred["loss_temp_dtssd"])
+        L["total"] = L["total"] + pred["loss_temp"]
+        if chosen is not None:
+            out = {k: v[:, :, chosen] for k, v in out.items()}
+        return out, L
+    out = {k: v[:, :, :n_i] for k, v in out.items()}
+    out["mem_feat"] = pred["mem_feat"]
+    # alpha-matte level aggregation over the 3-frame window (maggie_temp.py:37-75)
+    al = out["refined_masks"]
+    prev = al[:, 0] if prev_pred is None else prev_pred
+    nxt = al[:, -1]
+    dfw = (out["diff_pred_forward"] > 0.5).float()
+    dbw = (out["diff_pred_backward"] > 0.5).float()
+    p01 = prev * (1 - dfw[:, 1]) + al[:, 1] * dfw[:, 1]
+    p21 = nxt * (1 - dbw[:, 1]) + al[:, 1] * dbw[:, 1]
+    diff = torch.abs(p01 - p21)
+    p01[diff > 0.0] = al[:, 1][diff > 0.0]
+    al[:, 1] = p01
+    al[:, 2] = p01 * (1 - dfw[:, 2]) + nxt * dfw[:, 2]
+    return out

@@ -28,7 +28,13 @@ CASES = {
     # sees only `b` values per channel), inst_spec dropout off (CUDA and CPU dropout streams differ)
     "train_b8_128_2inst_nodrop": (dict(b=8, n_f=1, n_i=2, H=128, W=128, edge_px=4.0, seed=779, train=True, it=100000), True),
 }
-NO_DROPOUT = {"train_b8_128_2inst_nodrop"}
+# video model (MaGGIe_Temp): 3-frame eval window (with and without prev_pred) and a training clip
+VIDEO_CASES = {
+    "video_eval_3f_128x192_2inst": (dict(b=1, n_f=3, n_i=2, H=128, W=192, edge_px=4.0, seed=501), False),
+    "video_train_4f_128_2inst_nodrop": (dict(b=2, n_f=4, n_i=2, H=128, W=128, edge_px=4.0, seed=502, train=True, it=100000), True),
+}
+CASES.update(VIDEO_CASES)
+NO_DROPOUT = {"train_b8_128_2inst_nodrop", "video_train_4f_128_2inst_nodrop"}
 RNG_SEED = 2024
 SMALL_GRAD_NUMEL = 2048
 
@@ -39,9 +45,13 @@ def seed_all(seed=RNG_SEED):
     random.seed(seed)
 
 
-def build_reference(training):
+def cfg_for(case):
+    return synth.video_cfg() if case in VIDEO_CASES else synth.model_cfg()
+
+
+def build_reference(training, case=None):
     net = ref_shims.import_reference_network()
-    model, _ = net.build_model(ref_shims.CfgNode(synth.model_cfg()))
+    model, _ = net.build_model(ref_shims.CfgNode(cfg_for(case)))
     model.load_state_dict(synth.synth_state_dict(model.state_dict()), strict=True)
     model.train(training)
     return model
@@ -49,7 +59,7 @@ def build_reference(training):
 
 def run_reference(case):
     kw, training = CASES[case]
-    model = build_reference(training)
+    model = build_reference(training, case)
     if case in NO_DROPOUT:
         model.decoder.inst_spec_layer.dropout.p = 0.0
     batch = synth.make_batch(**kw)
@@ -77,9 +87,11 @@ def run_reference(case):
 def run_oracle(case):
     kw, training = CASES[case]
     net = ref_shims.import_reference_network()
-    tmpl, _ = net.build_model(ref_shims.CfgNode(synth.model_cfg()))
+    tmpl, _ = net.build_model(ref_shims.CfgNode(cfg_for(case)))
     P = synth.synth_state_dict(tmpl.state_dict())
     names = {n for n, p in tmpl.named_parameters() if p.requires_grad}
+    if case in VIDEO_CASES:
+        return run_oracle_video(case, P, names)
     for n in P:
         if training and n in names and P[n].is_floating_point():
             P[n].requires_grad_(True)
@@ -96,12 +108,31 @@ def run_oracle(case):
     return out, None, stages, None, P
 
 
+def run_oracle_video(case, P, names):
+    kw, training = CASES[case]
+    for n in P:
+        if training and n in names and P[n].is_floating_point():
+            P[n].requires_grad_(True)
+    batch = synth.make_batch(**kw)
+    seed_all()
+    stages = {k: torch.zeros(1) for k in ("os8_logits", "os8_feat", "queries", "aspp")}
+    if training:
+        out, loss = O.forward_video(P, batch, True, synth.video_cfg(), p_drop=0.0)
+        loss["total"].backward()
+        grads = {n: p.grad for n, p in P.items() if p.requires_grad and p.grad is not None}
+        return out, loss, stages, grads, P
+    with torch.no_grad():
+        out = O.forward_video(P, batch, False, synth.video_cfg())
+    return out, None, stages, None, P
+
+
 def pack(out, loss, stages, grads, state):
     z = {}
     for k, v in out.items():
         z["out/" + k] = v.detach().float().numpy()
     for k in ("os8_logits", "os8_feat", "queries", "aspp"):
-        z["stage/" + k] = stages[k].detach().float().numpy()
+        if k in stages:
+            z["stage/" + k] = stages[k].detach().float().numpy()
     if loss is not None:
         for k, v in loss.items():
             z["loss/" + k] = np.float64(float(v))

@@ -26,6 +26,13 @@ MODEL_CFG = dict(
 )  # configs/maggie_image.yaml:30-70
 
 
+def video_cfg(**over):
+    """configs/maggie_video.yaml:34-62."""
+    cfg = model_cfg(arch="MaGGIe_Temp", decoder="res_shortcut_inst_matt_spconv_temp_22", loss_dtSSD_w=1.0, **over)
+    cfg["decoder_args"]["temp_method"] = "bi_fusion"
+    return cfg
+
+
 def model_cfg(**over):
     import copy
 

@@ -223,16 +223,20 @@ def matte_loss_sums(a1, a4, a8, target, w1, w4, w8):
     return torch.stack(rows)
 
 
+def conv_bias(x, w, bias=None, *, padding=1):
+    return F.conv2d(x, w.to(x.dtype), None if bias is None else bias.to(x.dtype), padding=padding)
+
+
 @contextlib.contextmanager
 def injected(dtype=torch.float32):
     """Swap the native ops for the references above (CPU container only)."""
     names = ("unknown_mask", "build_sites", "mask_embed", "conv_bn_act", "rows_conv", "rows_head", "gather_dense",
-             "matte_loss_sums", "attention", "COMPUTE_DTYPE")
+             "matte_loss_sums", "attention", "conv_bias", "COMPUTE_DTYPE")
     saved = {n: getattr(ops, n) for n in names}
     ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.conv_bn_act, ops.COMPUTE_DTYPE = \
         unknown_mask, build_sites, mask_embed, conv_bn_act, dtype
     ops.rows_conv, ops.rows_head, ops.gather_dense = rows_conv, rows_head, gather_dense
-    ops.matte_loss_sums, ops.attention = matte_loss_sums, attention
+    ops.matte_loss_sums, ops.attention, ops.conv_bias = matte_loss_sums, attention, conv_bias
     try:
         yield
     finally:

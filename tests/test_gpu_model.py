@@ -124,3 +124,61 @@ def test_cuda_graph_dense_stage_matches_eager():
     assert g0.shape == g1.shape
     rel = ((g0 - g1).abs() / (g0.abs() + 1e-3 * g0.abs().max()))
     assert float(rel.median()) < 2e-2, float(rel.median())
+
+
+# ---- video model (MaGGIe_Temp, BASELINE config C4) -------------------------------------------------------------
+def _video_model(training):
+    m, _ = build_model(CfgNode(synth.video_cfg()))
+    m.load_state_dict(synth.synth_state_dict(m.state_dict()), strict=True)
+    m.decoder.inst_spec_layer.dropout.p = 0.0
+    return m.cuda().train(training)
+
+
+def test_video_eval_parity(golden):
+    case = "video_eval_3f_128x192_2inst"
+    kw, _ = G.CASES[case]
+    z, m = golden(case), _video_model(False)
+    G.seed_all()
+    with torch.no_grad():
+        out = m(_to_dev(synth.make_batch(**kw)), mem_feat=None)
+    out = {k: v.float().cpu().numpy() for k, v in out.items()}
+    d8 = np.abs(out["alpha_os8"] - z["out/alpha_os8"])
+    assert d8.max() < 5e-2 and d8.mean() < 2e-3, (d8.max(), d8.mean())     # 16-bit noise floor + the >=0.95 -> 1 snap
+    assert (out["detail_mask"] == z["out/detail_mask"]).mean() > 0.99
+    assert np.abs(out["mem_feat"] - z["out/mem_feat"]).mean() < 5e-3
+    for k in ("diff_pred_forward", "diff_pred_backward"):
+        assert np.abs(out[k] - z["out/" + k]).mean() < 5e-3, k
+    assert np.abs(out["refined_masks"] - z["out/refined_masks"]).mean() < 5e-3
+
+
+def test_video_train_loss_parity(golden):
+    case = "video_train_4f_128_2inst_nodrop"
+    kw, _ = G.CASES[case]
+    z, m = golden(case), _video_model(True)
+    G.seed_all()
+    out, loss = m(_to_dev(synth.make_batch(**kw)), mem_feat=None)
+    (loss["total"] * 64.0).backward()
+    for k in ("loss_rec_os8", "loss_max_atten", "loss_temp_bce", "loss_dtSSD_os8", "loss_lap_os8"):
+        ref = float(z["loss/" + k])
+        assert abs(float(loss[k]) - ref) < 0.05 * max(1.0, abs(ref)), (k, float(loss[k]), ref)
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    gru = m.decoder.os8_temp_module.ih[0].weight.grad
+    assert gru is not None and float(gru.abs().sum()) > 0
+
+
+def test_video_c4_shape_clip():
+    """BASELINE config C4: one 5-frame 480x832 clip, 2 instances - eval window of 3 and a training step."""
+    m = _video_model(False)
+    ev = _to_dev(synth.make_batch(b=1, n_f=3, n_i=2, H=480, W=832, edge_px=6.0, seed=9))
+    with torch.no_grad():
+        out = m(ev, mem_feat=None)
+        out2 = m(ev, mem_feat=None, prev_pred=out["refined_masks"][:, 1])
+    assert out["refined_masks"].shape == (1, 3, 2, 480, 832) and out["mem_feat"].shape == (1, 3, 128, 60, 104)
+    assert bool(torch.isfinite(out2["refined_masks"]).all())
+    m.train()
+    tr = _to_dev(synth.make_batch(b=1, n_f=5, n_i=2, H=480, W=832, edge_px=6.0, seed=9, train=True, it=1))
+    G.seed_all()
+    o, loss = m(tr, mem_feat=None)
+    (loss["total"] * 64.0).backward()
+    assert o["temp_alpha"].shape[:2] == (1, 5) and np.isfinite(float(loss["total"]))
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)

@@ -68,3 +68,50 @@ def test_train_step_matches_golden(case, golden):
         if "gradnorm/" + k in z:
             ref = float(z["gradnorm/" + k])
             assert abs(float(p.grad.double().norm()) - ref) < 2e-2 * ref + 1e-6, k
+
+
+# ---- video model (MaGGIe_Temp) ---------------------------------------------------------------------------------
+def _video_model(training):
+    m, _ = build_model(CfgNode(synth.video_cfg()))
+    m.load_state_dict(synth.synth_state_dict(m.state_dict()), strict=True)
+    m.decoder.inst_spec_layer.dropout.p = 0.0
+    return m.train(training)
+
+
+def test_video_state_dict_matches_reference():
+    z = np.load(G.GOLDEN_DIR + "/state_shapes_video.npz")
+    sd = _video_model(False).state_dict()
+    assert set(sd) == set(z.files) and len(sd) == 640
+    assert all(tuple(sd[k].shape) == tuple(z[k]) for k in z.files)
+
+
+def test_video_eval_matches_golden(golden):
+    case = "video_eval_3f_128x192_2inst"
+    kw, _ = G.CASES[case]
+    z, m = golden(case), _video_model(False)
+    G.seed_all()
+    with ops_ref.injected(), torch.no_grad():
+        out = m(synth.make_batch(**kw), mem_feat=None)
+    assert set(out) == {"alpha_os1", "alpha_os4", "alpha_os8", "refined_masks", "detail_mask", "diff_pred_backward",
+                        "diff_pred_forward", "temp_alpha", "mem_feat"}
+    assert (out["detail_mask"].numpy() == z["out/detail_mask"]).all()
+    for k in out:
+        if k != "detail_mask":
+            assert np.abs(out[k].float().numpy() - z["out/" + k]).max() < 1e-4, k
+
+
+def test_video_train_matches_golden(golden):
+    case = "video_train_4f_128_2inst_nodrop"
+    kw, _ = G.CASES[case]
+    z, m = golden(case), _video_model(True)
+    G.seed_all()
+    with ops_ref.injected():
+        out, loss = m(synth.make_batch(**kw), mem_feat=None)
+        loss["total"].backward()
+    for k, v in loss.items():
+        ref = float(z["loss/" + k])
+        assert abs(float(v) - ref) < 3e-4 * max(1.0, abs(ref)), k
+    for k, p in m.named_parameters():
+        if "gradnorm/" + k in z:
+            ref = float(z["gradnorm/" + k])
+            assert abs(float(p.grad.double().norm()) - ref) < 2e-2 * ref + 1e-6, k
