@@ -22,30 +22,38 @@ constexpr int MAX_TAPS = MG_CONV_MAX_TAPS;
 
 struct WArgs {
     int tap_dy[MAX_TAPS], tap_dx[MAX_TAPS], tap_koff[MAX_TAPS];
+    int n_taps, taps_per_cta;
     int sy, sx, ays, ay0, axs, ax0;
     int th, tw, tiles_y, tiles_x, n_tiles, tiles_per_cta;
-    int Co, Ci, Ktot, BN, atomw_b, swz_b, n_atoms_b, co_tiles, stages;
+    int Co, Ci, Ktot, BN, atomw_b, swz_b, n_atoms_b, co_tiles, stages, a_atoms;  // a_atoms: real 64-channel atoms of dY (1|2)
     float* dw;
 };
 
+// One CTA: a range of 128-pixel tiles (split-K) x a group of taps x one (Co tile, Ci tile).  Per pixel tile the dY
+// tile is loaded ONCE and multiplied with the shifted X tile of every tap of the group (accumulators side by side in
+// TMEM: taps_per_cta * BN columns).  A layer with <= 64 output channels has only one real 64-channel atom of dY; the
+// second atom of the M = 128 operand is a shared zero region reached through the descriptor's leading-byte offset.
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int a_bytes = 2 * 128 * 128;                       // two 64-channel atoms x 128 pixels
-    const int b_atom_bytes = 128 * a.swz_b, b_bytes = a.n_atoms_b * b_atom_bytes;
+    const int atom_bytes = 128 * 128;
+    const int a_bytes = a.a_atoms * atom_bytes;
+    const int b_atom_bytes = 128 * a.swz_b, b_tile = a.n_atoms_b * b_atom_bytes, b_bytes = a.taps_per_cta * b_tile;
     uint8_t* sA = smem;
     uint8_t* sB = sA + a.stages * a_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + a.stages * b_bytes);
+    uint8_t* sZ = sB + a.stages * b_bytes;                      // 16 KB of zeros (only read when a_atoms == 1)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sZ + atom_bytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * a.stages, tfull = empty0 + 8 * a.stages;
-    const int tap = blockIdx.y;
+    const int t0 = blockIdx.y * a.taps_per_cta, nt = min(a.taps_per_cta, a.n_taps - t0);
     const int co0 = (blockIdx.z % a.co_tiles) * 128, ci0 = (blockIdx.z / a.co_tiles) * a.BN;
     const int t_begin = blockIdx.x * a.tiles_per_cta, t_end = min(t_begin + a.tiles_per_cta, a.n_tiles);
     const int nk = t_end - t_begin;
-    const uint32_t tmem_cols = a.BN < 32 ? 32 : a.BN;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(nt * a.BN)) tmem_cols <<= 1;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmDY);
@@ -58,6 +66,10 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    if (a.a_atoms == 1) {
+        for (int i = threadIdx.x; i < atom_bytes / 16; i += THREADS) reinterpret_cast<uint4*>(sZ)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -74,30 +86,37 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
                     const int ty = t % a.tiles_y, img = t / a.tiles_y;
                     const int y0 = ty * a.th, x0 = tx * a.tw;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
-                    mbar_expect_tx(full0 + 8 * s, a_bytes + b_bytes);
+                    mbar_expect_tx(full0 + 8 * s, a_bytes + nt * b_tile);
                     const uint32_t dstA = smem_u32(sA + s * a_bytes), dstB = smem_u32(sB + s * b_bytes);
-                    for (int j = 0; j < 2; ++j)
-                        tma_load_4d(dstA + j * 128 * 128, &tmDY, full0 + 8 * s, co0 + 64 * j, x0 * a.axs + a.ax0,
+                    for (int j = 0; j < a.a_atoms; ++j)
+                        tma_load_4d(dstA + j * atom_bytes, &tmDY, full0 + 8 * s, co0 + 64 * j, x0 * a.axs + a.ax0,
                                     y0 * a.ays + a.ay0, img);
-                    for (int j = 0; j < a.n_atoms_b; ++j)
-                        tma_load_4d(dstB + j * b_atom_bytes, &tmX, full0 + 8 * s, ci0 + a.atomw_b * j,
-                                    x0 * a.sx + a.tap_dx[tap], y0 * a.sy + a.tap_dy[tap], img);
+                    for (int tt = 0; tt < nt; ++tt)
+                        for (int j = 0; j < a.n_atoms_b; ++j)
+                            tma_load_4d(dstB + tt * b_tile + j * b_atom_bytes, &tmX, full0 + 8 * s, ci0 + a.atomw_b * j,
+                                        x0 * a.sx + a.tap_dx[t0 + tt], y0 * a.sy + a.tap_dy[t0 + tt], img);
                 }
             }
         } else if (warp == 1) {
             if (lane == 0) {
                 const uint32_t idesc = instr_desc_f16(128, a.BN, 1, 1);  // both operands MN-major
                 const uint32_t layB = swizzle_layout(a.swz_b);
+                const uint32_t zbase = smem_u32(sZ);
                 for (int i = 0; i < nk; ++i) {
                     const int s = i % a.stages, ph = (i / a.stages) & 1;
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
-                    const uint32_t abase = smem_u32(sA + s * a_bytes), bbase = smem_u32(sB + s * b_bytes);
+                    const uint32_t abase = smem_u32(sA + s * a_bytes);
+                    const uint32_t lbo_a = a.a_atoms == 2 ? (uint32_t)atom_bytes : zbase - abase;
+                    // tap outer, k inner (measured: switching accumulator / B tile on every MMA is ~25 % slower)
+                    for (int tt = 0; tt < nt; ++tt) {
+                        const uint32_t bbase = smem_u32(sB + s * b_bytes + tt * b_tile);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {  // 128 pixels = 8 x UMMA_K(16)
-                        const uint64_t da = smem_desc(abase + k * 16 * 128, 128 * 128, 8 * 128, 2);
-                        const uint64_t db = smem_desc(bbase + k * 16 * a.swz_b, b_atom_bytes, 8 * a.swz_b, layB);
-                        mma_f16(tmem_base, da, db, idesc, (i | k) != 0);
+                        for (int k = 0; k < 8; ++k) {  // 128 pixels = 8 x UMMA_K(16)
+                            const uint64_t da = smem_desc(abase + k * 16 * 128, lbo_a, 8 * 128, 2);
+                            const uint64_t db = smem_desc(bbase + k * 16 * a.swz_b, b_atom_bytes, 8 * a.swz_b, layB);
+                            mma_f16(tmem_base + tt * a.BN, da, db, idesc, (i | k) != 0);
+                        }
                     }
                     mma_commit(empty0 + 8 * s);
                 }
@@ -106,17 +125,19 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
         } else {
             const int q = warp & 3;
             const int co = co0 + q * 32 + lane;
-            float* drow = a.dw + (size_t)co * a.Ktot + a.tap_koff[tap] + ci0;
             mbar_wait(tfull, 0);
             tc_fence_after();
-            for (int c0 = 0; c0 < a.BN; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
-                tmem_ld_wait();
-                if (co < a.Co) {
+            for (int tt = 0; tt < nt; ++tt) {
+                float* drow = a.dw + (size_t)co * a.Ktot + a.tap_koff[t0 + tt] + ci0;
+                for (int c0 = 0; c0 < a.BN; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tt * a.BN + c0, r);
+                    tmem_ld_wait();
+                    if (co < a.Co) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (ci0 + c0 + i < a.Ci) atomicAdd(drow + c0 + i, __uint_as_float(r[i]));
+                        for (int i = 0; i < 16; ++i)
+                            if (ci0 + c0 + i < a.Ci) atomicAdd(drow + c0 + i, __uint_as_float(r[i]));
+                    }
                 }
             }
         }
@@ -154,11 +175,20 @@ extern "C" int mg_conv_wgrad(const mg_wgrad_desc* d, void* stream) {
     a.n_atoms_b = a.BN / a.atomw_b;
     a.co_tiles = mg::ceil_div(d->Co, 128);
     const int ci_tiles = d->Ci / a.BN;
-    const int a_bytes = 2 * 128 * 128, b_bytes = a.n_atoms_b * 128 * a.swz_b;
-    a.stages = std::max(2, std::min(3, (100 * 1024) / (a_bytes + b_bytes)));  // <= ~100 KB: two CTAs per SM when N <= 128
-    const size_t smem = 1024 + 256 + (size_t)a.stages * (a_bytes + b_bytes);
-    const int base_ctas = d->n_taps * a.co_tiles * ci_tiles;
-    int splits = std::max(1, std::min(a.n_tiles, mg::ceil_div(2 * mg::kNumSMs, base_ctas)));
+    a.n_taps = d->n_taps;
+    a.a_atoms = d->Co > 64 ? 2 : 1;
+    const int a_bytes = a.a_atoms * 128 * 128, b_tile = a.n_atoms_b * 128 * a.swz_b;
+    // taps per CTA: bounded by TMEM (512 columns) and by two pipeline stages in ~200 KB of shared memory
+    a.taps_per_cta = std::max(1, std::min(std::min(d->n_taps, 512 / a.BN), (int)((100 * 1024 - a_bytes) / b_tile)));
+    while (d->n_taps % a.taps_per_cta) --a.taps_per_cta;   // equal-sized tap groups (9 -> 9 | 3 | 1, 4 -> 4 | 2 | 1)
+    if (a.BN == 64) a.taps_per_cta = 1;                    // measured: 64-channel layers prefer 2 small CTAs per SM
+    a.stages = a.taps_per_cta == 1 && a.BN <= 128 ? std::max(2, std::min(3, (int)((94 * 1024) / (a_bytes + b_tile))))
+                                                  : std::max(2, std::min(4, (int)((190 * 1024) / (a_bytes + a.taps_per_cta * b_tile))));
+    const size_t smem = 1024 + 256 + 128 * 128 + (size_t)a.stages * (a_bytes + a.taps_per_cta * b_tile);
+    const int tap_groups = mg::ceil_div(d->n_taps, a.taps_per_cta);
+    const int base_ctas = tap_groups * a.co_tiles * ci_tiles;
+    const int target_ctas = smem > 113 * 1024 ? mg::kNumSMs : 2 * mg::kNumSMs;  // one wave of resident CTAs
+    int splits = std::max(1, std::min(a.n_tiles, mg::ceil_div(target_ctas, base_ctas)));
     a.tiles_per_cta = mg::ceil_div(a.n_tiles, splits);
     splits = mg::ceil_div(a.n_tiles, a.tiles_per_cta);
 
@@ -181,7 +211,7 @@ extern "C" int mg_conv_wgrad(const mg_wgrad_desc* d, void* stream) {
         }
         attr_set = true;
     }
-    dim3 grid(splits, d->n_taps, a.co_tiles * ci_tiles);
+    dim3 grid(splits, tap_groups, a.co_tiles * ci_tiles);
     MG_LAUNCH(wgrad_tcgen05_kernel, grid, THREADS, smem, stream, tmDY, tmX, a);
     MG_CHECK_LAUNCH("mg_conv_wgrad");
     return MG_OK;
