@@ -83,6 +83,30 @@ int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, const int32_
                       float* grad_table, int B, int H, int W, int C, void* stream);
 
 
+/* ---- K0: grouped weight preparation (spectral norm + fp16 operand packs) and its backward -------------
+ * replaces: module/spectral_norm.py:22-35,73-80 (SpectralNorm._update_u_v + forward, ~12 tiny launches per layer x 54
+ *           layers), the implicit fp32->fp16 weight casts of autocast, and autograd's backward through W_bar / sigma.
+ * One call prepares EVERY dense conv layer: `layers` is a DEVICE array of descriptors, items_* are DEVICE int32[4]
+ * work-item tables built by the host ((layer, row0, col0, first)): vt tiles 64 rows x 256 columns, u tiles 8 rows,
+ * pack tiles 16 (dim0) x 32 (dim1) with dim1 (conv) / dim0 (transposed conv) running up to ci_pad.
+ * mg_wprep_fwd : per layer  v <- norm(W^T u), u <- norm(W v) (in place), sigma = u.Wv;  P[p_off..] = fp16 W/sigma as
+ *                [Co][taps_out][ci_pad];  D[d_off..] = fp16 W/sigma as [ci_pad][taps_out][Co] (D may be NULL).
+ *                vec: scratch (zeroed by the caller), per layer v_raw[width] then t[dim0];  scal: [n_layers][4] =
+ *                {sigma, 1/(|v_raw|+eps), 1/(|t|+eps), <G,W_bar> accumulator}.  fold: the stored 1x1 weight is emitted
+ *                as 4 taps of 0.25 W (AvgPool2d(2) + 1x1 conv == 2x2 stride-2 conv).  u == NULL: plain conv, sigma = 1.
+ * mg_wprep_bwd : G (fp32, P layout, at g_off) -> grad[grad_off..] = dL/dW_bar in the torch layout of `w`.             */
+typedef struct mg_wprep_layer {
+    const float* w;            /* master weight, torch layout [dim0][dim1][kh][kw]: conv dim0 = Co, transposed conv dim0 = Ci */
+    float* u; float* v;        /* spectral-norm vectors [dim0], [dim1*kh*kw] (updated in place) or NULL */
+    int32_t Co, Ci, taps, transposed, fold, ci_pad;
+    int32_t vec_off, pad_;
+    int64_t p_off, d_off, g_off, grad_off;
+} mg_wprep_layer;
+int mg_wprep_fwd(const mg_wprep_layer* layers, const int32_t* items_vt, int n_vt, const int32_t* items_u, int n_u,
+                 const int32_t* items_tile, int n_tile, float* vec, float* scal, void* P_f16, void* D_f16, void* stream);
+int mg_wprep_bwd(const mg_wprep_layer* layers, const int32_t* items_tile, int n_tile, const float* G, const float* vec,
+                 float* scal, float* grad, void* stream);
+
 /* ---- K2: dense convolution, implicit GEMM on tcgen05 tensor cores with TMA-staged operands ---------
  * replaces: every nn.Conv2d / nn.ConvTranspose2d call of the hot path (cuDNN via ATen): encoder
  *           encoder/resnet.py:177-200, ASPP module/aspp.py:35-56, decoder decoder/resnet.py:33-45,

@@ -46,6 +46,8 @@ SIGNATURES = {
                                  c_void_p]),
     "mg_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mg_wprep_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int] + [c_void_p] * 5),
+    "mg_wprep_bwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5),
     "mg_mask_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

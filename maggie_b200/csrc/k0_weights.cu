@@ -1,0 +1,243 @@
+// K0: grouped weight preparation for every dense conv layer of the hot path in a handful of launches.
+//
+// Forward  (3 kernels over ALL layers): spectral-norm power iteration (module/spectral_norm.py:22-35:
+//     v <- normalize(W^T u), u <- normalize(W v), sigma = u . W v), then W / sigma is written as fp16 in the two
+//     operand layouts the conv kernels consume:  P [Co][tap][Ci_pad] (fprop / wgrad layout) and
+//     D [Ci_pad][tap][Co] (data-gradient layout).  Plain (un-normalised) convs take sigma = 1.  The AvgPool2d(2)+1x1
+//     skip convs (encoder/resnet.py:111-116) are emitted as 2x2 stride-2 taps of 0.25 * W.
+// Backward (2 kernels over ALL layers): the conv weight gradients G (fp32, P layout, written by K4) are taken back
+//     through W = W_bar / sigma (u, v constants):  dW_bar = (G - <G, W_bar>/sigma * u v^T) / sigma, and re-laid-out to
+//     the torch layout of the master weights.
+// All kernels are HBM streams over the 30 M weights (~120 MB fp32): work items are (layer, tile) pairs from a
+// host-built table, so one launch covers the whole model.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TA = 16, TB = 32, MAX_TAPS = 16;     // pack tile: TA indices of dim0 x TB indices of dim1 (x taps)
+constexpr int SROW = TB * MAX_TAPS + 1;
+constexpr float kEps = 1e-12f;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t += red[i];
+    return t;
+}
+
+// ---- A: v_raw = W^T u   (tile of 64 rows x 256 columns per CTA, atomics into the zeroed scratch) ------------------
+__global__ void __launch_bounds__(256)
+wprep_vt_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, float* __restrict__ vec) {
+    const int4 it = items[blockIdx.x];
+    const mg_wprep_layer L = layers[it.x];
+    const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
+    const int width = d1 * L.taps, col = it.z + threadIdx.x;
+    if (col >= width) return;
+    const int r1 = min(it.y + 64, d0);
+    float acc = 0.f;
+    for (int r = it.y; r < r1; ++r) acc += L.w[(size_t)r * width + col] * __ldg(L.u + r);
+    atomicAdd(vec + L.vec_off + col, acc);
+}
+
+// ---- B: t = W v_raw / (|v_raw| + eps)   (one warp per row) --------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wprep_u_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, float* __restrict__ vec) {
+    const int4 it = items[blockIdx.x];
+    const mg_wprep_layer L = layers[it.x];
+    const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
+    const int width = d1 * L.taps, row = it.y + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= d0) return;
+    const float* vr = vec + L.vec_off;
+    const float* wr = L.w + (size_t)row * width;
+    float acc = 0.f, nn = 0.f;
+    for (int j = lane; j < width; j += 32) {
+        const float x = vr[j];
+        acc += wr[j] * x;
+        nn += x * x;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        nn += __shfl_xor_sync(0xffffffffu, nn, d);
+    }
+    if (lane == 0) vec[L.vec_off + width + row] = acc / (sqrtf(nn) + kEps);
+}
+
+// ---- C: sigma, in-place u / v update, fp16 packs -----------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wprep_pack_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ vec,
+                  float* __restrict__ scal, __half* __restrict__ P, __half* __restrict__ D) {
+    __shared__ float s[TA][SROW];
+    __shared__ float red[8];
+    const int4 it = items[blockIdx.x];
+    const mg_wprep_layer L = layers[it.x];
+    const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
+    const int taps = L.taps, width = d1 * taps, tid = threadIdx.x;
+    float inv_sigma = 1.f;
+    if (L.u) {
+        const float* vr = vec + L.vec_off;
+        const float* t = vr + width;
+        float tt = 0.f;
+        for (int i = tid; i < d0; i += 256) tt += t[i] * t[i];
+        tt = block_sum(tt, red);
+        const float tn = sqrtf(tt);
+        inv_sigma = (tn + kEps) / tt;                     // sigma = u . t = |t|^2 / (|t| + eps)
+        if (it.w) {                                       // first tile of the layer: publish u, v and the scalars
+            float vv = 0.f;
+            for (int j = tid; j < width; j += 256) vv += vr[j] * vr[j];
+            vv = block_sum(vv, red);
+            const float ivn = 1.f / (sqrtf(vv) + kEps), itn = 1.f / (tn + kEps);
+            for (int j = tid; j < width; j += 256) L.v[j] = vr[j] * ivn;
+            for (int i = tid; i < d0; i += 256) L.u[i] = t[i] * itn;
+            if (tid == 0) scal[it.x * 4 + 0] = tt * itn, scal[it.x * 4 + 1] = ivn, scal[it.x * 4 + 2] = itn, scal[it.x * 4 + 3] = 0.f;
+        }
+    } else if (it.w && tid == 0) {
+        scal[it.x * 4 + 0] = 1.f, scal[it.x * 4 + 1] = 0.f, scal[it.x * 4 + 2] = 0.f, scal[it.x * 4 + 3] = 0.f;
+    }
+    const int a0 = it.y, b0 = it.z, seg = TB * taps;
+    for (int i = tid; i < TA * seg; i += 256) {
+        const int a = i / seg, e = i - a * seg;
+        const int col = b0 * taps + e;
+        s[a][e] = (a0 + a < d0 && col < width) ? L.w[(size_t)(a0 + a) * width + col] : 0.f;
+    }
+    __syncthreads();
+    const float mul = inv_sigma * (L.fold ? 0.25f : 1.f);
+    const int to = L.fold ? 4 : taps, Co = L.Co, cip = L.ci_pad;
+    __half* Pl = P + L.p_off;
+    __half* Dl = D ? D + L.d_off : nullptr;
+    if (!L.transposed) {   // a = co, b = ci
+        for (int i = tid; i < TA * to * TB; i += 256) {             // P: ci fastest
+            const int b = i % TB, tp = (i / TB) % to, a = i / (TB * to);
+            const int co = a0 + a, ci = b0 + b;
+            if (co < Co && ci < cip) Pl[((size_t)co * to + tp) * cip + ci] = __float2half(s[a][b * taps + (L.fold ? 0 : tp)] * mul);
+        }
+        if (Dl)
+            for (int i = tid; i < TA * to * TB; i += 256) {         // D: co fastest
+                const int a = i % TA, tp = (i / TA) % to, b = i / (TA * to);
+                const int co = a0 + a, ci = b0 + b;
+                if (co < Co && ci < cip) Dl[((size_t)ci * to + tp) * Co + co] = __float2half(s[a][b * taps + (L.fold ? 0 : tp)] * mul);
+            }
+    } else {               // a = ci, b = co
+        for (int i = tid; i < TA * to * TB; i += 256) {             // P: ci fastest
+            const int a = i % TA, tp = (i / TA) % to, b = i / (TA * to);
+            const int ci = a0 + a, co = b0 + b;
+            if (co < Co && ci < cip) Pl[((size_t)co * to + tp) * cip + ci] = __float2half(s[a][b * taps + tp] * mul);
+        }
+        if (Dl)
+            for (int i = tid; i < TA * to * TB; i += 256) {         // D: co fastest
+                const int b = i % TB, tp = (i / TB) % to, a = i / (TB * to);
+                const int ci = a0 + a, co = b0 + b;
+                if (co < Co && ci < cip) Dl[((size_t)ci * to + tp) * Co + co] = __float2half(s[a][b * taps + tp] * mul);
+            }
+    }
+}
+
+// Loads the tile of dL/dW (torch layout order) from the packed gradient G [Co][taps_out][ci_pad] into s[a][b*taps+tap].
+__device__ __forceinline__ void load_grad_tile(const mg_wprep_layer& L, const float* __restrict__ G, int a0, int b0,
+                                               float (*s)[SROW]) {
+    const int taps = L.taps, to = L.fold ? 4 : taps, Co = L.Co, Ci = L.Ci, cip = L.ci_pad, tid = threadIdx.x;
+    const float* Gl = G + L.g_off;
+    if (!L.transposed) {
+        for (int i = tid; i < TA * taps * TB; i += 256) {
+            const int b = i % TB, tp = (i / TB) % taps, a = i / (TB * taps);
+            const int co = a0 + a, ci = b0 + b;
+            float v = 0.f;
+            if (co < Co && ci < Ci) {
+                if (L.fold) {
+                    const float* g = Gl + (size_t)co * 4 * cip + ci;
+                    v = 0.25f * (g[0] + g[cip] + g[2 * cip] + g[3 * cip]);
+                } else
+                    v = Gl[((size_t)co * to + tp) * cip + ci];
+            }
+            s[a][b * taps + tp] = v;
+        }
+    } else {
+        for (int i = tid; i < TA * taps * TB; i += 256) {
+            const int a = i % TA, tp = (i / TA) % taps, b = i / (TA * taps);
+            const int ci = a0 + a, co = b0 + b;
+            s[a][b * taps + tp] = (co < Co && ci < Ci) ? Gl[((size_t)co * to + tp) * cip + ci] : 0.f;
+        }
+    }
+}
+
+// ---- D: inner[layer] = <dL/dW, W_bar>  (spectral-norm layers only) -------------------------------------------------
+__global__ void __launch_bounds__(256)
+wprep_bwd_inner_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ G,
+                       float* __restrict__ scal) {
+    __shared__ float s[TA][SROW];
+    __shared__ float red[8];
+    const int4 it = items[blockIdx.x];
+    const mg_wprep_layer L = layers[it.x];
+    if (!L.u) return;
+    const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
+    const int taps = L.taps, width = d1 * taps, seg = TB * taps;
+    load_grad_tile(L, G, it.y, it.z, s);
+    __syncthreads();
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < TA * seg; i += 256) {
+        const int a = i / seg, e = i - a * seg, col = it.z * taps + e;
+        if (it.y + a < d0 && col < width) acc += s[a][e] * L.w[(size_t)(it.y + a) * width + col];
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0 && acc != 0.f) atomicAdd(scal + it.x * 4 + 3, acc);
+}
+
+// ---- E: dW_bar in the torch layout ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wprep_bwd_final_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ G,
+                       const float* __restrict__ vec, const float* __restrict__ scal, float* __restrict__ grad) {
+    __shared__ float s[TA][SROW];
+    const int4 it = items[blockIdx.x];
+    const mg_wprep_layer L = layers[it.x];
+    const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
+    const int taps = L.taps, width = d1 * taps, seg = TB * taps;
+    load_grad_tile(L, G, it.y, it.z, s);
+    __syncthreads();
+    float* gl = grad + L.grad_off;
+    if (L.u) {
+        const float sigma = scal[it.x * 4 + 0], ivn = scal[it.x * 4 + 1], itn = scal[it.x * 4 + 2], inner = scal[it.x * 4 + 3];
+        const float inv_sigma = 1.f / sigma, k = inner * inv_sigma * ivn * itn;
+        const float* vr = vec + L.vec_off;
+        const float* t = vr + width;
+        for (int i = threadIdx.x; i < TA * seg; i += 256) {
+            const int a = i / seg, e = i - a * seg, col = it.z * taps + e;
+            if (it.y + a < d0 && col < width)
+                gl[(size_t)(it.y + a) * width + col] = (s[a][e] - k * t[it.y + a] * vr[col]) * inv_sigma;
+        }
+    } else {
+        for (int i = threadIdx.x; i < TA * seg; i += 256) {
+            const int a = i / seg, e = i - a * seg, col = it.z * taps + e;
+            if (it.y + a < d0 && col < width) gl[(size_t)(it.y + a) * width + col] = s[a][e];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int mg_wprep_fwd(const mg_wprep_layer* layers, const int32_t* items_vt, int n_vt, const int32_t* items_u, int n_u,
+                            const int32_t* items_tile, int n_tile, float* vec, float* scal, void* P, void* D, void* stream) {
+    MG_REQUIRE(layers && items_tile && vec && scal && P, "mg_wprep_fwd: null pointer");
+    MG_REQUIRE(n_tile > 0, "mg_wprep_fwd: no work");
+    if (n_vt > 0) MG_LAUNCH(wprep_vt_kernel, n_vt, 256, 0, stream, layers, reinterpret_cast<const int4*>(items_vt), vec);
+    if (n_u > 0) MG_LAUNCH(wprep_u_kernel, n_u, 256, 0, stream, layers, reinterpret_cast<const int4*>(items_u), vec);
+    MG_LAUNCH(wprep_pack_kernel, n_tile, 256, 0, stream, layers, reinterpret_cast<const int4*>(items_tile), vec, scal,
+              static_cast<__half*>(P), static_cast<__half*>(D));
+    MG_CHECK_LAUNCH("mg_wprep_fwd");
+    return MG_OK;
+}
+
+extern "C" int mg_wprep_bwd(const mg_wprep_layer* layers, const int32_t* items_tile, int n_tile, const float* G, const float* vec,
+                            float* scal, float* grad, void* stream) {
+    MG_REQUIRE(layers && items_tile && G && vec && scal && grad, "mg_wprep_bwd: null pointer");
+    MG_REQUIRE(n_tile > 0, "mg_wprep_bwd: no work");
+    MG_LAUNCH(wprep_bwd_inner_kernel, n_tile, 256, 0, stream, layers, reinterpret_cast<const int4*>(items_tile), G, scal);
+    MG_LAUNCH(wprep_bwd_final_kernel, n_tile, 256, 0, stream, layers, reinterpret_cast<const int4*>(items_tile), G, vec,
+              const_cast<const float*>(scal), grad);
+    MG_CHECK_LAUNCH("mg_wprep_bwd");
+    return MG_OK;
+}

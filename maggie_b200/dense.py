@@ -7,7 +7,20 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from .weights import BankedWeight
 _need_cuda, _ptr, _stream = _lib.need_cuda, _lib.tensor_ptr, _lib.stream_ptr
+
+
+def _banked(w):
+    return isinstance(w, BankedWeight)
+
+
+def wshape(w):
+    """Torch-layout shape of a weight tensor, or the equivalent for a bank handle ([Ci,Co,4,4] when transposed)."""
+    if _banked(w):
+        Co, Ci, kh, kw = w.logical
+        return (Ci, Co, kh, kw) if w.transposed else (Co, Ci, kh, kw)
+    return tuple(w.shape)
 
 MAX_TAPS = 16
 STAT_COPIES = 64
@@ -87,9 +100,13 @@ def conv_launch(x, w_packed, taps, *, stride=1, grid_hw=None, out=None, out_hw=N
 
 def conv2d_nhwc(x, w, *, stride=1, padding=1, dilation=1, relu=False, stats=None, bias=None, out=None, c_off=0, **epi):
     """Forward conv: x NHWC fp16 (channels already padded to a multiple of 16), w torch layout [Co,Ci,kh,kw]."""
-    Co, Ci, kh, kw = w.shape
+    Co, Ci, kh, kw = wshape(w)
     ci_pad = x.shape[-1]
-    wp = pack_weight(w, ci_pad)
+    if _banked(w):
+        assert ci_pad == w.ci_pad
+        wp = w.P
+    else:
+        wp = pack_weight(w, ci_pad)
     Hi, Wi = x.shape[1:3]
     Ho = (Hi + 2 * padding - dilation * (kh - 1) - 1) // stride + 1
     Wo = (Wi + 2 * padding - dilation * (kw - 1) - 1) // stride + 1
@@ -100,11 +117,11 @@ def conv2d_nhwc(x, w, *, stride=1, padding=1, dilation=1, relu=False, stats=None
 def conv_transpose4x4s2_nhwc(x, w, *, stats=None):
     """ConvTranspose2d(k=4, s=2, p=1): w torch layout [Ci,Co,4,4]; four sub-pixel phase convs (2x2 taps each).
     out[2y+py, 2x+px] = sum_{ky,kx} w[:, :, ky, kx]^T x[y+dy, x+dx] with dy = (py + 1 - ky) / 2 (integer)."""
-    Ci, Co, kh, kw = w.shape
+    Ci, Co, kh, kw = wshape(w)
     assert kh == 4 and kw == 4
     N, Hi, Wi, ci_pad = x.shape
     out = torch.empty((N, 2 * Hi, 2 * Wi, Co), dtype=torch.float16, device=x.device)
-    wp = pack_weight(w.permute(1, 0, 2, 3), ci_pad)  # [Co][ky][kx][Ci]
+    wp = w.P if _banked(w) else pack_weight(w.permute(1, 0, 2, 3), ci_pad)  # [Co][ky][kx][Ci]
     for py in range(2):
         for px in range(2):
             taps = []
@@ -119,8 +136,71 @@ def conv_transpose4x4s2_nhwc(x, w, *, stats=None):
     return out
 
 
+# ---- per-forward scope: one zeroed scratch pool + deferred BatchNorm counters -----------------------------------
+# Every training conv needs a zeroed statistics buffer (forward) and a zeroed [2,C] sum buffer (backward), and every
+# BatchNorm bumps `num_batches_tracked`: inside a `step_scope` these ~200 tiny fill / add launches collapse into one
+# memset and one multi-tensor add.  The scope is opened INSIDE the region a CUDA graph captures, so replays redo both.
+class _Scope:
+    def __init__(self, device, capacity):
+        self.buf = torch.zeros(capacity, dtype=torch.float32, device=device) if capacity else None
+        self.used, self.asked, self.counters = 0, 0, []
+
+    def take(self, n, device):
+        n_al = (n + 31) // 32 * 32
+        self.asked += n_al
+        if self.buf is None or self.used + n_al > self.buf.numel() or self.buf.device != device:
+            return torch.zeros(n, dtype=torch.float32, device=device)
+        out = self.buf[self.used:self.used + n]
+        self.used += n_al
+        return out
+
+
+_SCOPES = []
+_SCOPE_CAPACITY = {}
+
+
+class step_scope:
+    """Context manager; `key` identifies the call site so that the pool is sized from the previous pass."""
+
+    def __init__(self, key, device):
+        self.key, self.device = (key, str(device)), device
+
+    def __enter__(self):
+        _SCOPES.append(_Scope(self.device, _SCOPE_CAPACITY.get(self.key, 0)))
+        return self
+
+    def __exit__(self, *exc):
+        sc = _SCOPES.pop()
+        _SCOPE_CAPACITY[self.key] = max(_SCOPE_CAPACITY.get(self.key, 0), sc.asked)
+        if sc.counters and exc[0] is None:
+            by_count = {}
+            seen = {}
+            for t in sc.counters:
+                seen[id(t)] = (t, seen.get(id(t), (t, 0))[1] + 1)
+            for t, c in seen.values():
+                by_count.setdefault(c, []).append(t)
+            for c, ts in by_count.items():
+                torch._foreach_add_(ts, c)
+        return False
+
+
+def zeros_f32(n, device):
+    """Zeroed fp32 scratch of n elements (from the enclosing scope's pool when there is one)."""
+    if _SCOPES:
+        return _SCOPES[-1].take(n, device)
+    return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+def bump_counter(t):
+    """`num_batches_tracked += 1`, deferred to the end of the enclosing scope when there is one."""
+    if _SCOPES:
+        _SCOPES[-1].counters.append(t)
+    else:
+        t.add_(1)
+
+
 def new_stats(co, device):
-    return torch.zeros((STAT_COPIES, 2, co), dtype=torch.float32, device=device)
+    return zeros_f32(STAT_COPIES * 2 * co, device).view(STAT_COPIES, 2, co)
 
 
 # ================================================================================================ wgrad (K4)
@@ -183,15 +263,22 @@ class ConvGeom:
         N, Hi, Wi, ci_pad = x_shape
         k, p, dl = self.k, self.pad, self.dil
         if self.kind == "convT":
-            Ci, Co = w.shape[:2]
-            wp = pack_weight(w, Co) if ci_pad == Ci else pack_weight(F.pad(w, (0, 0, 0, 0, 0, 0, 0, ci_pad - Ci)), Co)
+            Ci, Co = wshape(w)[:2]
+            if _banked(w):
+                wp = w.D
+            else:
+                wp = pack_weight(w, Co) if ci_pad == Ci else pack_weight(F.pad(w, (0, 0, 0, 0, 0, 0, 0, ci_pad - Ci)), Co)
             taps = [(ky - 1, kx - 1, (ky * 4 + kx) * Co) for ky in range(4) for kx in range(4)]
             return conv_launch(dy, wp, taps, stride=2, grid_hw=(Hi, Wi))
-        Co, Ci = w.shape[:2]
-        wt = w.permute(1, 0, 2, 3)  # [Ci,Co,k,k]
-        if ci_pad != Ci:
-            wt = F.pad(wt, (0, 0, 0, 0, 0, 0, 0, ci_pad - Ci))
-        wp = pack_weight(wt, Co)      # [Ci_pad][k*k][Co]
+        Co, Ci = wshape(w)[:2]
+        if _banked(w):
+            assert ci_pad == w.ci_pad
+            wp = w.D
+        else:
+            wt = w.permute(1, 0, 2, 3)  # [Ci,Co,k,k]
+            if ci_pad != Ci:
+                wt = F.pad(wt, (0, 0, 0, 0, 0, 0, 0, ci_pad - Ci))
+            wp = pack_weight(wt, Co)      # [Ci_pad][k*k][Co]
         if self.stride == 1:
             taps = [(p - ky * dl, p - kx * dl, (ky * k + kx) * Co) for ky in range(k) for kx in range(k)]
             return conv_launch(dy, wp, taps, grid_hw=(Hi, Wi))
@@ -208,22 +295,23 @@ class ConvGeom:
         return dx
 
     # ---- weight gradient in the torch layout, fp32
-    def wgrad(self, dy, x, w_shape):
+    def wgrad(self, dy, x, w_shape, bank=None):
+        """`bank` (a BankedWeight): accumulate into the bank's pre-zeroed fp32 buffer and return None."""
         ci_pad = x.shape[-1]
         k = self.k
         if self.kind == "convT":
             Ci, Co = w_shape[:2]
-            dwp = torch.zeros((Co, 16 * ci_pad), dtype=torch.float32, device=x.device)
+            dwp = bank.G if bank is not None else torch.zeros((Co, 16 * ci_pad), dtype=torch.float32, device=x.device)
             for py in range(2):
                 for px in range(2):
                     taps = [((py + 1 - ky) // 2, (px + 1 - kx) // 2, (ky * 4 + kx) * ci_pad)
                             for ky in range(4) if (py + 1 - ky) % 2 == 0 for kx in range(4) if (px + 1 - kx) % 2 == 0]
                     wgrad_launch(dy, x, taps, dwp, dy_map=(2, py, 2, px), grid_hw=x.shape[1:3])
-            return dwp.view(Co, 4, 4, ci_pad)[..., :Ci].permute(3, 0, 1, 2)
+            return None if bank is not None else dwp.view(Co, 4, 4, ci_pad)[..., :Ci].permute(3, 0, 1, 2)
         Co, Ci = w_shape[:2]
-        dwp = torch.zeros((Co, k * k * ci_pad), dtype=torch.float32, device=x.device)
+        dwp = bank.G if bank is not None else torch.zeros((Co, k * k * ci_pad), dtype=torch.float32, device=x.device)
         wgrad_launch(dy, x, conv_taps(k, k, self.pad, self.dil, ci_pad), dwp, stride=self.stride, grid_hw=dy.shape[1:3])
-        return dwp.view(Co, k, k, ci_pad)[..., :Ci].permute(0, 3, 1, 2)
+        return None if bank is not None else dwp.view(Co, k, k, ci_pad)[..., :Ci].permute(0, 3, 1, 2)
 
 
 # ================================================================================================ BN pieces (K3)
@@ -235,7 +323,7 @@ def bn_finalize(stats, count, bn, training):
     out = torch.empty((4, C), dtype=torch.float32, device=dev)
     L = _lib.lib()
     if training:
-        bn.num_batches_tracked.add_(1)
+        bump_counter(bn.num_batches_tracked)
         _lib.check(L.mg_bn_finalize(_ptr(stats), float(count), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean),
                                     _ptr(bn.running_var), float(bn.momentum), float(bn.eps), _ptr(out[0]), _ptr(out[1]),
                                     _ptr(out[2]), _ptr(out[3]), C, _stream()), "mg_bn_finalize")
@@ -250,12 +338,14 @@ class _ConvBNAct(torch.autograd.Function):
     """conv -> BN(batch stats) -> (+res) -> act   |   conv -> act -> BN   (act_first), training mode, all native."""
 
     @staticmethod
-    def forward(ctx, x, w, gamma, beta, res, geom, bn, act, act_first, res_up):
+    def forward(ctx, x, w, gamma, beta, res, geom, bn, act, act_first, res_up, handle=None):
+        """`handle` (BankedWeight): `w` is then the bank's token tensor (autograd link to the grouped weight prep)."""
         xn = x.permute(0, 2, 3, 1)
         assert xn.is_contiguous() and xn.dtype == torch.float16
-        Co = w.shape[1] if geom.kind == "convT" else w.shape[0]
+        wd = handle if handle is not None else w.detach()
+        w_shape = wshape(wd)
+        Co = w_shape[1] if geom.kind == "convT" else w_shape[0]
         stats = new_stats(Co, x.device)
-        wd = w.detach()
         r = geom.fwd(xn, wd, stats=stats) if not act_first else geom.fwd(xn, wd, stats=stats, pre_act=act)
         N, Ho, Wo, _ = r.shape
         scale, shift, mean, invstd = bn_finalize(stats, N * Ho * Wo, bn, True)
@@ -266,20 +356,27 @@ class _ConvBNAct(torch.autograd.Function):
             assert rn.is_contiguous() and rn.dtype == torch.float16
         _lib.check(_lib.lib().mg_bn_apply(_ptr(r), _ptr(scale), _ptr(shift), _ptr(rn), int(res_up), _ptr(y), N, Ho, Wo, Co,
                                           0 if act_first else ACT[act], _stream()), "mg_bn_apply")
-        ctx.save_for_backward(xn, wd, r, y, mean, invstd, gamma.detach())
-        ctx.cfg = (geom, act, act_first, res_up, res is not None, tuple(w.shape))
+        ctx.save_for_backward(xn, None if handle is not None else wd, r, y, mean, invstd, gamma.detach())
+        ctx.handle = handle
+        ctx.sums = zeros_f32(2 * Co, x.device).view(2, Co) if _SCOPES else None  # zeroed now, filled by the backward
+        ctx.cfg = (geom, act, act_first, res_up, res is not None, w_shape)
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, gy):
         xn, w, r, y, mean, invstd, gamma = ctx.saved_tensors
         geom, act, act_first, res_up, has_res, w_shape = ctx.cfg
+        handle = ctx.handle
+        if handle is not None:
+            w = handle
         dy = gy.permute(0, 2, 3, 1)
         if not dy.is_contiguous() or dy.dtype != torch.float16:
             dy = dy.contiguous().to(torch.float16)
         N, Ho, Wo, Co = r.shape
         L = _lib.lib()
-        sums = torch.zeros((2, Co), dtype=torch.float32, device=r.device)
+        sums, ctx.sums = ctx.sums, None
+        if sums is None:
+            sums = torch.zeros((2, Co), dtype=torch.float32, device=r.device)
         a_post = 0 if act_first else ACT[act]
         _lib.check(L.mg_bn_bwd_reduce(_ptr(dy), _ptr(y), _ptr(r), _ptr(mean), _ptr(invstd), _ptr(sums), N, Ho, Wo, Co, a_post,
                                       _stream()), "mg_bn_bwd_reduce")
@@ -289,12 +386,12 @@ class _ConvBNAct(torch.autograd.Function):
                                      _ptr(dres), N, Ho, Wo, Co, a_post, ACT[act] if act_first else 0, _stream()),
                    "mg_bn_bwd_apply")
         dx = geom.dgrad(dr, w, xn.shape).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
-        dw = geom.wgrad(dr, xn, w_shape) if ctx.needs_input_grad[1] else None
+        dw = geom.wgrad(dr, xn, w_shape, bank=handle) if ctx.needs_input_grad[1] else None
         if dres is not None:
             dres = dres.permute(0, 3, 1, 2)
             if res_up:
                 dres = F.avg_pool2d(dres.float(), 2).mul_(4.0).to(torch.float16)
-        return dx, dw, sums[1], sums[0], dres, None, None, None, None, None
+        return dx, dw, sums[1], sums[0], dres, None, None, None, None, None, None
 
 
 def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="relu", act_first=False, residual=None,
@@ -302,14 +399,17 @@ def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="rel
     """x NCHW-shaped channels-last fp16 (channels padded to a multiple of 16); w in the reference layout, fp32.
     Training: conv(stats epilogue) + finalize + apply kernels with a native backward.  Eval: BatchNorm is folded
     into the conv epilogue (one kernel)."""
-    _need_cuda(x, w)
-    geom = ConvGeom("convT", 4, 2, 1, 1) if transposed else ConvGeom("conv", w.shape[-1], stride, padding, dilation)
+    banked = _banked(w)
+    _need_cuda(x, None if banked else w)
+    geom = ConvGeom("convT", 4, 2, 1, 1) if transposed else ConvGeom("conv", wshape(w)[-1], stride, padding, dilation)
     if x.dtype != torch.float16 or not x.permute(0, 2, 3, 1).is_contiguous():
         x = x.to(torch.float16).contiguous(memory_format=torch.channels_last)
     if residual is not None and (residual.dtype != torch.float16 or not residual.permute(0, 2, 3, 1).is_contiguous()):
         residual = residual.to(torch.float16).contiguous(memory_format=torch.channels_last)
     if training:
         assert bn is not None
+        if banked:
+            return _ConvBNAct.apply(x, w.token, bn.weight, bn.bias, residual, geom, bn, act, act_first, res_up, w)
         return _ConvBNAct.apply(x, w, bn.weight, bn.bias, residual, geom, bn, act, act_first, res_up)
     xn = x.permute(0, 2, 3, 1)
     scale = shift = None
@@ -319,9 +419,9 @@ def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="rel
     if geom.kind == "convT":
         # four phase launches write disjoint output pixels; epilogue fusion applies per launch
         N, Hi, Wi, ci_pad = xn.shape
-        Ci, Co = w.shape[:2]
+        Ci, Co = wshape(w)[:2]
         y = torch.empty((N, 2 * Hi, 2 * Wi, Co), dtype=torch.float16, device=x.device)
-        wp = pack_weight(w.detach().permute(1, 0, 2, 3), ci_pad)
+        wp = w.P if banked else pack_weight(w.detach().permute(1, 0, 2, 3), ci_pad)
         for py in range(2):
             for px in range(2):
                 taps = [((py + 1 - ky) // 2, (px + 1 - kx) // 2, (ky * 4 + kx) * ci_pad)
@@ -329,7 +429,7 @@ def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="rel
                 conv_launch(xn, wp, taps, grid_hw=(Hi, Wi), out=y, out_map=(2, py, 2, px), scale=scale, shift=shift,
                             pre_act=act if act_first else None, post_act=None if act_first else act)
     else:
-        y = conv2d_nhwc(xn, w.detach(), stride=stride, padding=padding, dilation=dilation, scale=scale, shift=shift, res=rn,
+        y = conv2d_nhwc(xn, w if banked else w.detach(), stride=stride, padding=padding, dilation=dilation, scale=scale, shift=shift, res=rn,
                         res_up=res_up, pre_act=act if act_first else None, post_act=None if act_first else act)
     return y.permute(0, 3, 1, 2)
 

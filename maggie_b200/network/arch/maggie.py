@@ -20,6 +20,7 @@ except Exception:  # pragma: no cover
 
 from ...config import as_cfg
 from ... import ops
+from ...weights import WeightBank
 from .. import loss as losses
 from ..decoder import MaGGIeDecoder, MaGGIeTempDecoder
 from ..encoder import ASPP, ResMaskEmbedShortCutEncoder
@@ -36,8 +37,17 @@ class _DenseStage(nn.Module):
     def __init__(self, model):
         super().__init__()
         self.encoder, self.aspp, self.decoder = model.encoder, model.aspp, model.decoder
+        self.bank = WeightBank().attach(self)
 
     def forward(self, image, masks, slot_ids, mask_os8, gt_os8, mem_feat=None):
+        with ops.step_scope("dense_stage", image.device):
+            ops.prepare_weights(self.bank)  # K0: spectral norm + operand packs of every dense conv in one grouped op
+            try:
+                return self._forward(image, masks, slot_ids, mask_os8, gt_os8, mem_feat)
+            finally:
+                self.bank.release()
+
+    def _forward(self, image, masks, slot_ids, mask_os8, gt_os8, mem_feat=None):
         emb, fea = self.encoder(image, masks, slot_ids)
         emb = self.aspp(emb)
         extra = {} if mem_feat is None else {"mem_feat": mem_feat}
@@ -143,8 +153,9 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         mem_feat = kwargs.pop("mem_feat", None)
         fea1, fea2, fea3, *dense_out = self._dense(x, masks, slot_ids, mask_os8, gt_os8,
                                                    mem_feat if torch.is_tensor(mem_feat) else None)
-        pred = self.decoder(tuple(dense_out), (fea1, fea2, fea3), (h, w), b=b, n_f=n_f, n_i=n_i,
-                            masks=dec_masks, iter=batch.get("iter", 0), gt_alphas=alphas, spar_gt=trans, **kwargs)
+        with ops.step_scope("sparse_stage", x.device):
+            pred = self.decoder(tuple(dense_out), (fea1, fea2, fea3), (h, w), b=b, n_f=n_f, n_i=n_i,
+                                masks=dec_masks, iter=batch.get("iter", 0), gt_alphas=alphas, spar_gt=trans, **kwargs)
         self.last_site_counts = pred.pop("site_counts", None)
 
         alpha_pred = pred.pop("refined_masks")

@@ -116,8 +116,8 @@ class InstanceMatteDecoder(nn.Module):
 
     def _smooth(self, x):
         t = self.training
-        x = ops.conv_bn_act(x, self.conv[0].weight, self.conv[1], t, act="lrelu")
-        return ops.conv_bn_act(x, self.conv[3].weight, self.conv[4], t, padding=0, act="lrelu")
+        x = ops.conv_bn_act(x, self.conv[0].w(), self.conv[1], t, act="lrelu")
+        return ops.conv_bn_act(x, self.conv[3].w(), self.conv[4], t, padding=0, act="lrelu")
 
     def forward(self, feat, mask_os8, gt_mask_os8=None, temporal_fn=None):
         """feat [b*n_f, C, h, w] channels-last; mask_os8 [b, n_f, n_i, h, w] bool (avg-pool>0 of the input masks);
@@ -353,6 +353,8 @@ class MaGGIeTempDecoder(MaGGIeDecoder):
         self.os8_temp_module = gru
         self.diff_module = seq(SNConv(128, 64, 1), nn.BatchNorm2d(64), Slot(), SNConv(64, 32, 3), nn.BatchNorm2d(32), Slot(),
                                PlainConv(32, 1, 3))
+        for m in self.diff_module:  # runs 2(n_f-1) times per forward, one power iteration each: not a bank layer
+            m.bankable = False
 
     # -- ConvGRU -------------------------------------------------------------------------------------------
     def _gru_step(self, x, h):

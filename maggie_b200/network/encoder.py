@@ -24,6 +24,7 @@ class EncBlock(nn.Module):
         if stride != 1:
             # [AvgPool2d(2, stride), SN conv1x1, BN]  (resnet.py:111-116)
             self.downsample = seq(Slot(), SNConv(inplanes, planes, 1), nn.BatchNorm2d(planes))
+            self.downsample[1].fold = True  # weight() yields the equivalent 2x2 stride-2 kernel (W / 4 on every tap)
 
     def forward(self, x):
         t = self.training
@@ -31,8 +32,7 @@ class EncBlock(nn.Module):
         idt = x
         if self.downsample is not None:
             # AvgPool2d(2,2) followed by a 1x1 conv == one 2x2 stride-2 conv with the 1x1 weight / 4 on every tap
-            w2 = self.downsample[1].weight().expand(-1, -1, 2, 2) * 0.25
-            idt = ops.conv_bn_act(x, w2, self.downsample[2], t, stride=2, padding=0, act=None)
+            idt = ops.conv_bn_act(x, self.downsample[1].weight(), self.downsample[2], t, stride=2, padding=0, act=None)
         # conv2 -> bn2 -> (+identity) -> relu
         return ops.conv_bn_act(out, self.conv2.weight(), self.bn2, t, act="relu", residual=idt)
 
@@ -107,12 +107,12 @@ class ASPP(nn.Module):
 
     def forward(self, x):
         t = self.training
-        ys = [ops.conv_bn_act(x, self.aspp1.weight, self.aspp1_bn, t, padding=0)]
+        ys = [ops.conv_bn_act(x, self.aspp1.w(), self.aspp1_bn, t, padding=0)]
         for i, d in ((2, 2), (3, 4), (4, 8)):
-            ys.append(ops.conv_bn_act(x, getattr(self, f"aspp{i}").weight, getattr(self, f"aspp{i}_bn"), t,
+            ys.append(ops.conv_bn_act(x, getattr(self, f"aspp{i}").w(), getattr(self, f"aspp{i}_bn"), t,
                                       padding=d, dilation=d))
         g = x.float().mean((2, 3), keepdim=True).to(x.dtype)
-        g = ops.conv_bn_act(g, self.aspp5.weight, self.aspp5_bn, t, padding=0)
+        g = ops.conv_bn_act(g, self.aspp5.w(), self.aspp5_bn, t, padding=0)
         ys.append(g.expand(-1, -1, x.shape[2], x.shape[3]))
         y = torch.cat(ys, 1).contiguous(memory_format=torch.channels_last)
-        return ops.conv_bn_act(y, self.conv2.weight, self.bn2, t, padding=0)
+        return ops.conv_bn_act(y, self.conv2.w(), self.bn2, t, padding=0)

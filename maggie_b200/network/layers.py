@@ -38,8 +38,16 @@ class SNConv(nn.Module):
         self.module = _SNInner((cin, cout, k, k) if transposed else (cout, cin, k, k))
 
     def weight(self):
+        """The normalised weight: a bank handle (K0, `maggie_b200.weights`) while a banked forward is in flight,
+        otherwise a tensor from the per-layer torch composition."""
+        b = getattr(self, "_bank", None)
+        if b is not None and b[0].current is not None:
+            return b[0].current.handle(b[1])
         m = self.module
-        return ops.spectral_weight(m.weight_bar, m.weight_u, m.weight_v)
+        w = ops.spectral_weight(m.weight_bar, m.weight_u, m.weight_v)
+        if getattr(self, "fold", False):  # AvgPool2d(2,2) + 1x1 conv == 2x2 stride-2 conv with W / 4 on every tap
+            w = w.expand(-1, -1, 2, 2) * 0.25
+        return w
 
 
 class PlainConv(nn.Module):
@@ -49,6 +57,13 @@ class PlainConv(nn.Module):
         super().__init__()
         self.weight = nn.Parameter(torch.empty(cout, cin, k, k))
         nn.init.xavier_uniform_(self.weight)
+
+    def w(self):
+        """Bank handle while a banked forward is in flight, else the parameter itself."""
+        b = getattr(self, "_bank", None)
+        if b is not None and b[0].current is not None:
+            return b[0].current.handle(b[1])
+        return self.weight
 
 
 class SparseConvParams(nn.Module):

@@ -171,6 +171,20 @@ def matte_loss_sums(a1, a4, a8, target, w1, w4, w8):
     return _MatteLossSums.apply(a1, a4, a8, target, w1, w4, w8)
 
 
+# =============================================================================================== native: K0
+def prepare_weights(bank):
+    """Grouped weight preparation of every banked dense conv (spectral-norm power iteration, W / sigma, fp16 operand
+    packs) with a grouped backward.  NATIVE (K0, maggie_b200/weights.py).  Reference: module/spectral_norm.py:22-35."""
+    return bank.prepare()
+
+
+def step_scope(key, device):
+    """Per-forward scope (one zeroed scratch pool + deferred BatchNorm counters), see maggie_b200/dense.py."""
+    from . import dense
+
+    return dense.step_scope(key, device)
+
+
 # =============================================================================================== interim ops
 def _act(x, act):
     if act == "relu":
@@ -202,7 +216,8 @@ def batch_norm(x, bn, training):
     """Training-mode (batch statistics, running-stat update) or eval-mode BatchNorm from a container's
     tensors.  INTERIM (torch)."""
     if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+        from . import dense
+        dense.bump_counter(bn.num_batches_tracked)
     return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, training, bn.momentum, bn.eps)
 
 

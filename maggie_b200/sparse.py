@@ -7,7 +7,7 @@ from ctypes import c_int32, c_void_p
 import torch
 
 from . import _lib
-from .dense import ACT, bn_finalize, new_stats
+from .dense import ACT, bn_finalize, new_stats, zeros_f32
 
 _need_cuda, _ptr, _stream = _lib.need_cuda, _lib.tensor_ptr, _lib.stream_ptr
 
@@ -125,6 +125,7 @@ class _RowsConv(torch.autograd.Function):
         _lib.check(_lib.lib().mg_bn_apply(_ptr(r), _ptr(scale), _ptr(shift), None, 0, _ptr(y), No, 1, 1, co,
                                           0 if mode == "act_bn" else ACT[act], _stream()), "mg_bn_apply")
         ctx.save_for_backward(src, wd, table, table_t, r, y, mean, invstd, gamma.detach())
+        ctx.sums = zeros_f32(2 * co, src.device).view(2, co)  # zeroed now (scope pool), filled by the backward
         return y
 
     @staticmethod
@@ -139,7 +140,9 @@ class _RowsConv(torch.autograd.Function):
             src, w, table, table_t, r, y, mean, invstd, gamma = ctx.saved_tensors
             dy = _f16rows(gy)
             No = r.shape[0]
-            sums = torch.zeros((2, co), dtype=torch.float32, device=r.device)
+            sums, ctx.sums = ctx.sums, None
+            if sums is None:
+                sums = zeros_f32(2 * co, r.device).view(2, co)
             a_post = 0 if mode == "act_bn" else ACT[act]
             _lib.check(L.mg_bn_bwd_reduce(_ptr(dy), _ptr(y), _ptr(r), _ptr(mean), _ptr(invstd), _ptr(sums), No, 1, 1, co,
                                           a_post, _stream()), "mg_bn_bwd_reduce")

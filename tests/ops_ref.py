@@ -231,12 +231,13 @@ def conv_bias(x, w, bias=None, *, padding=1):
 def injected(dtype=torch.float32):
     """Swap the native ops for the references above (CPU container only)."""
     names = ("unknown_mask", "build_sites", "mask_embed", "conv_bn_act", "rows_conv", "rows_head", "gather_dense",
-             "matte_loss_sums", "attention", "conv_bias", "COMPUTE_DTYPE")
+             "matte_loss_sums", "attention", "conv_bias", "prepare_weights", "COMPUTE_DTYPE")
     saved = {n: getattr(ops, n) for n in names}
     ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.conv_bn_act, ops.COMPUTE_DTYPE = \
         unknown_mask, build_sites, mask_embed, conv_bn_act, dtype
     ops.rows_conv, ops.rows_head, ops.gather_dense = rows_conv, rows_head, gather_dense
     ops.matte_loss_sums, ops.attention, ops.conv_bias = matte_loss_sums, attention, conv_bias
+    ops.prepare_weights = lambda bank: None  # layers then use the per-layer torch composition (ops.spectral_weight)
     try:
         yield
     finally:

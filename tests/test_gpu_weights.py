@@ -1,0 +1,138 @@
+"""-m gpu: K0 grouped weight preparation (spectral norm + operand packs + backward) against the per-layer torch
+composition (`ops.spectral_weight` + `dense.pack_weight`), which itself follows module/spectral_norm.py:22-35."""
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+
+
+class _Net(nn.Module):
+    def __init__(self):
+        super().__init__()
+        from maggie_b200.network.layers import PlainConv, SNConv
+        self.a = SNConv(6, 32, 3)               # Ci padded 6 -> 16
+        self.b = SNConv(64, 128, 3)
+        self.c = SNConv(64, 128, 1)
+        self.c.fold = True                      # avg-pool skip: 2x2 taps of W/4
+        self.d = SNConv(256, 256, 4, transposed=True)
+        self.e = PlainConv(512, 256, 3)
+        self.f = PlainConv(128, 64, 1)
+        self.g = SNConv(48, 80, 3)              # channel counts that do not fill the 16 x 32 tiles
+
+
+def _reference(net):
+    """(P, D, u, v, W) per layer from the torch composition; W keeps the autograd graph to the master weight."""
+    from maggie_b200 import dense, ops
+    from maggie_b200.network.layers import SNConv
+    out = {}
+    for name, m in net.named_children():
+        if isinstance(m, SNConv):
+            u, v = m.module.weight_u.detach().clone(), m.module.weight_v.detach().clone()
+            W = ops.spectral_weight(m.module.weight_bar, u, v)
+        else:
+            u = v = None
+            W = m.weight
+        We = W
+        if getattr(m, "fold", False):
+            We = W.expand(-1, -1, 2, 2) * 0.25
+        tr = getattr(m, "transposed", False)
+        Wc = We.permute(1, 0, 2, 3) if tr else We                      # [Co,Ci,kh,kw]
+        Co, Ci = Wc.shape[:2]
+        cip = dense.pad_channels(Ci)
+        P = dense.pack_weight(Wc.detach(), cip)
+        Wt = Wc.detach().permute(1, 0, 2, 3)
+        if cip != Ci:
+            Wt = torch.nn.functional.pad(Wt, (0, 0, 0, 0, 0, 0, 0, cip - Ci))
+        D = dense.pack_weight(Wt, Co)
+        out[name] = (P, D, u, v, We)
+    return out
+
+
+def test_weight_bank_forward_backward():
+    from maggie_b200.weights import WeightBank
+    torch.manual_seed(3)
+    net = _Net().cuda()
+    ref = _reference(net)                       # on copies of u, v (the bank updates the parameters in place)
+    bank = WeightBank().attach(net)
+    prep = bank.prepare()
+    handles = {name: m.weight() if hasattr(m, "module") else m.w() for name, m in net.named_children()}
+    from maggie_b200.weights import BankedWeight
+    assert all(isinstance(h, BankedWeight) for h in handles.values())
+    gsum = 0.0
+    torch.manual_seed(5)
+    for name, m in net.named_children():
+        P, D, u, v, We = ref[name]
+        h = handles[name]
+        assert h.P.shape == P.shape and h.D.shape == D.shape, name
+        # W / sigma rounds to fp16 after fp32 arithmetic in both paths; sigma differs in the last fp32 bits
+        assert float((h.P.float() - P.float()).abs().max()) <= 2e-3 * float(P.float().abs().max()), name
+        assert float((h.D.float() - D.float()).abs().max()) <= 2e-3 * float(D.float().abs().max()), name
+        if u is not None:
+            assert torch.allclose(m.module.weight_u, u, atol=1e-5, rtol=1e-4), name
+            assert torch.allclose(m.module.weight_v, v, atol=1e-5, rtol=1e-4), name
+        # fake weight gradient in the bank layout G [Co][tap][ci_pad] and the same values in the torch layout
+        Co, Ci, kh, kw = h.logical
+        g = torch.randn(Co, kh, kw, h.ci_pad, device="cuda")
+        h.G.copy_(g.reshape(Co, -1))
+        gt = g[..., :Ci].permute(0, 3, 1, 2)                            # [Co,Ci,kh,kw]
+        if h.transposed:
+            gt = gt.permute(1, 0, 2, 3)
+        gsum = gsum + (We * gt).sum()
+    bank.release()
+    params = [m.module.weight_bar if hasattr(m, "module") else m.weight for m in net.children()]
+    want = torch.autograd.grad(gsum, params)
+    got = torch.autograd.grad(prep.token, params, allow_unused=True)
+    for (name, _), a, b in zip(net.named_children(), got, want):
+        assert a is not None and a.shape == b.shape, name
+        err = float((a - b).abs().max()) / (float(b.abs().max()) + 1e-12)
+        assert err < 2e-4, (name, err)
+
+
+def test_model_forward_uses_the_bank_and_matches_the_per_layer_path():
+    """Dense stage with the bank (K0) vs the same stage with per-layer torch weight preparation: same outputs (both
+    round W / sigma to fp16 from fp32), same u / v updates, same weight gradients."""
+    import copy
+    import numpy as np
+    from maggie_b200.config import CfgNode
+    from maggie_b200.network import build_model
+    from oracle import synth
+
+    torch.manual_seed(11)
+    m1, _ = build_model(CfgNode(synth.model_cfg()))
+    m1.cuda().train()
+    m2 = copy.deepcopy(m1)
+    for mod in m2.modules():                     # second model: detach every layer from its bank -> per-layer path
+        if hasattr(mod, "_bank"):
+            mod._bank = None
+    from maggie_b200.weights import WeightBank
+    m2._stage[0].bank = WeightBank()             # empty bank: prepare() is a no-op
+    batch = synth.make_batch(b=2, n_f=1, n_i=2, H=128, W=128, edge_px=4.0, train=True, it=1)
+    batch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    outs = []
+    for m in (m1, m2):
+        np.random.seed(7)
+        import random
+        random.seed(7)
+        torch.manual_seed(0)
+        _, loss = m(batch, mem_feat=None)
+        loss["total"].backward()
+        outs.append(float(loss["total"]))
+    assert abs(outs[0] - outs[1]) <= 2e-3 * abs(outs[1]), outs
+    p1, p2 = dict(m1.named_parameters()), dict(m2.named_parameters())
+    worst = (0.0, None)
+    for k, a in p1.items():
+        b = p2[k]
+        if k.endswith(("weight_u", "weight_v")):
+            assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), k
+        if a.grad is None:
+            assert b.grad is None, k
+            continue
+        if "weight_bar" in k or (a.dim() == 4 and "dummy" not in k):
+            # fp16 noise of the ill-conditioned tiny batch dominates; the direction of every weight gradient agrees
+            if float(b.grad.norm()) == 0.0:      # e.g. convs in front of a zero-initialised bn2.weight (resnet.py:97-99)
+                assert float(a.grad.abs().max()) == 0.0, k
+                continue
+            cos = float((a.grad * b.grad).sum() / (a.grad.norm() * b.grad.norm() + 1e-30))
+            worst = max(worst, (1 - cos, k))
+    assert worst[0] < 5e-2, worst
