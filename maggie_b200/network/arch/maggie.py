@@ -80,6 +80,10 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
 
     # -------------------------------------------------------------------------------------------
     def _prepare(self, batch):
+        """Flatten the batch dict.  Training with fewer instances than mask slots draws the reference's random slot
+        assignment (arch/maggie.py:206-229) but keeps every pixel-sized tensor COMPACT (one plane per real instance):
+        the reference's scattered `[B, num_masks, H, W]` tensors are zero in every other slot, and zero planes
+        contribute exactly nothing to alphas, weights, active sites or losses.  `chosen[j]` is the slot of plane j."""
         x, masks = batch["image"], batch["mask"]
         alphas, trans = batch.get("alpha"), batch.get("transition")
         b, n_f, _, h, w = x.shape
@@ -88,25 +92,20 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         masks = masks.reshape(b * n_f, n_i, *masks.shape[-2:]).float()
         if masks.shape[-1] != w:
             masks = F.interpolate(masks, size=(h, w), mode="nearest")
-        slot_ids, chosen = list(range(n_i)), None
-        dec_masks = masks
+        slot_ids, chosen, n_slots, unsort = list(range(n_i)), None, n_i, None
+        alphas = alphas.reshape(b * n_f, n_i, h, w).float() if alphas is not None else None
+        trans = trans.reshape(b * n_f, n_i, h, w).float() if trans is not None else None
         if self.num_masks - n_i > 0 and self.training:
-            chosen = np.random.choice(self.num_masks, n_i, replace=False)
-            slot_ids = [int(c) for c in chosen]
-
-            def scatter(t):
-                out = t.new_zeros((b * n_f, self.num_masks, h, w))
-                out[:, chosen] = t.reshape(b * n_f, n_i, h, w)
-                return out
-
-            dec_masks = scatter(masks)
-            alphas = scatter(alphas.float()) if alphas is not None else None
-            trans = scatter(trans.float()) if trans is not None else None
-            n_i = self.num_masks
-        else:
-            alphas = alphas.reshape(b * n_f, n_i, h, w).float() if alphas is not None else None
-            trans = trans.reshape(b * n_f, n_i, h, w).float() if trans is not None else None
-        return x, masks, slot_ids, dec_masks, alphas, trans, chosen, (b, n_f, n_i, h, w)
+            draw = [int(c) for c in np.random.choice(self.num_masks, n_i, replace=False)]
+            # planes are kept in ascending slot order, so that active sites are enumerated exactly as in the reference's
+            # scattered layout (row order decides which rows a dropout mask hits); `unsort` restores instance order
+            order = sorted(range(n_i), key=lambda j: draw[j])
+            chosen = [draw[j] for j in order]
+            if order != list(range(n_i)):
+                masks, alphas, trans = (None if t is None else t[:, order] for t in (masks, alphas, trans))
+                unsort = [order.index(j) for j in range(n_i)]
+            slot_ids, n_slots = chosen, self.num_masks
+        return x, masks, slot_ids, alphas, trans, chosen, n_slots, unsort, (b, n_f, n_i, h, w)
 
     def enable_cuda_graphs(self, on=True):
         """Replay the dense stage (encoder, ASPP, dense decoder blocks, attention; forward AND backward) as CUDA graphs.
@@ -141,29 +140,31 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
     def _extra_outputs(self, pred, output, n_i):
         pass
 
-    def _extra_losses(self, pred, loss_dict, w4, w1, alphas, shape5):
+    def _extra_losses(self, pred, loss_dict, w4, w1, alphas, shape5, pad_ratio=1.0):
         pass
 
     def _extra_decoder_losses(self, pred, loss_dict):
         pass
 
     def forward(self, batch, **kwargs):
-        x, masks, slot_ids, dec_masks, alphas, trans, chosen, (b, n_f, n_i, h, w) = self._prepare(batch)
-        mask_os8, gt_os8 = self.decoder.pooled_masks(dec_masks, alphas, b, n_f, n_i, h, w, self.training)
+        x, masks, slot_ids, alphas, trans, chosen, n_slots, unsort, (b, n_f, n_i, h, w) = self._prepare(batch)
+        mask_os8, gt_os8 = self.decoder.pooled_masks(masks, alphas, b, n_f, n_i, h, w, self.training, chosen, n_slots)
         mem_feat = kwargs.pop("mem_feat", None)
+        it = batch.get("iter", 0)
+        roi_plan = self.decoder.plan_roi(alphas, it)   # before the dense stage: see MaGGIeDecoder.plan_roi
         fea1, fea2, fea3, *dense_out = self._dense(x, masks, slot_ids, mask_os8, gt_os8,
                                                    mem_feat if torch.is_tensor(mem_feat) else None)
         with ops.step_scope("sparse_stage", x.device):
-            pred = self.decoder(tuple(dense_out), (fea1, fea2, fea3), (h, w), b=b, n_f=n_f, n_i=n_i,
-                                masks=dec_masks, iter=batch.get("iter", 0), gt_alphas=alphas, spar_gt=trans, **kwargs)
+            pred = self.decoder(tuple(dense_out), (fea1, fea2, fea3), (h, w), b=b, n_f=n_f, n_i=n_i, masks=masks,
+                                iter=it, gt_alphas=alphas, spar_gt=trans, slots=chosen, n_slots=n_slots,
+                                roi_plan=roi_plan, **kwargs)
         self.last_site_counts = pred.pop("site_counts", None)
 
         alpha_pred = pred.pop("refined_masks")
         w4 = w1 = pred["detail_mask"].to(alpha_pred.dtype)
         if self.training and np.random.rand() < 0.75:
             w4, w1 = pred.pop("weight_os4"), pred.pop("weight_os1")
-        n_out = self.num_masks if (self.training and self.num_masks > 0) else n_i
-        view = lambda t: t[:, :n_out].reshape(b, n_f, n_out, h, w)
+        view = lambda t: t[:, :n_i].reshape(b, n_f, n_i, h, w)
         output = {k: view(pred[k]) for k in ("alpha_os1", "alpha_os4", "alpha_os8")}
         output["refined_masks"] = view(alpha_pred)
         output["detail_mask"] = view(pred["detail_mask"])
@@ -176,16 +177,16 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
                     continue
                 pred[k] = pred[k] * valid
             loss_dict = losses.compute_loss(pred, w4, w1, alphas, self.cfg)
-            self._extra_losses(pred, loss_dict, w4, w1, alphas, (b, n_f, self.num_masks, h, w))
+            # planes per reference plane count (the reference sums an epsilon over its zero-padded slots too)
+            self._extra_losses(pred, loss_dict, w4, w1, alphas, (b, n_f, n_i, h, w), n_slots / n_i)
             if "loss_max_atten" in pred and self.cfg.loss_atten_w > 0:
                 loss_dict["loss_max_atten"] = pred["loss_max_atten"]
                 loss_dict["total"] = loss_dict["total"] + loss_dict["loss_max_atten"] * self.cfg.loss_atten_w
             self._extra_decoder_losses(pred, loss_dict)
-            if chosen is not None:
-                output = {k: v[:, :, chosen] for k, v in output.items()}
+            if unsort is not None:
+                output = {k: v[:, :, unsort] for k, v in output.items()}
             return output, loss_dict
 
-        output = {k: v[:, :, :n_i] for k, v in output.items()}
         for k in pred:
             if k.startswith("mem_"):
                 output[k] = pred[k]
@@ -203,7 +204,7 @@ class MaGGIe_Temp(MaGGIe):
             output["diff_pred_forward"] = df.repeat(1, 1, n_i, 1, 1)
             output["temp_alpha"] = ta
 
-    def _extra_losses(self, pred, L, w4, w1, alphas, shape5):
+    def _extra_losses(self, pred, L, w4, w1, alphas, shape5, pad_ratio=1.0):
         if self.cfg.loss_dtSSD_w <= 0:
             return
         r = lambda t: t.reshape(*shape5).float()
@@ -212,7 +213,7 @@ class MaGGIe_Temp(MaGGIe):
         if self.cfg.loss_reweight_os8:
             lo, hi = 1.0 / 255.0, 254.0 / 255.0
             w8 = (((alphas <= hi) & (alphas >= lo)) | ((a8 <= hi) & (a8 >= lo))).to(a8.dtype) + w8
-        dt = MaGGIeTempDecoder._loss_dtssd
+        dt = lambda p, g, m: MaGGIeTempDecoder._loss_dtssd(p, g, m, pad_ratio)
         d1 = dt(r(pred["alpha_os1"]), r(alphas), r(w1))
         d4 = dt(r(pred["alpha_os4"]), r(alphas), r(w4))
         d8 = dt(r(a8), r(alphas), r(w8))

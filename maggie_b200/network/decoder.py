@@ -183,6 +183,13 @@ class InstanceMatteDecoder(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------- full decoder
+def _scatter_slots(t, slots, n_slots):
+    """[B, len(slots), ...] compact planes -> the reference's zero-padded [B, n_slots, ...] slot layout."""
+    out = t.new_zeros((t.shape[0], n_slots) + tuple(t.shape[2:]))
+    out[:, slots] = t
+    return out
+
+
 def _draw_widths(n, k_size, is_train):
     """Ellipse sizes for compute_unknown: same numpy draws, in the same order, as utils/utils.py:45-50."""
     return [int(np.random.randint(1, k_size)) for _ in range(n)] if is_train else [k_size // 2] * n
@@ -218,12 +225,13 @@ class MaGGIeDecoder(nn.Module):
             p.requires_grad_(True)  # as in the reference: trainable flag set, but they never receive a gradient
 
     # -- sparse refinement ---------------------------------------------------------------------------
-    def predict_details(self, os8_feat, roi, queries, fea1, fea2, fea3):
-        """roi uint8 [B, n_i, H, W]; queries [B, 10, 64] fp32.  Returns fp32 logit maps
-        [B*n_i,1,H/4,W/4], [B*n_i,1,H,W] (-99 where inactive) and the site counts."""
+    def predict_details(self, os8_feat, roi, queries, fea1, fea2, fea3, T=None):
+        """roi uint8 [B, n_i, H, W]; queries [B, n_i, 64] fp32; T: site tables of `roi` when already built.  Returns
+        fp32 logit maps [B*n_i,1,H/4,W/4], [B*n_i,1,H,W] (-99 where inactive) and the site counts."""
         B, n_i, H, W = roi.shape
         slots = B * n_i
-        T = ops.build_sites(roi.reshape(slots, H, W))
+        if T is None:
+            T = ops.build_sites(roi.reshape(slots, H, W))
         c1, c2, c4, c8 = T.coords
         dt = os8_feat.dtype
         t = self.training
@@ -271,15 +279,25 @@ class MaGGIeDecoder(nn.Module):
         return self.refine_OS8(x, mask_os8, gt_os8)
 
     @staticmethod
-    def pooled_masks(masks, gt_alphas, b, n_f, n_i, H, W, training):
-        """mask -> OS8 by avg-pool > 0 (utils.py:16-21); GT alpha > 0 -> OS8 by max-pool (:11-15)."""
-        mask_os8 = F.avg_pool2d(masks.reshape(b * n_f, n_i, H, W), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0
+    def pooled_masks(masks, gt_alphas, b, n_f, n_i, H, W, training, slots=None, n_slots=None):
+        """mask -> OS8 by avg-pool > 0 (utils.py:16-21); GT alpha > 0 -> OS8 by max-pool (:11-15).  With `slots`
+        (compact training planes) the small OS8 masks are scattered into the reference's `n_slots` slot layout."""
+        def place(m):
+            if slots is None:
+                return m
+            out = m.new_zeros((b, n_f, n_slots, H // 8, W // 8))
+            out[:, :, slots] = m
+            return out
+
+        mask_os8 = place(F.avg_pool2d(masks.reshape(b * n_f, n_i, H, W), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0)
         gt_os8 = None
         if training:
-            gt_os8 = F.max_pool2d((gt_alphas > 0).float(), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0
+            gt_os8 = place(F.max_pool2d((gt_alphas > 0).float(), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0)
         return mask_os8, gt_os8
 
-    def _os8_alpha(self, os8_logits, masks, n_i, H, W):
+    def _os8_alpha(self, os8_logits, masks, n_i, H, W, slots=None):
+        if slots is not None:       # compact training planes: only the slots that hold an instance are upsampled
+            os8_logits = os8_logits[:, slots]
         valid = masks.flatten(2).sum(2)[:, :, None, None] > 0
         a8 = ops.upsample_tanh(os8_logits, size=(H, W))
         return a8 * valid if self.training else a8[:, :n_i]
@@ -291,17 +309,49 @@ class MaGGIeDecoder(nn.Module):
             return gt_alphas, True
         return a8, False
 
-    def _refine_and_fuse(self, x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W):
-        """process_os4_os1 + fuse (resnet_inst_matt_spconv.py:346-366, 272-290, 333-340)."""
+    def plan_roi(self, gt_alphas, iter):
+        """Warm-up iterations take the uncertain region from the ground-truth alphas (resnet_inst_matt_spconv.py:311-316),
+        i.e. from an INPUT: its mask and site tables can then be built before the dense stage is even launched, and the
+        one host read of the site counts no longer stalls the middle of the step.  Returns (unk, site tables) or None."""
+        if not (self.training and iter < self.warmup_detail_iter and gt_alphas is not None):
+            return None
+        unk = ops.unknown_mask(gt_alphas, _draw_widths(gt_alphas.shape[0] * gt_alphas.shape[1], 30, False))
+        T = ops.build_sites(unk.reshape(-1, *unk.shape[-2:]))
+        return (unk, T) if T.counts[0] > 0 else None   # empty set: the regular path handles the degenerate batch
+
+    def _guidance_and_roi(self, a8, gt_alphas, iter, roi_plan):
+        if roi_plan is not None:
+            return True, roi_plan[0], roi_plan[1]
+        guided, use_gt = self._choose_guidance(a8, gt_alphas, iter)
+        return use_gt, ops.unknown_mask(guided, _draw_widths(guided.shape[0] * guided.shape[1], 30, False)), None
+
+    def _refine_and_fuse(self, x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W, slots=None, n_slots=None, T=None):
+        """process_os4_os1 + fuse (resnet_inst_matt_spconv.py:346-366, 272-290, 333-340).  `slots`: the planes are
+        compact (plane j = reference slot slots[j] of n_slots); random ellipse sizes are drawn for all reference
+        slots, in the reference's order, and the compact planes pick theirs."""
         t = self.training
         fea1, fea2, fea3 = fea
-        n_sl = a8.shape[0] * a8.shape[1]
-        if t and int(unk.max()) == 0:
+        B = a8.shape[0]
+        n_ref = n_slots if slots is not None else a8.shape[1]
+        if T is None:
+            T = ops.build_sites(unk.reshape(-1, H, W))   # the one host read of the step: the four site counts
+        if t and T.counts[0] == 0:
+            if slots is not None:
+                # degenerate batch: the reference paints the dummy patch into EVERY slot, the empty ones included
+                # (their sites enter the sparse BatchNorm statistics) -> fall back to its full slot layout
+                full = lambda v: None if v is None else _scatter_slots(v, slots, n_slots)
+                ret = self._refine_and_fuse(x, queries, fea, full(a8), full(unk), use_gt, full(gt_alphas), b, n_f, H, W)
+                return {k: (v[:, slots] if torch.is_tensor(v) else v) for k, v in ret.items()}
             unk[:, :, 200:250, 200:250] = 1
+            T = ops.build_sites(unk.reshape(-1, H, W))
+        if slots is not None:
+            queries = queries[:, slots]
+        pick = (lambda ws: ws) if slots is None else (lambda ws: [ws[f * n_ref + s] for f in range(B) for s in slots])
+        widths = lambda k: pick(_draw_widths(B * n_ref, k, t))
         counts = [0, 0, 0, 0]
-        if t or int(unk.max()) > 0:
+        if T.counts[0] > 0:
             q = queries[:, None].expand(-1, n_f, -1, -1).reshape(b * n_f, *queries.shape[1:])
-            os4, os1, counts = self.predict_details(x, unk, q, fea1, fea2, fea3)
+            os4, os1, counts = self.predict_details(x, unk, q, fea1, fea2, fea3, T)
             os4 = os4.reshape(b * n_f, a8.shape[1], H // 4, W // 4)
             os1 = os1.reshape(b * n_f, a8.shape[1], H, W)
             a4 = ops.upsample_tanh(os4, scale=4.0)
@@ -310,27 +360,27 @@ class MaGGIeDecoder(nn.Module):
             a4 = torch.zeros_like(a8)
             a1 = torch.zeros_like(a8)
         ret = dict(alpha_os1=a1, alpha_os4=a4, alpha_os8=a8)
-        w4 = ops.unknown_mask(a8, _draw_widths(n_sl, 27, t), and_mask=unk).to(a8.dtype)
+        w4 = ops.unknown_mask(a8, widths(27), and_mask=unk).to(a8.dtype)
         a = a4 * w4 + a8 * (1 - w4)
-        w1 = ops.unknown_mask(a, _draw_widths(n_sl, 15, t), and_mask=unk).to(a8.dtype)
+        w1 = ops.unknown_mask(a, widths(15), and_mask=unk).to(a8.dtype)
         a = a1 * w1 + a * (1 - w1)
         ret["refined_masks"] = a
         if use_gt:
-            w4 = ops.unknown_mask(gt_alphas, _draw_widths(n_sl, 30, t), and_mask=unk)
-            w1 = ops.unknown_mask(gt_alphas, _draw_widths(n_sl, 15, t), and_mask=unk)
+            w4 = ops.unknown_mask(gt_alphas, widths(30), and_mask=unk)
+            w1 = ops.unknown_mask(gt_alphas, widths(15), and_mask=unk)
         ret["weight_os4"], ret["weight_os1"], ret["detail_mask"] = w4, w1, unk
         ret["site_counts"] = counts
         return ret
 
-    def forward(self, dense_out, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, **_):
+    def forward(self, dense_out, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, slots=None, n_slots=None,
+                roi_plan=None, **_):
         """dense_out: (os8_logits, os8_feat, queries, loss_atten) from `dense_stage`; fea: (fea1, fea2, fea3);
-        masks [b*n_f, n_i, H, W] fp32 {0,1}; gt_alphas [b*n_f, n_i, H, W]."""
+        masks [b*n_f, n_i, H, W] fp32 {0,1}; gt_alphas [b*n_f, n_i, H, W]; slots / n_slots: see `_refine_and_fuse`."""
         H, W = image_hw
         os8_logits, x, queries, loss_atten = dense_out
-        a8 = self._os8_alpha(os8_logits, masks, n_i, H, W)
-        guided, use_gt = self._choose_guidance(a8, gt_alphas, iter)
-        unk = ops.unknown_mask(guided, _draw_widths(guided.shape[0] * guided.shape[1], 30, False))
-        ret = self._refine_and_fuse(x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W)
+        a8 = self._os8_alpha(os8_logits, masks, n_i, H, W, slots)
+        use_gt, unk, T = self._guidance_and_roi(a8, gt_alphas, iter, roi_plan)
+        ret = self._refine_and_fuse(x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W, slots, n_slots, T)
         if self.training and iter >= self.warmup_mask_atten_iter:
             ret["loss_max_atten"] = loss_atten
         return ret
@@ -428,21 +478,28 @@ class MaGGIeTempDecoder(MaGGIeDecoder):
         return F.interpolate(y, size=x.shape[-2:], mode="bilinear", align_corners=False)
 
     @staticmethod
-    def _loss_dtssd(pred, gt, mask):
+    def _loss_dtssd(pred, gt, mask, pad_ratio=1.0):
+        """loss.py:9-16.  The reference sums `mask + 1e-6` over all of its planes; `pad_ratio` = reference planes per
+        plane given here (compact training planes leave the all-zero slots out)."""
         diff = ((pred[:, 1:] - pred[:, :-1]) - (gt[:, 1:] - gt[:, :-1])) ** 2 * mask[:, 1:]
-        return diff.sum() / torch.sum(mask[:, 1:] + 1e-6)
+        if pad_ratio == 1.0:
+            return diff.sum() / torch.sum(mask[:, 1:] + 1e-6)
+        return diff.sum() / (torch.sum(mask[:, 1:]) + 1e-6 * pad_ratio * mask[:, 1:].numel())
 
-    def forward(self, dense_out, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, spar_gt=None, **_):
+    def forward(self, dense_out, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, spar_gt=None, slots=None,
+                n_slots=None, roi_plan=None, **_):
         H, W = image_hw
         t = self.training
         os8_logits, x, queries, loss_atten, hidden = dense_out
         feat_os8 = x.reshape(b, n_f, *x.shape[1:]).detach()
-        a8 = self._os8_alpha(os8_logits, masks, n_i, H, W)
-        guided, use_gt = self._choose_guidance(a8, gt_alphas, iter)
-        if not t:
+        a8 = self._os8_alpha(os8_logits, masks, n_i, H, W, slots)
+        T = None
+        if t:
+            use_gt, unk, T = self._guidance_and_roi(a8, gt_alphas, iter, roi_plan)
+        else:
+            use_gt = False
             a8 = torch.where(a8 >= 0.95, torch.ones_like(a8), a8)
-            guided = a8
-        unk = ops.unknown_mask(guided, _draw_widths(guided.shape[0] * guided.shape[1], 30, False))
+            unk = ops.unknown_mask(a8, _draw_widths(a8.shape[0] * a8.shape[1], 30, False))
         if not t:
             # keep only a +-30 px box around each instance's smoothed coarse alpha (one D2H of the box table)
             sm = self._gaussian_smoothing(a8, 3) > 0.1
@@ -461,18 +518,22 @@ class MaGGIeTempDecoder(MaGGIeDecoder):
             keep = keep.to(a8.device)
             unk = unk * keep
             a8 = a8 * keep
-        ret = self._refine_and_fuse(x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W)
+        ret = self._refine_and_fuse(x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W, slots, n_slots, T)
         ret["mem_feat"] = hidden
         a = ret["refined_masks"]
         fd, bd, fused = self.bidirectional_fusion(feat_os8, a.reshape(b, n_f, *a.shape[1:]))
         ret["temp_alpha"], ret["diff_forward"], ret["diff_backward"] = fused, torch.sigmoid(fd), torch.sigmoid(bd)
         if t:
             ret["loss_max_atten"] = loss_atten
-            sg = spar_gt.reshape(fd.shape[0], -1, *spar_gt.shape[1:])
-            bce = F.binary_cross_entropy_with_logits(fd[:, 1:, 0], sg[:, 1:, 0]) + \
-                F.binary_cross_entropy_with_logits(bd[:, :-1, 0], sg[:, 1:, 0])
-            ones = torch.ones_like(sg[:, 1:, 0:1])
-            dtf = self._loss_dtssd(torch.sigmoid(fd[:, 1:]), sg[:, 1:, 0:1], ones)
-            dtb = self._loss_dtssd(torch.sigmoid(bd[:, :-1]), sg[:, 1:, 0:1], ones)
+            # the reference reads slot 0 of its scattered transition maps (resnet_inst_matt_spconv_temp.py:189-197): with
+            # compact planes that is plane 0 when slot 0 holds an instance (planes are in slot order) and zeros otherwise
+            sg = spar_gt.reshape(fd.shape[0], -1, *spar_gt.shape[1:])[:, 1:, 0:1]
+            if slots is not None and slots[0] != 0:
+                sg = torch.zeros_like(sg)
+            bce = F.binary_cross_entropy_with_logits(fd[:, 1:, 0], sg[:, :, 0]) + \
+                F.binary_cross_entropy_with_logits(bd[:, :-1, 0], sg[:, :, 0])
+            ones = torch.ones_like(sg)
+            dtf = self._loss_dtssd(torch.sigmoid(fd[:, 1:]), sg, ones)
+            dtb = self._loss_dtssd(torch.sigmoid(bd[:, :-1]), sg, ones)
             ret.update(loss_temp_bce=bce, loss_temp_dtssd=dtf + dtb, loss_temp=(bce + dtf + dtb) * 0.25)
         return ret

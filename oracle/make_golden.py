@@ -27,6 +27,9 @@ CASES = {
     # better-conditioned training case for the 16-bit GPU path: 8 samples per BatchNorm batch (the ASPP global-pool BN
     # sees only `b` values per channel), inst_spec dropout off (CUDA and CPU dropout streams differ)
     "train_b8_128_2inst_nodrop": (dict(b=8, n_f=1, n_i=2, H=128, W=128, edge_px=4.0, seed=779, train=True, it=100000), True),
+    # degenerate training batch: binary alphas -> empty uncertain set -> the reference paints its dummy 50x50 patch into
+    # every one of the 10 slots (resnet_inst_matt_spconv.py:347-348)
+    "train_256_2inst_empty_roi": (dict(b=2, n_f=1, n_i=2, H=256, W=256, edge_px=4.0, seed=780, train=True, it=1, binary_alpha=True), True),
 }
 # video model (MaGGIe_Temp): 3-frame eval window (with and without prev_pred) and a training clip
 VIDEO_CASES = {
@@ -34,7 +37,7 @@ VIDEO_CASES = {
     "video_train_4f_128_2inst_nodrop": (dict(b=2, n_f=4, n_i=2, H=128, W=128, edge_px=4.0, seed=502, train=True, it=100000), True),
 }
 CASES.update(VIDEO_CASES)
-NO_DROPOUT = {"train_b8_128_2inst_nodrop", "video_train_4f_128_2inst_nodrop"}
+NO_DROPOUT = {"train_b8_128_2inst_nodrop", "video_train_4f_128_2inst_nodrop", "train_256_2inst_empty_roi"}
 RNG_SEED = 2024
 SMALL_GRAD_NUMEL = 2048
 

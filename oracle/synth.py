@@ -61,11 +61,13 @@ def soft_ellipse_alphas(n_frames, n_inst, H, W, edge_px=6.0, shift=(3, 2), seed=
     return torch.from_numpy(out)
 
 
-def make_batch(b, n_f, n_i, H, W, edge_px=6.0, seed=1234, train=False, it=1, mask_os8=False):
+def make_batch(b, n_f, n_i, H, W, edge_px=6.0, seed=1234, train=False, it=1, mask_os8=False, binary_alpha=False):
     """Batch dict in the reference's input contract (maggie/network/arch/maggie.py:63-78)."""
     g = torch.Generator().manual_seed(seed)
     image = torch.randn(b, n_f, 3, H, W, generator=g)
     alphas = torch.stack([soft_ellipse_alphas(n_f, n_i, H, W, edge_px, seed=seed + 17 * k) for k in range(b)])
+    if binary_alpha:  # no uncertain pixel at all (degenerate batch)
+        alphas = (alphas > 0.5).float()
     mask = (alphas > 0.5).float()
     if mask_os8:
         mask = mask[..., ::8, ::8].contiguous()  # nearest downsample as dataloader/him.py:175-176

@@ -65,7 +65,8 @@ def sites_tables_ref(roi):
 def build_sites(roi):
     dev = roi.device
     coords, nbr, parent, child, shapes = sites_tables_ref(roi.cpu().numpy().astype(np.uint8))
-    tt = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a).astype(np.int32).reshape(len(a), -1)).to(dev)
+    tt = lambda a: None if a is None else torch.from_numpy(
+        np.ascontiguousarray(a).astype(np.int32).reshape(len(a), a.shape[1] if a.ndim > 1 else -1)).to(dev)
     return ops.SiteTables([len(c) for c in coords], [tt(c) for c in coords], [tt(a) for a in nbr],
                           [tt(a) for a in parent], [tt(a) for a in child], shapes)
 

@@ -35,3 +35,5 @@ ka = prof.key_averages()
 tot = sum(e.device_time_total for e in ka if e.device_type == torch.autograd.DeviceType.CUDA) if False else sum(e.self_device_time_total for e in ka)
 print("total self CUDA ms", tot / 1e3, "kernel-ish events", sum(e.count for e in ka if e.self_device_time_total > 0))
 print(ka.table(sort_by="self_cuda_time_total", row_limit=int(os.environ.get("ROWS", "45")), max_name_column_width=70))
+if os.environ.get("CPU_TABLE", "0") == "1":
+    print(ka.table(sort_by="self_cpu_time_total", row_limit=60, max_name_column_width=70))
