@@ -102,7 +102,7 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
             order = sorted(range(n_i), key=lambda j: draw[j])
             chosen = [draw[j] for j in order]
             if order != list(range(n_i)):
-                masks, alphas, trans = (None if t is None else t[:, order] for t in (masks, alphas, trans))
+                masks, alphas, trans = (None if t is None else ops.take(t, 1, order) for t in (masks, alphas, trans))
                 unsort = [order.index(j) for j in range(n_i)]
             slot_ids, n_slots = chosen, self.num_masks
         return x, masks, slot_ids, alphas, trans, chosen, n_slots, unsort, (b, n_f, n_i, h, w)
@@ -116,7 +116,8 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
 
     def _dense(self, x, masks, slot_ids, mask_os8, gt_os8, mem_feat=None):
         stage = self._stage[0]
-        stage.train(self.training)
+        if stage.training != self.training:
+            stage.train(self.training)
         ids = ops.slot_ids_tensor(slot_ids, x.device)
         args = (x.float().contiguous(), masks.contiguous(), ids, mask_os8.float(),
                 gt_os8.float() if gt_os8 is not None else mask_os8.float())
@@ -146,12 +147,48 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
     def _extra_decoder_losses(self, pred, loss_dict):
         pass
 
-    def forward(self, batch, **kwargs):
-        x, masks, slot_ids, alphas, trans, chosen, n_slots, unsort, (b, n_f, n_i, h, w) = self._prepare(batch)
+    def _input_stage(self, batch):
+        """Everything that depends on the inputs only: flattening, the pooled OS8 masks and - in warm-up iterations - the
+        uncertain-region mask with its site tables (the step's one host read)."""
+        prep = self._prepare(batch)
+        x, masks, slot_ids, alphas, trans, chosen, n_slots, unsort, (b, n_f, n_i, h, w) = prep
         mask_os8, gt_os8 = self.decoder.pooled_masks(masks, alphas, b, n_f, n_i, h, w, self.training, chosen, n_slots)
+        roi_plan = self.decoder.plan_roi(alphas, batch.get("iter", 0))
+        return prep, mask_os8, gt_os8, roi_plan
+
+    def _input_stage_async(self, batch, ready_event):
+        """`batch['ready_event']` (optional, a `torch.cuda.Event`): the caller produced the inputs on another stream (a
+        copy stream, as prefetching loaders do) and they are complete once the event has fired.  The input stage then
+        runs on a side stream that waits for that event only, NOT for the work already queued on the compute stream (the
+        previous step's backward): its host read no longer drains the GPU queue, and the CPU keeps running ahead."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side_stream", None) is None or self._side_stream.device != main.device:
+            self._side_stream = torch.cuda.Stream(device=main.device, priority=-1)
+        side = self._side_stream
+        side.wait_event(ready_event)
+        with torch.cuda.stream(side):
+            out = self._input_stage(batch)
+        main.wait_event(ready_event)
+        main.wait_stream(side)
+
+        def keep(o):   # tensors allocated on the side stream are consumed on the compute stream
+            if torch.is_tensor(o) and o.is_cuda:
+                o.record_stream(main)
+            elif isinstance(o, (tuple, list)):
+                for v in o:
+                    keep(v)
+        keep(out)
+        return out
+
+    def forward(self, batch, **kwargs):
+        ev = batch.get("ready_event")
+        if ev is not None and batch["image"].is_cuda:
+            prep, mask_os8, gt_os8, roi_plan = self._input_stage_async(batch, ev)
+        else:
+            prep, mask_os8, gt_os8, roi_plan = self._input_stage(batch)
+        x, masks, slot_ids, alphas, trans, chosen, n_slots, unsort, (b, n_f, n_i, h, w) = prep
         mem_feat = kwargs.pop("mem_feat", None)
         it = batch.get("iter", 0)
-        roi_plan = self.decoder.plan_roi(alphas, it)   # before the dense stage: see MaGGIeDecoder.plan_roi
         fea1, fea2, fea3, *dense_out = self._dense(x, masks, slot_ids, mask_os8, gt_os8,
                                                    mem_feat if torch.is_tensor(mem_feat) else None)
         with ops.step_scope("sparse_stage", x.device):
@@ -184,7 +221,7 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
                 loss_dict["total"] = loss_dict["total"] + loss_dict["loss_max_atten"] * self.cfg.loss_atten_w
             self._extra_decoder_losses(pred, loss_dict)
             if unsort is not None:
-                output = {k: v[:, :, unsort] for k, v in output.items()}
+                output = {k: ops.take(v, 2, unsort) for k, v in output.items()}
             return output, loss_dict
 
         for k in pred:

@@ -186,7 +186,7 @@ class InstanceMatteDecoder(nn.Module):
 def _scatter_slots(t, slots, n_slots):
     """[B, len(slots), ...] compact planes -> the reference's zero-padded [B, n_slots, ...] slot layout."""
     out = t.new_zeros((t.shape[0], n_slots) + tuple(t.shape[2:]))
-    out[:, slots] = t
+    ops.put(out, 1, slots, t)
     return out
 
 
@@ -286,7 +286,7 @@ class MaGGIeDecoder(nn.Module):
             if slots is None:
                 return m
             out = m.new_zeros((b, n_f, n_slots, H // 8, W // 8))
-            out[:, :, slots] = m
+            ops.put(out, 2, slots, m)
             return out
 
         mask_os8 = place(F.avg_pool2d(masks.reshape(b * n_f, n_i, H, W), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0)
@@ -297,7 +297,7 @@ class MaGGIeDecoder(nn.Module):
 
     def _os8_alpha(self, os8_logits, masks, n_i, H, W, slots=None):
         if slots is not None:       # compact training planes: only the slots that hold an instance are upsampled
-            os8_logits = os8_logits[:, slots]
+            os8_logits = ops.take(os8_logits, 1, slots)
         valid = masks.flatten(2).sum(2)[:, :, None, None] > 0
         a8 = ops.upsample_tanh(os8_logits, size=(H, W))
         return a8 * valid if self.training else a8[:, :n_i]
@@ -341,11 +341,11 @@ class MaGGIeDecoder(nn.Module):
                 # (their sites enter the sparse BatchNorm statistics) -> fall back to its full slot layout
                 full = lambda v: None if v is None else _scatter_slots(v, slots, n_slots)
                 ret = self._refine_and_fuse(x, queries, fea, full(a8), full(unk), use_gt, full(gt_alphas), b, n_f, H, W)
-                return {k: (v[:, slots] if torch.is_tensor(v) else v) for k, v in ret.items()}
+                return {k: (ops.take(v, 1, slots) if torch.is_tensor(v) else v) for k, v in ret.items()}
             unk[:, :, 200:250, 200:250] = 1
             T = ops.build_sites(unk.reshape(-1, H, W))
         if slots is not None:
-            queries = queries[:, slots]
+            queries = ops.take(queries, 1, slots)
         pick = (lambda ws: ws) if slots is None else (lambda ws: [ws[f * n_ref + s] for f in range(B) for s in slots])
         widths = lambda k: pick(_draw_widths(B * n_ref, k, t))
         counts = [0, 0, 0, 0]

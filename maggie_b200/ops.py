@@ -29,16 +29,79 @@ _WIDTHS_CACHE = {}
 
 
 def _widths_tensor(widths, device):
-    """Device int32 copy of the per-slice ellipse sizes; constant (eval) width lists are cached."""
+    """Device int32 copy of the per-slice ellipse sizes; constant (eval) width lists are cached, random ones (training)
+    go through a pinned staging ring so that the copy is asynchronous."""
     key = (widths, device)
     t = _WIDTHS_CACHE.get(key)
     if t is None:
-        t = torch.tensor(widths, dtype=torch.int32, device=device)
         if len(set(widths)) == 1 or len(widths) <= 16:
-            if len(_WIDTHS_CACHE) > 64:
+            t = torch.tensor(widths, dtype=torch.int32, device=device)
+            if len(_WIDTHS_CACHE) > 256:
                 _WIDTHS_CACHE.clear()
             _WIDTHS_CACHE[key] = t
+        elif len(widths) <= _IntStager.CAP and torch.device(device).type == "cuda":
+            st = _STAGERS.get(str(device))
+            if st is None:
+                st = _STAGERS[str(device)] = _IntStager(device)
+            t = st.put(widths)
+        else:
+            t = torch.tensor(widths, dtype=torch.int32, device=device)
     return t
+
+
+_INDEX_CACHE = {}
+
+
+def index_tensor(idx, device):
+    """Cached device int64 copy of a short python index list.  Indexing a CUDA tensor with a python list makes torch
+    build the index tensor with a synchronous host-to-device copy, which drains the launch queue; the cache pays that
+    once per distinct list (slot subsets: at most C(10, n) of them)."""
+    key = (tuple(int(i) for i in idx), str(device))
+    t = _INDEX_CACHE.get(key)
+    if t is None:
+        if len(_INDEX_CACHE) > 4096:
+            _INDEX_CACHE.clear()
+        t = _INDEX_CACHE[key] = torch.tensor(key[0], dtype=torch.long, device=device)
+    return t
+
+
+def take(t, dim, idx):
+    """t.index_select(dim, idx) for a python index list, without the host synchronisation of `t[:, idx]`."""
+    return t.index_select(dim, index_tensor(idx, t.device))
+
+
+def put(out, dim, idx, src):
+    """out.index_copy_(dim, idx, src) for a python index list (no host synchronisation)."""
+    return out.index_copy_(dim, index_tensor(idx, out.device), src)
+
+
+class _IntStager:
+    """Ring of pinned host buffers + device buffers for small per-call int32 lists that change every call (the random
+    ellipse sizes of training): `torch.tensor(list, device=cuda)` copies from pageable memory, i.e. synchronously."""
+    SLOTS, CAP = 32, 1024
+
+    def __init__(self, device):
+        self.host = torch.empty((self.SLOTS, self.CAP), dtype=torch.int32).pin_memory()
+        self.dev = torch.empty((self.SLOTS, self.CAP), dtype=torch.int32, device=device)
+        self.events = [None] * self.SLOTS
+        self.turn = 0
+
+    def put(self, values):
+        n = len(values)
+        i = self.turn % self.SLOTS
+        self.turn += 1
+        if self.events[i] is not None:
+            self.events[i].synchronize()       # long done unless the host is > SLOTS calls ahead
+        self.host[i, :n] = torch.tensor(values, dtype=torch.int32)
+        out = self.dev[i, :n]
+        out.copy_(self.host[i, :n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
+        return out
+
+
+_STAGERS = {}
 
 
 def unknown_mask(alpha, widths, and_mask=None):
