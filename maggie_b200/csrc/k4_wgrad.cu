@@ -135,8 +135,9 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
                     tmem_ld_wait();
                     if (co < a.Co) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (ci0 + c0 + i < a.Ci) atomicAdd(drow + c0 + i, __uint_as_float(r[i]));
+                        for (int i = 0; i < 16; i += 4)   // Ci is a multiple of 16 and every offset of 4: aligned
+                            red_add_v4(drow + c0 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                       __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
                     }
                 }
             }

@@ -342,7 +342,9 @@ sparse_wgrad_kernel(const SWArgs a) {
                 if (co < a.Cout) {
                     float* drow = a.dw + (size_t)co * a.T * a.Cin + (size_t)t0 * a.Cin + c0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) atomicAdd(drow + i, __uint_as_float(r[i]));
+                    for (int i = 0; i < 16; i += 4)
+                        red_add_v4(drow + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                   __uint_as_float(r[i + 3]));
                 }
             }
         } else if (lane == 0) {

@@ -83,6 +83,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- reductions to global memory ---------------------------------------------------------------------------
+// One 16-byte vector reduction instead of four scalar ones (sm_90+): the split-K epilogues of the weight-gradient
+// kernels are bound by the number of reduction requests the L2 has to retire.  `addr` must be 16-byte aligned.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 shared memory descriptor"): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), fixed 0b001 [46,49), base offset [49,52), layout [61,64): 2 = 128B, 4 = 64B, 6 = 32B swizzle.

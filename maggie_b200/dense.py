@@ -235,6 +235,35 @@ def wgrad_launch(dy, x, taps, dw, *, stride=1, dy_map=(1, 0, 1, 0), grid_hw):
     return dw
 
 
+# ================================================================================================ auxiliary stream
+# Weight gradients are leaves of the backward data-flow: nothing downstream of a layer waits for them until the grouped
+# weight-prep backward at the very end.  They run on ONE auxiliary stream, forked after the layer's BatchNorm backward
+# and joined once before `mg_wprep_bwd`, so that they overlap with the dgrad -> BN-backward chain of the layers below
+# (most launches of this network fill only a fraction of the 148 SMs).  Fork and join are plain event waits, i.e.
+# CUDA-graph capturable.
+_AUX = {}
+AUX_WGRAD = True
+
+
+def aux_stream(device):
+    st = _AUX.get(device.index)
+    if st is None:
+        st = _AUX[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
+def wgrad_async(geom, dr, xn, w_shape, bank):
+    """geom.wgrad into the bank's accumulator on the auxiliary stream (joined by WeightBank._backward)."""
+    main = torch.cuda.current_stream(dr.device)
+    side = aux_stream(dr.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        geom.wgrad(dr, xn, w_shape, bank=bank)
+    dr.record_stream(side)
+    xn.record_stream(side)
+    bank.prep.aux = side
+
+
 # ================================================================================================ geometry
 class ConvGeom:
     """Forward / dgrad / wgrad launch recipes of one conv layer.  kind 'conv': k x k, stride 1|2, pad, dilation
@@ -385,8 +414,13 @@ class _ConvBNAct(torch.autograd.Function):
         _lib.check(L.mg_bn_bwd_apply(_ptr(dy), _ptr(y), _ptr(r), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(sums), _ptr(dr),
                                      _ptr(dres), N, Ho, Wo, Co, a_post, ACT[act] if act_first else 0, _stream()),
                    "mg_bn_bwd_apply")
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if handle is not None and AUX_WGRAD:
+                wgrad_async(geom, dr, xn, w_shape, handle)
+            else:
+                dw = geom.wgrad(dr, xn, w_shape, bank=handle)
         dx = geom.dgrad(dr, w, xn.shape).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
-        dw = geom.wgrad(dr, xn, w_shape, bank=handle) if ctx.needs_input_grad[1] else None
         if dres is not None:
             dres = dres.permute(0, 3, 1, 2)
             if res_up:

@@ -85,7 +85,7 @@ class BankedWeight:
 
 
 class Prepared:
-    __slots__ = ("bank", "P", "D", "G", "vec", "scal", "token", "pools")
+    __slots__ = ("bank", "P", "D", "G", "vec", "scal", "token", "pools", "aux")
 
     def handle(self, idx):
         return BankedWeight(self, self.bank.entries[idx])
@@ -212,12 +212,16 @@ class WeightBank:
         prep.vec = torch.zeros(self.vec_size, dtype=torch.float32, device=dev)
         prep.scal = torch.empty((len(self.entries), 4), dtype=torch.float32, device=dev)
         prep.pools = None
+        prep.aux = None
         _lib.check(_lib.lib().mg_wprep_fwd(_ptr(self.layers_dev), _ptr(self.items_vt), self.n_vt, _ptr(self.items_u), self.n_u,
                                            _ptr(self.items_tile), self.n_tile, _ptr(prep.vec), _ptr(prep.scal), _ptr(prep.P),
                                            _ptr(prep.D), _stream()), "mg_wprep_fwd")
         return prep
 
     def _backward(self, prep):
+        if prep.aux is not None:   # weight gradients were accumulated on the auxiliary stream (dense.wgrad_async)
+            torch.cuda.current_stream(self.device).wait_stream(prep.aux)
+            prep.aux = None
         grad = torch.empty(self.grad_size, dtype=torch.float32, device=self.device)
         prep.scal[:, 3].zero_()  # <G, W_bar> accumulators (a second backward through the same graph starts clean)
         _lib.check(_lib.lib().mg_wprep_bwd(_ptr(self.layers_dev), _ptr(self.items_tile), self.n_tile, _ptr(prep.G), _ptr(prep.vec),
