@@ -204,6 +204,20 @@ int mg_sparse_conv(const mg_sparse_conv_desc* desc, void* stream);
 int mg_sparse_wgrad(const void* dout, int dout_stride, int Cout, const void* src, int src_stride, int Cin,
                     const int32_t* table, int T, int No, float* dw, void* stream);
 
+/* ---- K13: row-wise helpers (LayerNorm with fused residual, column sums) ---------------------------------
+ * replaces: nn.LayerNorm after the residual add of every post-norm attention / FFN layer (module/mask_attention.py:
+ *           `tgt = self.norm(tgt + self.dropout(tgt2))`, 11 per forward) with its backward, and the bias-gradient
+ *           reductions of the sparse layers.
+ * mg_layer_norm_fwd : y = LN(a + b) * gamma + beta over rows of E (64 | 128) fp16 elements; b optional; sum_out (optional,
+ *                     needed for the backward when b is given) receives the fp16 sum; stat [rows][2] = (mean, rstd).
+ * mg_layer_norm_bwd : dx (fp16) from s = a + b, gy; dgb [2][E] fp32 += (dgamma ; dbeta)  (caller zeroes).
+ * mg_col_sum        : out[c] += sum_r x[r][c], x fp16 rows with row stride `stride` (caller zeroes out).            */
+int mg_layer_norm_fwd(const void* a, const void* b, const float* gamma, const float* beta, float eps, void* sum_out, void* y,
+                      float* stat, int rows, int E, void* stream);
+int mg_layer_norm_bwd(const void* s, const void* gy, const float* gamma, const float* stat, void* dx, float* dgb, int rows,
+                      int E, void* stream);
+int mg_col_sum(const void* x, int stride, int rows, int C, float* out, void* stream);
+
 /* ---- K12: fused training losses (weighted L1 + 3-level Laplacian pyramid + Sobel gradient, 3 alpha scales) ----
  * replaces: arch/maggie.py:237-346 (regression_loss, compute_loss) + loss.py:67-191 (GradientLoss, LapLoss), ~9
  *           pyramid / stencil passes of tiny cuDNN convolutions per scale, and their autograd backward.

@@ -60,7 +60,7 @@ class _FFN(nn.Module):
         h = F.relu(ops.linear(x, self.linear1.weight, self.linear1.bias))
         h = F.dropout(h, p, t)
         h = F.dropout(ops.linear(h, self.linear2.weight, self.linear2.bias), p, t)
-        return ops.layer_norm(x + h, self.norm)
+        return ops.layer_norm(x, self.norm, residual=h)
 
 
 class _Attn(nn.Module):
@@ -85,7 +85,7 @@ class _Attn(nn.Module):
         v = ops.linear_rows(mem, w[2 * E:], b[2 * E:])
         o, stat = ops.attention(q, k, v, key_padding, guidance)
         o = ops.linear_rows(o, mha.out_proj.weight, mha.out_proj.bias)
-        return ops.layer_norm(tgt + o, self.norm), stat
+        return ops.layer_norm(tgt, self.norm, residual=o), stat
 
 
 class _MLP1(nn.Module):

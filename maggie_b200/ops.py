@@ -323,8 +323,61 @@ def linear_rows(x, w, b=None):
     return y.reshape(*x.shape[:-1], w.shape[0]).to(x.dtype)
 
 
-def layer_norm(x, ln):
+class _LayerNormRes(torch.autograd.Function):
+    """LayerNorm(a + b) on fp16 rows of 64 / 128 elements, fp32 statistics (K13)."""
+
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, eps):
+        E = a.shape[-1]
+        rows = a.numel() // E
+        ah = a.detach().contiguous()
+        bh = b.detach().contiguous() if b is not None else None
+        y = torch.empty_like(ah)
+        s = torch.empty_like(ah) if bh is not None else ah
+        stat = torch.empty((rows, 2), dtype=torch.float32, device=a.device)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        _lib.check(_lib.lib().mg_layer_norm_fwd(_ptr(ah), _ptr(bh), _ptr(g32), _ptr(b32), float(eps),
+                                               _ptr(s) if bh is not None else None, _ptr(y), _ptr(stat), rows, E, _stream()),
+                   "mg_layer_norm_fwd")
+        ctx.save_for_backward(s, g32, stat)
+        ctx.meta = (rows, E, b is not None, gamma.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        s, g32, stat = ctx.saved_tensors
+        rows, E, has_b, pdt = ctx.meta
+        g = gy.contiguous() if gy.dtype == torch.float16 else gy.to(torch.float16).contiguous()
+        dx = torch.empty_like(s)
+        from . import dense
+        dgb = dense.zeros_f32(2 * E, s.device).view(2, E)
+        _lib.check(_lib.lib().mg_layer_norm_bwd(_ptr(s), _ptr(g), _ptr(g32), _ptr(stat), _ptr(dx), _ptr(dgb), rows, E, _stream()),
+                   "mg_layer_norm_bwd")
+        return dx, (dx if has_b else None), dgb[0].to(pdt), dgb[1].to(pdt), None
+
+
+def layer_norm(x, ln, residual=None):
+    """LayerNorm(x + residual) from a container's tensors.  NATIVE (K13, residual add fused) for CUDA fp16 rows of 64 / 128
+    elements; torch composition otherwise (fp32 inputs, CPU tests)."""
+    if x.is_cuda and x.dtype == torch.float16 and x.shape[-1] in (64, 128) and (residual is None or residual.dtype == x.dtype):
+        if residual is not None and residual.shape != x.shape:
+            residual = residual.expand_as(x)
+        return _LayerNormRes.apply(x, residual, ln.weight, ln.bias, ln.eps)
+    if residual is not None:
+        x = x + residual
     return F.layer_norm(x.float(), (x.shape[-1],), ln.weight, ln.bias, ln.eps).to(x.dtype)
+
+
+def col_sum(x):
+    """fp32 column sums of fp16 rows [N, C] (bias gradients of the sparse layers).  NATIVE (K13)."""
+    _need_cuda(x)
+    N, C = x.shape
+    if x.dtype != torch.float16 or x.stride(1) != 1 or x.stride(0) % 8 or C % 8 or 256 % (C // 8):
+        return x.float().sum(0)
+    from . import dense
+    out = dense.zeros_f32(C, x.device)
+    _lib.check(_lib.lib().mg_col_sum(_ptr(x), x.stride(0), N, C, _ptr(out), _stream()), "mg_col_sum")
+    return out
 
 
 class _AttnTQ(torch.autograd.Function):

@@ -164,7 +164,8 @@ class _RowsConv(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = _wgrad(dr, co, src, ci, table, T).view(w_shape)
         if has_bias and ctx.needs_input_grad[2]:
-            dbias = dr.float().sum(0)
+            from . import ops
+            dbias = ops.col_sum(dr)
         return dsrc, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
 
 

@@ -1,0 +1,51 @@
+"""-m gpu: K13 row kernels (LayerNorm with fused residual, column sums) against plain PyTorch fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,E,with_res", [(32768, 128, True), (80, 128, True), (10094, 64, True), (7, 64, False), (0, 128, True)])
+def test_layer_norm_residual_fwd_bwd(rows, E, with_res):
+    from maggie_b200 import ops
+    torch.manual_seed(rows + E)
+    dev = torch.device("cuda")
+    ln = torch.nn.LayerNorm(E).to(dev)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+    a = torch.randn(rows, E, device=dev).half().requires_grad_(True)
+    b = (torch.randn(rows, E, device=dev) * 0.5).half().requires_grad_(True) if with_res else None
+    y = ops.layer_norm(a, ln, residual=b)
+    assert y.dtype == torch.float16 and y.shape == a.shape
+    gy = torch.randn(rows, E, device=dev).half()
+    y.backward(gy)
+    got = (a.grad.float(), ln.weight.grad.clone(), ln.bias.grad.clone(), b.grad.float() if with_res else None)
+    a2 = a.detach().float().requires_grad_(True)
+    s = a2 + b.detach().float() if with_res else a2
+    if with_res:
+        s = (a.detach() + b.detach()).float().detach().requires_grad_(True)   # the fp16 sum torch's `tgt + o` produces
+    ln.weight.grad = ln.bias.grad = None
+    ref = F.layer_norm(s, (E,), ln.weight, ln.bias, ln.eps)
+    ref.backward(gy.float())
+    if rows == 0:
+        return
+    assert (y.float() - ref).abs().max() < 4e-3
+    ds = s.grad
+    assert (got[0] - ds).abs().max() < 2e-2 * max(1.0, float(ds.abs().max()))
+    if with_res:
+        assert torch.equal(got[0], got[3])
+    tol = 2e-3 * rows ** 0.5 + 1e-2
+    assert (got[1] - ln.weight.grad).abs().max() < tol and (got[2] - ln.bias.grad).abs().max() < tol
+
+
+@pytest.mark.parametrize("rows,C,stride", [(349968, 32, 32), (29815, 64, 64), (1000, 32, 64), (5, 128, 128), (0, 32, 32)])
+def test_col_sum(rows, C, stride):
+    from maggie_b200 import ops
+    torch.manual_seed(rows)
+    x = torch.randn(rows, stride, device="cuda").half()[:, :C]
+    got = ops.col_sum(x)
+    ref = x.double().sum(0)
+    assert got.dtype == torch.float32 and got.shape == (C,)
+    assert (got.double() - ref).abs().max() < 1e-3 * max(1.0, rows ** 0.5)
