@@ -136,6 +136,11 @@ typedef struct mg_conv_desc {
     const void* res; int32_t res_up;          /* optional fp16 residual [N,Ho,Wo,Co] ([N,Ho/2,Wo/2,Co] if res_up) */
 } mg_conv_desc;
 int mg_conv_fprop(const mg_conv_desc* desc, void* stream);
+/* Stride-1 layers with Ci, Co <= 64 and taps within +-1 pixel (the 512^2 .. 128^2 3x3 convolutions and their data
+ * gradients) are routed by mg_conv_fprop to K2b, a persistent kernel that keeps a halo patch of the activations and all
+ * the weights resident in shared memory (csrc/k2b_conv_halo.cu; MAGGIE_B200_NO_HALO_CONV=1 disables the routing).
+ * mg_conv_halo_launches: how many launches took that path (tests / profiling). */
+unsigned long long mg_conv_halo_launches(void);
 
 /* ---- K4: convolution weight gradient (tcgen05, split-K over pixels) ---------------------------------
  * replaces: cuDNN's wgrad behind `loss.backward()` for every conv above (engine/train.py:266).

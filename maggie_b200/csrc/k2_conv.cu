@@ -223,6 +223,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 }  // namespace
 
+namespace mg {
+int conv_halo_launch(const mg_conv_desc* d, void* stream, bool* handled);   // k2b_conv_halo.cu
+}
+
 extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
     MG_REQUIRE(d && d->x && d->w && d->out, "mg_conv_fprop: null pointer");
     MG_REQUIRE(d->n_taps >= 1 && d->n_taps <= MAX_TAPS, "mg_conv_fprop: n_taps %d out of range", d->n_taps);
@@ -234,6 +238,13 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
     if (!enc) {
         mg::set_error("mg_conv_fprop: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
         return MG_ERR_CUDA;
+    }
+    MG_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "mg_conv_fprop: scale and shift go together");
+    {
+        // high-resolution, low-channel stride-1 layers: halo-resident persistent kernel (K2b)
+        bool handled = false;
+        const int rc = mg::conv_halo_launch(d, stream, &handled);
+        if (rc != MG_OK || handled) return rc;
     }
     KArgs a;
     a.n_taps = d->n_taps;

@@ -9,19 +9,34 @@ namespace {
 
 constexpr int STAT_COPIES = MG_CONV_STAT_COPIES;
 
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
-                                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// block = 8 copy-groups x 32 channels: the 64 statistic copies are summed by 8 threads per channel (coalesced over the
+// channels) and combined through shared memory - the kernel is pure latency, so the serial chain is kept short.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
+                   float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
+    __shared__ float s_s[8][32], s_q[8][32];
+    const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    if (stats) {
+        float s = 0.f, q = 0.f;
+        if (c < C) {
+#pragma unroll
+            for (int k = grp; k < STAT_COPIES; k += 8) {
+                s += __ldg(stats + (size_t)k * 2 * C + c);
+                q += __ldg(stats + (size_t)k * 2 * C + C + c);
+            }
+        }
+        s_s[grp][cl] = s, s_q[grp][cl] = q;
+        __syncthreads();
+    }
+    if (grp != 0 || c >= C) return;
     float mean, var;
     if (stats) {
         float s = 0.f, q = 0.f;
-        for (int k = 0; k < STAT_COPIES; ++k) {
-            s += stats[(size_t)k * 2 * C + c];
-            q += stats[(size_t)k * 2 * C + C + c];
-        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += s_s[k][cl], q += s_q[k][cl];
         mean = s / count;
         var = fmaxf(q / count - mean * mean, 0.f);
         if (rmean) {
@@ -204,7 +219,7 @@ extern "C" int mg_bn_finalize(const float* stats, float count, const float* gamm
     MG_REQUIRE(scale && shift && C > 0, "mg_bn_finalize: null pointer");
     MG_REQUIRE(stats || (running_mean && running_var), "mg_bn_finalize: need batch statistics or running statistics");
     MG_REQUIRE((save_mean == nullptr) == (save_invstd == nullptr), "mg_bn_finalize: save_mean/save_invstd go together");
-    MG_LAUNCH(bn_finalize_kernel, mg::ceil_div(C, 128), 128, 0, stream, stats, count, gamma, beta, running_mean, running_var,
+    MG_LAUNCH(bn_finalize_kernel, mg::ceil_div(C, 32), 256, 0, stream, stats, count, gamma, beta, running_mean, running_var,
               momentum, eps, scale, shift, save_mean, save_invstd, C);
     MG_CHECK_LAUNCH("mg_bn_finalize");
     return MG_OK;

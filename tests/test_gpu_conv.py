@@ -81,3 +81,61 @@ def test_conv_full_size_linearity():
     assert float((y12 - (2 * y1 + y2)).abs().max()) < 2e-2
     ref = F.conv2d(x1[3:4, :64].float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1)
     _close(y1[3:4, :62], ref[:, :62], "crop")
+
+
+# ---- K2b: halo-resident persistent kernel for the high-resolution, low-channel stride-1 layers --------------------
+@pytest.mark.parametrize("N,H,W,Ci,Co", [
+    (2, 40, 72, 32, 32),       # one strip (W <= 254), ragged last row block
+    (1, 128, 128, 64, 64),     # 128B-swizzled weights, 8 channel planes
+    (1, 24, 300, 32, 64),      # three 128-pixel strips, the last one partial
+    (8, 64, 64, 32, 64),
+    (1, 9, 64, 64, 32),        # fewer rows than a row block
+    (2, 512, 512, 32, 32),     # the heaviest C2 layer
+])
+def test_halo_conv_matches_torch_and_generic_kernel(N, H, W, Ci, Co, monkeypatch):
+    from maggie_b200 import _lib, dense
+    x, w = _mk(N, H, W, Ci, Co, 3, seed=H + W + Ci)
+    before = _lib.lib().mg_conv_halo_launches()
+    got = dense.conv2d_nhwc(x, w)
+    assert _lib.lib().mg_conv_halo_launches() == before + 1, "the layer was not routed to the halo kernel"
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1)
+    _close(got, ref, f"halo conv {Ci}->{Co} {H}x{W}")
+    monkeypatch.setenv("MAGGIE_B200_NO_HALO_CONV", "1")
+    gen = dense.conv2d_nhwc(x, w)
+    assert _lib.lib().mg_conv_halo_launches() == before + 1
+    # same products, fp32 accumulation in a different order: equal up to one fp16 ulp of the output
+    assert float((got.float() - gen.float()).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-3
+
+
+def test_halo_conv_epilogue_stats_bias_act_residual():
+    from maggie_b200 import _lib, dense
+    x, w = _mk(2, 48, 136, 32, 32, 3, seed=11)
+    bias = torch.randn(32).cuda()
+    stats = dense.new_stats(32, x.device)
+    before = _lib.lib().mg_conv_halo_launches()
+    out = dense.conv2d_nhwc(x, w, bias=bias, stats=stats, pre_act="lrelu")
+    assert _lib.lib().mg_conv_halo_launches() == before + 1
+    ref = F.leaky_relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1), 0.2).permute(0, 2, 3, 1)
+    _close(out, ref, "bias + leaky relu")
+    s, n = stats.sum(0), ref.numel() / 32
+    assert torch.allclose(s[0] / n, ref.mean((0, 1, 2)), atol=2e-3)
+    assert torch.allclose(s[1] / n, (ref * ref).mean((0, 1, 2)), rtol=2e-3, atol=2e-3)
+    # eval-mode epilogue: affine + residual + ReLU
+    scale, shift = torch.rand(32).cuda() + 0.5, torch.randn(32).cuda()
+    res = torch.randn(2, 48, 136, 32).half().cuda()
+    out2 = dense.conv2d_nhwc(x, w, scale=scale, shift=shift, res=res, post_act="relu")
+    conv = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1)
+    _close(out2, F.relu(conv * scale + shift + res.float()), "affine + residual + relu")
+
+
+def test_halo_conv_data_gradient_path():
+    """The stride-1 dgrad (flipped taps, transposed pack) of a 32 -> 32 layer also runs on the halo kernel."""
+    from maggie_b200 import _lib, dense
+    x, w = _mk(2, 64, 128, 32, 32, 3, seed=3)
+    dy = torch.randn(2, 64, 128, 32).half().cuda()
+    g = dense.ConvGeom("conv", 3, 1, 1, 1)
+    before = _lib.lib().mg_conv_halo_launches()
+    dx = g.dgrad(dy, w.float(), x.shape)
+    assert _lib.lib().mg_conv_halo_launches() == before + 1
+    ref = torch.nn.grad.conv2d_input((2, 32, 64, 128), w.float(), dy.float().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    _close(dx, ref, "halo dgrad")
