@@ -130,16 +130,21 @@ loss_down_kernel(const float* __restrict__ din, float* __restrict__ dout, int n_
 
 // U d_{k+1} at fine pixel (y,x): zero-inserted upsampling followed by 4*G with reflect padding.
 __device__ __forceinline__ float upsample_at(const float* __restrict__ dc, int hc, int wc, int y, int x, int h, int w) {
+    // Only taps that land on an even (= non-zero-inserted) fine pixel contribute, and reflection keeps parity (h, w are
+    // even): k = y & 1, y & 1 + 2, ... -> 3 x 3 taps on even / 2 x 2 on odd coordinates instead of 25 predicated ones.
     float v = 0.f;
+    const int ky0 = y & 1, kx0 = x & 1;
 #pragma unroll
-    for (int ky = 0; ky < 5; ++ky) {
-        const int yy = refl(y + ky - 2, h);
-        if (yy & 1) continue;
+    for (int a = 0; a < 3; ++a) {
+        const int ky = ky0 + 2 * a;
+        if (ky > 4) break;
+        const float* row = dc + (size_t)(refl(y + ky - 2, h) >> 1) * wc;
         float r = 0.f;
 #pragma unroll
-        for (int kx = 0; kx < 5; ++kx) {
-            const int xx = refl(x + kx - 2, w);
-            if (!(xx & 1)) r += gk(kx) * __ldg(dc + (size_t)(yy >> 1) * wc + (xx >> 1));
+        for (int b = 0; b < 3; ++b) {
+            const int kx = kx0 + 2 * b;
+            if (kx > 4) break;
+            r += gk(kx) * __ldg(row + (refl(x + kx - 2, w) >> 1));
         }
         v += gk(ky) * r;
     }

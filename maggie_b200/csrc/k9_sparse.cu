@@ -120,6 +120,48 @@ sparse_conv_kernel(const SArgs a) {
     if (warp < 4) {
         // ===== gather producers =====
         const int sub = tid % cpr, rr = tid / cpr, rstep = 128 / cpr;
+        if (a.stages == steps && a.kblocks == 1 && steps <= 9 && cpr <= 4) {
+            // Every tap has its own stage: nothing is recycled, so ALL gathers of the tile are put in flight at once -
+            // first every neighbour index of this thread's rows, then one 16-byte cp.async per (tap, row) straight into
+            // the swizzled operand tile (zero-fill form for missing neighbours) - and the stages are handed to the MMA
+            // thread in order as their copy groups land.  (The staged loop below serialises two dependent global-load
+            // latencies per tap: 18 latencies per tile instead of 2.)
+            int idx[9][4];
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int p = tile0 + rr + i * rstep;
+                    idx[t][i] = -1;
+                    if (t < steps && i < cpr && p < a.No) idx[t][i] = a.table ? __ldg(a.table + (size_t)p * a.T + t) : p;
+                }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                if (t < steps) {
+                    const uint32_t tile = smem_u32(sA + (size_t)t * a_tile);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (i < cpr) {
+                            const int r = rr + i * rstep;
+                            const __half* srcp = idx[t][i] >= 0 ? a.src + (size_t)idx[t][i] * a.src_stride + sub * 8 : a.src;
+                            const uint32_t nbytes = idx[t][i] >= 0 ? 16u : 0u;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile + r * a.rowb + swz_chunk(r, sub, a.rowb) * 16),
+                                         "l"(srcp), "r"(nbytes) : "memory");
+                        }
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+#define MG_HAND_OVER_STAGE(T)                                                         \
+    if (T < steps) {                                                                  \
+        asm volatile("cp.async.wait_group %0;" ::"n"(8 - T) : "memory");              \
+        fence_async_smem();                                                           \
+        mbar_arrive(full0 + 8 * T);                                                   \
+    }
+            MG_HAND_OVER_STAGE(0) MG_HAND_OVER_STAGE(1) MG_HAND_OVER_STAGE(2) MG_HAND_OVER_STAGE(3) MG_HAND_OVER_STAGE(4)
+            MG_HAND_OVER_STAGE(5) MG_HAND_OVER_STAGE(6) MG_HAND_OVER_STAGE(7) MG_HAND_OVER_STAGE(8)
+#undef MG_HAND_OVER_STAGE
+        } else
         for (int st = 0; st < steps; ++st) {
             const int s = st % a.stages, ph = (st / a.stages) & 1;
             const int t = st / a.kblocks, kb = st - t * a.kblocks;
@@ -294,40 +336,41 @@ sparse_wgrad_kernel(const SWArgs a) {
                 const int s = i % STAGES, ph = (i / STAGES) & 1;
                 const int row0 = (tile_begin + i) * 128;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
+                // Both operand tiles are filled with 16-byte cp.async (zero-fill form for rows past the end / missing
+                // neighbours): all neighbour indices of the tile first, then every copy of every tap in flight at once.
+                // (Register-staged loads serialised two dependent global-load latencies per tap.)
                 // A: d_out rows (K index = site)
-                uint8_t* ta = sA + (size_t)s * a_tile;
+                const uint32_t ta = smem_u32(sA + (size_t)s * a_tile);
 #pragma unroll 4
                 for (int e = tid; e < 128 * ca_chunks; e += 128) {
                     const int r = e / ca_chunks, c = e - r * ca_chunks;
                     const int p = row0 + r;
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (p < a.No) v = __ldg(reinterpret_cast<const uint4*>(a.dout + (size_t)p * a.dout_stride + c * 8));
-                    st_tile(ta + (size_t)(c / cpa) * a_atom, r, c % cpa, a.rowb_a, v);
+                    const bool ok = p < a.No;
+                    const __half* srcp = ok ? a.dout + (size_t)p * a.dout_stride + c * 8 : a.dout;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ta + (c / cpa) * a_atom + r * a.rowb_a +
+                                 swz_chunk(r, c % cpa, a.rowb_a) * 16), "l"(srcp), "r"(ok ? 16u : 0u) : "memory");
                 }
-                // B: gathered source rows, one tile per tap (indices, then loads, then stores: 4 gathers in flight)
-                for (int tt = 0; tt < nt; ++tt) {
-                    uint8_t* tb = sB + (size_t)(s * a.taps_per_cta + tt) * b_tile;
-                    for (int e0 = tid; e0 < 128 * cb_chunks; e0 += 4 * 128) {
-                        int idx[4], rr4[4], cc4[4];
-                        uint4 v4[4];
+                // B: gathered source rows, one tile per tap
+                for (int e0 = tid; e0 < 128 * cb_chunks; e0 += 128) {
+                    const int r = e0 / cb_chunks, c = e0 - r * cb_chunks;
+                    const int p = row0 + r;
+                    int idx[9];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int e = e0 + u * 128;
-                            rr4[u] = e / cb_chunks, cc4[u] = e - rr4[u] * cb_chunks;
-                            const int p = row0 + rr4[u];
-                            idx[u] = -1;
-                            if (e < 128 * cb_chunks && p < a.No) idx[u] = a.table ? __ldg(a.table + (size_t)p * a.T + t0 + tt) : p;
+                    for (int tt = 0; tt < 9; ++tt) {
+                        idx[tt] = -1;
+                        if (tt < nt && p < a.No) idx[tt] = a.table ? __ldg(a.table + (size_t)p * a.T + t0 + tt) : p;
+                    }
+#pragma unroll
+                    for (int tt = 0; tt < 9; ++tt) {
+                        if (tt < nt) {
+                            const uint32_t tb = smem_u32(sB + (size_t)(s * a.taps_per_cta + tt) * b_tile);
+                            const __half* srcp = idx[tt] >= 0 ? a.src + (size_t)idx[tt] * a.src_stride + c * 8 : a.src;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tb + (c / cpb) * b_atom + r * a.rowb_b +
+                                         swz_chunk(r, c % cpb, a.rowb_b) * 16), "l"(srcp), "r"(idx[tt] >= 0 ? 16u : 0u) : "memory");
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            v4[u] = make_uint4(0u, 0u, 0u, 0u);
-                            if (idx[u] >= 0) v4[u] = __ldg(reinterpret_cast<const uint4*>(a.src + (size_t)idx[u] * a.src_stride + cc4[u] * 8));
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (e0 + u * 128 < 128 * cb_chunks) st_tile(tb + (size_t)(cc4[u] / cpb) * b_atom, rr4[u], cc4[u] % cpb, a.rowb_b, v4[u]);
                     }
                 }
+                asm volatile("cp.async.wait_all;" ::: "memory");
                 fence_async_smem();
                 mbar_arrive(full0 + 8 * s);
             }
@@ -425,8 +468,12 @@ extern "C" int mg_sparse_conv(const mg_sparse_conv_desc* d, void* stream) {
     a.kblocks = d->Cin / a.BK, a.rowb = a.BK * 2;
     const int steps = a.T * a.kblocks;
     const int b_tile = ((a.Cout * a.rowb + 1023) / 1024) * 1024;
+    // Stage recycling costs a tcgen05.commit -> mbarrier -> producer round trip (~1.3 us measured in K2b): give every
+    // tap its own stage whenever two CTAs still fit per SM, so that the gathers of a tile never wait for the MMAs.
+    const size_t fixed_smem = 1024 + (size_t)steps * b_tile + 256 + 4 * 32 * 17 * 4 + 4 * 2 * a.Cout * 4;
     a.stages = std::min(4, std::max(2, steps));
-    const size_t smem = 1024 + (size_t)steps * b_tile + (size_t)a.stages * 128 * a.rowb + 256 + 4 * 32 * 17 * 4 + 4 * 2 * a.Cout * 4;
+    while (a.stages < steps && fixed_smem + (size_t)(a.stages + 1) * 128 * a.rowb <= 112 * 1024) ++a.stages;
+    const size_t smem = fixed_smem + (size_t)a.stages * 128 * a.rowb;
     MG_REQUIRE(smem <= 220 * 1024, "mg_sparse_conv: weight pack does not fit in shared memory (%zu B)", smem);
     static bool attr_set = false;
     if (!attr_set) {
