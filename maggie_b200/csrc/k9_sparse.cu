@@ -104,12 +104,15 @@ sparse_conv_kernel(const SArgs a) {
     {
         const int Ktot = a.T * a.Cin;
         const int chunks = steps * a.Cout * cpr;
+        // asynchronous copies: the whole pack (up to 74 KB) is in flight at once instead of one dependent
+        // load -> store round trip per 16 bytes and thread
         for (int i = tid; i < chunks; i += 160) {
             const int j = i % cpr, n = (i / cpr) % a.Cout, st = i / (cpr * a.Cout);
             const int t = st / a.kblocks, kb = st - t * a.kblocks;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.w + (size_t)n * Ktot + t * a.Cin + kb * a.BK + j * 8));
-            st_tile(sB + (size_t)st * b_tile, n, j, a.rowb, v);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB + (size_t)st * b_tile) + n * a.rowb +
+                         swz_chunk(n, j, a.rowb) * 16), "l"(a.w + (size_t)n * Ktot + t * a.Cin + kb * a.BK + j * 8) : "memory");
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         fence_async_smem();
     }
     tc_fence_before();
@@ -161,31 +164,59 @@ sparse_conv_kernel(const SArgs a) {
             MG_HAND_OVER_STAGE(0) MG_HAND_OVER_STAGE(1) MG_HAND_OVER_STAGE(2) MG_HAND_OVER_STAGE(3) MG_HAND_OVER_STAGE(4)
             MG_HAND_OVER_STAGE(5) MG_HAND_OVER_STAGE(6) MG_HAND_OVER_STAGE(7) MG_HAND_OVER_STAGE(8)
 #undef MG_HAND_OVER_STAGE
-        } else
-        for (int st = 0; st < steps; ++st) {
-            const int s = st % a.stages, ph = (st / a.stages) & 1;
-            const int t = st / a.kblocks, kb = st - t * a.kblocks;
-            mbar_wait(empty0 + 8 * s, ph ^ 1);
-            uint8_t* tile = sA + (size_t)s * a_tile;
-            // all neighbour indices first, then all row loads, then the stores: 4-8 independent loads in flight per thread
-            int idx[8];
-            uint4 v[8];
+        } else {
+            // General path (128-byte rows, several K blocks, or more steps than stages): steps go in batches of `stages`;
+            // within a batch every row copy is an asynchronous 16-byte cp.async, the neighbour indices of the next step
+            // are fetched while the copies of the current one are being issued, and the stages are handed to the MMA
+            // thread in order as their copy groups land.
+            for (int st0 = 0; st0 < steps; st0 += a.stages) {
+                const int nb = min(a.stages, steps - st0);
+                int idx[8], idx_n[8];
+                auto load_idx = [&](int st, int (&dst)[8]) {
+                    const int t = st / a.kblocks;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rr + i * rstep, p = tile0 + r;
-                idx[i] = -1;
-                if (i < cpr && p < a.No) idx[i] = a.table ? __ldg(a.table + (size_t)p * a.T + t) : p;
+                    for (int i = 0; i < 8; ++i) {
+                        const int p = tile0 + rr + i * rstep;
+                        dst[i] = -1;
+                        if (i < cpr && p < a.No) dst[i] = a.table ? __ldg(a.table + (size_t)p * a.T + t) : p;
+                    }
+                };
+                load_idx(st0, idx_n);
+                for (int b = 0; b < nb; ++b) {
+                    const int st = st0 + b, s = st % a.stages, ph = (st / a.stages) & 1;
+                    const int kb = st - (st / a.kblocks) * a.kblocks;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) idx[i] = idx_n[i];
+                    if (b + 1 < nb) load_idx(st + 1, idx_n);
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    const uint32_t tile = smem_u32(sA + (size_t)s * a_tile);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < cpr) {
+                            const int r = rr + i * rstep;
+                            const __half* srcp = idx[i] >= 0 ? a.src + (size_t)idx[i] * a.src_stride + kb * a.BK + sub * 8 : a.src;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile + r * a.rowb + swz_chunk(r, sub, a.rowb) * 16),
+                                         "l"(srcp), "r"(idx[i] >= 0 ? 16u : 0u) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+                for (int b = 0; b < nb; ++b) {
+                    switch (nb - 1 - b) {   // cp.async.wait_group takes an immediate
+                        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+                        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+                        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+                        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+                        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+                        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+                        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+                        case 7: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+                        default: asm volatile("cp.async.wait_group 8;" ::: "memory"); break;
+                    }
+                    fence_async_smem();
+                    mbar_arrive(full0 + 8 * ((st0 + b) % a.stages));
+                }
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                v[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (idx[i] >= 0) v[i] = __ldg(reinterpret_cast<const uint4*>(a.src + (size_t)idx[i] * a.src_stride + kb * a.BK + sub * 8));
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (i < cpr) st_tile(tile, rr + i * rstep, sub, a.rowb, v[i]);
-            fence_async_smem();
-            mbar_arrive(full0 + 8 * s);
         }
         // ===== epilogue =====
         const int q = warp, row = tile0 + q * 32 + lane;
@@ -473,6 +504,8 @@ extern "C" int mg_sparse_conv(const mg_sparse_conv_desc* d, void* stream) {
     const size_t fixed_smem = 1024 + (size_t)steps * b_tile + 256 + 4 * 32 * 17 * 4 + 4 * 2 * a.Cout * 4;
     a.stages = std::min(4, std::max(2, steps));
     while (a.stages < steps && fixed_smem + (size_t)(a.stages + 1) * 128 * a.rowb <= 112 * 1024) ++a.stages;
+    if (a.rowb == 128)   // 64-channel layers run on few sites (OS4 / OS8): latency matters there, not occupancy
+        while (a.stages < std::min(steps, 8) && fixed_smem + (size_t)(a.stages + 1) * 128 * a.rowb <= 216 * 1024) ++a.stages;
     const size_t smem = fixed_smem + (size_t)a.stages * 128 * a.rowb;
     MG_REQUIRE(smem <= 220 * 1024, "mg_sparse_conv: weight pack does not fit in shared memory (%zu B)", smem);
     static bool attr_set = false;
