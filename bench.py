@@ -180,29 +180,65 @@ def kernel_probes(torch, dev, peaks):
         t = timeit(fn, 10)
         out[name] = dict(bound="hbm", achieved=nbytes / t / 1e9, peak=peaks["hbm"], unit="GB/s",
                          frac=nbytes / t / 1e9 / peaks["hbm"], traffic=None, us_per_step=t * 1e6, algorithmic_bytes=nbytes)
+    # conv family: every layer of the C2 table, forward / data gradient / weight gradient, weight packs prepared outside
+    # the timed region (in the step they come from the grouped K0 kernel).  Launches that mg_conv_fprop routes to the
+    # halo-resident kernel K2b (high-resolution, <= 64 channels: HBM-bound) are accounted separately, in bytes.
+    from maggie_b200 import _lib
+    orig_pack, memo = dense.pack_weight, {}
+
+    def cached_pack(w, ci_pad=None):
+        key = (w.data_ptr(), tuple(w.shape), tuple(w.stride()), ci_pad)
+        if key not in memo:
+            memo[key] = (orig_pack(w, ci_pad), w)
+        return memo[key][0]
+
+    dense.pack_weight = cached_pack
     tot = {"conv_tcgen05_kernel[fprop]": [0.0, 0.0, 0], "conv_tcgen05_kernel[dgrad]": [0.0, 0.0, 0],
-           "wgrad_tcgen05_kernel": [0.0, 0.0, 0]}
-    for (hw, ci, co, k, s, d, tr, cnt) in C2_CONVS:
-        N = FRAMES_PER_GPU
-        x = torch.randn(N, hw, hw, ci, device=dev).half()
-        w = torch.randn((ci, co, k, k) if tr else (co, ci, k, k), device=dev) / (ci * k * k) ** 0.5
-        g = dense.ConvGeom("convT", 4, 2, 1, 1) if tr else dense.ConvGeom("conv", k, s, d * (k // 2) if k > 1 else 0, d)
-        if not tr and k == 2:
-            g = dense.ConvGeom("conv", 2, 2, 0, 1)
-        y = g.fwd(x, w)
-        flops = 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * co * ci * (4 if tr else k * k)
-        for key, fn, nl in (("conv_tcgen05_kernel[fprop]", lambda: g.fwd(x, w), 4 if tr else 1),
-                            ("conv_tcgen05_kernel[dgrad]", lambda: g.dgrad(y, w, x.shape), 4 if (s == 2 and not tr) else 1),
-                            ("wgrad_tcgen05_kernel", lambda: g.wgrad(y, x, w.shape), 4 if tr else 1)):
-            t = timeit(fn, 3)
-            tot[key][0] += flops * cnt
-            tot[key][1] += t * cnt
-            tot[key][2] += nl * cnt
-    for key, (fl, t, nl) in tot.items():
-        out[key] = dict(bound="tensor", achieved=fl / t / 1e12, peak=peaks["tf_sustained"], unit="TFLOP/s",
-                        frac=fl / t / 1e12 / peaks["tf_sustained"], traffic=None, us_per_step=t * 1e6,
-                        algorithmic_flops_per_step=fl, launches_per_step=nl,
-                        note="sum over the 62 C2 conv layers; each timed eagerly incl. its weight-pack torch ops, L2 flushed")
+           "wgrad_tcgen05_kernel": [0.0, 0.0, 0], "conv_halo_tcgen05_kernel": [0.0, 0.0, 0]}
+    try:
+        for (hw, ci, co, k, s, d, tr, cnt) in C2_CONVS:
+            N = FRAMES_PER_GPU
+            x = torch.randn(N, hw, hw, ci, device=dev).half()
+            w = torch.randn((ci, co, k, k) if tr else (co, ci, k, k), device=dev) / (ci * k * k) ** 0.5
+            g = dense.ConvGeom("convT", 4, 2, 1, 1) if tr else dense.ConvGeom("conv", k, s, d * (k // 2) if k > 1 else 0, d)
+            if not tr and k == 2:
+                g = dense.ConvGeom("conv", 2, 2, 0, 1)
+            y = g.fwd(x, w)
+            flops = 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * co * ci * (4 if tr else k * k)
+            nbytes = 2.0 * (x.numel() + y.numel())
+            dwp = torch.zeros_like(dense.pack_weight(w.permute(1, 0, 2, 3) if tr else w, ci), dtype=torch.float32)
+
+            class Bank:   # accumulate into a pre-zeroed pack as the weight bank does (no fill inside the timing)
+                G = dwp
+
+            for key, fn, nl in (("conv_tcgen05_kernel[fprop]", lambda: g.fwd(x, w), 4 if tr else 1),
+                                ("conv_tcgen05_kernel[dgrad]", lambda: g.dgrad(y, w, x.shape), 4 if (s == 2 and not tr) else 1),
+                                ("wgrad_tcgen05_kernel", lambda: g.wgrad(y, x, w.shape, bank=Bank), 4 if tr else 1)):
+                h0 = _lib.lib().mg_conv_halo_launches()
+                fn()
+                halo = _lib.lib().mg_conv_halo_launches() > h0
+                t = timeit(fn, 3)
+                if halo:
+                    key = "conv_halo_tcgen05_kernel"
+                tot[key][0] += (nbytes if halo else flops) * cnt
+                tot[key][1] += t * cnt
+                tot[key][2] += nl * cnt
+    finally:
+        dense.pack_weight = orig_pack
+    for key, (work, t, nl) in tot.items():
+        if nl == 0:
+            continue
+        if key == "conv_halo_tcgen05_kernel":
+            out[key] = dict(bound="hbm", achieved=work / t / 1e9, peak=peaks["hbm"], unit="GB/s",
+                            frac=work / t / 1e9 / peaks["hbm"], traffic=None, us_per_step=t * 1e6, algorithmic_bytes_per_step=work,
+                            launches_per_step=nl,
+                            note="K2b launches of the C2 layer table (forward + data gradients of the stride-1 layers with <= 64 "
+                                 "channels); bytes = input + output activations, L2 flushed")
+        else:
+            out[key] = dict(bound="tensor", achieved=work / t / 1e12, peak=peaks["tf_sustained"], unit="TFLOP/s",
+                            frac=work / t / 1e12 / peaks["tf_sustained"], traffic=None, us_per_step=t * 1e6,
+                            algorithmic_flops_per_step=work, launches_per_step=nl,
+                            note="sum over the C2 conv layers served by this kernel; each launch timed with CUDA events, L2 flushed")
     return out
 
 
