@@ -33,6 +33,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // ---- A: v_raw = W^T u   (tile of 64 rows x 256 columns per CTA, atomics into the zeroed scratch) ------------------
 __global__ void __launch_bounds__(256)
 wprep_vt_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, float* __restrict__ vec) {
+    mg::pdl_prologue();
     const int4 it = items[blockIdx.x];
     const mg_wprep_layer L = layers[it.x];
     const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
@@ -47,6 +48,7 @@ wprep_vt_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restric
 // ---- B: t = W v_raw / (|v_raw| + eps)   (one warp per row) --------------------------------------------------------
 __global__ void __launch_bounds__(256)
 wprep_u_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, float* __restrict__ vec) {
+    mg::pdl_prologue();
     const int4 it = items[blockIdx.x];
     const mg_wprep_layer L = layers[it.x];
     const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
@@ -72,6 +74,7 @@ wprep_u_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict
 __global__ void __launch_bounds__(256)
 wprep_pack_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ vec,
                   float* __restrict__ scal, __half* __restrict__ P, __half* __restrict__ D) {
+    mg::pdl_prologue();
     __shared__ float s[TA][SROW];
     __shared__ float red[8];
     const int4 it = items[blockIdx.x];
@@ -169,6 +172,7 @@ __device__ __forceinline__ void load_grad_tile(const mg_wprep_layer& L, const fl
 __global__ void __launch_bounds__(256)
 wprep_bwd_inner_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ G,
                        float* __restrict__ scal) {
+    mg::pdl_prologue();
     __shared__ float s[TA][SROW];
     __shared__ float red[8];
     const int4 it = items[blockIdx.x];
@@ -191,6 +195,7 @@ wprep_bwd_inner_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __
 __global__ void __launch_bounds__(256)
 wprep_bwd_final_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ G,
                        const float* __restrict__ vec, const float* __restrict__ scal, float* __restrict__ grad) {
+    mg::pdl_prologue();
     __shared__ float s[TA][SROW];
     const int4 it = items[blockIdx.x];
     const mg_wprep_layer L = layers[it.x];

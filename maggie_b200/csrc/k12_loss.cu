@@ -44,6 +44,7 @@ __device__ __forceinline__ void block_accumulate(float* vals, int n, float* dst)
 __global__ void __launch_bounds__(256)
 loss_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, float* __restrict__ D1, float* __restrict__ sums, int S, int H,
                    int W) {
+    mg::pdl_prologue();
     __shared__ float s_d[36][37], s_pw[34][35], s_tw[34][35];
     const int scale = blockIdx.z / S, sl = blockIdx.z - scale * S;
     const float* p = P.p[scale] + (size_t)sl * H * W;
@@ -110,6 +111,7 @@ loss_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, float* __restri
 // ---- F2: d_{k+1} = D G d_k on the small levels (one thread per output) ----------------------------------------
 __global__ void __launch_bounds__(256)
 loss_down_kernel(const float* __restrict__ din, float* __restrict__ dout, int n_img, int h, int w) {
+    mg::pdl_prologue();
     const int ho = h >> 1, wo = w >> 1;
     const size_t total = (size_t)n_img * ho * wo;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -156,6 +158,7 @@ __device__ __forceinline__ float upsample_at(const float* __restrict__ dc, int h
 __global__ void __launch_bounds__(256)
 loss_lap_kernel(Ptr3 P, const float* __restrict__ T, const float* __restrict__ dk, const float* __restrict__ dk1, Ptr3 Wt,
                 __half* __restrict__ sg, float* __restrict__ sums, int S, int H, int W, int level) {
+    mg::pdl_prologue();
     const int h = H >> level, w = W >> level, hc = h >> 1, wc = w >> 1, wstep = 1 << level;
     const int scale = blockIdx.y;                                   // one scale per grid row: partial sums never mix
     const size_t per_scale = (size_t)S * h * w, base = scale * per_scale;
@@ -275,6 +278,7 @@ __device__ __forceinline__ float bwd_level_value(const __half* __restrict__ sg_k
 __global__ void __launch_bounds__(256)
 loss_bwd_small_kernel(const __half* __restrict__ sg_k, const float* __restrict__ g_k1, const __half* __restrict__ sg_km1,
                       const float* __restrict__ coef, float* __restrict__ g_out, int S, int h, int w, int level) {
+    mg::pdl_prologue();
     const size_t per_scale = (size_t)S * h * w, total = 3 * per_scale;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int scale = (int)(i / per_scale);
@@ -291,6 +295,7 @@ loss_bwd_small_kernel(const __half* __restrict__ sg_k, const float* __restrict__
 __global__ void __launch_bounds__(256)
 loss_bwd_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const __half* __restrict__ sg0, const float* __restrict__ g1,
                        const float* __restrict__ coef, MPtr3 G, int S, int H, int W) {
+    mg::pdl_prologue();
     __shared__ float s_pw[36][37], s_tw[36][37], s_gx[34][35], s_gy[34][35];
     const int scale = blockIdx.z / S, sl = blockIdx.z - scale * S;
     const float* p = P.p[scale] + (size_t)sl * H * W;

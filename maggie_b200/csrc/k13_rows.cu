@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256)
 layer_norm_fwd_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float eps, __half* __restrict__ s_out, __half* __restrict__ y,
                       float2* __restrict__ stat, int rows) {
+    mg::pdl_prologue();
     constexpr int E = PER * 32;
     const int lane = threadIdx.x & 31, c0 = lane * PER;
     float g[PER], bt[PER];
@@ -92,6 +93,7 @@ template <int PER>
 __global__ void __launch_bounds__(256)
 layer_norm_bwd_kernel(const __half* __restrict__ s, const __half* __restrict__ gy, const float* __restrict__ gamma,
                       const float2* __restrict__ stat, __half* __restrict__ dx, float* __restrict__ dgb, int rows) {
+    mg::pdl_prologue();
     constexpr int E = PER * 32;
     __shared__ float s_acc[8][2 * E];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c0 = lane * PER;
@@ -132,6 +134,7 @@ layer_norm_bwd_kernel(const __half* __restrict__ s, const __half* __restrict__ g
 // out[c] += sum over rows of x[r][c]; 8 channels per thread, C/8 threads per row group.
 __global__ void __launch_bounds__(256)
 col_sum_kernel(const __half* __restrict__ x, int stride, int rows, int C, float* __restrict__ out) {
+    mg::pdl_prologue();
     __shared__ float s_red[256 * 8];
     const int G = C >> 3, per = 256 / G;
     const int g = threadIdx.x % G, sub = threadIdx.x / G;

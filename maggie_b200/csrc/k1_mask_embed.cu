@@ -15,6 +15,7 @@ template <int C>
 __global__ void __launch_bounds__(256)
 mask_embed_fwd_kernel(const float* __restrict__ image, const float* __restrict__ masks, const int32_t* __restrict__ slot_ids,
                       int M, const float* __restrict__ table, __half* __restrict__ out, int B, int HW) {
+    mg::pdl_prologue();
     __shared__ float s_tab[33];
     __shared__ SlotIds ids;
     if (threadIdx.x < 33) s_tab[threadIdx.x] = table[threadIdx.x];
@@ -61,6 +62,7 @@ template <int C>
 __global__ void __launch_bounds__(256)
 mask_embed_bwd_kernel(const __half* __restrict__ gout, const float* __restrict__ masks, const int32_t* __restrict__ slot_ids,
                       int M, float* __restrict__ gtable, int B, int HW) {
+    mg::pdl_prologue();
     __shared__ float s_acc[33];
     __shared__ SlotIds ids;
     if (threadIdx.x < 33) s_acc[threadIdx.x] = 0.f;

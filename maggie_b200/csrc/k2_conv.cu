@@ -52,6 +52,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 __global__ void __launch_bounds__(THREADS, 2)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs a) {
+    mg::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

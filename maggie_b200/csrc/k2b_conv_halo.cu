@@ -68,6 +68,7 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
 template <int KS, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HArgs a) {
+    mg::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // [1 KB guard][A0][A1][4 KB guard][B taps][barriers][tmem slot][epilogue staging][stat partials]
@@ -369,8 +370,7 @@ int conv_halo_launch(const mg_conv_desc* d, void* stream, bool* handled) {
     }
     const int grid = std::min(a.n_tiles, kNumSMs);
     const KernelFn fn = table[d->Ci == 64 ? 1 : 0][epi];
-    fn<<<grid, THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, a);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    MG_LAUNCH(fn, grid, THREADS, smem, stream, tmA, tmB, a);
     MG_CHECK_LAUNCH("mg_conv_fprop(halo)");
     g_halo_launches.fetch_add(1, std::memory_order_relaxed);
     *handled = true;

@@ -16,6 +16,7 @@ bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __
                    const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
                    float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
                    float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
+    mg::pdl_prologue();
     __shared__ float s_s[8][32], s_q[8][32];
     const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -81,6 +82,7 @@ struct H8 {
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                 const __half* __restrict__ res, int res_up, __half* __restrict__ y, size_t npix, int C, int H, int W, int act) {
+    mg::pdl_prologue();
     extern __shared__ float s_ss[];  // [2][C]
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_ss[i] = scale[i], s_ss[C + i] = shift[i];
     __syncthreads();
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __half* __restrict__ dy, const __half* __restrict__ yout, const __half* __restrict__ r,
                      const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ sums,
                      size_t npix, int C, int act) {
+    mg::pdl_prologue();
     __shared__ float s_red[256 * 16];
     const int G = C >> 3, lanes_per_g = 256 / G;  // G in {4..64} divides 256
     const int g = threadIdx.x % G, sub = threadIdx.x / G, c0 = g << 3;
@@ -175,6 +178,7 @@ bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ yo
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ sums, float inv_count, __half* __restrict__ dx, __half* __restrict__ dres,
                     size_t npix, int C, int act, int pre_act) {
+    mg::pdl_prologue();
     extern __shared__ float s_p[];  // [4][C]: mean, scale=gamma*invstd, mean_dz, invstd*mean_dzx
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         const float is = invstd[i];

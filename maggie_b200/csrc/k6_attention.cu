@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(128)
 attn_tq_partial_kernel(const float* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V,
                        const uint8_t* __restrict__ key_pad, const uint8_t* __restrict__ guid, int F, int S, float scale,
                        float* __restrict__ pm, float* __restrict__ pl, float* __restrict__ po, float* __restrict__ pstat) {
+    mg::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     __half (*sK)[ROWP] = reinterpret_cast<__half (*)[ROWP]>(smem_raw);
     __half (*sV)[ROWP] = sK + TM;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(128)
 attn_tq_merge_kernel(const float* __restrict__ pm, const float* __restrict__ pl, const float* __restrict__ po,
                      const float* __restrict__ pstat, int F, int nsplit, float* __restrict__ O, float* __restrict__ stat,
                      float* __restrict__ M, float* __restrict__ L) {
+    mg::pdl_prologue();
     const int f = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     float m = -INFINITY;
     for (int s = 0; s < nsplit; ++s) m = fmaxf(m, pm[((size_t)b * nsplit + s) * F + f]);
@@ -118,6 +120,7 @@ attn_tq_bwd_kernel(const float* __restrict__ Q, const __half* __restrict__ K, co
                    const float* __restrict__ stat, const float* __restrict__ M, const float* __restrict__ L,
                    const float* __restrict__ dO, const float* __restrict__ dstat, int F, int S, float scale,
                    float* __restrict__ dQ, __half* __restrict__ dK, __half* __restrict__ dV) {
+    mg::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     __half (*sK)[ROWP] = reinterpret_cast<__half (*)[ROWP]>(smem_raw);
     __half (*sV)[ROWP] = sK + TM;
@@ -173,6 +176,7 @@ attn_tq_bwd_kernel(const float* __restrict__ Q, const __half* __restrict__ K, co
 __global__ void __launch_bounds__(128)
 attn_fq_fwd_kernel(const __half* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                    const uint8_t* __restrict__ key_pad, int F, int S, float scale, __half* __restrict__ O) {
+    mg::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     __half (*sQ)[ROWP] = reinterpret_cast<__half (*)[ROWP]>(smem_raw);
     float* sK = reinterpret_cast<float*>(sQ + TM);   // [MAXF][E]
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(128)
 attn_fq_bwd_kernel(const __half* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                    const uint8_t* __restrict__ key_pad, const __half* __restrict__ dO, int F, int S, float scale,
                    __half* __restrict__ dQ, float* __restrict__ dK, float* __restrict__ dV) {
+    mg::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     __half (*sQ)[ROWP] = reinterpret_cast<__half (*)[ROWP]>(smem_raw);
     __half (*sdO)[ROWP] = sQ + TM;

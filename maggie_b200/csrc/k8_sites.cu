@@ -41,6 +41,7 @@ Layout make_layout(int slots, int H, int W) {
 // ---- level 0 bits from the uint8 roi ------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bits_from_u8_kernel(const uint8_t* __restrict__ roi, uint32_t* __restrict__ bits, int rows, int W, int Wd) {
+    mg::pdl_prologue();
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)rows * Wd) return;
     const int row = idx / Wd, j = idx - row * Wd;
@@ -75,6 +76,7 @@ __device__ __forceinline__ uint32_t compress_even(uint64_t x) {
 __global__ void __launch_bounds__(256)
 downscale_bits_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int slots, int Hi, int Wdi,
                       int Ho, int Wo, int Wdo) {
+    mg::pdl_prologue();
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)slots * Ho * Wdo) return;
     const int jw = idx % Wdo, qy = (idx / Wdo) % Ho, s = idx / (Wdo * Ho);
@@ -100,6 +102,7 @@ downscale_bits_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ ou
 // ---- rank structure ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 scan_local_kernel(const uint32_t* __restrict__ bits, uint32_t* __restrict__ rank, uint32_t* __restrict__ blocksum) {
+    mg::pdl_prologue();
     // one block = SCAN_BLOCK words, 4 per thread
     __shared__ uint32_t warp_tot[8];
     const unsigned base = blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
@@ -131,6 +134,7 @@ struct LevelBlocks {
 __global__ void __launch_bounds__(1024)
 scan_blocks_kernel(uint32_t* __restrict__ blocksum, unsigned nblocks, LevelBlocks lb, uint32_t* __restrict__ sitebase,
                    int32_t* __restrict__ counts) {
+    mg::pdl_prologue();
     // exclusive scan of blocksum[0..nblocks) in place (single CTA), blocksum[nblocks] = total
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry_s;
@@ -184,6 +188,7 @@ __device__ __forceinline__ int site_row(const LevelView& L, int s, int y, int x)
 
 __global__ void __launch_bounds__(256)
 coords_kernel(LevelView L, unsigned words, int32_t* __restrict__ coords) {
+    mg::pdl_prologue();
     const unsigned widx = blockIdx.x * blockDim.x + threadIdx.x;
     if (widx >= words) return;
     uint32_t w = L.bits[widx];
@@ -203,6 +208,7 @@ coords_kernel(LevelView L, unsigned words, int32_t* __restrict__ coords) {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 table_kernel(LevelView other, const int32_t* __restrict__ coords, int n, int32_t* __restrict__ table) {
+    mg::pdl_prologue();
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (unsigned)n * 9) return;
     const int r = t / 9, k = t - r * 9, ky = k / 3, kx = k - ky * 3;

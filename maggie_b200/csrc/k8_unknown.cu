@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(THREADS)
 unknown_mask_kernel(const float* __restrict__ alpha, int H, int W, const int32_t* __restrict__ widths,
                     const uint8_t* __restrict__ and_mask, uint8_t* __restrict__ out_u8,
                     uint32_t* __restrict__ out_bits) {
+    mg::pdl_prologue();
     extern __shared__ uint32_t sbits[];  // [TH + MAXK - 1][Wd + 2]
     __shared__ int s_lo[MAXK], s_w[MAXK];
 

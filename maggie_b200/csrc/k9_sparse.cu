@@ -33,6 +33,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const __half* __restrict__ dense, const int32_t* __restrict__ coords, int n, int n_i, int H, int W, int C,
                    __half* __restrict__ out, int out_stride, int c_off) {
+    mg::pdl_prologue();
     const int G = C >> 3;
     const size_t total = (size_t)n * G;
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
@@ -48,6 +49,7 @@ gather_rows_kernel(const __half* __restrict__ dense, const int32_t* __restrict__
 __global__ void __launch_bounds__(256)
 scatter_rows_add_kernel(const __half* __restrict__ g, int g_stride, int c_off, const int32_t* __restrict__ coords, int n,
                         int n_i, int H, int W, int C, __half* __restrict__ ddense) {
+    mg::pdl_prologue();
     const int G = C >> 1;
     const size_t total = (size_t)n * G;
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
@@ -73,6 +75,7 @@ struct SArgs {
 
 __global__ void __launch_bounds__(160, 1)
 sparse_conv_kernel(const SArgs a) {
+    mg::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int steps = a.T * a.kblocks;
@@ -324,6 +327,7 @@ struct SWArgs {
 
 __global__ void __launch_bounds__(160, 1)
 sparse_wgrad_kernel(const SWArgs a) {
+    mg::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int STAGES = 2;

@@ -1,9 +1,20 @@
 // Library-level entry points: version, error string, launch counter.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace mg {
 std::atomic<unsigned long long> g_launches{0};
 static thread_local char t_error[512] = "";
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("MAGGIE_B200_NO_PDL");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
