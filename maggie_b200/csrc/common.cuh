@@ -24,9 +24,11 @@ void set_error(const char* fmt, ...);
 bool pdl_enabled();
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_launch();
+    pdl_wait();
 }
 #endif
 

@@ -52,7 +52,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 __global__ void __launch_bounds__(THREADS, 2)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs a) {
-    mg::pdl_prologue();
+    mg::pdl_launch();   // the next kernel may be scheduled; its own griddepcontrol.wait orders the memory accesses
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -89,6 +89,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mg::pdl_wait();   // barriers, TMEM and descriptors are set up while the previous kernel drains; now wait for its data
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {

@@ -68,7 +68,7 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
 template <int KS, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HArgs a) {
-    mg::pdl_prologue();
+    mg::pdl_launch();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // [1 KB guard][A0][A1][4 KB guard][B taps][barriers][tmem slot][epilogue staging][stat partials]
@@ -99,6 +99,7 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mg::pdl_wait();   // set-up overlapped with the previous kernel's tail; its data is needed from here on
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_img = a.rblocks * a.strips;
 

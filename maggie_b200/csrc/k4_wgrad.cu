@@ -35,7 +35,7 @@ struct WArgs {
 // second atom of the M = 128 operand is a shared zero region reached through the descriptor's leading-byte offset.
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WArgs a) {
-    mg::pdl_prologue();
+    mg::pdl_launch();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int atom_bytes = 128 * 128;
@@ -74,6 +74,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mg::pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
 
     if (nk > 0) {
