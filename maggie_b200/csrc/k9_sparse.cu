@@ -483,6 +483,10 @@ extern "C" int mg_scatter_rows_add(const void* g, int g_stride, int c_off, const
     return MG_OK;
 }
 
+namespace mg {
+int sparse_conv_persistent_launch(const mg_sparse_conv_desc* d, void* stream, bool* handled);   // k9b_sparse_persistent.cu
+}
+
 extern "C" int mg_sparse_conv(const mg_sparse_conv_desc* d, void* stream) {
     MG_REQUIRE(d && d->src && d->w && (d->out || d->map), "mg_sparse_conv: null pointer");
     MG_REQUIRE(d->T >= 1 && d->T <= 9 && (d->table || d->T == 1), "mg_sparse_conv: T=%d needs a table", d->T);
@@ -492,6 +496,12 @@ extern "C" int mg_sparse_conv(const mg_sparse_conv_desc* d, void* stream) {
     MG_REQUIRE(!d->map || d->coords, "mg_sparse_conv: head mode needs coords");
     MG_REQUIRE(d->map || (d->Cout % 16 == 0 && d->out_stride % 8 == 0 && d->c_off % 8 == 0), "mg_sparse_conv: row output needs Cout %% 16 == 0");
     if (d->No <= 0) return MG_OK;
+    {
+        // 32-channel layers on the large site lists: persistent kernel (K9b)
+        bool handled = false;
+        const int rc = mg::sparse_conv_persistent_launch(d, stream, &handled);
+        if (rc != MG_OK || handled) return rc;
+    }
     SArgs a;
     a.src = static_cast<const __half*>(d->src), a.src_stride = d->src_stride;
     a.table = d->table, a.T = d->T, a.No = d->No, a.Cin = d->Cin;
