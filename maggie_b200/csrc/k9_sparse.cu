@@ -386,6 +386,35 @@ sparse_wgrad_kernel(const SWArgs a) {
                                  swz_chunk(r, c % cpa, a.rowb_a) * 16), "l"(srcp), "r"(ok ? 16u : 0u) : "memory");
                 }
                 // B: gathered source rows, one tile per tap
+                if (cb_chunks <= 4) {
+                    // <= 4 (row, chunk) pairs per thread: fetch every neighbour index of the tile first (one latency),
+                    // then put every copy in flight
+                    int idx[4][9];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int e0 = tid + i * 128, r = e0 / cb_chunks, p = row0 + r;
+#pragma unroll
+                        for (int tt = 0; tt < 9; ++tt) {
+                            idx[i][tt] = -1;
+                            if (e0 < 128 * cb_chunks && tt < nt && p < a.No) idx[i][tt] = a.table ? __ldg(a.table + (size_t)p * a.T + t0 + tt) : p;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int e0 = tid + i * 128, r = e0 / cb_chunks, c = e0 - r * cb_chunks;
+                        if (e0 < 128 * cb_chunks) {
+#pragma unroll
+                            for (int tt = 0; tt < 9; ++tt) {
+                                if (tt < nt) {
+                                    const uint32_t tb = smem_u32(sB + (size_t)(s * a.taps_per_cta + tt) * b_tile);
+                                    const __half* srcp = idx[i][tt] >= 0 ? a.src + (size_t)idx[i][tt] * a.src_stride + c * 8 : a.src;
+                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tb + (c / cpb) * b_atom + r * a.rowb_b +
+                                                 swz_chunk(r, c % cpb, a.rowb_b) * 16), "l"(srcp), "r"(idx[i][tt] >= 0 ? 16u : 0u) : "memory");
+                                }
+                            }
+                        }
+                    }
+                } else
                 for (int e0 = tid; e0 < 128 * cb_chunks; e0 += 128) {
                     const int r = e0 / cb_chunks, c = e0 - r * cb_chunks;
                     const int p = row0 + r;
