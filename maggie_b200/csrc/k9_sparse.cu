@@ -514,6 +514,8 @@ extern "C" int mg_scatter_rows_add(const void* g, int g_stride, int c_off, const
 
 namespace mg {
 int sparse_conv_persistent_launch(const mg_sparse_conv_desc* d, void* stream, bool* handled);   // k9b_sparse_persistent.cu
+int sparse_wgrad_persistent_launch(const void* dout, int dout_stride, int Cout, const void* src, int src_stride, int Cin,
+                                   const int32_t* table, int T, int No, float* dw, void* stream, bool* handled);
 }
 
 extern "C" int mg_sparse_conv(const mg_sparse_conv_desc* d, void* stream) {
@@ -571,6 +573,11 @@ extern "C" int mg_sparse_wgrad(const void* dout, int dout_stride, int Cout, cons
                "mg_sparse_wgrad: unsupported shape Cout=%d Cin=%d T=%d", Cout, Cin, T);
     MG_REQUIRE(dout_stride % 8 == 0 && src_stride % 8 == 0, "mg_sparse_wgrad: strides must be multiples of 8");
     if (No <= 0) return MG_OK;
+    {
+        bool handled = false;
+        const int rc = mg::sparse_wgrad_persistent_launch(dout, dout_stride, Cout, src, src_stride, Cin, table, T, No, dw, stream, &handled);
+        if (rc != MG_OK || handled) return rc;
+    }
     SWArgs a;
     a.dout = static_cast<const __half*>(dout), a.dout_stride = dout_stride, a.Cout = Cout;
     a.src = static_cast<const __half*>(src), a.src_stride = src_stride, a.Cin = Cin;

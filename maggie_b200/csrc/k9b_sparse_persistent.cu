@@ -256,3 +256,180 @@ int sparse_conv_persistent_launch(const mg_sparse_conv_desc* d, void* stream, bo
 }
 
 }  // namespace mg
+
+// ================================================================================================ K9c: weight gradient
+// Persistent weight gradient of the same layers:  dW[co][t*32 + ci] = sum_p dout[p][co] * src[table[p][t]][ci].
+// GEMM with the sites as K: both operand tiles are MN-major rows of 64 bytes (32 channels).  One CTA per SM accumulates
+// its share of the site tiles for ALL taps in TMEM ([128 x T*32] fp32, M padded with zero atoms) and flushes ONCE with
+// 16-byte vector reductions; the gathers of the next tile are in flight while the current one is multiplied.
+namespace {
+
+struct GArgs {
+    const __half* dout; int dout_stride, Cout, cout_eff;   // cout_eff = Cout rounded up to 32 (columns are readable)
+    const __half* src; int src_stride;
+    const int32_t* table; int T, No, n_tiles;
+    float* dw;                                             // [Cout][T*32]
+    int tmem_cols;
+};
+
+constexpr int G_THREADS = PRODUCERS + 32;   // warps 0..3 gather (+ epilogue at the end), warp 4 MMA
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+sparse_wgrad_persistent_kernel(const GArgs a) {
+    mg::pdl_prologue();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int atom = 128 * ROWB, a_buf = 4 * atom, b_buf = a.T * atom;   // A: 4 atoms of 32 channels (M = 128), B: T tiles
+    uint8_t* sA = smem;                         // [2][4 atoms]; atoms beyond cout_eff stay zero
+    uint8_t* sB = sA + 2 * (size_t)a_buf;       // [2][T]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * (size_t)b_buf);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t full = bar0, empty = bar0 + 16, tfull = bar0 + 32;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) mbar_init(full + 8 * i, PRODUCERS), mbar_init(empty + 8 * i, 1);
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), a.tmem_cols);
+    for (int i = tid; i < 2 * a_buf / 16; i += G_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int my_tiles = blockIdx.x < a.n_tiles ? (a.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+    if (warp < 4) {
+        const int sub = tid & 3, rr = tid >> 2, real_atoms = a.cout_eff / 32;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1, ph = (it >> 1) & 1;
+            const int tile0 = tile * 128;
+            int idx[9][4];
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int p = tile0 + rr + i * 32;
+                    idx[t][i] = -1;
+                    if (t < a.T && p < a.No) idx[t][i] = a.table ? __ldg(a.table + (size_t)p * a.T + t) : p;
+                }
+            mbar_wait(empty + 8 * buf, ph ^ 1);
+            // A: d_out rows, one 32-channel atom per 64 bytes of a row
+            const uint32_t abase = smem_u32(sA + (size_t)buf * a_buf);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = rr + i * 32, p = tile0 + r;
+                for (int j = 0; j < real_atoms; ++j) {
+                    const bool ok = p < a.No;
+                    const __half* srcp = ok ? a.dout + (size_t)p * a.dout_stride + j * 32 + sub * 8 : a.dout;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(abase + j * atom + r * ROWB + swz64(r, sub) * 16),
+                                 "l"(srcp), "r"(ok ? 16u : 0u) : "memory");
+                }
+            }
+            // B: gathered source rows, one tile per tap
+            const uint32_t bbase = smem_u32(sB + (size_t)buf * b_buf);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                if (t < a.T) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = rr + i * 32;
+                        const __half* srcp = idx[t][i] >= 0 ? a.src + (size_t)idx[t][i] * a.src_stride + sub * 8 : a.src;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(bbase + t * atom + r * ROWB + swz64(r, sub) * 16),
+                                     "l"(srcp), "r"(idx[t][i] >= 0 ? 16u : 0u) : "memory");
+                    }
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(full + 8 * buf);
+        }
+        // epilogue (once): D[co][t*32 + ci] -> vector reductions; accumulator row = output channel = TMEM lane
+        if (my_tiles > 0) {
+            const int q = warp, co = q * 32 + lane;
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+            if (q * 32 < a.Cout) {
+                for (int c0 = 0; c0 < a.T * 32; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+                    tmem_ld_wait();
+                    if (co < a.Cout) {
+                        float* drow = a.dw + (size_t)co * a.T * 32 + c0;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            red_add_v4(drow + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                       __uint_as_float(r[i + 3]));
+                    }
+                }
+            }
+        }
+    } else if (lane == 0) {
+        const uint32_t idesc = instr_desc_f16(128, 32, 1, 1);   // both operands MN-major
+        const uint32_t lay = swizzle_layout(ROWB);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1, ph = (it >> 1) & 1;
+            mbar_wait(full + 8 * buf, ph);
+            tc_fence_after();
+            const uint32_t abase = smem_u32(sA + (size_t)buf * a_buf), bbase = smem_u32(sB + (size_t)buf * b_buf);
+            for (int t = 0; t < a.T; ++t) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {   // 128 sites = 8 x UMMA_K(16)
+                    const uint64_t da = smem_desc(abase + k * 16 * ROWB, atom, 8 * ROWB, lay);
+                    const uint64_t db = smem_desc(bbase + t * atom + k * 16 * ROWB, atom, 8 * ROWB, lay);
+                    mma_f16(tmem_base + t * 32, da, db, idesc, (it | k) != 0);
+                }
+            }
+            mma_commit(empty + 8 * buf);
+        }
+        if (my_tiles > 0) mma_commit(tfull);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+}  // namespace
+
+namespace mg {
+
+int sparse_wgrad_persistent_launch(const void* dout, int dout_stride, int Cout, const void* src, int src_stride, int Cin,
+                                   const int32_t* table, int T, int No, float* dw, void* stream, bool* handled) {
+    *handled = false;
+    const char* e = std::getenv("MAGGIE_B200_NO_PERSISTENT_SPARSE");
+    if (e && e[0] == '1') return MG_OK;
+    const int cout_eff = (Cout + 31) / 32 * 32;
+    if (Cin != 32 || cout_eff > 128 || dout_stride < cout_eff || T > 9) return MG_OK;
+    const int n_tiles = ceil_div(No, 128);
+    if (n_tiles < 2 * kNumSMs) return MG_OK;
+    GArgs a;
+    a.dout = static_cast<const __half*>(dout), a.dout_stride = dout_stride, a.Cout = Cout, a.cout_eff = cout_eff;
+    a.src = static_cast<const __half*>(src), a.src_stride = src_stride;
+    a.table = table, a.T = T, a.No = No, a.n_tiles = n_tiles, a.dw = dw;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < T * 32) a.tmem_cols <<= 1;
+    const size_t smem = 1024 + 2 * (size_t)(4 + T) * 128 * ROWB + 256;
+    if (smem > 224 * 1024) return MG_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(sparse_wgrad_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
+            set_error("mg_sparse_wgrad: cannot raise dynamic shared memory limit (persistent kernel)");
+            return MG_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    MG_LAUNCH(sparse_wgrad_persistent_kernel, std::min(n_tiles, kNumSMs), G_THREADS, smem, stream, a);
+    MG_CHECK_LAUNCH("mg_sparse_wgrad(persistent)");
+    *handled = true;
+    return MG_OK;
+}
+
+}  // namespace mg
