@@ -32,6 +32,7 @@ struct PArgs {
     const float* bias;
     __half* out; int out_stride, c_off;
     float* stats;
+    float* map; const int32_t* coords; int mapH, mapW, Cout_real;   // head mode: fp32 logit map, column 0 only
     int pre_act, n_tiles, b_tile, acc_cols, tmem_cols;
 };
 
@@ -164,8 +165,16 @@ sparse_conv_persistent_kernel(const PArgs a) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     v[i] = __uint_as_float(r[i]);
-                    if (a.bias) v[i] += __ldg(a.bias + c0 + i);
+                    if (a.bias && c0 + i < a.Cout_real) v[i] += __ldg(a.bias + c0 + i);
                     if (a.pre_act == 1) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (a.map) {
+                    // the two 32 -> 1 heads: the reference computes dense() - 99 and then += 99 at the active sites
+                    if (valid && c0 == 0) {
+                        const int s = a.coords[row * 3], y = a.coords[row * 3 + 1], x = a.coords[row * 3 + 2];
+                        a.map[((size_t)s * a.mapH + y) * a.mapW + x] = (v[0] - 99.0f) + 99.0f;
+                    }
+                    continue;
                 }
                 if (a.stats) {
                     __syncwarp();
@@ -226,20 +235,22 @@ int sparse_conv_persistent_launch(const mg_sparse_conv_desc* d, void* stream, bo
     *handled = false;
     const char* e = std::getenv("MAGGIE_B200_NO_PERSISTENT_SPARSE");
     if (e && e[0] == '1') return MG_OK;
-    if (d->map || d->Cin != 32 || d->Cout % 16 || d->Cout > 64 || d->T > 9) return MG_OK;
+    const int cout_pad = (d->Cout + 15) / 16 * 16;     // the caller packs the weights with rows padded to 16
+    if (d->Cin != 32 || cout_pad > 64 || d->T > 9 || (!d->map && d->Cout % 16) || (d->map && d->stats)) return MG_OK;
     const int n_tiles = ceil_div(d->No, 128);
     if (n_tiles < 2 * kNumSMs) return MG_OK;              // small site lists: the one-tile-per-CTA kernel has more parallelism
     PArgs a;
     a.src = static_cast<const __half*>(d->src), a.src_stride = d->src_stride;
-    a.table = d->table, a.T = d->T, a.No = d->No, a.Cout = d->Cout;
+    a.table = d->table, a.T = d->T, a.No = d->No, a.Cout = cout_pad, a.Cout_real = d->Cout;
+    a.map = d->map, a.coords = d->coords, a.mapH = d->mapH, a.mapW = d->mapW;
     a.w = static_cast<const __half*>(d->w), a.bias = d->bias;
     a.out = static_cast<__half*>(d->out), a.out_stride = d->out_stride, a.c_off = d->c_off;
     a.stats = d->stats, a.pre_act = d->pre_act, a.n_tiles = n_tiles;
-    a.b_tile = ((d->Cout * ROWB + 1023) / 1024) * 1024;
-    a.acc_cols = d->Cout < 32 ? 32 : d->Cout;
+    a.b_tile = ((cout_pad * ROWB + 1023) / 1024) * 1024;
+    a.acc_cols = cout_pad < 32 ? 32 : cout_pad;
     a.tmem_cols = 2 * a.acc_cols;                          // 64 or 128
     const size_t smem = 1024 + (size_t)d->T * a.b_tile + 2 * (size_t)d->T * 128 * ROWB + 256 + EPI_WARPS * 16 * 36 * 4 +
-                        EPI_WARPS * 2 * d->Cout * 4;
+                        EPI_WARPS * 2 * cout_pad * 4;
     if (smem > 224 * 1024) return MG_OK;
     static bool attr_set = false;
     if (!attr_set) {

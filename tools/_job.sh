@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s35_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/s35_tests.log
-timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/s35_bench.json 2> gpurun_out/s35_bench.err; echo "bench rc=$?"; tail -2 gpurun_out/s35_bench.err
-ROWS=60 timeout 300 python tools/profile_step.py > gpurun_out/s35_profile_eager.txt 2>&1
+timeout 600 python -m pytest tests/test_gpu_sparse.py tests/test_gpu_model.py -x -q 2>&1 | tail -3
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/s36_bench.json 2> gpurun_out/s36_bench.err; echo "bench rc=$?"; tail -2 gpurun_out/s36_bench.err
