@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .. import ops
+from .. import ops, packs
 from .layers import PlainConv, Slot, SNConv, SparseConvParams, seq
 
 
@@ -113,6 +113,7 @@ class InstanceMatteDecoder(nn.Module):
         nn.init.xavier_uniform_(self.query_feat.weight)
         self.conv = seq(PlainConv(d, d, 3), nn.BatchNorm2d(d), Slot(), PlainConv(d, output_dim, 1),
                         nn.BatchNorm2d(output_dim), Slot())
+        self._packs = packs.PackSet()
 
     def _smooth(self, x):
         t = self.training
@@ -125,6 +126,15 @@ class InstanceMatteDecoder(nn.Module):
         temporal_fn (video): [b, n_f, C, h, w] -> (propagated features, hidden states); the smoothing convs then run
         on the un-propagated features (-> out_feat) and on the propagated ones (-> logits), as the reference does.
         Returns logits [b*n_f, 10, h, w] fp32, out_feat [b*n_f, 64, h, w], tokens [b, 10, 64] fp32, loss (, hidden)."""
+        if feat.is_cuda and packs.active() is not self._packs:
+            # operand packs of every projection that runs on the pixel rows: one grouped preparation per forward
+            ws = [self.feat_proj.layers[0].weight]
+            for layer in (*self.token_feat_ca_layers, *self.feat_token_ca_layers, self.final_token_feat_ca):
+                E = layer.multihead_attn.in_proj_weight.shape[1]
+                wq = layer.multihead_attn.in_proj_weight
+                ws += [wq[:E], wq[E:2 * E], wq[2 * E:], layer.multihead_attn.out_proj.weight]
+            with self._packs.prepare(ws, need_bwd=torch.is_grad_enabled()):
+                return self.forward(feat, mask_os8, gt_mask_os8, temporal_fn)
         b, n_f, n_i, h, w = mask_os8.shape
         hw, nq, t = h * w, self.max_inst, self.training
         dt = feat.dtype
@@ -223,6 +233,7 @@ class MaGGIeDecoder(nn.Module):
         self.refine_OS1 = seq(S(32, 32, 3), BN(32), Slot(), S(32, 1, 3, bias=True))
         for p in self.dummy_downscale.parameters():
             p.requires_grad_(True)  # as in the reference: trainable flag set, but they never receive a gradient
+        self._packs = packs.PackSet()
 
     # -- sparse refinement ---------------------------------------------------------------------------
     def predict_details(self, os8_feat, roi, queries, fea1, fea2, fea3, T=None):
@@ -230,6 +241,10 @@ class MaGGIeDecoder(nn.Module):
         fp32 logit maps [B*n_i,1,H/4,W/4], [B*n_i,1,H,W] (-99 where inactive) and the site counts."""
         B, n_i, H, W = roi.shape
         slots = B * n_i
+        if os8_feat.is_cuda and packs.active() is not self._packs:
+            ws = [m.weight for m in self.modules() if isinstance(m, SparseConvParams) and m.weight.shape[-1] % 32 == 0]
+            with self._packs.prepare(ws, need_bwd=torch.is_grad_enabled()):
+                return self.predict_details(os8_feat, roi, queries, fea1, fea2, fea3, T)
         if T is None:
             T = ops.build_sites(roi.reshape(slots, H, W))
         c1, c2, c4, c8 = T.coords

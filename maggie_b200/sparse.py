@@ -6,7 +6,7 @@ from ctypes import c_int32, c_void_p
 
 import torch
 
-from . import _lib
+from . import _lib, packs
 from .dense import ACT, bn_finalize, new_stats, zeros_f32
 
 _need_cuda, _ptr, _stream = _lib.need_cuda, _lib.tensor_ptr, _lib.stream_ptr
@@ -50,6 +50,30 @@ def pack_bwd(w, mirror):
     if cop != co:
         wt = torch.cat([wt, wt.new_zeros(ci, wt.shape[1], cop - co)], 2)
     return _pack_rows(wt.reshape(ci, -1)), cop
+
+
+def _packs_for(w):
+    """(pack set, entry) when the grouped packs of the running stage cover this weight (maggie_b200/packs.py)."""
+    ps = packs.active()
+    if ps is not None:
+        e = ps.lookup(w)
+        if e is not None:
+            return ps, e
+    return None, None
+
+
+def _fwd_pack(w):
+    """-> (forward pack, handle for the backward pack: the gathered buffer of THIS forward + the layer's entry)."""
+    ps, e = _packs_for(w)
+    return (ps.pack_fwd(e), (ps.bwd, e)) if ps is not None else (pack_fwd(w), None)
+
+
+def _bwd_pack(w, mirror, handle):
+    if handle is not None and handle[0] is not None:
+        buf, e = handle
+        o, shape = e["bwd", bool(mirror)]
+        return buf[o:o + shape[0] * shape[1]].view(shape), e["cop"]
+    return pack_bwd(w, mirror)
 
 
 def sparse_conv_launch(src, wp, T, cin, cout, *, table=None, bias=None, out=None, out_stride=None, c_off=0, stats=None,
@@ -103,7 +127,7 @@ class _RowsConv(torch.autograd.Function):
         co, ci = w.shape[0], w.shape[-1]
         T = w.numel() // (co * ci)
         wd = w.detach()
-        wp = pack_fwd(wd)
+        wp, ctx.packs = _fwd_pack(wd)
         b32 = bias.detach().float().contiguous() if bias is not None else None
         No = table.shape[0] if table is not None else src.shape[0]
         ctx.cfg = (mode, act, T, co, ci, mirror, tuple(w.shape), bias is not None, training)
@@ -153,7 +177,7 @@ class _RowsConv(torch.autograd.Function):
             dgamma, dbeta = sums[1], sums[0]
         dsrc = dw = dbias = None
         if ctx.needs_input_grad[0]:
-            wt, cop = pack_bwd(w, mirror)
+            wt, cop = _bwd_pack(w, mirror, ctx.packs)
             g = dr
             if cop != co:  # pad the gradient rows to the K granularity
                 g = torch.zeros((dr.shape[0], cop), dtype=torch.float16, device=dr.device)
@@ -187,7 +211,8 @@ class _Head(torch.autograd.Function):
         ci = w.shape[-1]
         wd = w.detach()
         mp = torch.full((slots, 1, H, W), -99.0, dtype=torch.float32, device=src.device)
-        sparse_conv_launch(src, pack_fwd(wd), 9, ci, 1, table=nbr, bias=bias.detach().float().contiguous(), head=(mp, coords))
+        wp, ctx.packs = _fwd_pack(wd)
+        sparse_conv_launch(src, wp, 9, ci, 1, table=nbr, bias=bias.detach().float().contiguous(), head=(mp, coords))
         ctx.save_for_backward(src, wd, nbr, coords)
         return mp
 
@@ -198,7 +223,7 @@ class _Head(torch.autograd.Function):
         c = coords.long()
         g = torch.zeros((coords.shape[0], 32), dtype=torch.float16, device=src.device)
         g[:, 0] = gmap[c[:, 0], 0, c[:, 1], c[:, 2]].to(torch.float16)
-        wt, cop = pack_bwd(w, True)
+        wt, cop = _bwd_pack(w, True, ctx.packs)
         dsrc = sparse_conv_launch(g, wt, 9, cop, ci, table=nbr, n_out=src.shape[0]) if ctx.needs_input_grad[0] else None
         dw = _wgrad(g, 8, src, ci, nbr, 9)[:1].view(w.shape) if ctx.needs_input_grad[1] else None
         dbias = g[:, 0].float().sum().reshape(1) if ctx.needs_input_grad[2] else None
