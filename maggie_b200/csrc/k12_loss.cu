@@ -165,17 +165,24 @@ loss_lap_kernel(Ptr3 P, const float* __restrict__ T, const float* __restrict__ d
     float acc[2] = {0.f, 0.f};
     for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < per_scale; r += (size_t)gridDim.x * blockDim.x) {
         const int x = (int)(r % w), y = (int)((r / w) % h), sl = (int)(r / ((size_t)w * h));
-        float d;
-        if (dk) d = dk[base + r];
-        else {
-            const size_t o = ((size_t)sl * H + y) * W + x;
-            d = P.p[scale][o] - T[o];
-        }
-        const float L = d - upsample_at(dk1 + (size_t)(scale * S + sl) * hc * wc, hc, wc, y, x, h, w);
+        // the Laplacian value only matters under a non-zero weight (the OS1 / OS4 weights are the ~5 % wide refinement
+        // bands): everywhere else the term and its stored sign are exactly zero, and neither the difference image nor the
+        // 3x3 coarse neighbourhood is read
         const float ww = Wt.p[scale][((size_t)sl * H + (size_t)y * wstep) * W + (size_t)x * wstep];
-        acc[0] += fabsf(L) * ww;
-        acc[1] += ww;
-        sg[base + r] = __float2half(sgn(L) * ww);
+        float sv = 0.f;
+        if (ww != 0.f) {
+            float d;
+            if (dk) d = dk[base + r];
+            else {
+                const size_t o = ((size_t)sl * H + y) * W + x;
+                d = P.p[scale][o] - T[o];
+            }
+            const float L = d - upsample_at(dk1 + (size_t)(scale * S + sl) * hc * wc, hc, wc, y, x, h, w);
+            acc[0] += fabsf(L) * ww;
+            acc[1] += ww;
+            sv = sgn(L) * ww;
+        }
+        sg[base + r] = __float2half(sv);
     }
     float* dst = sums + ((size_t)(blockIdx.x % NCOPY) * 3 + scale) * NQ;
     block_accumulate(&acc[0], 1, dst + 1 + level);
@@ -303,16 +310,20 @@ loss_bwd_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const __hal
     const float* w = Wt.p[scale] + (size_t)sl * H * W;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, tid = threadIdx.y * 32 + threadIdx.x;
     const float c_rec = coef[scale * 5 + 0], c_lap0 = coef[scale * 5 + 1], c_sob = coef[scale * 5 + 4];
+    int any_w = 0;
     for (int i = tid; i < 36 * 36; i += 256) {
         const int ly = i / 36, lx = i - ly * 36;
         const int gy = clampi(y0 + ly - 2, H), gx = clampi(x0 + lx - 2, W);
         const float ww = w[(size_t)gy * W + gx];
-        s_pw[ly][lx] = p[(size_t)gy * W + gx] * ww;
-        s_tw[ly][lx] = t[(size_t)gy * W + gx] * ww;
+        any_w |= ww != 0.f;
+        s_pw[ly][lx] = ww != 0.f ? p[(size_t)gy * W + gx] * ww : 0.f;
+        s_tw[ly][lx] = ww != 0.f ? t[(size_t)gy * W + gx] * ww : 0.f;
     }
-    __syncthreads();
+    // Tiles whose weights are zero over the whole halo (most tiles of the OS1 / OS4 scales: their weights are the narrow
+    // refinement bands) have no weighted-L1 and no Sobel contribution at all: only the Laplacian adjoint remains.
+    const bool weighted = __syncthreads_or(any_w) != 0;
     // d(sum |m_p - m_t|) / d(gx_p, gy_p) at the tile + halo 1 (only for output pixels inside the image)
-    for (int i = tid; i < 34 * 34; i += 256) {
+    for (int i = tid; weighted && i < 34 * 34; i += 256) {
         const int ly = i / 34, lx = i - ly * 34;
         const int oy = y0 + ly - 1, ox = x0 + lx - 1;
         float ggx = 0.f, ggy = 0.f;
@@ -340,9 +351,13 @@ loss_bwd_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const __hal
         const int y = y0 + row, x = x0 + threadIdx.x;
         if (y >= H || x >= W) continue;
         const size_t o = (size_t)y * W + x;
-        const float ww = w[o];
         // Laplacian level 0 + (DG)^T g_1
         float g = bwd_level_value(sg0, c_lap0, g1, nullptr, 0.f, img, y, x, H, W);
+        if (!weighted) {
+            G.p[scale][(size_t)sl * H * W + o] = g;
+            continue;
+        }
+        const float ww = w[o];
         // weighted L1
         g += c_rec * sgn(s_pw[row + 2][threadIdx.x + 2] - s_tw[row + 2][threadIdx.x + 2]) * ww;
         // Sobel adjoint (replicate padding: taps that were clamped onto this pixel come back to it)
