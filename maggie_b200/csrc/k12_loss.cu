@@ -56,21 +56,24 @@ loss_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, float* __restri
         const int gy = refl(y0 + ly - 2, H), gx = refl(x0 + lx - 2, W);
         s_d[ly][lx] = p[(size_t)gy * W + gx] - t[(size_t)gy * W + gx];
     }
+    int any_w = 0;
     for (int i = tid; i < 34 * 34; i += 256) {
         const int ly = i / 34, lx = i - ly * 34;
         const int gy = clampi(y0 + ly - 1, H), gx = clampi(x0 + lx - 1, W);
         const float ww = w[(size_t)gy * W + gx];
-        s_pw[ly][lx] = p[(size_t)gy * W + gx] * ww;
-        s_tw[ly][lx] = t[(size_t)gy * W + gx] * ww;
+        any_w |= ww != 0.f;
+        s_pw[ly][lx] = ww != 0.f ? p[(size_t)gy * W + gx] * ww : 0.f;
+        s_tw[ly][lx] = ww != 0.f ? t[(size_t)gy * W + gx] * ww : 0.f;
     }
-    __syncthreads();
+    // tiles without any weight (most of the OS1 / OS4 scales) contribute nothing to the weighted-L1 / Sobel / weight sums
+    const bool weighted = __syncthreads_or(any_w) != 0;
     float acc[3] = {0.f, 0.f, 0.f};  // rec, sobel, wsum
 #pragma unroll
     for (int qy = 0; qy < 2; ++qy)
 #pragma unroll
         for (int qx = 0; qx < 2; ++qx) {
             const int ly = threadIdx.y * 2 + qy, lx = threadIdx.x * 2 + qx;  // tile-local pixel
-            if (y0 + ly >= H || x0 + lx >= W) continue;
+            if (!weighted || y0 + ly >= H || x0 + lx >= W) continue;
             const int cy = ly + 1, cx = lx + 1;                              // index into the halo-1 arrays
             acc[0] += fabsf(s_pw[cy][cx] - s_tw[cy][cx]);
             acc[2] += w[(size_t)(y0 + ly) * W + x0 + lx];

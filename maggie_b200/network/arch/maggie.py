@@ -97,9 +97,11 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         trans = trans.reshape(b * n_f, n_i, h, w).float() if trans is not None else None
         if self.num_masks - n_i > 0 and self.training:
             draw = [int(c) for c in np.random.choice(self.num_masks, n_i, replace=False)]
-            # planes are kept in ascending slot order, so that active sites are enumerated exactly as in the reference's
-            # scattered layout (row order decides which rows a dropout mask hits); `unsort` restores instance order
-            order = sorted(range(n_i), key=lambda j: draw[j])
+            # On the host (golden tests) planes are kept in ascending slot order, so that active sites are enumerated
+            # exactly as in the reference's scattered layout (row order decides which rows a dropout mask hits) and
+            # `unsort` restores instance order.  On the GPU the dropout stream differs from the reference's anyway and
+            # every other result is independent of the site order, so the planes stay where they are (no gathers).
+            order = sorted(range(n_i), key=lambda j: draw[j]) if not x.is_cuda else list(range(n_i))
             chosen = [draw[j] for j in order]
             if order != list(range(n_i)):
                 masks, alphas, trans = (None if t is None else ops.take(t, 1, order) for t in (masks, alphas, trans))

@@ -541,9 +541,10 @@ class MaGGIeTempDecoder(MaGGIeDecoder):
         if t:
             ret["loss_max_atten"] = loss_atten
             # the reference reads slot 0 of its scattered transition maps (resnet_inst_matt_spconv_temp.py:189-197): with
-            # compact planes that is plane 0 when slot 0 holds an instance (planes are in slot order) and zeros otherwise
-            sg = spar_gt.reshape(fd.shape[0], -1, *spar_gt.shape[1:])[:, 1:, 0:1]
-            if slots is not None and slots[0] != 0:
+            # compact planes that is the plane that was assigned slot 0, or zeros when no instance got that slot
+            j0 = 0 if slots is None else (list(slots).index(0) if 0 in slots else -1)
+            sg = spar_gt.reshape(fd.shape[0], -1, *spar_gt.shape[1:])[:, 1:, max(j0, 0):max(j0, 0) + 1]
+            if j0 < 0:
                 sg = torch.zeros_like(sg)
             bce = F.binary_cross_entropy_with_logits(fd[:, 1:, 0], sg[:, :, 0]) + \
                 F.binary_cross_entropy_with_logits(bd[:, :-1, 0], sg[:, :, 0])
