@@ -51,6 +51,9 @@ mask_embed_fwd_kernel(const float* __restrict__ image, const float* __restrict__
         } else if (C == 16) {
             reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(v)[0];
             reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(v)[1];
+        } else if (C == 32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(o)[i] = reinterpret_cast<uint4*>(v)[i];
         } else {
 #pragma unroll
             for (int i = 0; i < C / 2; ++i) o[i] = v[i];
@@ -106,7 +109,7 @@ mask_embed_bwd_kernel(const __half* __restrict__ gout, const float* __restrict__
 
 int check(const int32_t* slot_ids, int M, int C, const char* who) {
     MG_REQUIRE((slot_ids || M == 0) && M >= 0 && M <= MAX_M, "%s: M must be 0..%d (got %d) with slot ids", who, MAX_M, M);
-    MG_REQUIRE(C == 6 || C == 8 || C == 16, "%s: C must be 6, 8 or 16 (got %d)", who, C);
+    MG_REQUIRE(C == 6 || C == 8 || C == 16 || C == 32, "%s: C must be 6, 8, 16 or 32 (got %d)", who, C);
     return MG_OK;
 }
 
@@ -122,7 +125,8 @@ extern "C" int mg_mask_embed_fwd(const float* image, const float* masks, const i
     __half* out = static_cast<__half*>(out_f16);
     if (C == 6) MG_LAUNCH(mask_embed_fwd_kernel<6>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
     else if (C == 8) MG_LAUNCH(mask_embed_fwd_kernel<8>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
-    else MG_LAUNCH(mask_embed_fwd_kernel<16>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
+    else if (C == 16) MG_LAUNCH(mask_embed_fwd_kernel<16>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
+    else MG_LAUNCH(mask_embed_fwd_kernel<32>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
     MG_CHECK_LAUNCH("mg_mask_embed_fwd");
     return MG_OK;
 }
@@ -137,7 +141,8 @@ extern "C" int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, c
     const __half* g = static_cast<const __half*>(grad_out_f16);
     if (C == 6) MG_LAUNCH(mask_embed_bwd_kernel<6>, grid, 256, 0, stream, g, masks, slot_ids, M, grad_table, B, HW);
     else if (C == 8) MG_LAUNCH(mask_embed_bwd_kernel<8>, grid, 256, 0, stream, g, masks, slot_ids, M, grad_table, B, HW);
-    else MG_LAUNCH(mask_embed_bwd_kernel<16>, grid, 256, 0, stream, g, masks, slot_ids, M, grad_table, B, HW);
+    else if (C == 16) MG_LAUNCH(mask_embed_bwd_kernel<16>, grid, 256, 0, stream, g, masks, slot_ids, M, grad_table, B, HW);
+    else MG_LAUNCH(mask_embed_bwd_kernel<32>, grid, 256, 0, stream, g, masks, slot_ids, M, grad_table, B, HW);
     MG_CHECK_LAUNCH("mg_mask_embed_bwd");
     return MG_OK;
 }

@@ -52,7 +52,10 @@ def _make_shortcut(inplane, planes):
 class ResMaskEmbedShortCutEncoder(nn.Module):
     """`res_shortcut_embed_29`: blocks [3,4,4,2], num_embed mask-embedding channels."""
 
-    IN_PAD = 16  # packed input channels: 3 image + num_embed + zero padding (tcgen05 K granularity)
+    # packed input channels: 3 image + num_embed + zero padding.  32 (not 16): the two convolutions that read the packed
+    # input then qualify for the halo-resident kernel K2b (forward and data gradient), which more than pays for the wider
+    # tensor.
+    IN_PAD = 32
 
     def __init__(self, num_mask=10, num_embed=3, **_):
         super().__init__()
@@ -71,6 +74,7 @@ class ResMaskEmbedShortCutEncoder(nn.Module):
         self.shortcut = nn.ModuleList([_make_shortcut(i, o) for i, o in
                                        ((cin, 32), (32, 32), (64, 64), (128, 128), (256, 256))])
         self.mask_embed_layer = nn.Embedding(num_mask + 1, num_embed)
+        self.conv1.ci_pad_min = self.shortcut[0][0].ci_pad_min = self.IN_PAD   # the two layers that read the packed input
 
     def _shortcut(self, i, x):
         sc, t = self.shortcut[i], self.training

@@ -136,7 +136,7 @@ class WeightBank:
             e.taps = e.kh * e.kw
             e.taps_out = 4 if e.fold else e.taps
             assert e.taps <= 16 and (not e.fold or e.taps == 1) and e.Co % 16 == 0, (e.w.shape, e.fold)
-            e.ci_pad = _pad16(e.Ci)
+            e.ci_pad = max(_pad16(e.Ci), int(getattr(m, "ci_pad_min", 0)))   # layers fed by a wider-padded tensor
             e.numel = e.w.numel()
             m._bank = (self, len(self.entries))
             self.entries.append(e)

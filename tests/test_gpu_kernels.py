@@ -101,7 +101,7 @@ def test_site_tables_on_dilated_band_full_size(dev):
     assert ((T.parent[0].cpu().numpy() >= 0).sum(1) >= 1).all()
 
 
-@pytest.mark.parametrize("C", [6, 8, 16])
+@pytest.mark.parametrize("C", [6, 8, 16, 32])
 def test_mask_embed_fwd_bwd(dev, C):
     from maggie_b200 import ops
     torch.manual_seed(0)
