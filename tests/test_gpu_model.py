@@ -182,3 +182,37 @@ def test_video_c4_shape_clip():
     (loss["total"] * 64.0).backward()
     assert o["temp_alpha"].shape[:2] == (1, 5) and np.isfinite(float(loss["total"]))
     assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+
+
+def test_varying_batches_specialised_kernels_match_generic_kernels(monkeypatch):
+    """Different batches (site counts, slot draws, ellipse sizes) through the routed kernels (K2b halo conv, K9b / K9c
+    persistent sparse kernels) give the same losses and gradient norms as the generic kernels (K2, K9) they replace."""
+    from maggie_b200 import _lib
+    results = {}
+    for mode in ("routed", "generic"):
+        if mode == "generic":
+            monkeypatch.setenv("MAGGIE_B200_NO_HALO_CONV", "1")
+            monkeypatch.setenv("MAGGIE_B200_NO_PERSISTENT_SPARSE", "1")
+        m = _model(True)
+        m.decoder.inst_spec_layer.dropout.p = 0.0
+        out = []
+        for k, (seed, edge) in enumerate(((11, 3.0), (12, 8.0), (13, 5.0))):
+            batch = _to_dev(synth.make_batch(b=4, n_f=1, n_i=3, H=256, W=256, edge_px=edge, seed=seed, train=True, it=1))
+            for p in m.parameters():
+                p.grad = None
+            np.random.seed(100 + k)
+            import random
+            random.seed(100 + k)
+            h0 = _lib.lib().mg_conv_halo_launches()
+            _, loss = m(batch, mem_feat=None)
+            (loss["total"] * 64.0).backward()
+            gn = torch.stack([p.grad.float().norm() for p in m.parameters() if p.grad is not None])
+            out.append((float(loss["total"]), gn, list(m.last_site_counts), _lib.lib().mg_conv_halo_launches() - h0))
+        results[mode] = out
+    for (l0, g0, c0, h0), (l1, g1, c1, h1) in zip(results["routed"], results["generic"]):
+        assert c0 == c1 and c0[0] > 20000
+        assert h0 > 0 and h1 == 0
+        assert abs(l0 - l1) < 2e-2 * abs(l1), (l0, l1)
+        rel = (g0 - g1).abs() / (g1.abs() + 1e-3 * g1.abs().max())
+        assert float(rel.median()) < 2e-2, float(rel.median())
+    assert len({tuple(c) for _, _, c, _ in results["routed"]}) == 3   # the three batches really differ
