@@ -155,6 +155,10 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 
 }  // namespace
 
+namespace mg {
+int wgrad_halo_launch(const mg_wgrad_desc* d, void* stream, bool* handled);   // k4b_wgrad_halo.cu
+}
+
 extern "C" int mg_conv_wgrad(const mg_wgrad_desc* d, void* stream) {
     MG_REQUIRE(d && d->dy && d->x && d->dw, "mg_conv_wgrad: null pointer");
     MG_REQUIRE(d->n_taps >= 1 && d->n_taps <= MAX_TAPS, "mg_conv_wgrad: n_taps %d out of range", d->n_taps);
@@ -163,6 +167,12 @@ extern "C" int mg_conv_wgrad(const mg_wgrad_desc* d, void* stream) {
     if (!mg::get_encode()) {
         mg::set_error("mg_conv_wgrad: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
         return MG_ERR_CUDA;
+    }
+    {
+        // high-resolution 32-channel 3x3 layers: persistent halo-resident kernel (K4b)
+        bool handled = false;
+        const int rc = mg::wgrad_halo_launch(d, stream, &handled);
+        if (rc != MG_OK || handled) return rc;
     }
     WArgs a;
     for (int t = 0; t < d->n_taps; ++t) a.tap_dy[t] = d->tap_dy[t], a.tap_dx[t] = d->tap_dx[t], a.tap_koff[t] = d->tap_koff[t];

@@ -242,7 +242,7 @@ def wgrad_launch(dy, x, taps, dw, *, stride=1, dy_map=(1, 0, 1, 0), grid_hw):
 # (most launches of this network fill only a fraction of the 148 SMs).  Fork and join are plain event waits, i.e.
 # CUDA-graph capturable.
 _AUX = {}
-AUX_WGRAD = True
+AUX_WGRAD = __import__("os").environ.get("MAGGIE_B200_NO_AUX_STREAM", "0") != "1"
 
 
 def aux_stream(device):
