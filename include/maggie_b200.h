@@ -223,6 +223,16 @@ int mg_layer_norm_bwd(const void* s, const void* gy, const float* gamma, const f
                       int E, void* stream);
 int mg_col_sum(const void* x, int stride, int rows, int C, float* out, void* stream);
 
+/* ---- K7: alpha heads (bilinear upsampling + (tanh + 1) / 2 + per-plane factor) ---------------------------------
+ * replaces: F.interpolate(..., mode='bilinear', align_corners=False) + (tanh(x) + 1) / 2 (+ `* valid_masks`) of the three
+ *           alpha scales (decoder/resnet_inst_matt_spconv.py:302-309, 357-362) and their autograd backward.
+ * logits fp32 [planes,h,w]; out / g fp32 [planes,h*S,w*S]; S in {1,2,4,8}; plane_scale optional fp32 [planes].
+ * fwd: out = (tanh(bilerp(logits)) + 1) / 2 * plane_scale.   bwd: glogits = d out / d logits applied to g (gather form). */
+int mg_upsample_tanh_fwd(const float* logits, const float* plane_scale, float* out, int planes, int h, int w, int S,
+                         void* stream);
+int mg_upsample_tanh_bwd(const float* logits, const float* plane_scale, const float* g, float* glogits, int planes, int h,
+                         int w, int S, void* stream);
+
 /* ---- K12: fused training losses (weighted L1 + 3-level Laplacian pyramid + Sobel gradient, 3 alpha scales) ----
  * replaces: arch/maggie.py:237-346 (regression_loss, compute_loss) + loss.py:67-191 (GradientLoss, LapLoss), ~9
  *           pyramid / stencil passes of tiny cuDNN convolutions per scale, and their autograd backward.

@@ -1,0 +1,165 @@
+// K7: alpha heads - bilinear upsampling (align_corners = False, integer scale 1 / 2 / 4 / 8) + (tanh + 1) / 2 + optional
+// per-plane factor (the `valid` mask of the OS8 head), forward and backward, fp32.
+//   forward : one thread per output pixel (coalesced stores; the <= 4 coarse taps come from L1 / L2)
+//   backward: gather form - a block owns a tile of COARSE pixels, evaluates d alpha / d (interpolated logit) * upstream
+//             gradient once per fine pixel of the tile's footprint into shared memory, and every coarse pixel then sums
+//             its (2 S)^2 window with the separable bilinear weights: no atomics, no scatter.
+// Same arithmetic as torch: src = (dst + 0.5) / S - 0.5 clamped at 0, x1 = x0 + (x0 < n - 1), weights (1 - l, l).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void src_index(int d, float rs, int n, int& i0, int& i1, float& l1) {
+    float s = rs * ((float)d + 0.5f) - 0.5f;
+    s = s < 0.f ? 0.f : s;
+    i0 = (int)s;
+    i1 = i0 + (i0 < n - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+}
+
+__device__ __forceinline__ float bilerp(const float* __restrict__ p, int w, int y0, int y1, float ly, int x0, int x1, float lx) {
+    const float h0 = 1.f - ly, w0 = 1.f - lx;
+    return h0 * (w0 * __ldg(p + (size_t)y0 * w + x0) + lx * __ldg(p + (size_t)y0 * w + x1)) +
+           ly * (w0 * __ldg(p + (size_t)y1 * w + x0) + lx * __ldg(p + (size_t)y1 * w + x1));
+}
+
+__global__ void __launch_bounds__(256)
+upsample_tanh_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ plane_scale, float* __restrict__ out,
+                         int planes, int h, int w, int S) {
+    mg::pdl_prologue();
+    const int H = h * S, W = w * S;
+    const float rs = 1.f / (float)S;
+    const size_t total = (size_t)planes * H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H), pl = (int)(i / ((size_t)W * H));
+        const float* p = logits + (size_t)pl * h * w;
+        float v;
+        if (S == 1) {
+            v = __ldg(p + (size_t)y * w + x);
+        } else {
+            int y0, y1, x0, x1;
+            float ly, lx;
+            src_index(y, rs, h, y0, y1, ly);
+            src_index(x, rs, w, x0, x1, lx);
+            v = bilerp(p, w, y0, y1, ly, x0, x1, lx);
+        }
+        float a = (tanhf(v) + 1.0f) * 0.5f;
+        if (plane_scale) a *= __ldg(plane_scale + pl);
+        out[i] = a;
+    }
+}
+
+// grid (w / TC, h / TC, planes), block 256;  TC = coarse tile edge, footprint edge F = S * TC + S
+template <int S, int TC>
+__global__ void __launch_bounds__(256)
+upsample_tanh_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ plane_scale, const float* __restrict__ g,
+                         float* __restrict__ glogits, int h, int w) {
+    mg::pdl_prologue();
+    constexpr int F = S * TC + S;
+    __shared__ float s_v[F][F + 1];
+    const int H = h * S, W = w * S, pl = blockIdx.z;
+    const int cy0 = blockIdx.y * TC, cx0 = blockIdx.x * TC;
+    const int fy0 = S * cy0 - S / 2, fx0 = S * cx0 - S / 2;     // first fine pixel that can touch the tile
+    const float* p = logits + (size_t)pl * h * w;
+    const float* gp = g + (size_t)pl * H * W;
+    const float ps = plane_scale ? __ldg(plane_scale + pl) : 1.f;
+    const float rs = 1.f / (float)S;
+    for (int i = threadIdx.x; i < F * F; i += 256) {
+        const int ly_ = i / F, lx_ = i - ly_ * F;
+        const int y = fy0 + ly_, x = fx0 + lx_;
+        float v = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            int y0, y1, x0, x1;
+            float ly, lx;
+            src_index(y, rs, h, y0, y1, ly);
+            src_index(x, rs, w, x0, x1, lx);
+            const float t = tanhf(bilerp(p, w, y0, y1, ly, x0, x1, lx));
+            v = __ldg(gp + (size_t)y * W + x) * ps * 0.5f * (1.f - t * t);
+        }
+        s_v[ly_][lx_] = v;
+    }
+    __syncthreads();
+    // 256 threads = TC*TC coarse pixels x PARTS row groups of the 2S-row window
+    constexpr int PARTS = 256 / (TC * TC);
+    const int c = threadIdx.x / PARTS, part = threadIdx.x - c * PARTS;
+    const int cy = cy0 + c / TC, cx = cx0 + c % TC;
+    float acc = 0.f;
+    if (cy < h && cx < w) {
+        // fine rows that can touch coarse row cy: [S*cy - S/2, S*cy + 3S/2), split over the PARTS threads of this pixel
+        constexpr int ROWS = 2 * S / PARTS > 0 ? 2 * S / PARTS : 1;
+        for (int ry = part * ROWS; ry < (part + 1) * ROWS && ry < 2 * S; ++ry) {
+            const int y = S * cy - S / 2 + ry;
+            if (y < 0 || y >= H) continue;
+            int y0, y1;
+            float ly;
+            src_index(y, rs, h, y0, y1, ly);
+            const float wy = (y0 == cy ? 1.f - ly : 0.f) + (y1 == cy ? ly : 0.f);
+            if (wy == 0.f) continue;
+            float racc = 0.f;
+#pragma unroll 4
+            for (int rx = 0; rx < 2 * S; ++rx) {
+                const int x = S * cx - S / 2 + rx;
+                if (x < 0 || x >= W) continue;
+                int x0, x1;
+                float lx;
+                src_index(x, rs, w, x0, x1, lx);
+                const float wx = (x0 == cx ? 1.f - lx : 0.f) + (x1 == cx ? lx : 0.f);
+                racc += wx * s_v[y - fy0][x - fx0];
+            }
+            acc += wy * racc;
+        }
+    }
+#pragma unroll
+    for (int d = PARTS / 2; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (part == 0 && cy < h && cx < w) glogits[((size_t)pl * h + cy) * w + cx] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+tanh_head_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ plane_scale, const float* __restrict__ g,
+                     float* __restrict__ glogits, int planes, int hw) {
+    mg::pdl_prologue();
+    const size_t total = (size_t)planes * hw;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float t = tanhf(__ldg(logits + i));
+        const float ps = plane_scale ? __ldg(plane_scale + i / hw) : 1.f;
+        glogits[i] = __ldg(g + i) * ps * 0.5f * (1.f - t * t);
+    }
+}
+
+}  // namespace
+
+extern "C" int mg_upsample_tanh_fwd(const float* logits, const float* plane_scale, float* out, int planes, int h, int w, int S,
+                                    void* stream) {
+    MG_REQUIRE(S == 1 || S == 2 || S == 4 || S == 8, "mg_upsample_tanh_fwd: scale must be 1, 2, 4 or 8 (got %d)", S);
+    if (planes <= 0 || h <= 0 || w <= 0) return MG_OK;
+    MG_REQUIRE(logits && out, "mg_upsample_tanh_fwd: null pointer");
+    const size_t total = (size_t)planes * h * S * w * S;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)mg::kNumSMs * 16);
+    MG_LAUNCH(upsample_tanh_fwd_kernel, grid, 256, 0, stream, logits, plane_scale, out, planes, h, w, S);
+    MG_CHECK_LAUNCH("mg_upsample_tanh_fwd");
+    return MG_OK;
+}
+
+extern "C" int mg_upsample_tanh_bwd(const float* logits, const float* plane_scale, const float* g, float* glogits, int planes,
+                                    int h, int w, int S, void* stream) {
+    MG_REQUIRE(S == 1 || S == 2 || S == 4 || S == 8, "mg_upsample_tanh_bwd: scale must be 1, 2, 4 or 8 (got %d)", S);
+    if (planes <= 0 || h <= 0 || w <= 0) return MG_OK;
+    MG_REQUIRE(logits && g && glogits, "mg_upsample_tanh_bwd: null pointer");
+    MG_REQUIRE(planes <= 65535, "mg_upsample_tanh_bwd: too many planes");
+    if (S == 1) {
+        const size_t total = (size_t)planes * h * w;
+        const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)mg::kNumSMs * 16);
+        MG_LAUNCH(tanh_head_bwd_kernel, grid, 256, 0, stream, logits, plane_scale, g, glogits, planes, h * w);
+    } else if (S == 2) {
+        MG_LAUNCH((upsample_tanh_bwd_kernel<2, 16>), dim3(mg::ceil_div(w, 16), mg::ceil_div(h, 16), planes), 256, 0, stream, logits,
+                  plane_scale, g, glogits, h, w);
+    } else if (S == 4) {
+        MG_LAUNCH((upsample_tanh_bwd_kernel<4, 8>), dim3(mg::ceil_div(w, 8), mg::ceil_div(h, 8), planes), 256, 0, stream, logits,
+                  plane_scale, g, glogits, h, w);
+    } else {
+        MG_LAUNCH((upsample_tanh_bwd_kernel<8, 8>), dim3(mg::ceil_div(w, 8), mg::ceil_div(h, 8), planes), 256, 0, stream, logits,
+                  plane_scale, g, glogits, h, w);
+    }
+    MG_CHECK_LAUNCH("mg_upsample_tanh_bwd");
+    return MG_OK;
+}

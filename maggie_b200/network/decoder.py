@@ -313,9 +313,10 @@ class MaGGIeDecoder(nn.Module):
     def _os8_alpha(self, os8_logits, masks, n_i, H, W, slots=None):
         if slots is not None:       # compact training planes: only the slots that hold an instance are upsampled
             os8_logits = ops.take(os8_logits, 1, slots)
-        valid = masks.flatten(2).sum(2)[:, :, None, None] > 0
-        a8 = ops.upsample_tanh(os8_logits, size=(H, W))
-        return a8 * valid if self.training else a8[:, :n_i]
+        if self.training:
+            valid = (masks.flatten(2).sum(2) > 0).float()          # [B, planes]: alpha of a plane without a mask is zeroed
+            return ops.upsample_tanh(os8_logits, size=(H, W), plane_scale=valid)
+        return ops.upsample_tanh(os8_logits, size=(H, W))[:, :n_i]
 
     def _choose_guidance(self, a8, gt_alphas, iter):
         """Warm-up switch of resnet_inst_matt_spconv.py:311-316 (same python RNG draw)."""

@@ -487,9 +487,45 @@ def gather_dense(dense, coords, n_i):
     return sparse.gather_dense(dense, coords, n_i)
 
 
-def upsample_tanh(logits, size=None, scale=None):
-    """bilinear (align_corners=False) -> (tanh+1)/2 in fp32. INTERIM."""
+class _UpsampleTanh(torch.autograd.Function):
+    """(tanh(bilinear_upsample(logits)) + 1) / 2 * plane_scale, fp32 (K7)."""
+
+    @staticmethod
+    def forward(ctx, logits, plane_scale, S):
+        x = logits.detach().to(torch.float32).contiguous()
+        h, w = x.shape[-2:]
+        planes = x.numel() // (h * w) if x.numel() else 0
+        ps = plane_scale.detach().to(torch.float32).contiguous() if plane_scale is not None else None
+        out = torch.empty(x.shape[:-2] + (h * S, w * S), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().mg_upsample_tanh_fwd(_ptr(x), _ptr(ps), _ptr(out), planes, h, w, S, _stream()), "mg_upsample_tanh_fwd")
+        ctx.save_for_backward(x, ps)
+        ctx.meta = (planes, h, w, S, logits.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, ps = ctx.saved_tensors
+        planes, h, w, S, dt = ctx.meta
+        gl = torch.empty_like(x)
+        _lib.check(_lib.lib().mg_upsample_tanh_bwd(_ptr(x), _ptr(ps), _ptr(g.to(torch.float32).contiguous()), _ptr(gl), planes, h, w,
+                                                  S, _stream()), "mg_upsample_tanh_bwd")
+        return gl.to(dt), None, None
+
+
+def upsample_tanh(logits, size=None, scale=None, plane_scale=None):
+    """bilinear (align_corners=False) -> (tanh+1)/2 (-> * plane_scale [planes]) in fp32.  NATIVE (K7) on CUDA for the integer
+    scales 1 / 2 / 4 / 8 the path uses; torch composition otherwise (host goldens)."""
+    S = 1
+    if size is not None:
+        S = size[-1] // logits.shape[-1] if size[-1] % logits.shape[-1] == 0 and size[-2] == logits.shape[-2] * (size[-1] // logits.shape[-1]) else 0
+    elif scale is not None:
+        S = int(scale) if float(scale) == int(scale) else 0
+    if logits.is_cuda and S in (1, 2, 4, 8) and logits.shape[-3:].numel() > 0:
+        return _UpsampleTanh.apply(logits, plane_scale, S)
     x = logits.float()
     if size is not None or scale is not None:
         x = F.interpolate(x, size=size, scale_factor=scale, mode="bilinear", align_corners=False)
-    return (torch.tanh(x) + 1.0) / 2.0
+    a = (torch.tanh(x) + 1.0) / 2.0
+    if plane_scale is not None:
+        a = a * plane_scale.reshape(a.shape[:-2] + (1, 1)).to(a.dtype)
+    return a

@@ -166,7 +166,7 @@ class WeightBank:
             d0 = e.Ci if e.transposed else e.Co
             width = (e.Co if e.transposed else e.Ci) * e.taps
             if e.u is not None:
-                vt += [(i, r, c, 0) for r in range(0, d0, 64) for c in range(0, width, 256)]
+                vt += [(i, 0, c, 0) for c in range(0, width, 64)]   # one CTA per 64 columns, all rows (deterministic)
                 uu += [(i, r, 0, 0) for r in range(0, d0, 8)]
                 vec += width + d0
             ra, rb = (e.ci_pad, e.Co) if e.transposed else (e.Co, e.ci_pad)

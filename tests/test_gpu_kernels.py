@@ -3,6 +3,7 @@ Integer / bit work is compared bit-exact."""
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 import ops_ref
 from oracle import synth
@@ -121,3 +122,27 @@ def test_mask_embed_fwd_bwd(dev, C):
     (got.float() * gout.to(dev).half().float()).sum().backward()
     assert (tab_d.grad.cpu() - table.grad).abs().max() < 2e-2 * float(table.grad.abs().max())
     assert float(tab_d.grad[[2, 3, 4, 6, 7, 9, 10]].abs().max()) == 0.0   # unused slots get no gradient
+
+
+@pytest.mark.parametrize("planes,h,w,S,with_scale", [((8, 3), 64, 64, 8, True), ((24, 1), 128, 128, 4, False), ((2, 3), 40, 24, 1, True),
+                                                     ((1, 2), 9, 7, 2, False), ((3,), 5, 6, 8, True)])
+def test_upsample_tanh_fwd_bwd_matches_torch(dev, planes, h, w, S, with_scale):
+    """K7 against F.interpolate(bilinear, align_corners=False) + (tanh + 1) / 2 (* per-plane factor) and its autograd."""
+    from maggie_b200 import ops
+    torch.manual_seed(h + S)
+    x = (torch.randn(*planes, h, w, device=dev) * 2).requires_grad_(True)
+    x.data[..., : h // 2, :] -= 99.0 * (torch.rand(*planes, h // 2, w, device=dev) > 0.7)   # the -99 fill of the logit maps
+    ps = (torch.rand(*planes, device=dev) > 0.3).float() if with_scale else None
+    y = ops.upsample_tanh(x, scale=float(S) if S > 1 else None, plane_scale=ps)
+    g = torch.randn_like(y)
+    y.backward(g)
+    got = x.grad.clone()
+    x2 = x.detach().clone().requires_grad_(True)
+    xi = x2.reshape(-1, 1, h, w)
+    up = F.interpolate(xi, scale_factor=float(S), mode="bilinear", align_corners=False) if S > 1 else xi
+    ref = ((torch.tanh(up) + 1.0) / 2.0).reshape(y.shape)
+    if ps is not None:
+        ref = ref * ps.reshape(*planes, 1, 1)
+    ref.backward(g)
+    assert y.shape == ref.shape and (y - ref).abs().max() < 1e-6
+    assert (got - x2.grad).abs().max() < 1e-5 * max(1.0, float(x2.grad.abs().max()))
