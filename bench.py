@@ -194,7 +194,8 @@ def kernel_probes(torch, dev, peaks):
 
     dense.pack_weight = cached_pack
     tot = {"conv_tcgen05_kernel[fprop]": [0.0, 0.0, 0], "conv_tcgen05_kernel[dgrad]": [0.0, 0.0, 0],
-           "wgrad_tcgen05_kernel": [0.0, 0.0, 0], "conv_halo_tcgen05_kernel": [0.0, 0.0, 0]}
+           "wgrad_tcgen05_kernel": [0.0, 0.0, 0], "conv_halo_tcgen05_kernel": [0.0, 0.0, 0],
+           "wgrad_halo_tcgen05_kernel": [0.0, 0.0, 0]}
     try:
         for (hw, ci, co, k, s, d, tr, cnt) in C2_CONVS:
             N = FRAMES_PER_GPU
@@ -214,12 +215,12 @@ def kernel_probes(torch, dev, peaks):
             for key, fn, nl in (("conv_tcgen05_kernel[fprop]", lambda: g.fwd(x, w), 4 if tr else 1),
                                 ("conv_tcgen05_kernel[dgrad]", lambda: g.dgrad(y, w, x.shape), 4 if (s == 2 and not tr) else 1),
                                 ("wgrad_tcgen05_kernel", lambda: g.wgrad(y, x, w.shape, bank=Bank), 4 if tr else 1)):
-                h0 = _lib.lib().mg_conv_halo_launches()
+                h0, w0 = _lib.lib().mg_conv_halo_launches(), _lib.lib().mg_wgrad_halo_launches()
                 fn()
-                halo = _lib.lib().mg_conv_halo_launches() > h0
+                halo = _lib.lib().mg_conv_halo_launches() > h0 or _lib.lib().mg_wgrad_halo_launches() > w0
                 t = timeit(fn, 3)
                 if halo:
-                    key = "conv_halo_tcgen05_kernel"
+                    key = "wgrad_halo_tcgen05_kernel" if key == "wgrad_tcgen05_kernel" else "conv_halo_tcgen05_kernel"
                 tot[key][0] += (nbytes if halo else flops) * cnt
                 tot[key][1] += t * cnt
                 tot[key][2] += nl * cnt
@@ -228,12 +229,12 @@ def kernel_probes(torch, dev, peaks):
     for key, (work, t, nl) in tot.items():
         if nl == 0:
             continue
-        if key == "conv_halo_tcgen05_kernel":
+        if key in ("conv_halo_tcgen05_kernel", "wgrad_halo_tcgen05_kernel"):
             out[key] = dict(bound="hbm", achieved=work / t / 1e9, peak=peaks["hbm"], unit="GB/s",
                             frac=work / t / 1e9 / peaks["hbm"], traffic=None, us_per_step=t * 1e6, algorithmic_bytes_per_step=work,
                             launches_per_step=nl,
-                            note="K2b launches of the C2 layer table (forward + data gradients of the stride-1 layers with <= 64 "
-                                 "channels); bytes = input + output activations, L2 flushed")
+                            note="K2b / K4b launches of the C2 layer table (stride-1 3x3 layers with <= 64 channels at >= 128-wide "
+                                 "resolutions); bytes = the two activation tensors the kernel streams, L2 flushed")
         else:
             out[key] = dict(bound="tensor", achieved=work / t / 1e12, peak=peaks["tf_sustained"], unit="TFLOP/s",
                             frac=work / t / 1e12 / peaks["tf_sustained"], traffic=None, us_per_step=t * 1e6,
@@ -416,8 +417,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="run the dense stage eagerly instead of as CUDA graphs")

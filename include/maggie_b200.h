@@ -155,6 +155,9 @@ typedef struct mg_wgrad_desc {
     int32_t sy, sx, ays, ay0, axs, ax0, Hg, Wg;
 } mg_wgrad_desc;
 int mg_conv_wgrad(const mg_wgrad_desc* desc, void* stream);
+/* 3x3 stride-1 layers with 32 input channels at widths that are multiples of 128 are routed to K4b
+ * (csrc/k4b_wgrad_halo.cu); mg_wgrad_halo_launches counts those launches (tests / profiling). */
+unsigned long long mg_wgrad_halo_launches(void);
 
 /* ---- K3: BatchNorm pieces around the conv kernel (NHWC fp16 activations, fp32 statistics) ----------
  * replaces: nn.BatchNorm2d forward/backward (cuDNN via ATen) + the separate ReLU/LeakyReLU/add passes of

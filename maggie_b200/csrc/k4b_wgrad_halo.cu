@@ -29,6 +29,8 @@ constexpr int WS = 128, P = WS + 2;
 constexpr int XROW = 64;       // bytes per patch pixel (32 channels)
 constexpr int YROW = 128;      // bytes per dY row (64-channel atom)
 
+std::atomic<unsigned long long> g_wgrad_halo_launches{0};
+
 struct WHArgs {
     int H, W, Co, R, strips, rblocks, n_tiles, mode;
     int x_bytes, y_bytes;
@@ -187,8 +189,11 @@ int wgrad_halo_launch(const mg_wgrad_desc* d, void* stream, bool* handled) {
     }
     MG_LAUNCH(wgrad_halo_tcgen05_kernel, std::min(a.n_tiles, kNumSMs), THREADS, smem, stream, tmDY, tmX, a);
     MG_CHECK_LAUNCH("mg_conv_wgrad(halo)");
+    g_wgrad_halo_launches.fetch_add(1, std::memory_order_relaxed);
     *handled = true;
     return MG_OK;
 }
 
 }  // namespace mg
+
+extern "C" unsigned long long mg_wgrad_halo_launches(void) { return g_wgrad_halo_launches.load(); }
