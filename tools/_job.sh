@@ -1,4 +1,4 @@
+# scratch job script for `gpurun -- 'bash tools/_job.sh'` (edited per experiment)
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/r1_bench_default.json 2> gpurun_out/r1_bench_default.err; echo "bench rc=$?"
-timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r1_launches_step.csv python tools/ncu_step.py > gpurun_out/s62_ncu_step.log 2>&1; echo "ncu step rc=$?"
-ROWS=200 timeout 300 python tools/profile_step.py > gpurun_out/r1_profile_eager.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/tests.log
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
