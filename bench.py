@@ -212,8 +212,8 @@ def kernel_probes(torch, dev, peaks):
             class Bank:   # accumulate into a pre-zeroed pack as the weight bank does (no fill inside the timing)
                 G = dwp
 
-            for key, fn, nl in (("conv_tcgen05_kernel[fprop]", lambda: g.fwd(x, w), 4 if tr else 1),
-                                ("conv_tcgen05_kernel[dgrad]", lambda: g.dgrad(y, w, x.shape), 4 if (s == 2 and not tr) else 1),
+            for key, fn, nl in (("conv_tcgen05_kernel[fprop]", lambda: g.fwd(x, w), 1),       # sub-pixel phases: one launch
+                                ("conv_tcgen05_kernel[dgrad]", lambda: g.dgrad(y, w, x.shape), 1),
                                 ("wgrad_tcgen05_kernel", lambda: g.wgrad(y, x, w.shape, bank=Bank), 4 if tr else 1)):
                 h0, w0 = _lib.lib().mg_conv_halo_launches(), _lib.lib().mg_wgrad_halo_launches()
                 fn()

@@ -134,6 +134,10 @@ typedef struct mg_conv_desc {
     const float* bias;
     const float* scale; const float* shift;   /* optional per-channel affine (eval-mode BN folded in) */
     const void* res; int32_t res_up;          /* optional fp16 residual [N,Ho,Wo,Co] ([N,Ho/2,Wo/2,Co] if res_up) */
+    /* n_phases in 2..4: ONE launch computes several output phases that differ only in their taps and (oy0, ox0) - the
+     * sub-pixel phases of a stride-2 data gradient or of the 4x4 stride-2 transposed conv.  Phase p uses the taps
+     * [phase_tap0[p], phase_tap0[p+1]) of the table and the offsets phase_oy0[p], phase_ox0[p]; 0 or 1: plain launch. */
+    int32_t n_phases, phase_tap0[5], phase_oy0[4], phase_ox0[4];
 } mg_conv_desc;
 int mg_conv_fprop(const mg_conv_desc* desc, void* stream);
 /* Stride-1 layers with Ci, Co <= 64 and taps within +-1 pixel (the 512^2 .. 128^2 3x3 convolutions and their data

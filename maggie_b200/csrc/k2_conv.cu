@@ -33,6 +33,9 @@ constexpr int STAT_COPIES = MG_CONV_STAT_COPIES;
 struct KArgs {
     int n_taps;
     int tap_dy[MAX_TAPS], tap_dx[MAX_TAPS], tap_koff[MAX_TAPS];
+    // several launches that differ only in their tap list and output phase (the four sub-pixel phases of a stride-2 data
+    // gradient / transposed conv) run as ONE grid: blockIdx.z selects the phase, taps [tap0[z], tap0[z+1]) of the table
+    int n_phases, phase_tap0[5], phase_oy0[4], phase_ox0[4];
     int sy, sx, Hg, Wg, th, tw, tiles_y, tiles_x;
     int BK, kchunks, BN, Co, stages, swizzle;
     __half* out;
@@ -73,7 +76,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     t /= a.tiles_x;
     const int ty = t % a.tiles_y, img = t / a.tiles_y;
     const int y0 = ty * a.th, x0 = tx * a.tw, n0 = blockIdx.y * a.BN;
-    const int nkb = a.n_taps * a.kchunks;
+    const int tap_first = a.phase_tap0[blockIdx.z];
+    const int nkb = (a.phase_tap0[blockIdx.z + 1] - tap_first) * a.kchunks;
+    const int oy0 = a.phase_oy0[blockIdx.z], ox0 = a.phase_ox0[blockIdx.z];
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -99,7 +104,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int s = kb % a.stages, ph = (kb / a.stages) & 1;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 mbar_expect_tx(full0 + 8 * s, a_bytes + b_bytes);
-                const int tap = kb / a.kchunks, c = kb - tap * a.kchunks;
+                const int tap = tap_first + kb / a.kchunks, c = kb - (kb / a.kchunks) * a.kchunks;
                 tma_load_4d(smem_u32(sA + s * a_bytes), &tmA, full0 + 8 * s, c * a.BK, x0 * a.sx + a.tap_dx[tap],
                             y0 * a.sy + a.tap_dy[tap], img);
                 tma_load_2d(smem_u32(sB + s * b_bytes), &tmB, full0 + 8 * s, a.tap_koff[tap] + c * a.BK, n0);
@@ -130,7 +135,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m = q * 32 + lane;                  // accumulator row = pixel within the tile
         const int py = y0 + m / a.tw, px = x0 + m % a.tw;
         const bool valid = (py < a.Hg) && (px < a.Wg);
-        const int oy = py * a.oys + a.oy0, ox = px * a.oxs + a.ox0;
+        const int oy = py * a.oys + oy0, ox = px * a.oxs + ox0;
         __half* orow = a.out + (((size_t)img * a.Ho + oy) * a.Wo + ox) * a.Cs + a.c_off + n0;
         const __half* rrow = nullptr;
         if (a.res)
@@ -264,6 +269,18 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
     a.out = static_cast<__half*>(d->out);
     a.Ho = d->Ho, a.Wo = d->Wo, a.Cs = d->Cs, a.c_off = d->c_off;
     a.oys = d->oys, a.oy0 = d->oy0, a.oxs = d->oxs, a.ox0 = d->ox0;
+    a.n_phases = 1;
+    a.phase_tap0[0] = 0, a.phase_tap0[1] = d->n_taps, a.phase_oy0[0] = d->oy0, a.phase_ox0[0] = d->ox0;
+    if (d->n_phases > 1) {
+        MG_REQUIRE(d->n_phases <= 4, "mg_conv_fprop: at most 4 phases");
+        a.n_phases = d->n_phases;
+        for (int p = 0; p < d->n_phases; ++p) {
+            a.phase_tap0[p] = d->phase_tap0[p], a.phase_oy0[p] = d->phase_oy0[p], a.phase_ox0[p] = d->phase_ox0[p];
+            MG_REQUIRE(d->phase_tap0[p + 1] > d->phase_tap0[p], "mg_conv_fprop: every phase needs at least one tap");
+        }
+        a.phase_tap0[d->n_phases] = d->phase_tap0[d->n_phases];
+        MG_REQUIRE(a.phase_tap0[0] == 0 && a.phase_tap0[d->n_phases] == d->n_taps, "mg_conv_fprop: phase tap ranges must cover the tap table");
+    }
     a.pre_act = d->pre_act, a.post_act = d->post_act, a.stats = d->stats, a.bias = d->bias;
     a.scale = d->scale, a.shift = d->shift, a.res = static_cast<const __half*>(d->res), a.res_up = d->res_up;
     MG_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "mg_conv_fprop: scale and shift go together");
@@ -312,7 +329,7 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
         }
         attr_set = true;
     }
-    dim3 grid(d->N * a.tiles_y * a.tiles_x, mg::ceil_div(d->Co, a.BN));
+    dim3 grid(d->N * a.tiles_y * a.tiles_x, mg::ceil_div(d->Co, a.BN), a.n_phases);
     MG_LAUNCH(conv_tcgen05_kernel, grid, THREADS, smem, stream, tmA, tmB, a);
     MG_CHECK_LAUNCH("mg_conv_fprop");
     return MG_OK;

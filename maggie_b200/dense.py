@@ -37,6 +37,7 @@ class ConvDesc(ctypes.Structure):
         ("oys", c_int32), ("oy0", c_int32), ("oxs", c_int32), ("ox0", c_int32),
         ("pre_act", c_int32), ("post_act", c_int32), ("stats", c_void_p), ("bias", c_void_p),
         ("scale", c_void_p), ("shift", c_void_p), ("res", c_void_p), ("res_up", c_int32),
+        ("n_phases", c_int32), ("phase_tap0", c_int32 * 5), ("phase_oy0", c_int32 * 4), ("phase_ox0", c_int32 * 4),
     ]
 
 ACT = {None: 0, "relu": 1, "lrelu": 2}
@@ -63,10 +64,14 @@ def conv_taps(kh, kw, pad, dil, ci_pad):
 
 def conv_launch(x, w_packed, taps, *, stride=1, grid_hw=None, out=None, out_hw=None, out_map=(1, 0, 1, 0), c_off=0,
                 relu=False, stats=None, bias=None, pre_act=None, post_act=None, scale=None, shift=None, res=None,
-                res_up=False):
+                res_up=False, phases=None):
     """Generic launch of mg_conv_fprop.  x [N,Hi,Wi,Ci] fp16 NHWC; w_packed [Co,Ktot] fp16; taps [(dy,dx,koff)].
     grid_hw: logical output grid (defaults to ceil(Hi/stride)); out: preallocated NHWC fp16 (or None);
-    out_map = (oys, oy0, oxs, ox0)."""
+    out_map = (oys, oy0, oxs, ox0).
+    phases: [(taps, oy0, ox0), ...] (2..4 entries, `taps` ignored): the sub-pixel phases of a stride-2 data gradient /
+    transposed conv as ONE launch; out_map supplies the common output strides (oys, _, oxs, _)."""
+    if phases is not None:
+        taps = [t for ph in phases for t in ph[0]]
     _need_cuda(x, w_packed)
     assert x.dtype == torch.float16 and x.is_contiguous() and w_packed.dtype == torch.float16 and w_packed.is_contiguous()
     N, Hi, Wi, Ci = x.shape
@@ -94,6 +99,13 @@ def conv_launch(x, w_packed, taps, *, stride=1, grid_hw=None, out=None, out_hw=N
     d.shift = shift.data_ptr() if shift is not None else None
     d.res = res.data_ptr() if res is not None else None
     d.res_up = int(res_up)
+    if phases is not None:
+        d.n_phases = len(phases)
+        t0 = 0
+        for i, (ptaps, oy0, ox0) in enumerate(phases):
+            d.phase_tap0[i], d.phase_oy0[i], d.phase_ox0[i] = t0, oy0, ox0
+            t0 += len(ptaps)
+        d.phase_tap0[len(phases)] = t0
     _lib.check(_lib.lib().mg_conv_fprop(ctypes.byref(d), _stream()), "mg_conv_fprop")
     return out
 
@@ -122,18 +134,19 @@ def conv_transpose4x4s2_nhwc(x, w, *, stats=None):
     N, Hi, Wi, ci_pad = x.shape
     out = torch.empty((N, 2 * Hi, 2 * Wi, Co), dtype=torch.float16, device=x.device)
     wp = w.P if _banked(w) else pack_weight(w.permute(1, 0, 2, 3), ci_pad)  # [Co][ky][kx][Ci]
+    conv_launch(x, wp, None, grid_hw=(Hi, Wi), out=out, out_map=(2, 0, 2, 0), stats=stats, phases=convT_phases(ci_pad))
+    return out
+
+
+def convT_phases(ci_pad):
+    """The four sub-pixel phases of ConvTranspose2d(4, 2, 1): [(taps, oy0, ox0)], 2 x 2 taps each."""
+    phases = []
     for py in range(2):
         for px in range(2):
-            taps = []
-            for ky in range(4):
-                if (py + 1 - ky) % 2:
-                    continue
-                for kx in range(4):
-                    if (px + 1 - kx) % 2:
-                        continue
-                    taps.append(((py + 1 - ky) // 2, (px + 1 - kx) // 2, (ky * 4 + kx) * ci_pad))
-            conv_launch(x, wp, taps, grid_hw=(Hi, Wi), out=out, out_map=(2, py, 2, px), stats=stats)
-    return out
+            taps = [((py + 1 - ky) // 2, (px + 1 - kx) // 2, (ky * 4 + kx) * ci_pad)
+                    for ky in range(4) if (py + 1 - ky) % 2 == 0 for kx in range(4) if (px + 1 - kx) % 2 == 0]
+            phases.append((taps, py, px))
+    return phases
 
 
 # ---- per-forward scope: one zeroed scratch pool + deferred BatchNorm counters -----------------------------------
@@ -313,14 +326,21 @@ class ConvGeom:
             return conv_launch(dy, wp, taps, grid_hw=(Hi, Wi))
         assert Hi % 2 == 0 and Wi % 2 == 0
         dx = torch.empty((N, Hi, Wi, ci_pad), dtype=torch.float16, device=dy.device)
+        phases = []
         for py in range(2):
             for px in range(2):
                 taps = [((py + p - ky) // 2, (px + p - kx) // 2, (ky * k + kx) * Co)
                         for ky in range(k) if (py + p - ky) % 2 == 0 for kx in range(k) if (px + p - kx) % 2 == 0]
-                if not taps:
-                    dx[:, py::2, px::2] = 0
-                    continue
-                conv_launch(dy, wp, taps, grid_hw=(Hi // 2, Wi // 2), out=dx, out_map=(2, py, 2, px))
+                phases.append((taps, py, px))
+        if all(ph[0] for ph in phases) and sum(len(ph[0]) for ph in phases) <= MAX_TAPS:
+            # the four output parities as ONE launch (blockIdx.z = phase)
+            conv_launch(dy, wp, None, grid_hw=(Hi // 2, Wi // 2), out=dx, out_map=(2, 0, 2, 0), phases=phases)
+            return dx
+        for taps, py, px in phases:
+            if not taps:
+                dx[:, py::2, px::2] = 0
+                continue
+            conv_launch(dy, wp, taps, grid_hw=(Hi // 2, Wi // 2), out=dx, out_map=(2, py, 2, px))
         return dx
 
     # ---- weight gradient in the torch layout, fp32
@@ -456,12 +476,8 @@ def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="rel
         Ci, Co = wshape(w)[:2]
         y = torch.empty((N, 2 * Hi, 2 * Wi, Co), dtype=torch.float16, device=x.device)
         wp = w.P if banked else pack_weight(w.detach().permute(1, 0, 2, 3), ci_pad)
-        for py in range(2):
-            for px in range(2):
-                taps = [((py + 1 - ky) // 2, (px + 1 - kx) // 2, (ky * 4 + kx) * ci_pad)
-                        for ky in range(4) if (py + 1 - ky) % 2 == 0 for kx in range(4) if (px + 1 - kx) % 2 == 0]
-                conv_launch(xn, wp, taps, grid_hw=(Hi, Wi), out=y, out_map=(2, py, 2, px), scale=scale, shift=shift,
-                            pre_act=act if act_first else None, post_act=None if act_first else act)
+        conv_launch(xn, wp, None, grid_hw=(Hi, Wi), out=y, out_map=(2, 0, 2, 0), scale=scale, shift=shift,
+                    pre_act=act if act_first else None, post_act=None if act_first else act, phases=convT_phases(ci_pad))
     else:
         y = conv2d_nhwc(xn, w if banked else w.detach(), stride=stride, padding=padding, dilation=dilation, scale=scale, shift=shift, res=rn,
                         res_up=res_up, pre_act=act if act_first else None, post_act=None if act_first else act)
