@@ -251,11 +251,14 @@ int mg_upsample_tanh_bwd(const float* logits, const float* plane_scale, const fl
  * mg_loss_bwd : coef [3][5] (device) = upstream gradient of numerators [0..4]; writes d/d(a1), d/d(a4), d/d(a8).   */
 #define MG_LOSS_COPIES 32
 size_t mg_loss_workspace_floats(int S, int H, int W);
+/* plane_scale (optional, fp32 [S]): the predictions enter as a * plane_scale[slice] (the reference's `pred * valid_masks`,
+ * arch/maggie.py:112-117, without materialising the products); the returned gradients are w.r.t. the unscaled a. */
 int mg_loss_fwd(const float* a1, const float* a4, const float* a8, const float* target, const float* w1, const float* w4,
-                const float* w8, int S, int H, int W, float* ws, void* sg_f16, float* sums, void* stream);
+                const float* w8, const float* plane_scale, int S, int H, int W, float* ws, void* sg_f16, float* sums,
+                void* stream);
 int mg_loss_bwd(const float* a1, const float* a4, const float* a8, const float* target, const float* w1, const float* w4,
-                const float* w8, int S, int H, int W, float* ws, const void* sg_f16, const float* coef, float* g1_out,
-                float* g4_out, float* g8_out, void* stream);
+                const float* w8, const float* plane_scale, int S, int H, int W, float* ws, const void* sg_f16,
+                const float* coef, float* g1_out, float* g4_out, float* g8_out, void* stream);
 
 /* ---- K6: mask-guided attention cores (single head, E = 128) ------------------------------------------
  * replaces: nn.MultiheadAttention's QK^T / softmax / PV (unfused, weights materialised) inside

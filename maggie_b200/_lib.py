@@ -34,8 +34,8 @@ SIGNATURES = {
     "mg_attn_fq_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 2),
     "mg_attn_fq_bwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 4),
     "mg_loss_workspace_floats": (c_size_t, [c_int, c_int, c_int]),
-    "mg_loss_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mg_loss_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "mg_loss_fwd": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mg_loss_bwd": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p]),
     "mg_gather_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "mg_scatter_rows_add": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

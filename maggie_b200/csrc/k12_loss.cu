@@ -42,8 +42,8 @@ __device__ __forceinline__ void block_accumulate(float* vals, int n, float* dst)
 // ---- F1: full-resolution pass: weighted L1, Sobel term, weight sum; writes d1 = D G (p - t) -------------------
 // grid (W/32, H/32, 3*S), block 16x16; each thread owns a 2x2 pixel quad and one d1 output.
 __global__ void __launch_bounds__(256)
-loss_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, float* __restrict__ D1, float* __restrict__ sums, int S, int H,
-                   int W) {
+loss_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const float* __restrict__ plane_scale, float* __restrict__ D1,
+                   float* __restrict__ sums, int S, int H, int W) {
     mg::pdl_prologue();
     __shared__ float s_d[36][37], s_pw[34][35], s_tw[34][35];
     const int scale = blockIdx.z / S, sl = blockIdx.z - scale * S;
@@ -51,10 +51,11 @@ loss_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, float* __restri
     const float* t = T + (size_t)sl * H * W;
     const float* w = Wt.p[scale] + (size_t)sl * H * W;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, tid = threadIdx.y * 16 + threadIdx.x;
+    const float ps = plane_scale ? __ldg(plane_scale + sl) : 1.f;   // per-plane factor on the prediction (`pred * valid`)
     for (int i = tid; i < 36 * 36; i += 256) {
         const int ly = i / 36, lx = i - ly * 36;
         const int gy = refl(y0 + ly - 2, H), gx = refl(x0 + lx - 2, W);
-        s_d[ly][lx] = p[(size_t)gy * W + gx] - t[(size_t)gy * W + gx];
+        s_d[ly][lx] = p[(size_t)gy * W + gx] * ps - t[(size_t)gy * W + gx];
     }
     int any_w = 0;
     for (int i = tid; i < 34 * 34; i += 256) {
@@ -62,7 +63,7 @@ loss_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, float* __restri
         const int gy = clampi(y0 + ly - 1, H), gx = clampi(x0 + lx - 1, W);
         const float ww = w[(size_t)gy * W + gx];
         any_w |= ww != 0.f;
-        s_pw[ly][lx] = ww != 0.f ? p[(size_t)gy * W + gx] * ww : 0.f;
+        s_pw[ly][lx] = ww != 0.f ? p[(size_t)gy * W + gx] * ps * ww : 0.f;
         s_tw[ly][lx] = ww != 0.f ? t[(size_t)gy * W + gx] * ww : 0.f;
     }
     // tiles without any weight (most of the OS1 / OS4 scales) contribute nothing to the weighted-L1 / Sobel / weight sums
@@ -160,7 +161,8 @@ __device__ __forceinline__ float upsample_at(const float* __restrict__ dc, int h
 // level 0: d_0 = p - t on the fly (dk == nullptr).  wstep = 2^k (sub-sampling of the full-resolution weight).
 __global__ void __launch_bounds__(256)
 loss_lap_kernel(Ptr3 P, const float* __restrict__ T, const float* __restrict__ dk, const float* __restrict__ dk1, Ptr3 Wt,
-                __half* __restrict__ sg, float* __restrict__ sums, int S, int H, int W, int level) {
+                const float* __restrict__ plane_scale, __half* __restrict__ sg, float* __restrict__ sums, int S, int H, int W,
+                int level) {
     mg::pdl_prologue();
     const int h = H >> level, w = W >> level, hc = h >> 1, wc = w >> 1, wstep = 1 << level;
     const int scale = blockIdx.y;                                   // one scale per grid row: partial sums never mix
@@ -178,7 +180,7 @@ loss_lap_kernel(Ptr3 P, const float* __restrict__ T, const float* __restrict__ d
             if (dk) d = dk[base + r];
             else {
                 const size_t o = ((size_t)sl * H + y) * W + x;
-                d = P.p[scale][o] - T[o];
+                d = P.p[scale][o] * (plane_scale ? __ldg(plane_scale + sl) : 1.f) - T[o];
             }
             const float L = d - upsample_at(dk1 + (size_t)(scale * S + sl) * hc * wc, hc, wc, y, x, h, w);
             acc[0] += fabsf(L) * ww;
@@ -303,8 +305,9 @@ loss_bwd_small_kernel(const __half* __restrict__ sg_k, const float* __restrict__
 // full-resolution backward: lap (level 0) + weighted L1 + Sobel; one gradient tensor per scale.
 // grid (W/32, H/32, 3*S), block 32x8 (each thread 4 rows).
 __global__ void __launch_bounds__(256)
-loss_bwd_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const __half* __restrict__ sg0, const float* __restrict__ g1,
-                       const float* __restrict__ coef, MPtr3 G, int S, int H, int W) {
+loss_bwd_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const float* __restrict__ plane_scale,
+                       const __half* __restrict__ sg0, const float* __restrict__ g1, const float* __restrict__ coef, MPtr3 G, int S,
+                       int H, int W) {
     mg::pdl_prologue();
     __shared__ float s_pw[36][37], s_tw[36][37], s_gx[34][35], s_gy[34][35];
     const int scale = blockIdx.z / S, sl = blockIdx.z - scale * S;
@@ -313,13 +316,14 @@ loss_bwd_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const __hal
     const float* w = Wt.p[scale] + (size_t)sl * H * W;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, tid = threadIdx.y * 32 + threadIdx.x;
     const float c_rec = coef[scale * 5 + 0], c_lap0 = coef[scale * 5 + 1], c_sob = coef[scale * 5 + 4];
+    const float ps = plane_scale ? __ldg(plane_scale + sl) : 1.f;   // prediction = p * ps; the gradient w.r.t. p gets ps too
     int any_w = 0;
     for (int i = tid; i < 36 * 36; i += 256) {
         const int ly = i / 36, lx = i - ly * 36;
         const int gy = clampi(y0 + ly - 2, H), gx = clampi(x0 + lx - 2, W);
         const float ww = w[(size_t)gy * W + gx];
         any_w |= ww != 0.f;
-        s_pw[ly][lx] = ww != 0.f ? p[(size_t)gy * W + gx] * ww : 0.f;
+        s_pw[ly][lx] = ww != 0.f ? p[(size_t)gy * W + gx] * ps * ww : 0.f;
         s_tw[ly][lx] = ww != 0.f ? t[(size_t)gy * W + gx] * ww : 0.f;
     }
     // Tiles whose weights are zero over the whole halo (most tiles of the OS1 / OS4 scales: their weights are the narrow
@@ -357,7 +361,7 @@ loss_bwd_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const __hal
         // Laplacian level 0 + (DG)^T g_1
         float g = bwd_level_value(sg0, c_lap0, g1, nullptr, 0.f, img, y, x, H, W);
         if (!weighted) {
-            G.p[scale][(size_t)sl * H * W + o] = g;
+            G.p[scale][(size_t)sl * H * W + o] = g * ps;
             continue;
         }
         const float ww = w[o];
@@ -396,7 +400,7 @@ loss_bwd_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const __hal
                 }
             }
         g += sa * ww;
-        G.p[scale][(size_t)sl * H * W + o] = g;
+        G.p[scale][(size_t)sl * H * W + o] = g * ps;
     }
 }
 
@@ -411,8 +415,8 @@ extern "C" size_t mg_loss_workspace_floats(int S, int H, int W) {
 }
 
 extern "C" int mg_loss_fwd(const float* a1, const float* a4, const float* a8, const float* target, const float* w1,
-                           const float* w4, const float* w8, int S, int H, int W, float* ws, void* sg_f16, float* sums,
-                           void* stream) {
+                           const float* w4, const float* w8, const float* plane_scale, int S, int H, int W, float* ws,
+                           void* sg_f16, float* sums, void* stream) {
     MG_REQUIRE(a1 && a4 && a8 && target && w1 && w4 && w8 && ws && sg_f16 && sums, "mg_loss_fwd: null pointer");
     MG_REQUIRE(S > 0 && H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16, "mg_loss_fwd: H, W must be multiples of 8, >= 16");
     MG_REQUIRE(3 * S <= 65535, "mg_loss_fwd: too many slices");
@@ -422,18 +426,19 @@ extern "C" int mg_loss_fwd(const float* a1, const float* a4, const float* a8, co
     __half* sg0 = static_cast<__half*>(sg_f16);
     __half *sg1 = sg0 + n0, *sg2 = sg1 + n1;
     dim3 grid0(mg::ceil_div(W, 32), mg::ceil_div(H, 32), 3 * S);
-    MG_LAUNCH(loss_level0_kernel, grid0, dim3(16, 16), 0, stream, P, target, Wt, d1, sums, S, H, W);
+    MG_LAUNCH(loss_level0_kernel, grid0, dim3(16, 16), 0, stream, P, target, Wt, plane_scale, d1, sums, S, H, W);
     MG_LAUNCH(loss_down_kernel, small_grid(n2), 256, 0, stream, d1, d2, 3 * S, H / 2, W / 2);
     MG_LAUNCH(loss_down_kernel, small_grid(n3), 256, 0, stream, d2, d3, 3 * S, H / 4, W / 4);
-    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n0 / 3), 3), 256, 0, stream, P, target, (const float*)nullptr, d1, Wt, sg0, sums, S, H, W, 0);
-    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n1 / 3), 3), 256, 0, stream, P, target, d1, d2, Wt, sg1, sums, S, H, W, 1);
-    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n2 / 3), 3), 256, 0, stream, P, target, d2, d3, Wt, sg2, sums, S, H, W, 2);
+    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n0 / 3), 3), 256, 0, stream, P, target, (const float*)nullptr, d1, Wt, plane_scale, sg0, sums, S, H, W, 0);
+    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n1 / 3), 3), 256, 0, stream, P, target, d1, d2, Wt, plane_scale, sg1, sums, S, H, W, 1);
+    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n2 / 3), 3), 256, 0, stream, P, target, d2, d3, Wt, plane_scale, sg2, sums, S, H, W, 2);
     MG_CHECK_LAUNCH("mg_loss_fwd");
     return MG_OK;
 }
 
 extern "C" int mg_loss_bwd(const float* a1, const float* a4, const float* a8, const float* target, const float* w1,
-                           const float* w4, const float* w8, int S, int H, int W, float* ws, const void* sg_f16,
+                           const float* w4, const float* w8, const float* plane_scale, int S, int H, int W, float* ws,
+                           const void* sg_f16,
                            const float* coef, float* g1_out, float* g4_out, float* g8_out, void* stream) {
     MG_REQUIRE(a1 && a4 && a8 && target && w1 && w4 && w8 && ws && sg_f16 && coef && g1_out && g4_out && g8_out,
                "mg_loss_bwd: null pointer");
@@ -450,7 +455,7 @@ extern "C" int mg_loss_bwd(const float* a1, const float* a4, const float* a8, co
     MG_LAUNCH(loss_bwd_small_kernel, small_grid(n2), 256, 0, stream, sg2, (const float*)g3, sg1, coef, g2, S, H / 4, W / 4, 2);
     MG_LAUNCH(loss_bwd_small_kernel, small_grid(n1), 256, 0, stream, sg1, (const float*)g2, sg0, coef, g1, S, H / 2, W / 2, 1);
     dim3 grid0(mg::ceil_div(W, 32), mg::ceil_div(H, 32), 3 * S);
-    MG_LAUNCH(loss_bwd_level0_kernel, grid0, dim3(32, 8), 0, stream, P, target, Wt, sg0, (const float*)g1, coef, G, S, H, W);
+    MG_LAUNCH(loss_bwd_level0_kernel, grid0, dim3(32, 8), 0, stream, P, target, Wt, plane_scale, sg0, (const float*)g1, coef, G, S, H, W);
     MG_CHECK_LAUNCH("mg_loss_bwd");
     return MG_OK;
 }

@@ -211,11 +211,15 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
 
         if self.training:
             valid = (trans.sum((2, 3), keepdim=True) > 0).float()
-            for k in list(pred):
-                if "loss" in k or "mem_" in k:
-                    continue
-                pred[k] = pred[k] * valid
-            loss_dict = losses.compute_loss(pred, w4, w1, alphas, self.cfg)
+            if type(self)._extra_losses is MaGGIe._extra_losses:
+                # image model: the only consumer of `pred * valid` is the loss, which applies the factor itself
+                loss_dict = losses.compute_loss(pred, w4, w1, alphas, self.cfg, valid=valid)
+            else:
+                for k in list(pred):
+                    if "loss" in k or "mem_" in k:
+                        continue
+                    pred[k] = pred[k] * valid
+                loss_dict = losses.compute_loss(pred, w4, w1, alphas, self.cfg)
             # planes per reference plane count (the reference sums an epsilon over its zero-padded slots too)
             self._extra_losses(pred, loss_dict, w4, w1, alphas, (b, n_f, n_i, h, w), n_slots / n_i)
             if "loss_max_atten" in pred and self.cfg.loss_atten_w > 0:

@@ -6,16 +6,21 @@ LapLoss).  The heavy part - every per-pixel stencil and reduction, forward and b
 from .. import ops
 
 
-def compute_loss(pred, w4, w1, alphas, cfg):
-    """Image-model loss dictionary (dtSSD is handled by the video subclass)."""
+def compute_loss(pred, w4, w1, alphas, cfg, valid=None):
+    """Image-model loss dictionary (dtSSD is handled by the video subclass).  `valid` [B, planes, 1, 1] {0,1}: the
+    predictions are the UNMASKED alphas and the reference's `pred * valid_masks` (arch/maggie.py:112-117) is applied inside
+    the loss kernels (three full-size products and their backward less)."""
     a1, a4, a8 = pred["alpha_os1"], pred["alpha_os4"], pred["alpha_os8"]
     w8 = (alphas.sum((2, 3), keepdim=True) > 0).to(a8.dtype).expand_as(a8)
     if cfg.loss_reweight_os8:
         lo, hi = 1.0 / 255.0, 254.0 / 255.0
-        unk = ((alphas <= hi) & (alphas >= lo)) | ((a8 <= hi) & (a8 >= lo))
+        unk_pred = (a8 <= hi) & (a8 >= lo)
+        if valid is not None:
+            unk_pred = unk_pred & (valid > 0)       # a masked-out plane is identically 0: never "unknown"
+        unk = ((alphas <= hi) & (alphas >= lo)) | unk_pred
         w8 = unk.to(a8.dtype) + w8
     # sums[scale] = [sum|p w - t w|, sum|L_0| w_0, sum|L_1| w_1, sum|L_2| w_2, sum|sobel(pw) - sobel(tw)|, sum w_0, sum w_1, sum w_2]
-    s = ops.matte_loss_sums(a1, a4, a8, alphas, w1, w4, w8)
+    s = ops.matte_loss_sums(a1, a4, a8, alphas, w1, w4, w8, valid.reshape(-1) if valid is not None else None)
     L = {}
     total = 0.0
     if cfg.loss_alpha_w > 0:

@@ -199,39 +199,42 @@ def mask_embed(image, masks, table, slot_ids, C=8):
 # =============================================================================================== native: K12
 class _MatteLossSums(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a1, a4, a8, target, w1, w4, w8):
+    def forward(ctx, a1, a4, a8, target, w1, w4, w8, plane_scale):
         _need_cuda(a1, a4, a8, target, w1, w4, w8)
         f = lambda t: t.detach().to(torch.float32).contiguous()
         a1d, a4d, a8d, td, w1d, w4d, w8d = (f(t) for t in (a1, a4, a8, target, w1, w4, w8))
+        psd = f(plane_scale).reshape(-1) if plane_scale is not None else None
         H, W = a1d.shape[-2:]
         S = a1d.numel() // (H * W)
+        assert psd is None or psd.numel() == S
         L = _lib.lib()
         ws = torch.empty(L.mg_loss_workspace_floats(S, H, W), dtype=torch.float32, device=a1.device)
         n0 = 3 * S * H * W
         sg = torch.empty(n0 + n0 // 4 + n0 // 16, dtype=torch.float16, device=a1.device)
         sums = torch.zeros((32, 3, 8), dtype=torch.float32, device=a1.device)
-        _lib.check(L.mg_loss_fwd(_ptr(a1d), _ptr(a4d), _ptr(a8d), _ptr(td), _ptr(w1d), _ptr(w4d), _ptr(w8d), S, H, W, _ptr(ws),
-                                 _ptr(sg), _ptr(sums), _stream()), "mg_loss_fwd")
-        ctx.save_for_backward(a1d, a4d, a8d, td, w1d, w4d, w8d, ws, sg)
+        _lib.check(L.mg_loss_fwd(_ptr(a1d), _ptr(a4d), _ptr(a8d), _ptr(td), _ptr(w1d), _ptr(w4d), _ptr(w8d), _ptr(psd), S, H, W,
+                                 _ptr(ws), _ptr(sg), _ptr(sums), _stream()), "mg_loss_fwd")
+        ctx.save_for_backward(a1d, a4d, a8d, td, w1d, w4d, w8d, ws, sg, psd)
         ctx.shape = (S, H, W, a1.shape)
         return sums.sum(0)
 
     @staticmethod
     def backward(ctx, gs):
-        a1d, a4d, a8d, td, w1d, w4d, w8d, ws, sg = ctx.saved_tensors
+        a1d, a4d, a8d, td, w1d, w4d, w8d, ws, sg, psd = ctx.saved_tensors
         S, H, W, shape = ctx.shape
         coef = gs[:, :5].to(torch.float32).contiguous()
         g = torch.empty((3,) + tuple(a1d.shape), dtype=torch.float32, device=a1d.device)
-        _lib.check(_lib.lib().mg_loss_bwd(_ptr(a1d), _ptr(a4d), _ptr(a8d), _ptr(td), _ptr(w1d), _ptr(w4d), _ptr(w8d), S, H, W,
-                                         _ptr(ws), _ptr(sg), _ptr(coef), _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _stream()),
+        _lib.check(_lib.lib().mg_loss_bwd(_ptr(a1d), _ptr(a4d), _ptr(a8d), _ptr(td), _ptr(w1d), _ptr(w4d), _ptr(w8d), _ptr(psd), S,
+                                         H, W, _ptr(ws), _ptr(sg), _ptr(coef), _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _stream()),
                    "mg_loss_bwd")
-        return g[0].view(shape), g[1].view(shape), g[2].view(shape), None, None, None, None
+        return g[0].view(shape), g[1].view(shape), g[2].view(shape), None, None, None, None, None
 
 
-def matte_loss_sums(a1, a4, a8, target, w1, w4, w8):
+def matte_loss_sums(a1, a4, a8, target, w1, w4, w8, plane_scale=None):
     """Partial sums [3 scales, 8] of the matting losses (weighted L1, Laplacian pyramid levels, Sobel gradient, weight
-    sums) with a native backward to the three predictions.  NATIVE (K12).  Reference: arch/maggie.py:268-346."""
-    return _MatteLossSums.apply(a1, a4, a8, target, w1, w4, w8)
+    sums) with a native backward to the three predictions.  plane_scale [planes] (optional): the predictions enter as
+    a * plane_scale (the reference's `pred * valid_masks`).  NATIVE (K12).  Reference: arch/maggie.py:268-346."""
+    return _MatteLossSums.apply(a1, a4, a8, target, w1, w4, w8, plane_scale)
 
 
 # =============================================================================================== native: K0

@@ -207,7 +207,10 @@ def _sobel_mag(x, eps=1e-6):
     return torch.sqrt(gx * gx + gy * gy + eps)
 
 
-def matte_loss_sums(a1, a4, a8, target, w1, w4, w8):
+def matte_loss_sums(a1, a4, a8, target, w1, w4, w8, plane_scale=None):
+    if plane_scale is not None:
+        ps = plane_scale.reshape(a1.shape[:-2] + (1, 1)).to(a1.dtype)
+        a1, a4, a8 = a1 * ps, a4 * ps, a8 * ps
     h, w = a1.shape[-2:]
     t = target.reshape(-1, 1, h, w).float()
     rows = []

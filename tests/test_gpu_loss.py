@@ -27,12 +27,15 @@ def test_matte_loss_sums_forward_backward(S, H, W):
         else:
             gs[:, term] = torch.tensor([1.0, 0.5, 2.0]).cuda()
         _check(ops, S, H, W, preds, tgt, ws, gs, name)
+    # per-plane factor on the predictions (the reference's `pred * valid_masks`), applied inside the kernels
+    scale = (torch.rand(S, generator=g) > 0.3).float().cuda()
+    _check(ops, S, H, W, preds, tgt, ws, torch.rand(3, 8, generator=g).cuda(), "all, plane scale", scale)
 
 
-def _check(ops, S, H, W, preds, tgt, ws, gs, name):
+def _check(ops, S, H, W, preds, tgt, ws, gs, name, plane_scale=None):
     def run(fn):
         ps = [p.clone().requires_grad_(True) for p in preds]
-        s = fn(ps[0], ps[1], ps[2], tgt, ws[0], ws[1], ws[2])
+        s = fn(ps[0], ps[1], ps[2], tgt, ws[0], ws[1], ws[2], plane_scale)
         (s * gs).sum().backward()
         return s.detach(), [p.grad for p in ps]
 
