@@ -229,6 +229,12 @@ int mg_layer_norm_fwd(const void* a, const void* b, const float* gamma, const fl
 int mg_layer_norm_bwd(const void* s, const void* gy, const float* gamma, const float* stat, void* dx, float* dgb, int rows,
                       int E, void* stream);
 int mg_col_sum(const void* x, int stride, int rows, int C, float* out, void* stream);
+/* mg_token_logits_fwd/bwd : logits[bt][q][p] = sum_c tok[bt / n_f][q][c] * x[bt][p][c] - the `einsum('bqc,btchw->btqhw')` of
+ *     the OS8 head (module/instance_matte_decoder.py:302); x NHWC fp16 with C = 64, tok fp32 [B][Q][C], logits / g fp32
+ *     [BT][Q][HW].  bwd: dx fp16 [BT][HW][C] and / or dtok fp32 [B][Q][C] (+=, caller zeroes); either may be NULL. */
+int mg_token_logits_fwd(const float* tok, const void* x, float* logits, int BT, int n_f, int Q, int HW, int C, void* stream);
+int mg_token_logits_bwd(const float* tok, const void* x, const float* g, void* dx, float* dtok, int BT, int n_f, int Q, int HW,
+                        int C, void* stream);
 
 /* ---- K7: alpha heads (bilinear upsampling + (tanh + 1) / 2 + per-plane factor) ---------------------------------
  * replaces: F.interpolate(..., mode='bilinear', align_corners=False) + (tanh(x) + 1) / 2 (+ `* valid_masks`) of the three

@@ -208,3 +208,126 @@ extern "C" int mg_col_sum(const void* x, int stride, int rows, int C, float* out
     MG_CHECK_LAUNCH("mg_col_sum");
     return MG_OK;
 }
+
+// ---- token logits: logits[bt][q][p] = sum_c tok[bt / n_f][q][c] * x[bt][p][c]  (the einsum of the OS8 head) -----------
+// x is the NHWC fp16 feature map (rows of C = 64 channels), tok the 10 instance tokens per sample in fp32.  Replaces an
+// fp32 copy of x plus three cuBLAS batched GEMMs with K = 10 / 64 / 4096 shapes it handles badly (147 us for the token
+// gradient alone).
+namespace {
+
+constexpr int TL_C = 64, TL_QMAX = 16;
+
+__global__ void __launch_bounds__(256)
+token_logits_fwd_kernel(const float* __restrict__ tok, const __half* __restrict__ x, float* __restrict__ logits, int BT, int n_f,
+                        int Q, int HW) {
+    mg::pdl_prologue();
+    __shared__ float s_tok[TL_QMAX][TL_C];
+    const int bt = blockIdx.y, b = bt / n_f;
+    for (int i = threadIdx.x; i < Q * TL_C; i += 256) s_tok[i / TL_C][i % TL_C] = tok[(size_t)b * Q * TL_C + i];
+    __syncthreads();
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < HW; p += gridDim.x * 256) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + ((size_t)bt * HW + p) * TL_C);
+        float xv[TL_C];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 u = __ldg(xr + j);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                xv[j * 8 + 2 * i] = f.x, xv[j * 8 + 2 * i + 1] = f.y;
+            }
+        }
+        for (int q = 0; q < Q; ++q) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < TL_C; ++c) acc += s_tok[q][c] * xv[c];
+            logits[((size_t)bt * Q + q) * HW + p] = acc;
+        }
+    }
+}
+
+// dx[bt][p][c] = sum_q g[bt][q][p] * tok[b][q][c]   (fp16 NHWC)
+__global__ void __launch_bounds__(256)
+token_logits_bwd_x_kernel(const float* __restrict__ tok, const float* __restrict__ g, __half* __restrict__ dx, int BT, int n_f,
+                          int Q, int HW) {
+    mg::pdl_prologue();
+    __shared__ float s_tok[TL_QMAX][TL_C];
+    const int bt = blockIdx.y, b = bt / n_f;
+    for (int i = threadIdx.x; i < Q * TL_C; i += 256) s_tok[i / TL_C][i % TL_C] = tok[(size_t)b * Q * TL_C + i];
+    __syncthreads();
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < HW; p += gridDim.x * 256) {
+        float gv[TL_QMAX];
+        for (int q = 0; q < Q; ++q) gv[q] = __ldg(g + ((size_t)bt * Q + q) * HW + p);
+        uint4* orow = reinterpret_cast<uint4*>(dx + ((size_t)bt * HW + p) * TL_C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int q = 0; q < Q; ++q) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] += gv[q] * s_tok[q][j * 8 + i];
+            }
+            uint4 u;
+            __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+            orow[j] = u;
+        }
+    }
+}
+
+// dtok[b][q][c] += sum over the block's 128 pixels  g[bt][q][p] * x[bt][p][c]
+constexpr int TL_TILE = 128;
+__global__ void __launch_bounds__(256)
+token_logits_bwd_tok_kernel(const __half* __restrict__ x, const float* __restrict__ g, float* __restrict__ dtok, int BT, int n_f,
+                            int Q, int HW) {
+    mg::pdl_prologue();
+    __shared__ __half s_x[TL_TILE][TL_C + 2];
+    __shared__ float s_g[TL_QMAX][TL_TILE];
+    const int bt = blockIdx.y, b = bt / n_f, p0 = blockIdx.x * TL_TILE;
+    for (int i = threadIdx.x; i < TL_TILE * TL_C / 2; i += 256) {
+        const int r = i / (TL_C / 2), c2 = i - r * (TL_C / 2);
+        const __half2 v = p0 + r < HW ? *reinterpret_cast<const __half2*>(x + ((size_t)bt * HW + p0 + r) * TL_C + 2 * c2) : __floats2half2_rn(0.f, 0.f);
+        *reinterpret_cast<__half2*>(&s_x[r][2 * c2]) = v;
+    }
+    for (int i = threadIdx.x; i < Q * TL_TILE; i += 256) {
+        const int q = i / TL_TILE, r = i - q * TL_TILE;
+        s_g[q][r] = p0 + r < HW ? __ldg(g + ((size_t)bt * Q + q) * HW + p0 + r) : 0.f;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < Q * TL_C; o += 256) {
+        const int q = o / TL_C, c = o - q * TL_C;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < TL_TILE; ++r) acc += s_g[q][r] * __half2float(s_x[r][c]);
+        atomicAdd(dtok + ((size_t)b * Q + q) * TL_C + c, acc);
+    }
+}
+
+}  // namespace
+
+extern "C" int mg_token_logits_fwd(const float* tok, const void* x, float* logits, int BT, int n_f, int Q, int HW, int C,
+                                   void* stream) {
+    MG_REQUIRE(C == TL_C && Q >= 1 && Q <= TL_QMAX && n_f >= 1, "mg_token_logits_fwd: C must be 64 and Q <= 16 (C=%d Q=%d)", C, Q);
+    if (BT <= 0 || HW <= 0) return MG_OK;
+    MG_REQUIRE(tok && x && logits, "mg_token_logits_fwd: null pointer");
+    MG_LAUNCH(token_logits_fwd_kernel, dim3(std::min(mg::ceil_div(HW, 256), 64), BT), 256, 0, stream, tok,
+              static_cast<const __half*>(x), logits, BT, n_f, Q, HW);
+    MG_CHECK_LAUNCH("mg_token_logits_fwd");
+    return MG_OK;
+}
+
+extern "C" int mg_token_logits_bwd(const float* tok, const void* x, const float* g, void* dx, float* dtok, int BT, int n_f, int Q,
+                                   int HW, int C, void* stream) {
+    MG_REQUIRE(C == TL_C && Q >= 1 && Q <= TL_QMAX && n_f >= 1, "mg_token_logits_bwd: C must be 64 and Q <= 16 (C=%d Q=%d)", C, Q);
+    if (BT <= 0 || HW <= 0) return MG_OK;
+    MG_REQUIRE(tok && x && g && (dx || dtok), "mg_token_logits_bwd: null pointer");
+    if (dx)
+        MG_LAUNCH(token_logits_bwd_x_kernel, dim3(std::min(mg::ceil_div(HW, 256), 64), BT), 256, 0, stream, tok, g,
+                  static_cast<__half*>(dx), BT, n_f, Q, HW);
+    if (dtok)   // caller zeroes dtok [B][Q][C]
+        MG_LAUNCH(token_logits_bwd_tok_kernel, dim3(mg::ceil_div(HW, TL_TILE), BT), 256, 0, stream, static_cast<const __half*>(x), g, dtok,
+                  BT, n_f, Q, HW);
+    MG_CHECK_LAUNCH("mg_token_logits_bwd");
+    return MG_OK;
+}

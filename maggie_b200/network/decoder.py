@@ -186,7 +186,7 @@ class InstanceMatteDecoder(nn.Module):
         tok = ops.linear(tok, self.final_mlp.layers[0].weight, self.final_mlp.layers[0].bias)
         tok = F.layer_norm(tok.float(), (tok.shape[-1],), self.decoder_norm.weight, self.decoder_norm.bias,
                            self.decoder_norm.eps)                                           # [b,10,64] fp32
-        logits = torch.einsum("bqc,btchw->btqhw", tok, x.float().reshape(b, n_f, -1, h, w)).flatten(0, 1)
+        logits = ops.token_logits(tok, x, n_f)
         if temporal_fn is not None:
             return logits, out_feat, tok, loss, hidden
         return logits, out_feat, tok, loss
@@ -376,11 +376,14 @@ class MaGGIeDecoder(nn.Module):
             a4 = torch.zeros_like(a8)
             a1 = torch.zeros_like(a8)
         ret = dict(alpha_os1=a1, alpha_os4=a4, alpha_os8=a8)
-        w4 = ops.unknown_mask(a8, widths(27), and_mask=unk).to(a8.dtype)
-        a = a4 * w4 + a8 * (1 - w4)
-        w1 = ops.unknown_mask(a, widths(15), and_mask=unk).to(a8.dtype)
-        a = a1 * w1 + a * (1 - w1)
+        # progressive fusion (fuse(), :272-290): the weights are {0,1} masks, so `x*w + y*(1-w)` is a select
+        w4 = ops.unknown_mask(a8, widths(27), and_mask=unk)
+        a = torch.where(w4 != 0, a4, a8)
+        w1 = ops.unknown_mask(a, widths(15), and_mask=unk)
+        a = torch.where(w1 != 0, a1, a)
         ret["refined_masks"] = a
+        if not use_gt:
+            w4, w1 = w4.to(a8.dtype), w1.to(a8.dtype)
         if use_gt:
             w4 = ops.unknown_mask(gt_alphas, widths(30), and_mask=unk)
             w1 = ops.unknown_mask(gt_alphas, widths(15), and_mask=unk)

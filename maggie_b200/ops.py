@@ -371,6 +371,46 @@ def layer_norm(x, ln, residual=None):
     return F.layer_norm(x.float(), (x.shape[-1],), ln.weight, ln.bias, ln.eps).to(x.dtype)
 
 
+class _TokenLogits(torch.autograd.Function):
+    """logits[bt, q, h, w] = sum_c tok[bt // n_f, q, c] * x[bt, c, h, w] with x channels-last fp16 (K13)."""
+
+    @staticmethod
+    def forward(ctx, tok, x, n_f):
+        xn = x.permute(0, 2, 3, 1)
+        assert xn.is_contiguous() and xn.dtype == torch.float16
+        BT, H, W, C = xn.shape
+        tk = tok.detach().to(torch.float32).contiguous()
+        Q = tk.shape[1]
+        out = torch.empty((BT, Q, H, W), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().mg_token_logits_fwd(_ptr(tk), _ptr(xn), _ptr(out), BT, n_f, Q, H * W, C, _stream()),
+                   "mg_token_logits_fwd")
+        ctx.save_for_backward(tk, xn)
+        ctx.meta = (n_f, tok.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        tk, xn = ctx.saved_tensors
+        n_f, tdt = ctx.meta
+        BT, H, W, C = xn.shape
+        Q = tk.shape[1]
+        gc = g.to(torch.float32).contiguous()
+        dx = torch.empty_like(xn) if ctx.needs_input_grad[1] else None
+        dtok = torch.zeros_like(tk) if ctx.needs_input_grad[0] else None
+        _lib.check(_lib.lib().mg_token_logits_bwd(_ptr(tk), _ptr(xn), _ptr(gc), _ptr(dx), _ptr(dtok), BT, n_f, Q, H * W, C,
+                                                 _stream()), "mg_token_logits_bwd")
+        return (dtok.to(tdt) if dtok is not None else None), (dx.permute(0, 3, 1, 2) if dx is not None else None), None
+
+
+def token_logits(tok, x, n_f):
+    """The OS8 head's `einsum('bqc,btchw->btqhw')` (instance_matte_decoder.py:302) flattened to [b*n_f, q, h, w], fp32.
+    tok [b, q, 64] fp32; x [b*n_f, 64, h, w].  NATIVE (K13) on CUDA channels-last fp16 features; torch otherwise."""
+    if x.is_cuda and x.dtype == torch.float16 and x.shape[1] == 64 and tok.shape[1] <= 16 and x.permute(0, 2, 3, 1).is_contiguous():
+        return _TokenLogits.apply(tok, x, n_f)
+    b = tok.shape[0]
+    return torch.einsum("bqc,btchw->btqhw", tok, x.float().reshape(b, n_f, *x.shape[1:])).flatten(0, 1)
+
+
 def col_sum(x):
     """fp32 column sums of fp16 rows [N, C] (bias gradients of the sparse layers).  NATIVE (K13)."""
     _need_cuda(x)

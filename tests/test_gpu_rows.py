@@ -49,3 +49,23 @@ def test_col_sum(rows, C, stride):
     ref = x.double().sum(0)
     assert got.dtype == torch.float32 and got.shape == (C,)
     assert (got.double() - ref).abs().max() < 1e-3 * max(1.0, rows ** 0.5)
+
+
+@pytest.mark.parametrize("b,n_f,Q,h,w", [(8, 1, 10, 64, 64), (2, 3, 10, 16, 24), (1, 1, 3, 9, 7)])
+def test_token_logits_fwd_bwd(b, n_f, Q, h, w):
+    """K13 token logits against the reference einsum('bqc,btchw->btqhw') in fp32 (and its autograd)."""
+    from maggie_b200 import ops
+    torch.manual_seed(b + h)
+    dev = torch.device("cuda")
+    tok = torch.randn(b, Q, 64, device=dev, requires_grad=True)
+    x = torch.randn(b * n_f, 64, h, w, device=dev).half().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = ops.token_logits(tok, x, n_f)
+    g = torch.randn_like(y)
+    y.backward(g)
+    tok2 = tok.detach().clone().requires_grad_(True)
+    x2 = x.detach().float().clone().requires_grad_(True)
+    ref = torch.einsum("bqc,btchw->btqhw", tok2, x2.reshape(b, n_f, 64, h, w)).flatten(0, 1)
+    ref.backward(g)
+    assert y.shape == ref.shape and (y - ref).abs().max() < 1e-4 * max(1.0, float(ref.abs().max()))
+    assert (tok.grad - tok2.grad).abs().max() < 1e-3 * max(1.0, float(tok2.grad.abs().max()))
+    assert (x.grad.float() - x2.grad).abs().max() < 4e-3 * max(1.0, float(x2.grad.abs().max()))   # fp16 gradient
