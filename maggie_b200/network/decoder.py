@@ -143,7 +143,7 @@ class InstanceMatteDecoder(nn.Module):
         ids = torch.arange(1, n_i + 1, device=feat.device).view(1, 1, n_i, 1, 1)
         id_pos = (mask_os8 * ids).amax(2)                                                   # [b,n_f,h,w]
         emb = self.id_embedding.weight
-        x_pos = F.embedding(id_pos.reshape(b, n_f, hw).permute(0, 2, 1).reshape(b, hw * n_f), emb).to(dt)  # [b,S,E]
+        x_pos = ops.id_embedding(id_pos.reshape(b, n_f, hw).permute(0, 2, 1).reshape(b, hw * n_f), emb, dt)   # [b,S,E]
         x = ops.linear_rows(x, self.feat_proj.layers[0].weight, self.feat_proj.layers[0].bias)
         tok = self.query_feat.weight.to(dt)[None].expand(b, -1, -1)
         tok_pos = emb[1:nq + 1].to(dt)[None].expand(b, -1, -1)

@@ -411,6 +411,32 @@ def token_logits(tok, x, n_f):
     return torch.einsum("bqc,btchw->btqhw", tok, x.float().reshape(b, n_f, *x.shape[1:])).flatten(0, 1)
 
 
+class _IdEmbedding(torch.autograd.Function):
+    """table[ids] for a tiny table (11 id rows) and many ids (b * 4096 * n_f pixels).  The forward is a plain gather; the
+    backward is ONE one-hot GEMM (table^T-shaped: [rows, ids] x [ids, E], fp32) instead of torch's sort-based
+    embedding_dense_backward (128 us at C2 for a [11, 128] gradient)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, dtype):
+        flat = ids.reshape(-1)
+        ctx.save_for_backward(flat)
+        ctx.meta = (table.shape[0], table.dtype)
+        return table.detach().index_select(0, flat).view(*ids.shape, table.shape[1]).to(dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (flat,) = ctx.saved_tensors
+        rows, tdt = ctx.meta
+        onehot = F.one_hot(flat, (rows + 7) // 8 * 8).to(torch.float32)             # [ids, rows padded to 8]
+        grad = onehot.t().matmul(g.reshape(flat.numel(), -1).to(torch.float32))     # [rows_pad, E]
+        return None, grad[:rows].to(tdt), None
+
+
+def id_embedding(ids, table, dtype):
+    """F.embedding(ids, table).to(dtype) with a GEMM backward (see _IdEmbedding); ids int64 [...], table [rows, E]."""
+    return _IdEmbedding.apply(ids, table, dtype)
+
+
 def col_sum(x):
     """fp32 column sums of fp16 rows [N, C] (bias gradients of the sparse layers).  NATIVE (K13)."""
     _need_cuda(x)
