@@ -216,6 +216,22 @@ int mg_sparse_conv(const mg_sparse_conv_desc* desc, void* stream);
 int mg_sparse_wgrad(const void* dout, int dout_stride, int Cout, const void* src, int src_stride, int Cin,
                     const int32_t* table, int T, int No, float* dw, void* stream);
 
+/* ---- K14: optimizer tail (GradScaler.unscale_ + clip_grad_norm_ + AdamW.step) ------------------------------
+ * replaces: engine/train.py:265-283 (scaler.unscale_, torch.nn.utils.clip_grad_norm_(all_params, 0.01), scaler.step) with
+ *           engine/optim.py:118 (torch.optim.AdamW) - ~600 parameter tensors -> two multi-tensor launches, no host sync.
+ * grad / m / v: flat fp32 buffers of n_flat elements (tensor t occupies [flat_off, flat_off + numel)); tensors[] gives each
+ * parameter's address; items[k] = (tensor index, element offset) work items of <= 16384 elements.
+ * acc [2] (zero before the first call; the call leaves it zeroed), step [1] (number of updates applied so far, advanced on
+ * the device unless a gradient was inf / nan, in which case nothing is updated), report [2] = (unscaled gradient norm,
+ * found_inf) of this call.  inv_scale = 1 / loss scale. */
+typedef struct mg_optim_tensor {
+    float* param;
+    int64_t flat_off, numel;
+} mg_optim_tensor;
+int mg_optim_adamw_step(const mg_optim_tensor* tensors, const int32_t* items, int n_items, const float* grad, size_t n_flat,
+                        float* m, float* v, float* acc, float* step, float* report, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, float max_norm, float inv_scale, void* stream);
+
 /* ---- K13: row-wise helpers (LayerNorm with fused residual, column sums) ---------------------------------
  * replaces: nn.LayerNorm after the residual add of every post-norm attention / FFN layer (module/mask_attention.py:
  *           `tgt = self.norm(tgt + self.dropout(tgt2))`, 11 per forward) with its backward, and the bias-gradient

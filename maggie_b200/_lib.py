@@ -50,6 +50,8 @@ SIGNATURES = {
                                 c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_wprep_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int] + [c_void_p] * 5),
     "mg_wprep_bwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5),
+    "mg_optim_adamw_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+                            + [c_float] * 7 + [c_void_p]),
     "mg_upsample_tanh_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_upsample_tanh_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_layer_norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int,
