@@ -264,6 +264,10 @@ def run_gpu(args):
     torch.manual_seed(1234)  # identical initial weights on every rank
     model, _ = build_model(CfgNode(synth.model_cfg()))
     model.to(dev).train()
+    sync_bn = bool(args.sync_bn) and world > 1
+    if sync_bn:  # SyncBatchNorm-equivalent statistics exchange (`model.sync_bn: true`); the dense stage then runs eagerly
+        from maggie_b200.dp import set_sync_bn
+        set_sync_bn(True)
     model.enable_cuda_graphs(not args.no_graphs)
     flat = FlatGradAllReduce(model.parameters())
 
@@ -389,7 +393,7 @@ def run_gpu(args):
         "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd per GPU (iter=1, edge {EDGE_PX}px)",
                    "frames_per_gpu": FRAMES_PER_GPU, "active_sites_os1_os2_os4_os8": counts,
                    "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                   "loss_scale": LOSS_SCALE, "sync_bn": False, "cuda_graphs_dense_stage": not args.no_graphs},
+                   "loss_scale": LOSS_SCALE, "sync_bn": sync_bn, "cuda_graphs_dense_stage": not args.no_graphs and not sync_bn},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e, "h2d": "pinned host memory -> device on a copy stream, every step",
                 "d2h": "loss copied to pinned memory every step, value consumed one step later"},
@@ -422,6 +426,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="run the dense stage eagerly instead of as CUDA graphs")
+    ap.add_argument("--sync-bn", action="store_true", help="N>1: exchange BatchNorm statistics across ranks (model.sync_bn true)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

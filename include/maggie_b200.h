@@ -173,17 +173,21 @@ unsigned long long mg_wgrad_halo_launches(void);
  *                  res_up: residual is [N,H/2,W/2,C] and replicated 2x2 (nearest upsampling).
  * mg_bn_bwd_reduce / mg_bn_bwd_apply : dz = dy*act'(y); sums = [sum dz ; sum dz*xhat] (caller zeroes sums [2][C]);
  *                  dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (* pre_act'(conv_out) if pre_act),
- *                  dres = dz (optional).  dgamma = sums[1], dbeta = sums[0].                                  */
+ *                  dres = dz (optional).  dgamma = sums[1], dbeta = sums[0].
+ * count_dev (mg_bn_finalize, mg_bn_bwd_apply; may be NULL): device scalar that replaces the host-side element count.
+ *                  SyncBatchNorm-equivalent training (engine/train.py:160-161): the caller sums `stats` / `sums` and the
+ *                  element count over the ranks (one all-reduce each) and passes the global count here, so that ranks
+ *                  with different numbers of active sites need no host synchronisation.                          */
 int mg_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
-                   float* save_invstd, int C, void* stream);
+                   float* save_invstd, int C, const float* count_dev, void* stream);
 int mg_bn_apply(const void* x, const float* scale, const float* shift, const void* res, int res_up, void* y, int N,
                 int H, int W, int C, int act, void* stream);
 int mg_bn_bwd_reduce(const void* dy, const void* y, const void* conv_out, const float* mean, const float* invstd,
                      float* sums, int N, int H, int W, int C, int act, void* stream);
 int mg_bn_bwd_apply(const void* dy, const void* y, const void* conv_out, const float* mean, const float* invstd,
                     const float* gamma, const float* sums, void* dx, void* dres, int N, int H, int W, int C, int act,
-                    int pre_act, void* stream);
+                    int pre_act, const float* count_dev, void* stream);
 
 /* ---- K9: sparse refinement on the active-site lists (no spconv) -------------------------------------
  * replaces: spconv SubMConv2d / SparseInverseConv2d / SparseConvTensor.dense() and the dense<->sparse gathers of

@@ -42,12 +42,12 @@ SIGNATURES = {
     "mg_sparse_conv": (c_int, [c_void_p, c_void_p]),
     "mg_sparse_wgrad": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "mg_bn_finalize": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
-                               c_void_p, c_void_p, c_int, c_void_p]),
+                               c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mg_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
     "mg_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mg_wprep_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int] + [c_void_p] * 5),
     "mg_wprep_bwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5),
     "mg_optim_adamw_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

@@ -12,11 +12,12 @@ constexpr int STAT_COPIES = MG_CONV_STAT_COPIES;
 // block = 8 copy-groups x 32 channels: the 64 statistic copies are summed by 8 threads per channel (coalesced over the
 // channels) and combined through shared memory - the kernel is pure latency, so the serial chain is kept short.
 __global__ void __launch_bounds__(256)
-bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
-                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
+bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ count_dev,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ rmean,
+                   float* __restrict__ rvar, float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
                    float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
     mg::pdl_prologue();
+    if (count_dev) count = fmaxf(__ldg(count_dev), 1.f);   // statistics exchanged across ranks: the global element count
     __shared__ float s_s[8][32], s_q[8][32];
     const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -176,9 +177,10 @@ bn_bwd_reduce_kernel(const __half* __restrict__ dy, const __half* __restrict__ y
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ yout, const __half* __restrict__ r,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                    const float* __restrict__ sums, float inv_count, __half* __restrict__ dx, __half* __restrict__ dres,
-                    size_t npix, int C, int act, int pre_act) {
+                    const float* __restrict__ sums, float inv_count, const float* __restrict__ count_dev,
+                    __half* __restrict__ dx, __half* __restrict__ dres, size_t npix, int C, int act, int pre_act) {
     mg::pdl_prologue();
+    if (count_dev) inv_count = 1.f / fmaxf(__ldg(count_dev), 1.f);
     extern __shared__ float s_p[];  // [4][C]: mean, scale=gamma*invstd, mean_dz, invstd*mean_dzx
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
         const float is = invstd[i];
@@ -231,11 +233,11 @@ int stream_grid(size_t work_items) {
 
 extern "C" int mg_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
                               float* running_var, float momentum, float eps, float* scale, float* shift,
-                              float* save_mean, float* save_invstd, int C, void* stream) {
+                              float* save_mean, float* save_invstd, int C, const float* count_dev, void* stream) {
     MG_REQUIRE(scale && shift && C > 0, "mg_bn_finalize: null pointer");
     MG_REQUIRE(stats || (running_mean && running_var), "mg_bn_finalize: need batch statistics or running statistics");
     MG_REQUIRE((save_mean == nullptr) == (save_invstd == nullptr), "mg_bn_finalize: save_mean/save_invstd go together");
-    MG_LAUNCH(bn_finalize_kernel, mg::ceil_div(C, 32), 256, 0, stream, stats, count, gamma, beta, running_mean, running_var,
+    MG_LAUNCH(bn_finalize_kernel, mg::ceil_div(C, 32), 256, 0, stream, stats, count, count_dev, gamma, beta, running_mean, running_var,
               momentum, eps, scale, shift, save_mean, save_invstd, C);
     MG_CHECK_LAUNCH("mg_bn_finalize");
     return MG_OK;
@@ -270,14 +272,14 @@ extern "C" int mg_bn_bwd_reduce(const void* dy, const void* y, const void* conv_
 
 extern "C" int mg_bn_bwd_apply(const void* dy, const void* y, const void* conv_out, const float* mean, const float* invstd,
                                const float* gamma, const float* sums, void* dx, void* dres, int N, int H, int W, int C,
-                               int act, int pre_act, void* stream) {
+                               int act, int pre_act, const float* count_dev, void* stream) {
     MG_REQUIRE(dy && conv_out && mean && invstd && sums && dx && (y || !act), "mg_bn_bwd_apply: null pointer");
     MG_REQUIRE(C % 8 == 0 && C <= 2048, "mg_bn_bwd_apply: C must be a multiple of 8 (got %d)", C);
     const size_t npix = (size_t)N * H * W;
     if (npix == 0) return MG_OK;
     MG_LAUNCH(bn_bwd_apply_kernel, stream_grid(npix * (C / 8)), 256, 4 * C * sizeof(float), stream,
               static_cast<const __half*>(dy), static_cast<const __half*>(y), static_cast<const __half*>(conv_out), mean,
-              invstd, gamma, sums, 1.0f / (float)npix, static_cast<__half*>(dx), static_cast<__half*>(dres), npix, C, act,
+              invstd, gamma, sums, 1.0f / (float)npix, count_dev, static_cast<__half*>(dx), static_cast<__half*>(dres), npix, C, act,
               pre_act);
     MG_CHECK_LAUNCH("mg_bn_bwd_apply");
     return MG_OK;

@@ -212,8 +212,65 @@ def bump_counter(t):
         t.add_(1)
 
 
-def new_stats(co, device):
-    return zeros_f32(STAT_COPIES * 2 * co, device).view(STAT_COPIES, 2, co)
+def new_stats(co, device, flat=False):
+    """Zeroed conv-epilogue statistics [STAT_COPIES, 2, co]; `flat`: also return the underlying flat buffer, which then
+    carries one extra element for the element count (the unit that is exchanged across ranks, see `sync_group`)."""
+    n = STAT_COPIES * 2 * co
+    if not flat:
+        return zeros_f32(n, device).view(STAT_COPIES, 2, co)
+    buf = zeros_f32(n + 1, device)
+    return buf[:n].view(STAT_COPIES, 2, co), buf
+
+
+# ================================================================================================ statistics exchange
+# SyncBatchNorm-equivalent training (engine/train.py:160-161, `model.sync_bn: true` in both live configs): the batch
+# statistics of every BatchNorm are taken over the frames / active sites of ALL ranks.  Per layer and direction ONE small
+# all-reduce: forward = the conv-epilogue sums + the element count, backward = [sum dz ; sum dz*xhat].  The global count
+# stays on the device (`count_dev` of mg_bn_finalize / mg_bn_bwd_apply), so ranks with different numbers of active sites
+# need no host synchronisation.  dgamma / dbeta stay LOCAL sums (the gradient all-reduce averages them, as DDP does).
+_SYNC_ALL = None
+
+
+def set_sync_bn(group=True):
+    """Exchange the statistics of EVERY BatchNorm over `group` (True: the default group; None / False: off), without
+    converting the containers.  Containers converted by `nn.SyncBatchNorm.convert_sync_batchnorm` exchange anyway."""
+    global _SYNC_ALL
+    _SYNC_ALL = group if group not in (False, None) else None
+
+
+def sync_group(bn):
+    """The process group `bn` shares its batch statistics over, or None (local statistics)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    if isinstance(bn, torch.nn.SyncBatchNorm):
+        grp = bn.process_group if bn.process_group is not None else dist.group.WORLD
+    elif _SYNC_ALL is not None:
+        grp = dist.group.WORLD if _SYNC_ALL is True else _SYNC_ALL
+    else:
+        return None
+    return grp if dist.get_world_size(grp) > 1 else None
+
+
+def sync_bn_active(model):
+    """True when some BatchNorm of `model` exchanges statistics (the dense stage then cannot replay as a CUDA graph)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+        return False
+    return _SYNC_ALL is not None or any(isinstance(m, torch.nn.SyncBatchNorm) for m in model.modules())
+
+
+def exchange(t, group):
+    """In-place sum of `t` over `group`, ordered on the current stream (NCCL).  A gloo group (single-GPU tests with two
+    processes on one device) is served through a host copy of the few hundred floats."""
+    import torch.distributed as dist
+    if t.is_cuda and dist.get_backend(group) == "gloo":
+        h = t.cpu()
+        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+        t.copy_(h)
+        return t
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
 
 
 # ================================================================================================ wgrad (K4)
@@ -364,21 +421,28 @@ class ConvGeom:
 
 
 # ================================================================================================ BN pieces (K3)
-def bn_finalize(stats, count, bn, training):
+def bn_finalize(stats, count, bn, training, sync=None):
     """-> scale, shift, mean, invstd (fp32 [C]).  Training: batch statistics from the conv epilogue + running-stat
-    update; eval: running statistics."""
+    update; eval: running statistics.  `sync` = (process group, flat statistics buffer of `new_stats(flat=True)`):
+    sums and element count are first summed over the group; the global count is then `sync[1][-1:]` (device)."""
     C = bn.weight.shape[0]
     dev = bn.weight.device
     out = torch.empty((4, C), dtype=torch.float32, device=dev)
     L = _lib.lib()
     if training:
         bump_counter(bn.num_batches_tracked)
+        count_dev = None
+        if sync is not None:
+            group, buf = sync
+            count_dev = buf[-1:]
+            count_dev.fill_(float(count))
+            exchange(buf, group)
         _lib.check(L.mg_bn_finalize(_ptr(stats), float(count), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean),
                                     _ptr(bn.running_var), float(bn.momentum), float(bn.eps), _ptr(out[0]), _ptr(out[1]),
-                                    _ptr(out[2]), _ptr(out[3]), C, _stream()), "mg_bn_finalize")
+                                    _ptr(out[2]), _ptr(out[3]), C, _ptr(count_dev), _stream()), "mg_bn_finalize")
     else:
         _lib.check(L.mg_bn_finalize(None, 1.0, _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean), _ptr(bn.running_var),
-                                    0.0, float(bn.eps), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), C,
+                                    0.0, float(bn.eps), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), C, None,
                                     _stream()), "mg_bn_finalize")
     return out[0], out[1], out[2], out[3]
 
@@ -394,10 +458,12 @@ class _ConvBNAct(torch.autograd.Function):
         wd = handle if handle is not None else w.detach()
         w_shape = wshape(wd)
         Co = w_shape[1] if geom.kind == "convT" else w_shape[0]
-        stats = new_stats(Co, x.device)
+        group = sync_group(bn)
+        stats, buf = new_stats(Co, x.device, flat=True) if group is not None else (new_stats(Co, x.device), None)
         r = geom.fwd(xn, wd, stats=stats) if not act_first else geom.fwd(xn, wd, stats=stats, pre_act=act)
         N, Ho, Wo, _ = r.shape
-        scale, shift, mean, invstd = bn_finalize(stats, N * Ho * Wo, bn, True)
+        scale, shift, mean, invstd = bn_finalize(stats, N * Ho * Wo, bn, True, sync=(group, buf) if group is not None else None)
+        ctx.sync = (group, buf[-1:]) if group is not None else None    # (group, global element count on the device)
         y = torch.empty_like(r)
         rn = None
         if res is not None:
@@ -431,9 +497,12 @@ class _ConvBNAct(torch.autograd.Function):
                                       _stream()), "mg_bn_bwd_reduce")
         dr = torch.empty_like(r)
         dres = torch.empty_like(r) if has_res else None
-        _lib.check(L.mg_bn_bwd_apply(_ptr(dy), _ptr(y), _ptr(r), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(sums), _ptr(dr),
-                                     _ptr(dres), N, Ho, Wo, Co, a_post, ACT[act] if act_first else 0, _stream()),
-                   "mg_bn_bwd_apply")
+        gsums, count_dev = sums, None
+        if ctx.sync is not None:
+            gsums, count_dev = exchange(sums.clone(), ctx.sync[0]), ctx.sync[1]
+        _lib.check(L.mg_bn_bwd_apply(_ptr(dy), _ptr(y), _ptr(r), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(gsums), _ptr(dr),
+                                     _ptr(dres), N, Ho, Wo, Co, a_post, ACT[act] if act_first else 0, _ptr(count_dev),
+                                     _stream()), "mg_bn_bwd_apply")
         dw = None
         if ctx.needs_input_grad[1]:
             if handle is not None and AUX_WGRAD:

@@ -54,3 +54,11 @@ def shard_frames(n_frames_global, rank, world):
     """Contiguous per-rank frame range (frames of one clip never split: shard by clip at the caller)."""
     per = n_frames_global // world
     return rank * per, (rank + 1) * per
+
+
+def set_sync_bn(group=True):
+    """SyncBatchNorm-equivalent training (`model.sync_bn: true`, engine/train.py:160-161): every BatchNorm takes its
+    batch statistics over the frames / active sites of all ranks of `group`.  Equivalent to running the model after
+    `nn.SyncBatchNorm.convert_sync_batchnorm(model)`, which the native path also honours.  See maggie_b200/dense.py."""
+    from . import dense
+    dense.set_sync_bn(group)

@@ -19,7 +19,7 @@ except Exception:  # pragma: no cover
         pass
 
 from ...config import as_cfg
-from ... import ops
+from ... import dense, ops
 from ...weights import WeightBank
 from .. import loss as losses
 from ..decoder import MaGGIeDecoder, MaGGIeTempDecoder
@@ -125,8 +125,8 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
                 gt_os8.float() if gt_os8 is not None else mask_os8.float())
         if mem_feat is not None:
             args = args + (mem_feat,)
-        if not (self._use_graphs and self.training and torch.is_grad_enabled()):
-            return stage(*args)
+        if not (self._use_graphs and self.training and torch.is_grad_enabled()) or dense.sync_bn_active(self):
+            return stage(*args)      # (the per-layer statistics exchange of SyncBatchNorm-equivalent training stays eager)
         key = tuple((tuple(a.shape), a.dtype) for a in args)
         entry = self._graphs.get(key)
         if entry is None:

@@ -28,7 +28,25 @@ def _worker(rank, world, port):
     want = torch.cat([p.grad.flatten() for p in ref.parameters()])
     assert torch.allclose(got, want, atol=1e-5), (got, want)
     assert all(p.grad.data_ptr() >= fr.flat.data_ptr() for p in lin.parameters())
+    _sync_bn_switches(rank, world)
     dist.destroy_process_group()
+
+
+def _sync_bn_switches(rank, world):
+    """Host logic of the SyncBatchNorm-equivalent statistics exchange: which containers exchange, and over what."""
+    from maggie_b200 import dense, dp
+    plain, conv = torch.nn.BatchNorm2d(8), torch.nn.SyncBatchNorm(8)
+    assert dense.sync_group(plain) is None
+    assert dense.sync_group(conv) is dist.group.WORLD
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 1), plain)
+    assert not dense.sync_bn_active(model)
+    assert dense.sync_bn_active(torch.nn.SyncBatchNorm.convert_sync_batchnorm(model))
+    dp.set_sync_bn(True)
+    assert dense.sync_group(plain) is dist.group.WORLD and dense.sync_bn_active(torch.nn.Sequential(plain))
+    dp.set_sync_bn(False)
+    assert dense.sync_group(plain) is None
+    t = torch.full((5,), float(rank + 1))
+    assert torch.equal(dense.exchange(t, dist.group.WORLD), torch.full((5,), 3.0))
 
 
 def test_flat_allreduce_matches_full_batch_gradient():

@@ -20,5 +20,5 @@ for (N, H, C) in ((8, 512, 32), (8, 256, 32), (8, 128, 64), (8, 64, 128), (8, 32
     mb = r.numel() * 2 / 1e6
     t1 = timeit(lambda: L.mg_bn_apply(P(r), P(g), P(mean), None, 0, P(yo), N, H, H, C, 1, S()))
     t2 = timeit(lambda: L.mg_bn_bwd_reduce(P(dy), P(y), P(r), P(mean), P(inv), P(sums), N, H, H, C, 1, S()))
-    t3 = timeit(lambda: L.mg_bn_bwd_apply(P(dy), P(y), P(r), P(mean), P(inv), P(g), P(sums), P(dx), None, N, H, H, C, 1, 0, S()))
+    t3 = timeit(lambda: L.mg_bn_bwd_apply(P(dy), P(y), P(r), P(mean), P(inv), P(g), P(sums), P(dx), None, N, H, H, C, 1, 0, None, S()))
     print(f"{N}x{H}x{H}x{C} ({mb:6.1f} MB): apply {t1:6.1f} us {2*mb/t1:6.2f} TB/s | bwd_reduce {t2:6.1f} us {3*mb/t2:6.2f} TB/s | bwd_apply {t3:6.1f} us {4*mb/t3:6.2f} TB/s", flush=True)
