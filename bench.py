@@ -46,7 +46,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.skip = [], None, index, 0
+
+    def mark(self):
+        """The timed region starts here: samples taken so far (warm-up) are dropped.  The sampler is started BEFORE the
+        warm-up steps because nvidia-smi's start-up (NVML initialisation) stalls CUDA submissions for a while."""
+        self.skip = len(self.rows)
 
     def start(self):
         try:
@@ -64,6 +69,8 @@ class ClockSampler:
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
+        if len(self.rows) > self.skip:
+            self.rows = self.rows[self.skip:]
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -335,11 +342,13 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n
 
-    for _ in range(max(args.warmup, 3)):
-        step(resident)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    torch.cuda.synchronize()
+    sampler.mark()
     _lib.reset_launch_count()
     replayed0 = model.replayed_native_launches
     ms = timed(lambda: step(resident), args.steps)
@@ -374,6 +383,10 @@ def run_gpu(args):
     assert last_loss == last_loss, "loss is NaN"
     clocks = sampler.stop() if rank == 0 else None
     counts = model.last_site_counts
+    if sync_bn:
+        from maggie_b200 import dense as _dense
+        sync_bn_path = ("peer-memory kernel (K15), 2 per BatchNorm per step" if all(w is not None for w in _dense._WINDOWS.values())
+                        else "one all-reduce per BatchNorm and direction")
 
     if rank != 0:
         if world > 1:
@@ -393,7 +406,8 @@ def run_gpu(args):
         "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd per GPU (iter=1, edge {EDGE_PX}px)",
                    "frames_per_gpu": FRAMES_PER_GPU, "active_sites_os1_os2_os4_os8": counts,
                    "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                   "loss_scale": LOSS_SCALE, "sync_bn": sync_bn, "cuda_graphs_dense_stage": not args.no_graphs and not sync_bn},
+                   "loss_scale": LOSS_SCALE, "sync_bn": sync_bn, "cuda_graphs_dense_stage": bool(model._graphs),
+                   **({"sync_bn_exchange": sync_bn_path} if sync_bn else {})},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e, "h2d": "pinned host memory -> device on a copy stream, every step",
                 "d2h": "loss copied to pinned memory every step, value consumed one step later"},

@@ -175,9 +175,9 @@ unsigned long long mg_wgrad_halo_launches(void);
  *                  dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (* pre_act'(conv_out) if pre_act),
  *                  dres = dz (optional).  dgamma = sums[1], dbeta = sums[0].
  * count_dev (mg_bn_finalize, mg_bn_bwd_apply; may be NULL): device scalar that replaces the host-side element count.
- *                  SyncBatchNorm-equivalent training (engine/train.py:160-161): the caller sums `stats` / `sums` and the
- *                  element count over the ranks (one all-reduce each) and passes the global count here, so that ranks
- *                  with different numbers of active sites need no host synchronisation.                          */
+ *                  SyncBatchNorm-equivalent training (engine/train.py:160-161): `stats` / `sums` then hold ONE copy
+ *                  [2][C] of sums taken over all ranks (mg_stats_exchange, K15) and count_dev the global element count,
+ *                  so that ranks with different numbers of active sites need no host synchronisation.             */
 int mg_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
                    float* save_invstd, int C, const float* count_dev, void* stream);
@@ -235,6 +235,32 @@ typedef struct mg_optim_tensor {
 int mg_optim_adamw_step(const mg_optim_tensor* tensors, const int32_t* items, int n_items, const float* grad, size_t n_flat,
                         float* m, float* v, float* acc, float* step, float* report, float lr, float beta1, float beta2,
                         float eps, float weight_decay, float max_norm, float inv_scale, void* stream);
+
+/* ---- K15: SyncBatchNorm-equivalent statistics exchange over peer memory ---------------------------------------
+ * replaces: the per-layer all-reduces of nn.SyncBatchNorm (engine/train.py:160-161 converts all 71 BatchNorms when
+ *           `model.sync_bn` is true): forward sum / sum-of-squares / element count, backward sum dz / sum dz*xhat.
+ * Each rank creates ONE exchange window (device memory of mg_xchg_window_bytes() bytes, exported as a CUDA IPC handle of
+ * MG_XCHG_HANDLE_BYTES bytes), the handles travel over the host-side process group, every rank maps every peer's window.
+ * mg_stats_exchange : in = `n_copies` copies of [2][C] partial sums (conv epilogue: MG_CONV_STAT_COPIES; backward: 1),
+ *                     count = this rank's element count (< 0: none).  The kernel reduces the copies, stores the result
+ *                     into every rank's window (NVLink / NVSwitch peer stores), waits for the peers' parts and sums them in
+ *                     rank order: out [2][C] (+ out[2*C] = global count) is bit-identical on all ranks.  x == NULL or
+ *                     world == 1: local reduction of the copies only (the caller then all-reduces `out` itself).
+ *                     Stream-ordered, no host synchronisation, CUDA-graph capturable (the exchange counter lives in the
+ *                     window); all ranks must issue the same sequence of exchanges.  A peer that does not show up within
+ *                     20 s traps the kernel (the next synchronisation reports the failure).                         */
+#define MG_XCHG_MAX_RANKS 16
+#define MG_XCHG_HANDLE_BYTES 64
+typedef struct mg_xchg_desc {
+    void* window[MG_XCHG_MAX_RANKS]; /* window[r]: rank r's window as mapped into this process (window[rank]: the local one) */
+    int32_t rank, world;
+} mg_xchg_desc;
+size_t mg_xchg_window_bytes(void);
+int mg_xchg_window_create(void** window, void* ipc_handle);
+int mg_xchg_window_open(const void* ipc_handle, void** mapped);
+int mg_xchg_window_close(void* mapped);
+int mg_xchg_window_destroy(void* window);
+int mg_stats_exchange(const mg_xchg_desc* x, const float* in, int n_copies, int C, float count, float* out, void* stream);
 
 /* ---- K13: row-wise helpers (LayerNorm with fused residual, column sums) ---------------------------------
  * replaces: nn.LayerNorm after the residual add of every post-norm attention / FFN layer (module/mask_attention.py:

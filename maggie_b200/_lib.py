@@ -48,6 +48,12 @@ SIGNATURES = {
                                  c_void_p]),
     "mg_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mg_xchg_window_bytes": (ctypes.c_size_t, []),
+    "mg_xchg_window_create": (c_int, [c_void_p, c_void_p]),
+    "mg_xchg_window_open": (c_int, [c_void_p, c_void_p]),
+    "mg_xchg_window_close": (c_int, [c_void_p]),
+    "mg_xchg_window_destroy": (c_int, [c_void_p]),
+    "mg_stats_exchange": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     "mg_wprep_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int] + [c_void_p] * 5),
     "mg_wprep_bwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5),
     "mg_optim_adamw_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

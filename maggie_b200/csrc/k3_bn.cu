@@ -17,7 +17,9 @@ bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __
                    float* __restrict__ rvar, float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
                    float* __restrict__ save_mean, float* __restrict__ save_invstd, int C) {
     mg::pdl_prologue();
-    if (count_dev) count = fmaxf(__ldg(count_dev), 1.f);   // statistics exchanged across ranks: the global element count
+    // statistics exchanged across ranks (K15): ONE copy of global sums + the global element count on the device
+    const int n_copies = count_dev ? 1 : STAT_COPIES;
+    if (count_dev) count = fmaxf(__ldg(count_dev), 1.f);
     __shared__ float s_s[8][32], s_q[8][32];
     const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -25,7 +27,7 @@ bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __
         float s = 0.f, q = 0.f;
         if (c < C) {
 #pragma unroll
-            for (int k = grp; k < STAT_COPIES; k += 8) {
+            for (int k = grp; k < n_copies; k += 8) {
                 s += __ldg(stats + (size_t)k * 2 * C + c);
                 q += __ldg(stats + (size_t)k * 2 * C + C + c);
             }

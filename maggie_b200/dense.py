@@ -1,6 +1,7 @@
 """Native dense ops (K2 conv on tcgen05/TMA, ...) - python side of the C ABI: descriptor structs, weight packs,
 tap tables.  Tensors are NHWC fp16 (`[N,H,W,C]` contiguous)."""
 import ctypes
+import os
 from ctypes import c_int32, c_void_p
 
 import torch
@@ -212,30 +213,31 @@ def bump_counter(t):
         t.add_(1)
 
 
-def new_stats(co, device, flat=False):
-    """Zeroed conv-epilogue statistics [STAT_COPIES, 2, co]; `flat`: also return the underlying flat buffer, which then
-    carries one extra element for the element count (the unit that is exchanged across ranks, see `sync_group`)."""
-    n = STAT_COPIES * 2 * co
-    if not flat:
-        return zeros_f32(n, device).view(STAT_COPIES, 2, co)
-    buf = zeros_f32(n + 1, device)
-    return buf[:n].view(STAT_COPIES, 2, co), buf
+def new_stats(co, device):
+    return zeros_f32(STAT_COPIES * 2 * co, device).view(STAT_COPIES, 2, co)
 
 
 # ================================================================================================ statistics exchange
 # SyncBatchNorm-equivalent training (engine/train.py:160-161, `model.sync_bn: true` in both live configs): the batch
-# statistics of every BatchNorm are taken over the frames / active sites of ALL ranks.  Per layer and direction ONE small
-# all-reduce: forward = the conv-epilogue sums + the element count, backward = [sum dz ; sum dz*xhat].  The global count
-# stays on the device (`count_dev` of mg_bn_finalize / mg_bn_bwd_apply), so ranks with different numbers of active sites
-# need no host synchronisation.  dgamma / dbeta stay LOCAL sums (the gradient all-reduce averages them, as DDP does).
+# statistics of every BatchNorm are taken over the frames / active sites of ALL ranks.  Per layer and direction ONE
+# exchange of [2][C] sums (+ the element count in the forward): K15 (`mg_stats_exchange`) reduces the conv-epilogue
+# copies, pushes the result into every rank's exchange window over peer memory (NVLink / NVSwitch), waits for the peers
+# inside the kernel and sums in rank order - no NCCL launch, no host involvement, bit-identical statistics on all ranks.
+# The global count stays on the device (`count_dev` of mg_bn_finalize / mg_bn_bwd_apply), so ranks with different numbers
+# of active sites need no host synchronisation.  dgamma / dbeta stay LOCAL sums (the gradient all-reduce averages them,
+# as DDP does).  Without peer windows (gloo groups, MAGGIE_B200_NO_PEER_EXCHANGE=1, IPC mapping refused) the same [2C+1]
+# vector goes through one all-reduce of the process group instead.
 _SYNC_ALL = None
+_SYNC_EPOCH = 0
+_WINDOWS = {}
 
 
 def set_sync_bn(group=True):
     """Exchange the statistics of EVERY BatchNorm over `group` (True: the default group; None / False: off), without
     converting the containers.  Containers converted by `nn.SyncBatchNorm.convert_sync_batchnorm` exchange anyway."""
-    global _SYNC_ALL
+    global _SYNC_ALL, _SYNC_EPOCH
     _SYNC_ALL = group if group not in (False, None) else None
+    _SYNC_EPOCH += 1
 
 
 def sync_group(bn):
@@ -253,16 +255,39 @@ def sync_group(bn):
 
 
 def sync_bn_active(model):
-    """True when some BatchNorm of `model` exchanges statistics (the dense stage then cannot replay as a CUDA graph)."""
+    """True when some BatchNorm of `model` exchanges statistics."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
         return False
     return _SYNC_ALL is not None or any(isinstance(m, torch.nn.SyncBatchNorm) for m in model.modules())
 
 
+def sync_bn_needs_eager(model, device):
+    """The collective fallback of the exchange cannot be captured into the dense stage's CUDA graphs; K15 can."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+        return False
+    key = (_SYNC_EPOCH, device.index)
+    cached = model.__dict__.get("_mg_sync_eager")
+    if cached is None or cached[0] != key:
+        cached = model.__dict__["_mg_sync_eager"] = (key, _sync_bn_needs_eager(model, device))
+    return cached[1]
+
+
+def _sync_bn_needs_eager(model, device):
+    if not sync_bn_active(model):
+        return False
+    import torch.distributed as dist
+    groups = {id(g): g for g in (sync_group(m) for m in model.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm))
+              if g is not None}
+    if not groups:
+        groups = {0: dist.group.WORLD}
+    return any(peer_window(g, device) is None for g in groups.values())
+
+
 def exchange(t, group):
-    """In-place sum of `t` over `group`, ordered on the current stream (NCCL).  A gloo group (single-GPU tests with two
-    processes on one device) is served through a host copy of the few hundred floats."""
+    """In-place sum of `t` over `group`, ordered on the current stream (the collective fallback of K15).  A gloo group is
+    served through a host copy of the few hundred floats."""
     import torch.distributed as dist
     if t.is_cuda and dist.get_backend(group) == "gloo":
         h = t.cpu()
@@ -271,6 +296,83 @@ def exchange(t, group):
         return t
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+class XchgDesc(ctypes.Structure):
+    """Mirror of `mg_xchg_desc`."""
+    _fields_ = [("window", c_void_p * 16), ("rank", c_int32), ("world", c_int32)]
+
+
+class PeerWindow:
+    """This rank's exchange window and the mapped windows of its peers (CUDA IPC; handles travel over the process group)."""
+
+    def __init__(self, group, device):
+        import torch.distributed as dist
+        L = _lib.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 16:
+            raise RuntimeError("statistics exchange windows support up to 16 ranks")
+        with torch.cuda.device(device):
+            win, handle = c_void_p(), ctypes.create_string_buffer(64)
+            mine = None
+            if L.mg_xchg_window_create(ctypes.byref(win), handle) == 0:
+                self.local, mine = win.value, bytes(handle.raw)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+            self.desc, self.mapped = XchgDesc(), []
+            self.desc.rank, self.desc.world = self.rank, self.world
+            ok = all(h is not None for h in handles)
+            for r, h in enumerate(handles if ok else []):
+                if r == self.rank:
+                    self.desc.window[r] = self.local
+                    continue
+                p = c_void_p()
+                if L.mg_xchg_window_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)) != 0:
+                    ok = False
+                    break
+                self.mapped.append(p.value)
+                self.desc.window[r] = p.value
+            # everybody or nobody: one rank falling back to the collective alone would dead-lock the others
+            votes = [None] * self.world
+            dist.all_gather_object(votes, bool(ok), group=group)
+            self.ok = all(votes)
+
+    def ptr(self):
+        return ctypes.byref(self.desc)
+
+
+def peer_window(group, device):
+    """The PeerWindow of (group, device), created on first use (a collective call); None: use the collective fallback."""
+    key = (id(group), device.index)
+    if key not in _WINDOWS:
+        w = None
+        import torch.distributed as dist
+        if os.environ.get("MAGGIE_B200_NO_PEER_EXCHANGE", "0") != "1" and device.type == "cuda":
+            try:
+                w = PeerWindow(group, device)
+                if not w.ok:
+                    w = None
+            except RuntimeError:
+                w = None
+        if w is None and dist.get_rank(group) == 0:
+            import warnings
+            warnings.warn("maggie_b200: BatchNorm statistics are exchanged with one all-reduce per layer "
+                          "(peer-memory exchange windows unavailable or disabled)")
+        _WINDOWS[key] = w
+    return _WINDOWS[key]
+
+
+def exchange_sums(src, n_copies, C, count, group):
+    """[2][C] sums (`n_copies` partial copies) + element count (None: no count) of this rank -> sums over all ranks of
+    `group`: fp32 [2*C + 1], the last element being the global count."""
+    out = torch.empty(2 * C + 1, dtype=torch.float32, device=src.device)
+    w = peer_window(group, src.device)
+    cnt = -1.0 if count is None else float(count)
+    _lib.check(_lib.lib().mg_stats_exchange(w.ptr() if w is not None else None, _ptr(src), n_copies, C, cnt, _ptr(out),
+                                            _stream()), "mg_stats_exchange")
+    if w is None:
+        exchange(out if count is not None else out[:2 * C], group)
+    return out
 
 
 # ================================================================================================ wgrad (K4)
@@ -312,7 +414,7 @@ def wgrad_launch(dy, x, taps, dw, *, stride=1, dy_map=(1, 0, 1, 0), grid_hw):
 # (most launches of this network fill only a fraction of the 148 SMs).  Fork and join are plain event waits, i.e.
 # CUDA-graph capturable.
 _AUX = {}
-AUX_WGRAD = __import__("os").environ.get("MAGGIE_B200_NO_AUX_STREAM", "0") != "1"
+AUX_WGRAD = os.environ.get("MAGGIE_B200_NO_AUX_STREAM", "0") != "1"
 
 
 def aux_stream(device):
@@ -421,22 +523,20 @@ class ConvGeom:
 
 
 # ================================================================================================ BN pieces (K3)
-def bn_finalize(stats, count, bn, training, sync=None):
-    """-> scale, shift, mean, invstd (fp32 [C]).  Training: batch statistics from the conv epilogue + running-stat
-    update; eval: running statistics.  `sync` = (process group, flat statistics buffer of `new_stats(flat=True)`):
-    sums and element count are first summed over the group; the global count is then `sync[1][-1:]` (device)."""
+def bn_finalize(stats, count, bn, training, group=None):
+    """-> scale, shift, mean, invstd (fp32 [C]) and, with `group`, the device scalar holding the global element count.
+    Training: batch statistics from the conv epilogue + running-stat update; eval: running statistics.  `group`: the sums
+    and the element count are first taken over all ranks of the process group (`exchange_sums`)."""
     C = bn.weight.shape[0]
     dev = bn.weight.device
     out = torch.empty((4, C), dtype=torch.float32, device=dev)
     L = _lib.lib()
+    count_dev = None
     if training:
         bump_counter(bn.num_batches_tracked)
-        count_dev = None
-        if sync is not None:
-            group, buf = sync
-            count_dev = buf[-1:]
-            count_dev.fill_(float(count))
-            exchange(buf, group)
+        if group is not None:
+            stats = exchange_sums(stats, STAT_COPIES, C, count, group)
+            count_dev = stats[2 * C:]
         _lib.check(L.mg_bn_finalize(_ptr(stats), float(count), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean),
                                     _ptr(bn.running_var), float(bn.momentum), float(bn.eps), _ptr(out[0]), _ptr(out[1]),
                                     _ptr(out[2]), _ptr(out[3]), C, _ptr(count_dev), _stream()), "mg_bn_finalize")
@@ -444,6 +544,8 @@ def bn_finalize(stats, count, bn, training, sync=None):
         _lib.check(L.mg_bn_finalize(None, 1.0, _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean), _ptr(bn.running_var),
                                     0.0, float(bn.eps), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), C, None,
                                     _stream()), "mg_bn_finalize")
+    if group is not None:
+        return out[0], out[1], out[2], out[3], count_dev
     return out[0], out[1], out[2], out[3]
 
 
@@ -459,11 +561,11 @@ class _ConvBNAct(torch.autograd.Function):
         w_shape = wshape(wd)
         Co = w_shape[1] if geom.kind == "convT" else w_shape[0]
         group = sync_group(bn)
-        stats, buf = new_stats(Co, x.device, flat=True) if group is not None else (new_stats(Co, x.device), None)
+        stats = new_stats(Co, x.device)
         r = geom.fwd(xn, wd, stats=stats) if not act_first else geom.fwd(xn, wd, stats=stats, pre_act=act)
         N, Ho, Wo, _ = r.shape
-        scale, shift, mean, invstd = bn_finalize(stats, N * Ho * Wo, bn, True, sync=(group, buf) if group is not None else None)
-        ctx.sync = (group, buf[-1:]) if group is not None else None    # (group, global element count on the device)
+        scale, shift, mean, invstd, *cnt = bn_finalize(stats, N * Ho * Wo, bn, True, group)
+        ctx.sync = (group, cnt[0]) if group is not None else None    # (group, global element count on the device)
         y = torch.empty_like(r)
         rn = None
         if res is not None:
@@ -499,7 +601,7 @@ class _ConvBNAct(torch.autograd.Function):
         dres = torch.empty_like(r) if has_res else None
         gsums, count_dev = sums, None
         if ctx.sync is not None:
-            gsums, count_dev = exchange(sums.clone(), ctx.sync[0]), ctx.sync[1]
+            gsums, count_dev = exchange_sums(sums, 1, Co, None, ctx.sync[0]), ctx.sync[1]
         _lib.check(L.mg_bn_bwd_apply(_ptr(dy), _ptr(y), _ptr(r), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(gsums), _ptr(dr),
                                      _ptr(dres), N, Ho, Wo, Co, a_post, ACT[act] if act_first else 0, _ptr(count_dev),
                                      _stream()), "mg_bn_bwd_apply")

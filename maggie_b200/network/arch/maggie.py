@@ -125,8 +125,8 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
                 gt_os8.float() if gt_os8 is not None else mask_os8.float())
         if mem_feat is not None:
             args = args + (mem_feat,)
-        if not (self._use_graphs and self.training and torch.is_grad_enabled()) or dense.sync_bn_active(self):
-            return stage(*args)      # (the per-layer statistics exchange of SyncBatchNorm-equivalent training stays eager)
+        if not (self._use_graphs and self.training and torch.is_grad_enabled()) or dense.sync_bn_needs_eager(self, x.device):
+            return stage(*args)      # (the collective fallback of the BatchNorm statistics exchange cannot be captured)
         key = tuple((tuple(a.shape), a.dtype) for a in args)
         entry = self._graphs.get(key)
         if entry is None:

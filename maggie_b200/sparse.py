@@ -7,7 +7,7 @@ from ctypes import c_int32, c_void_p
 import torch
 
 from . import _lib, packs
-from .dense import ACT, bn_finalize, exchange, new_stats, sync_group, zeros_f32
+from .dense import ACT, bn_finalize, exchange_sums, new_stats, sync_group, zeros_f32
 
 _need_cuda, _ptr, _stream = _lib.need_cuda, _lib.tensor_ptr, _lib.stream_ptr
 
@@ -143,13 +143,10 @@ class _RowsConv(torch.autograd.Function):
                                               0 if mode == "act_bn" else ACT[act], _stream()), "mg_bn_apply")
             return y
         group = sync_group(bn)   # SyncBatchNorm-equivalent: statistics over the active sites of all ranks (dense.py)
-        stats, buf = new_stats(co, src.device, flat=True) if group is not None else (new_stats(co, src.device), None)
+        stats = new_stats(co, src.device)
         r = sparse_conv_launch(src, wp, T, ci, co, table=table, bias=b32, stats=stats, pre_act=1 if mode == "act_bn" else 0)
-        if group is None:
-            scale, shift, mean, invstd = bn_finalize(stats, max(No, 1), bn, True)
-        else:
-            scale, shift, mean, invstd = bn_finalize(stats, No, bn, True, sync=(group, buf))
-        ctx.sync = (group, buf[-1:]) if group is not None else None
+        scale, shift, mean, invstd, *cnt = bn_finalize(stats, max(No, 1) if group is None else No, bn, True, group)
+        ctx.sync = (group, cnt[0]) if group is not None else None
         y = torch.empty_like(r)
         _lib.check(_lib.lib().mg_bn_apply(_ptr(r), _ptr(scale), _ptr(shift), None, 0, _ptr(y), No, 1, 1, co,
                                           0 if mode == "act_bn" else ACT[act], _stream()), "mg_bn_apply")
@@ -178,7 +175,7 @@ class _RowsConv(torch.autograd.Function):
             dr = torch.empty_like(r)
             gsums, count_dev = sums, None
             if ctx.sync is not None:
-                gsums, count_dev = exchange(sums.clone(), ctx.sync[0]), ctx.sync[1]
+                gsums, count_dev = exchange_sums(sums, 1, co, None, ctx.sync[0]), ctx.sync[1]
             _lib.check(L.mg_bn_bwd_apply(_ptr(dy), _ptr(y), _ptr(r), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(gsums),
                                          _ptr(dr), None, No, 1, 1, co, a_post, 1 if mode == "act_bn" else 0, _ptr(count_dev),
                                          _stream()), "mg_bn_bwd_apply")
