@@ -417,10 +417,11 @@ _AUX = {}
 AUX_WGRAD = os.environ.get("MAGGIE_B200_NO_AUX_STREAM", "0") != "1"
 
 
-def aux_stream(device):
-    st = _AUX.get(device.index)
+def aux_stream(device, which=0):
+    """which 0: the weight-gradient stream; 1: the encoder's shortcut-branch stream."""
+    st = _AUX.get((device.index, which))
     if st is None:
-        st = _AUX[device.index] = torch.cuda.Stream(device=device)
+        st = _AUX[(device.index, which)] = torch.cuda.Stream(device=device)
     return st
 
 

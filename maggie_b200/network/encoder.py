@@ -4,11 +4,15 @@ Reference: encoder/resnet.py:7-39 (BasicBlock), :42-153 (ResNet_D), :155-200 (Re
 :202-229 (ResMaskEmbedShortCut_D), module/aspp.py:4-57.  Attribute paths equal the reference's so that the
 state dict is interchangeable.  Tensors flow as fp16 channels-last (NHWC in memory).
 """
+import os
+
 import torch
 from torch import nn
 
-from .. import ops
+from .. import dense, ops
 from .layers import PlainConv, Slot, SNConv, seq
+
+SIDE_SHORTCUTS = os.environ.get("MAGGIE_B200_NO_SIDE_SHORTCUTS", "0") != "1"
 
 
 class EncBlock(nn.Module):
@@ -83,18 +87,47 @@ class ResMaskEmbedShortCutEncoder(nn.Module):
 
     def forward(self, image, masks, slot_ids):
         """image [B,3,H,W] fp32; masks [B,M,H,W] {0,1} fp32 with slot_ids[M] (slot of each mask).
-        Returns (os32 feature, (fea1..fea5))."""
+        Returns (os32 feature, (fea1..fea5)).
+
+        The five shortcut branches are leaves of the trunk (nothing reads them before the decoder): on the GPU they run on
+        a side stream, forked where their input appears and joined once at the end, so that they fill the SMs the
+        latency-bound trunk layers leave idle.  Autograd replays each op's backward on its forward stream, so the same
+        overlap happens in the backward pass; fork and join are plain event waits (CUDA-graph capturable)."""
         t = self.training
         x = ops.mask_embed(image, masks, self.mask_embed_layer.weight, slot_ids, self.IN_PAD)
+        side = None
+        # (with exchanged BatchNorm statistics all exchanges must stay in ONE stream order on every rank)
+        if x.is_cuda and SIDE_SHORTCUTS and dense.sync_group(self.bn1) is None:
+            side = dense.aux_stream(x.device, 1)
+        main = torch.cuda.current_stream(x.device) if side is not None else None
+        fea = [None] * 5
+
+        def branch(i, f):
+            if side is None:
+                fea[i] = self._shortcut(i, f)
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fea[i] = self._shortcut(i, f)
+            f.record_stream(side)
+
+        branch(0, x)
         out = ops.conv_bn_act(x, self.conv1.weight(), self.bn1, t, stride=2)
         x1 = ops.conv_bn_act(out, self.conv2.weight(), self.bn2, t)
+        branch(1, x1)
         out = ops.conv_bn_act(x1, self.conv3.weight(), self.bn3, t, stride=2)
         x2 = self.layer1(out)
+        branch(2, x2)
         x3 = self.layer2(x2)
+        branch(3, x3)
         x4 = self.layer3(x3)
+        branch(4, x4)
         out = self.layer_bottleneck(x4)
-        fea = tuple(self._shortcut(i, f) for i, f in enumerate((x, x1, x2, x3, x4)))
-        return out, fea
+        if side is not None:
+            main.wait_stream(side)
+            for f in fea:
+                f.record_stream(main)
+        return out, tuple(fea)
 
 
 class ASPP(nn.Module):
@@ -111,12 +144,27 @@ class ASPP(nn.Module):
 
     def forward(self, x):
         t = self.training
+        # the three dilated branches are 32-CTA launches each: they run side by side on their own streams (see the encoder)
+        par = x.is_cuda and SIDE_SHORTCUTS and dense.sync_group(self.aspp1_bn) is None
+        main = torch.cuda.current_stream(x.device) if par else None
         ys = [ops.conv_bn_act(x, self.aspp1.w(), self.aspp1_bn, t, padding=0)]
         for i, d in ((2, 2), (3, 4), (4, 8)):
-            ys.append(ops.conv_bn_act(x, getattr(self, f"aspp{i}").w(), getattr(self, f"aspp{i}_bn"), t,
-                                      padding=d, dilation=d))
+            if not par:
+                ys.append(ops.conv_bn_act(x, getattr(self, f"aspp{i}").w(), getattr(self, f"aspp{i}_bn"), t,
+                                          padding=d, dilation=d))
+                continue
+            side = dense.aux_stream(x.device, i)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ys.append(ops.conv_bn_act(x, getattr(self, f"aspp{i}").w(), getattr(self, f"aspp{i}_bn"), t,
+                                          padding=d, dilation=d))
+            x.record_stream(side)
         g = x.float().mean((2, 3), keepdim=True).to(x.dtype)
         g = ops.conv_bn_act(g, self.aspp5.w(), self.aspp5_bn, t, padding=0)
         ys.append(g.expand(-1, -1, x.shape[2], x.shape[3]))
+        if par:
+            for i in (2, 3, 4):
+                main.wait_stream(dense.aux_stream(x.device, i))
+                ys[i - 1].record_stream(main)
         y = torch.cat(ys, 1).contiguous(memory_format=torch.channels_last)
         return ops.conv_bn_act(y, self.conv2.w(), self.bn2, t, padding=0)
