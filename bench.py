@@ -316,12 +316,23 @@ def run_gpu(args):
     import numpy as np
     import random
 
+    # Host flow control: the host may run at most two steps ahead of the GPU (as any training loop that reads its loss
+    # does).  Unbounded run-ahead lets the caching allocator pile up blocks that other streams have not released yet.
+    in_flight = []
+    throttle = os.environ.get("MAGGIE_B200_BENCH_NO_THROTTLE", "0") != "1"
+
     def step(batch):
+        if throttle and len(in_flight) >= 2:
+            in_flight.pop(0).synchronize()
         np.random.seed(7), random.seed(7)
         flat.zero()
         _, loss = model(batch, mem_feat=None)
         (loss["total"] * LOSS_SCALE).backward()
         flat.allreduce()
+        if throttle:
+            ev = torch.cuda.Event()
+            ev.record()
+            in_flight.append(ev)
         return loss["total"]
 
     def barrier():
@@ -406,7 +417,7 @@ def run_gpu(args):
         "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd per GPU (iter=1, edge {EDGE_PX}px)",
                    "frames_per_gpu": FRAMES_PER_GPU, "active_sites_os1_os2_os4_os8": counts,
                    "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                   "loss_scale": LOSS_SCALE, "sync_bn": sync_bn, "cuda_graphs_dense_stage": bool(model._graphs),
+                   "loss_scale": LOSS_SCALE, "host_run_ahead_steps": 2 if throttle else "unbounded", "sync_bn": sync_bn, "cuda_graphs_dense_stage": bool(model._graphs),
                    **({"sync_bn_exchange": sync_bn_path} if sync_bn else {})},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e, "h2d": "pinned host memory -> device on a copy stream, every step",

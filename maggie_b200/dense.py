@@ -425,6 +425,28 @@ def aux_stream(device, which=0):
     return st
 
 
+SIDE_BRANCHES = os.environ.get("MAGGIE_B200_NO_SIDE_SHORTCUTS", "0") != "1"
+
+
+def side_branch(x, bn, which, fn):
+    """fn() on auxiliary stream `which`, forked from the current stream -> (result, join).  `join()` must be called on the
+    main stream before the result is used.  Runs inline (join = no-op) on the CPU, when disabled, and when `bn` exchanges
+    statistics across ranks (all exchanges must then keep one stream order on every rank)."""
+    if not (x.is_cuda and SIDE_BRANCHES and sync_group(bn) is None):
+        return fn(), (lambda: None)
+    main, side = torch.cuda.current_stream(x.device), aux_stream(x.device, which)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        y = fn()
+    x.record_stream(side)
+
+    def join():
+        main.wait_stream(side)
+        y.record_stream(main)
+
+    return y, join
+
+
 def wgrad_async(geom, dr, xn, w_shape, bank):
     """geom.wgrad into the bank's accumulator on the auxiliary stream (joined by WeightBank._backward)."""
     main = torch.cuda.current_stream(dr.device)

@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .. import ops, packs
+from .. import dense, ops, packs
 from .layers import PlainConv, Slot, SNConv, SparseConvParams, seq
 
 
@@ -35,12 +35,15 @@ class DecBlock(nn.Module):
 
     def forward(self, x):
         t = self.training
-        out = ops.conv_bn_act(x, self.conv1.weight(), self.bn1, t, act="lrelu", transposed=self.up)
-        idt = x
+        idt, join = x, None
         if self.up:
             # nearest x2 commutes with a 1x1 conv and leaves BN batch statistics unchanged, so the skip path runs
-            # at the low resolution and is replicated afterwards
-            idt = ops.conv_bn_act(x, self.upsample[1].weight(), self.upsample[2], t, padding=0, act=None)
+            # at the low resolution and is replicated afterwards (beside conv1, on a side stream)
+            idt, join = dense.side_branch(x, self.bn1, 5, lambda: ops.conv_bn_act(
+                x, self.upsample[1].weight(), self.upsample[2], t, padding=0, act=None))
+        out = ops.conv_bn_act(x, self.conv1.weight(), self.bn1, t, act="lrelu", transposed=self.up)
+        if join is not None:
+            join()
         return ops.conv_bn_act(out, self.conv2.weight(), self.bn2, t, act="lrelu", residual=idt, res_up=self.up)
 
 

@@ -32,11 +32,15 @@ class EncBlock(nn.Module):
 
     def forward(self, x):
         t = self.training
-        out = ops.conv_bn_act(x, self.conv1.weight(), self.bn1, t, stride=self.stride, act="relu")
-        idt = x
+        idt, join = x, None
         if self.downsample is not None:
-            # AvgPool2d(2,2) followed by a 1x1 conv == one 2x2 stride-2 conv with the 1x1 weight / 4 on every tap
-            idt = ops.conv_bn_act(x, self.downsample[1].weight(), self.downsample[2], t, stride=2, padding=0, act=None)
+            # AvgPool2d(2,2) followed by a 1x1 conv == one 2x2 stride-2 conv with the 1x1 weight / 4 on every tap; the skip
+            # path runs beside conv1 on a side stream
+            idt, join = dense.side_branch(x, self.bn1, 5, lambda: ops.conv_bn_act(
+                x, self.downsample[1].weight(), self.downsample[2], t, stride=2, padding=0, act=None))
+        out = ops.conv_bn_act(x, self.conv1.weight(), self.bn1, t, stride=self.stride, act="relu")
+        if join is not None:
+            join()
         # conv2 -> bn2 -> (+identity) -> relu
         return ops.conv_bn_act(out, self.conv2.weight(), self.bn2, t, act="relu", residual=idt)
 
