@@ -48,9 +48,13 @@ class ClockSampler:
     def __init__(self, index=0):
         self.rows, self.proc, self.index, self.skip = [], None, index, 0
 
-    def mark(self):
-        """The timed region starts here: samples taken so far (warm-up) are dropped.  The sampler is started BEFORE the
-        warm-up steps because nvidia-smi's start-up (NVML initialisation) stalls CUDA submissions for a while."""
+    def mark(self, wait_s=30.0):
+        """The timed region starts here: samples taken so far (warm-up) are dropped.  The sampler is started long before
+        (nvidia-smi's start-up - NVML initialisation over all GPUs of the box - stalls CUDA submissions for seconds), and
+        the timed region does not begin until its first sample has arrived."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and self.proc.poll() is None and time.time() - t0 < wait_s:
+            time.sleep(0.05)
         self.skip = len(self.rows)
 
     def start(self):
@@ -268,6 +272,9 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     torch.manual_seed(1234)  # identical initial weights on every rank
     model, _ = build_model(CfgNode(synth.model_cfg()))
     model.to(dev).train()
@@ -343,19 +350,24 @@ def run_gpu(args):
     def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []
         e0.record()
-        for _ in range(n):
+        for i in range(n):
             fn()
+            if (i + 1) % 10 == 0 and i + 1 < n:      # diagnostic split of the same region (stderr only)
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
         e1.record()
         barrier()
+        if rank == 0 and marks:
+            pts = [e0] + marks + [e1]
+            print("timed region, ms per 10-step chunk:", [round(a.elapsed_time(b), 1) for a, b in zip(pts, pts[1:])],
+                  file=sys.stderr)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(resident)
     torch.cuda.synchronize()
