@@ -236,6 +236,21 @@ int mg_optim_adamw_step(const mg_optim_tensor* tensors, const int32_t* items, in
                         float* m, float* v, float* acc, float* step, float* report, float lr, float beta1, float beta2,
                         float eps, float weight_decay, float max_norm, float inv_scale, void* stream);
 
+/* ---- K16: loader / evaluator ends of the path ------------------------------------------------------------------
+ * mg_input_stage    replaces ToTensor + Normalize (dataloader/transforms.py:720-783) and the dataset's scaling / nearest 1/8
+ *                   mask down-sampling (dataloader/him.py:156-157, 175-176): frames uint8 [B][H][W][3], alphas / masks uint8
+ *                   [B][n_i][H][W] (either may be NULL together with its output) -> image fp32 [B][3][H][W] =
+ *                   (v / 255 - mean) / std, alpha = (a < 5 ? 0 : a) / 255, mask = m / 255 at full size (mask_div 1) or
+ *                   [B][n_i][H/8][W/8] (mask_div 8).  mean3 / std3 are HOST arrays of three floats.
+ * mg_alpha_finalize replaces reverse_transform_tensor (utils/postprocessing.py:36-64) + the clamps of engine/test.py:141-142:
+ *                   in fp32 [planes][h][w]; the (h - pad_h) x (w - pad_w) top-left crop is resized bilinearly
+ *                   (align_corners = True) to out_h x out_w (0: no resize, out = the crop); values <= lo become 0, values
+ *                   >= hi become 1.                                                                                  */
+int mg_input_stage(const void* frames_u8, const void* alphas_u8, const void* masks_u8, float* image, float* alpha, float* mask,
+                   const float* mean3, const float* std3, int B, int n_i, int H, int W, int mask_div, void* stream);
+int mg_alpha_finalize(const float* in, float* out, int planes, int h, int w, int pad_h, int pad_w, int out_h, int out_w,
+                      float lo, float hi, void* stream);
+
 /* ---- K15: SyncBatchNorm-equivalent statistics exchange over peer memory ---------------------------------------
  * replaces: the per-layer all-reduces of nn.SyncBatchNorm (engine/train.py:160-161 converts all 71 BatchNorms when
  *           `model.sync_bn` is true): forward sum / sum-of-squares / element count, backward sum dz / sum dz*xhat.

@@ -48,6 +48,8 @@ SIGNATURES = {
                                  c_void_p]),
     "mg_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mg_input_stage": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_void_p]),
+    "mg_alpha_finalize": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_float, c_float, c_void_p]),
     "mg_xchg_window_bytes": (ctypes.c_size_t, []),
     "mg_xchg_window_create": (c_int, [c_void_p, c_void_p]),
     "mg_xchg_window_open": (c_int, [c_void_p, c_void_p]),
