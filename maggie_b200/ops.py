@@ -7,6 +7,11 @@ Two kinds of ops live here:
   * INTERIM ops - the parts of the path whose kernels are not written yet are composed from torch CUDA ops
     (cuDNN/cuBLAS/ATen).  They are listed in DESIGN.md ("native coverage") and are replaced one by one; the
     model code above this layer does not change when that happens.
+  * ROUTED ops (`layer_norm`, `token_logits`, `upsample_tanh`, `col_sum`) - a native kernel for the shapes the path
+    uses and the equivalent torch composition for anything else (other shapes on the GPU).  The composition is also
+    what runs when the CPU test-suite drives the model's host logic with CPU tensors (`tests/test_host_model.py`,
+    where `tests/ops_ref.py` stands in for the native-only ops); a model on a GPU never takes it for the path's shapes,
+    and a CUDA tensor with the library missing raises (`_lib.lib()`), it does not fall back.
 Activations are fp16, channels-last in memory (NHWC) and NCHW-shaped for torch; statistics, logits and
 alphas are fp32.
 """
