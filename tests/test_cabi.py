@@ -35,3 +35,28 @@ def test_argument_errors_are_reported_not_fatal():
     L = _lib.lib()
     rc = L.mg_unknown_mask(None, 1, 8, 8, None, None, None, None, None)
     assert rc != 0 and b"null" in L.mg_last_error()
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """Every ctypes mirror has the size and field offsets a C compiler gives the struct declared in the header."""
+    import subprocess
+
+    from maggie_b200 import dense, optim, sparse, weights
+
+    pairs = {"mg_wprep_layer": weights.WprepLayer, "mg_conv_desc": dense.ConvDesc, "mg_wgrad_desc": dense.WgradDesc,
+             "mg_sparse_conv_desc": sparse.SparseConvDesc, "mg_optim_tensor": optim._OptimTensor, "mg_xchg_desc": dense.XchgDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "maggie_b200.h"', "int main(void) {"]
+    for cname, mirror in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, mirror in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(mirror), f"sizeof({cname})"
+        for fname, _ in mirror._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(mirror, fname).offset, f"offsetof({cname}, {fname})"

@@ -50,3 +50,40 @@ def test_token_logits_torch_path():
     got = ops.token_logits(tok, x, 3)
     ref = torch.einsum("bqc,btchw->btqhw", tok, x.reshape(2, 3, 64, 4, 5)).flatten(0, 1)
     assert got.shape == (6, 10, 4, 5) and torch.allclose(got, ref)
+
+
+def test_side_branch_runs_inline_without_a_gpu():
+    from maggie_b200 import dense
+    x = torch.ones(2, 3)
+    calls = []
+    y, join = dense.side_branch(x, torch.nn.BatchNorm2d(3), 5, lambda: (calls.append(1), x * 2)[1])
+    assert calls == [1] and torch.equal(y, x * 2)
+    assert join() is None
+
+
+def test_fused_optimizer_refuses_cpu_parameters():
+    import pytest
+    from maggie_b200.dp import FlatGradAllReduce
+    from maggie_b200.optim import FusedAdamW
+    flat = FlatGradAllReduce(torch.nn.Linear(3, 2).parameters())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FusedAdamW(flat)
+
+
+def test_flat_gradient_hand_over_single_process():
+    """zero() drops the gradients, pack() gathers them into the flat buffer and re-points p.grad at its views."""
+    from maggie_b200.dp import FlatGradAllReduce
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(4, 3)
+    frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+    flat = FlatGradAllReduce(list(lin.parameters()) + [frozen])
+    assert flat.flat.numel() == 15 and len(flat.params) == 2
+    flat.zero()
+    assert all(p.grad is None for p in lin.parameters())
+    lin(torch.randn(5, 4)).sum().backward()
+    want = torch.cat([p.grad.flatten().clone() for p in lin.parameters()])
+    assert flat.allreduce() is flat.flat              # one process: nothing is packed, nothing is reduced
+    assert torch.equal(flat.pack(), want)
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(flat.params, flat.views))
+    lin.bias.grad = None                               # a parameter without a gradient contributes zeros
+    assert torch.equal(flat.pack()[12:], torch.zeros(3))
