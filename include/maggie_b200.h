@@ -138,6 +138,10 @@ typedef struct mg_conv_desc {
      * sub-pixel phases of a stride-2 data gradient or of the 4x4 stride-2 transposed conv.  Phase p uses the taps
      * [phase_tap0[p], phase_tap0[p+1]) of the table and the offsets phase_oy0[p], phase_ox0[p]; 0 or 1: plain launch. */
     int32_t n_phases, phase_tap0[5], phase_oy0[4], phase_ox0[4];
+    /* EXPERIMENTAL (NULL = off, the default): zero-initialised device workspace of splitk_ws_bytes bytes that lets layers
+     * with few CTAs split the K range of every tile over several CTAs (csrc/k2s_conv_splitk.cu).  The kernel leaves the
+     * workspace zeroed; launches that may run concurrently (different streams) need different workspaces. */
+    void* splitk_ws; int64_t splitk_ws_bytes;
 } mg_conv_desc;
 int mg_conv_fprop(const mg_conv_desc* desc, void* stream);
 /* Stride-1 layers with Ci, Co <= 64 and taps within +-1 pixel (the 512^2 .. 128^2 3x3 convolutions and their data

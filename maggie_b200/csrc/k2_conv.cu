@@ -231,7 +231,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }  // namespace
 
 namespace mg {
-int conv_halo_launch(const mg_conv_desc* d, void* stream, bool* handled);   // k2b_conv_halo.cu
+int conv_halo_launch(const mg_conv_desc* d, void* stream, bool* handled);     // k2b_conv_halo.cu
+int conv_splitk_launch(const mg_conv_desc* d, void* stream, bool* handled);   // k2s_conv_splitk.cu (opt-in)
 }
 
 extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
@@ -251,6 +252,12 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
         // high-resolution, low-channel stride-1 layers: halo-resident persistent kernel (K2b)
         bool handled = false;
         const int rc = mg::conv_halo_launch(d, stream, &handled);
+        if (rc != MG_OK || handled) return rc;
+    }
+    if (d->splitk_ws) {
+        // opt-in: layers with few CTAs split the K range of a tile over several CTAs (K2s)
+        bool handled = false;
+        const int rc = mg::conv_splitk_launch(d, stream, &handled);
         if (rc != MG_OK || handled) return rc;
     }
     KArgs a;
