@@ -1,4 +1,5 @@
-"""Dev tool: per-layer CUDA-event timing (L2 flushed, weight packs cached) of fprop / dgrad / wgrad over the C2 layer table."""
+"""Dev tool: per-layer CUDA-event timing (L2 flushed, weight packs cached) of fprop / dgrad / wgrad over the C2 layer table.
+`--splitk` adds the fprop / dgrad times with the experimental split-K kernel (K2s) switched on, side by side."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -28,9 +29,10 @@ def timeit(fn, n=5):
         ts.append(e0.elapsed_time(e1) * 1e3)
     return sorted(ts)[len(ts) // 2]
 
-tot = [0.0, 0.0, 0.0]
+tot = [0.0, 0.0, 0.0, 0.0, 0.0]
 N = 8
-print(f"{'layer':34s} cnt |   fwd us   TF/s |  dgrad us  TF/s |  wgrad us  TF/s | hbm-floor us (fwd)")
+AB = "--splitk" in sys.argv
+print(f"{'layer':34s} cnt |   fwd us   TF/s |  dgrad us  TF/s |  wgrad us  TF/s | hbm-floor us (fwd)" + (" | split-K fwd / dgrad us" if AB else ""))
 for (hw, ci, co, k, s, d, tr, cnt) in bench.C2_CONVS:
     x = torch.randn(N, hw, hw, ci, device=dev).half()
     w = torch.randn((ci, co, k, k) if tr else (co, ci, k, k), device=dev) / (ci * k * k) ** 0.5
@@ -48,5 +50,12 @@ for (hw, ci, co, k, s, d, tr, cnt) in bench.C2_CONVS:
     hbm = (x.numel() + y.numel()) * 2 / 6.55e12 * 1e6
     tot[0] += tf * cnt; tot[1] += td * cnt; tot[2] += tw * cnt
     name = f"{hw}^2 {ci}->{co} k{k} s{s} d{d}{' T' if tr else ''}"
-    print(f"{name:34s} {cnt:3d} | {tf:8.1f} {flops/tf/1e6:6.0f} | {td:8.1f} {flops/td/1e6:6.0f} | {tw:8.1f} {flops/tw/1e6:6.0f} | {hbm:6.1f}", flush=True)
-print(f"totals per step (us): fwd {tot[0]:.0f} dgrad {tot[1]:.0f} wgrad {tot[2]:.0f}")
+    extra = ""
+    if AB:
+        dense.SPLITK = True
+        tfs, tds = timeit(lambda: g.fwd(x, w)), timeit(lambda: g.dgrad(y, w, x.shape))
+        dense.SPLITK = False
+        tot[3] += tfs * cnt; tot[4] += tds * cnt
+        extra = f" | {tfs:8.1f} {tds:8.1f}"
+    print(f"{name:34s} {cnt:3d} | {tf:8.1f} {flops/tf/1e6:6.0f} | {td:8.1f} {flops/td/1e6:6.0f} | {tw:8.1f} {flops/tw/1e6:6.0f} | {hbm:6.1f}{extra}", flush=True)
+print(f"totals per step (us): fwd {tot[0]:.0f} dgrad {tot[1]:.0f} wgrad {tot[2]:.0f}" + (f" | split-K fwd {tot[3]:.0f} dgrad {tot[4]:.0f}" if AB else ""))
