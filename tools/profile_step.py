@@ -37,3 +37,19 @@ print("total self CUDA ms", tot / 1e3, "kernel-ish events", sum(e.count for e in
 print(ka.table(sort_by="self_cuda_time_total", row_limit=int(os.environ.get("ROWS", "45")), max_name_column_width=70))
 if os.environ.get("CPU_TABLE", "0") == "1":
     print(ka.table(sort_by="self_cpu_time_total", row_limit=60, max_name_column_width=70))
+if os.environ.get("STACKS", "0") == "1":
+    # where the torch glue comes from: ATen ops with device time, grouped by the innermost maggie_b200 frame
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof2:
+        step(); torch.cuda.synchronize()
+    sites = {}
+    for e in prof2.key_averages(group_by_stack_n=12):
+        if not e.key.startswith("aten::") or e.self_device_time_total <= 0:
+            continue
+        frame = next((f for f in e.stack if "maggie_b200/" in f), "(autograd engine / other)")
+        frame = frame.split("maggie_b200/")[-1]
+        k = (frame, e.key)
+        c, t = sites.get(k, (0, 0.0))
+        sites[k] = (c + e.count, t + e.self_device_time_total)
+    print("\nATen device time by call site (us, launches):")
+    for (frame, op), (c, t) in sorted(sites.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("ROWS", "45"))]:
+        print(f"{t:9.1f} {c:5d}  {op:32s} {frame}")
