@@ -116,6 +116,31 @@ def cpu_step_fn(frames=2):
     return step, frames
 
 
+def cpu_c1_eval_ms():
+    """Oracle port, eval forward of BASELINE config C1 (1 x 256x256, 1 instance), median of 3 after one warm-up."""
+    import numpy as np
+    import torch
+
+    from oracle import maggie_oracle as O
+    from oracle import make_golden as G
+    from oracle import synth
+
+    z = np.load(os.path.join(G.GOLDEN_DIR, "state_shapes.npz"))
+    tmpl = {k: torch.zeros(tuple(z[k]), dtype=torch.long if k.endswith("num_batches_tracked") else torch.float32)
+            for k in z.files}
+    P = synth.synth_state_dict(tmpl)
+    batch = synth.make_batch(b=1, n_f=1, n_i=1, H=256, W=256, edge_px=6.0)
+    cfg = synth.model_cfg()
+    ts = []
+    with torch.no_grad():
+        for i in range(4):
+            t0 = time.perf_counter()
+            O.forward(P, batch, False, cfg)
+            if i:
+                ts.append((time.perf_counter() - t0) * 1e3)
+    return sorted(ts)[1]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -130,6 +155,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     v = frames / dt
     sample = f"{frames} frames x {H}x{W} x {N_INST} inst per step (BatchNorm needs >=2), fp32, {warm} warm-up"
+    c1 = cpu_c1_eval_ms()
     print(json.dumps({
         "impl": "reference", "metric": "frames_per_sec_fwd_bwd", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -137,6 +163,8 @@ def run_reference(args):
         "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd (CPU sample: {frames} frames/step)"},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # BASELINE config C1 (the reference's own CPU-runnable case), for the record: eval forward of one 256x256 image
+        "c1_eval_forward": {"ms": c1, "frames_per_sec": 1e3 / c1, "sample": "1 x 256x256 x 1 inst, 1 warm-up, median of 3"},
     }))
 
 
