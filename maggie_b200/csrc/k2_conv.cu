@@ -19,6 +19,7 @@
 #include "ptx.cuh"
 #include "tma_host.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace {
@@ -297,7 +298,9 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
     const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 17 * 4 + 4 * 2 * a.BN * 4;
     // this non-persistent kernel hides its prologue / epilogue behind the main loop of co-resident CTAs: keep the
     // per-CTA footprint at <= ~100 KB so that at least two CTAs (TMEM: 2 x BN <= 512 columns) share an SM
-    a.stages = std::max(2, std::min(4, (100 * 1024 - fixed) / (a_bytes + b_bytes)));
+    // (MAGGIE_B200_CONV_SMEM_KB: experiment knob - 111 gives the 128 x 128 x 64 layers a third stage and still fits two CTAs)
+    static const int budget_kb = [] { const char* e = std::getenv("MAGGIE_B200_CONV_SMEM_KB"); const int v = e ? std::atoi(e) : 0; return v >= 64 && v <= 220 ? v : 100; }();
+    a.stages = std::max(2, std::min(4, (budget_kb * 1024 - fixed) / (a_bytes + b_bytes)));
     const size_t smem = (size_t)fixed + (size_t)a.stages * (a_bytes + b_bytes);
 
     CUtensorMap tmA, tmB;
