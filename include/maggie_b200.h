@@ -78,6 +78,9 @@ int mg_sites_tables(const void* ws, int slots, int H, int W, const int32_t* coun
  * table [11,3] fp32; out [B,H,W,C] fp16 NHWC, C >= 6: ch 0-2 image, 3-5 mean embedding, rest zero.     */
 int mg_mask_embed_fwd(const float* image, const float* masks, const int32_t* slot_ids, int M,
                       const float* table, void* out_f16, int B, int H, int W, int C, void* stream);
+/* the same with an fp32 NHWC output (evaluation at fp32-level accuracy)                                  */
+int mg_mask_embed_fwd_f32(const float* image, const float* masks, const int32_t* slot_ids, int M,
+                          const float* table, float* out_f32, int B, int H, int W, int C, void* stream);
 /* grad_table [11,3] fp32 += d(out[...,3:6]) / d(table)   (caller zeroes grad_table)                     */
 int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, const int32_t* slot_ids, int M,
                       float* grad_table, int B, int H, int W, int C, void* stream);
@@ -144,6 +147,14 @@ typedef struct mg_conv_desc {
     void* splitk_ws; int64_t splitk_ws_bytes;
 } mg_conv_desc;
 int mg_conv_fprop(const mg_conv_desc* desc, void* stream);
+/* Evaluation at fp32-level accuracy ("x3" mode; the reference evaluates in fp32: engine/test.py:131 runs without autocast).
+ * Every operand is an unevaluated sum of two fp16 tensors, x = desc->x + x_lo and w = desc->w + w_lo (mg_split_f32 below),
+ * and the tensor cores accumulate x_hi*w_hi + x_lo*w_hi + x_hi*w_lo into one fp32 TMEM accumulator (the dropped x_lo*w_lo
+ * term is 2^-22 relative).  desc->out and desc->res are FP32 tensors here (same shapes / indexing); desc->stats must be NULL;
+ * always the generic kernel (no K2b / K2s routing).  Everything else as in mg_conv_fprop. */
+int mg_conv_fprop_x3(const mg_conv_desc* desc, const void* x_lo, const void* w_lo, void* stream);
+/* K17: hi = fp16(x), lo = fp16(x - hi) for n fp32 elements (n % 4 == 0). */
+int mg_split_f32(const float* x, void* hi_f16, void* lo_f16, size_t n, void* stream);
 /* Stride-1 layers with Ci, Co <= 64 and taps within +-1 pixel (the 512^2 .. 128^2 3x3 convolutions and their data
  * gradients) are routed by mg_conv_fprop to K2b, a persistent kernel that keeps a halo patch of the activations and all
  * the weights resident in shared memory (csrc/k2b_conv_halo.cu; MAGGIE_B200_NO_HALO_CONV=1 disables the routing).
@@ -266,8 +277,10 @@ int mg_alpha_finalize(const float* in, float* out, int planes, int h, int w, int
  *                     rank order: out [2][C] (+ out[2*C] = global count) is bit-identical on all ranks.  x == NULL or
  *                     world == 1: local reduction of the copies only (the caller then all-reduces `out` itself).
  *                     Stream-ordered, no host synchronisation, CUDA-graph capturable (the exchange counter lives in the
- *                     window); all ranks must issue the same sequence of exchanges.  A peer that does not show up within
- *                     20 s traps the kernel (the next synchronisation reports the failure).                         */
+ *                     window); all ranks must issue the same sequence of exchanges.  Like a collective the kernel WAITS
+ *                     for late peers (rank-0-only validation, slow loader workers); a watchdog of NCCL order
+ *                     (MAGGIE_B200_XCHG_TIMEOUT_S seconds, default 600 as torch's process groups, 0 = none) traps the kernel
+ *                     when a peer never shows up (the next synchronisation reports the failure).                    */
 #define MG_XCHG_MAX_RANKS 16
 #define MG_XCHG_HANDLE_BYTES 64
 typedef struct mg_xchg_desc {
@@ -294,10 +307,15 @@ int mg_layer_norm_fwd(const void* a, const void* b, const float* gamma, const fl
 int mg_layer_norm_bwd(const void* s, const void* gy, const float* gamma, const float* stat, void* dx, float* dgb, int rows,
                       int E, void* stream);
 int mg_col_sum(const void* x, int stride, int rows, int C, float* out, void* stream);
+/* fp32 rows, forward only (evaluation at fp32-level accuracy): y = LN(a + b) * gamma + beta                          */
+int mg_layer_norm_fwd_f32(const float* a, const float* b, const float* gamma, const float* beta, float eps, float* y, int rows,
+                          int E, void* stream);
 /* mg_token_logits_fwd/bwd : logits[bt][q][p] = sum_c tok[bt / n_f][q][c] * x[bt][p][c] - the `einsum('bqc,btchw->btqhw')` of
  *     the OS8 head (module/instance_matte_decoder.py:302); x NHWC fp16 with C = 64, tok fp32 [B][Q][C], logits / g fp32
  *     [BT][Q][HW].  bwd: dx fp16 [BT][HW][C] and / or dtok fp32 [B][Q][C] (+=, caller zeroes); either may be NULL. */
 int mg_token_logits_fwd(const float* tok, const void* x, float* logits, int BT, int n_f, int Q, int HW, int C, void* stream);
+int mg_token_logits_fwd_f32(const float* tok, const float* x, float* logits, int BT, int n_f, int Q, int HW, int C,
+                            void* stream);   /* x NHWC fp32 */
 int mg_token_logits_bwd(const float* tok, const void* x, const float* g, void* dx, float* dtok, int BT, int n_f, int Q, int HW,
                         int C, void* stream);
 
@@ -351,6 +369,11 @@ int mg_attn_fq_fwd(const void* q, const float* k, const float* v, const uint8_t*
                    void* out, void* stream);
 int mg_attn_fq_bwd(const void* q, const float* k, const float* v, const uint8_t* key_pad, const void* d_out, int B, int F,
                    int S, int E, void* dq, float* dk, float* dv, void* stream);
+/* forward cores with an fp32 many side (evaluation at fp32-level accuracy; accurate expf)                          */
+int mg_attn_tq_fwd_f32(const float* q, const float* k, const float* v, const uint8_t* key_pad, const uint8_t* guidance, int B,
+                       int F, int S, int E, float* out, float* stat, float* row_max, float* row_sum, float* ws, void* stream);
+int mg_attn_fq_fwd_f32(const float* q, const float* k, const float* v, const uint8_t* key_pad, int B, int F, int S, int E,
+                       float* out, void* stream);
 
 #ifdef __cplusplus
 }

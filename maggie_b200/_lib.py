@@ -25,6 +25,13 @@ SIGNATURES = {
     "mg_sites_tables": (c_int, [c_void_p, c_int, c_int, c_int, _I32P, _PP, _PP, _PP, _PP, c_void_p]),
     "mg_mask_embed_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_conv_fprop": (c_int, [c_void_p, c_void_p]),
+    "mg_conv_fprop_x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mg_split_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mg_mask_embed_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mg_layer_norm_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
+    "mg_token_logits_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mg_attn_tq_fwd_f32": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 6),
+    "mg_attn_fq_fwd_f32": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 2),
     "mg_conv_wgrad": (c_int, [c_void_p, c_void_p]),
     "mg_conv_halo_launches": (c_ulonglong, []),
     "mg_wgrad_halo_launches": (c_ulonglong, []),
@@ -121,6 +128,18 @@ def tensor_ptr(t):
 
 
 def need_cuda(*tensors):
+    """Every tensor must live on the CURRENT CUDA device: kernels are launched on that device's current stream
+    (`stream_ptr`), so a tensor on another GPU would be touched from the wrong context / without stream ordering."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("maggie_b200 native op called with a non-CUDA tensor; there is no CPU fallback")
+        if cur is None:
+            import torch
+
+            cur = torch._C._cuda_getDevice()
+        if t.device.index != cur:
+            raise RuntimeError(f"maggie_b200 native op called with a tensor on cuda:{t.device.index} while the current device "
+                               f"is cuda:{cur}; call torch.cuda.set_device() (or use `with torch.cuda.device(...)`) first")

@@ -40,6 +40,19 @@ struct Vec<2> {
     }
 };
 
+// fp32 rows (evaluation at fp32-level accuracy, forward only)
+template <int PER>
+struct VecF {
+    static __device__ __forceinline__ void load(const float* p, float (&f)[PER]) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) f[i] = __ldg(p + i);
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&f)[PER]) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) p[i] = f[i];
+    }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -85,6 +98,42 @@ layer_norm_fwd_kernel(const __half* __restrict__ a, const __half* __restrict__ b
         for (int i = 0; i < PER; ++i) o[i] = (v[i] - mean) * rstd * g[i] + bt[i];
         Vec<PER>::store(y + (size_t)r * E + c0, o);
         if (stat && lane == 0) stat[r] = make_float2(mean, rstd);
+    }
+}
+
+// y = LN(a + b) on fp32 rows (no rounding of the sum, sqrt + divide instead of rsqrt)
+template <int PER>
+__global__ void __launch_bounds__(256)
+layer_norm_fwd_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float eps, float* __restrict__ y, int rows) {
+    mg::pdl_prologue();
+    constexpr int E = PER * 32;
+    const int lane = threadIdx.x & 31, c0 = lane * PER;
+    float g[PER], bt[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) g[i] = gamma[c0 + i], bt[i] = beta[c0 + i];
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+        float v[PER];
+        VecF<PER>::load(a + (size_t)r * E + c0, v);
+        if (b) {
+            float w[PER];
+            VecF<PER>::load(b + (size_t)r * E + c0, w);
+#pragma unroll
+            for (int i = 0; i < PER; ++i) v[i] += w[i];
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) sum += v[i];
+        const float mean = warp_sum(sum) * (1.f / E);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) sq += (v[i] - mean) * (v[i] - mean);
+        const float rstd = 1.f / sqrtf(warp_sum(sq) * (1.f / E) + eps);
+        float o[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) o[i] = (v[i] - mean) * rstd * g[i] + bt[i];
+        VecF<PER>::store(y + (size_t)r * E + c0, o);
     }
 }
 
@@ -181,6 +230,19 @@ extern "C" int mg_layer_norm_fwd(const void* a, const void* b, const float* gamm
     return MG_OK;
 }
 
+extern "C" int mg_layer_norm_fwd_f32(const float* a, const float* b, const float* gamma, const float* beta, float eps, float* y,
+                                     int rows, int E, void* stream) {
+    MG_REQUIRE(E == 64 || E == 128, "mg_layer_norm_fwd_f32: E must be 64 or 128 (got %d)", E);
+    if (rows <= 0) return MG_OK;
+    MG_REQUIRE(a && gamma && beta && y, "mg_layer_norm_fwd_f32: null pointer");
+    if (E == 128)
+        MG_LAUNCH(layer_norm_fwd_f32_kernel<4>, row_grid(rows), 256, 0, stream, a, b, gamma, beta, eps, y, rows);
+    else
+        MG_LAUNCH(layer_norm_fwd_f32_kernel<2>, row_grid(rows), 256, 0, stream, a, b, gamma, beta, eps, y, rows);
+    MG_CHECK_LAUNCH("mg_layer_norm_fwd_f32");
+    return MG_OK;
+}
+
 extern "C" int mg_layer_norm_bwd(const void* s, const void* gy, const float* gamma, const float* stat, void* dx, float* dgb,
                                  int rows, int E, void* stream) {
     MG_REQUIRE(E == 64 || E == 128, "mg_layer_norm_bwd: E must be 64 or 128 (got %d)", E);
@@ -242,6 +304,32 @@ token_logits_fwd_kernel(const float* __restrict__ tok, const __half* __restrict_
             float acc = 0.f;
 #pragma unroll
             for (int c = 0; c < TL_C; ++c) acc += s_tok[q][c] * xv[c];
+            logits[((size_t)bt * Q + q) * HW + p] = acc;
+        }
+    }
+}
+
+// the same with fp32 NHWC features (evaluation at fp32-level accuracy)
+__global__ void __launch_bounds__(256)
+token_logits_fwd_f32_kernel(const float* __restrict__ tok, const float* __restrict__ x, float* __restrict__ logits, int BT,
+                            int n_f, int Q, int HW) {
+    mg::pdl_prologue();
+    __shared__ float s_tok[TL_QMAX][TL_C];
+    const int bt = blockIdx.y, b = bt / n_f;
+    for (int i = threadIdx.x; i < Q * TL_C; i += 256) s_tok[i / TL_C][i % TL_C] = tok[(size_t)b * Q * TL_C + i];
+    __syncthreads();
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < HW; p += gridDim.x * 256) {
+        const float4* xr = reinterpret_cast<const float4*>(x + ((size_t)bt * HW + p) * TL_C);
+        float xv[TL_C];
+#pragma unroll
+        for (int j = 0; j < TL_C / 4; ++j) {
+            const float4 u = __ldg(xr + j);
+            xv[4 * j] = u.x, xv[4 * j + 1] = u.y, xv[4 * j + 2] = u.z, xv[4 * j + 3] = u.w;
+        }
+        for (int q = 0; q < Q; ++q) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < TL_C; ++c) acc = fmaf(s_tok[q][c], xv[c], acc);
             logits[((size_t)bt * Q + q) * HW + p] = acc;
         }
     }
@@ -314,6 +402,17 @@ extern "C" int mg_token_logits_fwd(const float* tok, const void* x, float* logit
     MG_LAUNCH(token_logits_fwd_kernel, dim3(std::min(mg::ceil_div(HW, 256), 64), BT), 256, 0, stream, tok,
               static_cast<const __half*>(x), logits, BT, n_f, Q, HW);
     MG_CHECK_LAUNCH("mg_token_logits_fwd");
+    return MG_OK;
+}
+
+extern "C" int mg_token_logits_fwd_f32(const float* tok, const float* x, float* logits, int BT, int n_f, int Q, int HW, int C,
+                                       void* stream) {
+    MG_REQUIRE(C == TL_C && Q >= 1 && Q <= TL_QMAX && n_f >= 1, "mg_token_logits_fwd_f32: C must be 64 and Q <= 16 (C=%d Q=%d)", C, Q);
+    if (BT <= 0 || HW <= 0) return MG_OK;
+    MG_REQUIRE(tok && x && logits, "mg_token_logits_fwd_f32: null pointer");
+    MG_LAUNCH(token_logits_fwd_f32_kernel, dim3(std::min(mg::ceil_div(HW, 256), 64), BT), 256, 0, stream, tok, x, logits, BT,
+              n_f, Q, HW);
+    MG_CHECK_LAUNCH("mg_token_logits_fwd_f32");
     return MG_OK;
 }
 

@@ -16,6 +16,8 @@
 // so nothing is ever reset.  The counter lives on the device: the kernel is CUDA-graph capturable.
 #include "common.cuh"
 
+#include <cstdlib>
+
 #include <cstring>
 
 namespace {
@@ -34,6 +36,7 @@ struct XArgs {
     int n_copies, C;
     float count;            // < 0: the payload carries no element count
     float* out;             // [2][C] (+ [1] global count)
+    unsigned long long timeout_ns;   // 0: wait for the peers without limit (like a collective)
 };
 
 __device__ __forceinline__ float* recv_of(float* win, int slot, int r) { return win + ((size_t)slot * MAX_RANKS + r) * PAYLOAD; }
@@ -113,7 +116,7 @@ stats_exchange_kernel(const XArgs a) {
         const uint32_t* f = flag_of(mine, slot, threadIdx.x, blockIdx.x);
         const unsigned long long t0 = globaltimer_ns();
         while ((int32_t)(ld_acquire_sys(f) - want) < 0) {
-            if (globaltimer_ns() - t0 > 20000000000ull) {
+            if (a.timeout_ns && globaltimer_ns() - t0 > a.timeout_ns) {
                 printf("maggie_b200: statistics exchange %u timed out waiting for rank %d (block %d)\n", seq, (int)threadIdx.x,
                        (int)blockIdx.x);
                 __trap();
@@ -202,6 +205,15 @@ extern "C" int mg_stats_exchange(const mg_xchg_desc* x, const float* in, int n_c
         a.rank = x->rank, a.world = x->world;
     }
     a.in = in, a.n_copies = n_copies, a.C = C, a.count = count, a.out = out;
+    // A rank may legitimately arrive late (rank-0-only validation between steps, a slow loader worker, a checkpoint save):
+    // like NCCL's SyncBatchNorm collective the exchange WAITS.  The limit is a watchdog of NCCL order (torch's process
+    // groups abort after 600 s), not a pacing requirement: MAGGIE_B200_XCHG_TIMEOUT_S seconds, 0 = never give up.
+    static const unsigned long long timeout_ns = [] {
+        const char* e = std::getenv("MAGGIE_B200_XCHG_TIMEOUT_S");
+        const double sec = e ? std::atof(e) : 600.0;
+        return sec <= 0.0 ? 0ull : (unsigned long long)(sec * 1e9);
+    }();
+    a.timeout_ns = timeout_ns;
     MG_LAUNCH(stats_exchange_kernel, mg::ceil_div(C, 32), 256, 0, stream, a);
     MG_CHECK_LAUNCH("mg_stats_exchange");
     return MG_OK;

@@ -11,10 +11,11 @@ struct SlotIds {
     int v[MAX_M];
 };
 
+// out32 (optional, evaluation at fp32-level accuracy): the packed pixel is written as C floats instead of C halfs
 template <int C>
 __global__ void __launch_bounds__(256)
 mask_embed_fwd_kernel(const float* __restrict__ image, const float* __restrict__ masks, const int32_t* __restrict__ slot_ids,
-                      int M, const float* __restrict__ table, __half* __restrict__ out, int B, int HW) {
+                      int M, const float* __restrict__ table, __half* __restrict__ out, float* __restrict__ out32, int B, int HW) {
     mg::pdl_prologue();
     __shared__ float s_tab[33];
     __shared__ SlotIds ids;
@@ -39,6 +40,18 @@ mask_embed_fwd_kernel(const float* __restrict__ image, const float* __restrict__
             }
         }
         const float inv = 1.f / (cnt + 1e-6f);
+        if (out32) {
+            float* o = out32 + p * C;
+            if (C % 4 == 0) {
+                reinterpret_cast<float4*>(o)[0] = make_float4(r, g, bl, e0 * inv);
+                reinterpret_cast<float4*>(o)[1] = make_float4(e1 * inv, e2 * inv, 0.f, 0.f);
+#pragma unroll
+                for (int i = 2; i < C / 4; ++i) reinterpret_cast<float4*>(o)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                o[0] = r, o[1] = g, o[2] = bl, o[3] = e0 * inv, o[4] = e1 * inv, o[5] = e2 * inv;
+            }
+            continue;
+        }
         __align__(16) __half2 v[C / 2 < 4 ? 4 : C / 2];
         v[0] = __floats2half2_rn(r, g);
         v[1] = __floats2half2_rn(bl, e0 * inv);
@@ -115,20 +128,32 @@ int check(const int32_t* slot_ids, int M, int C, const char* who) {
 
 }  // namespace
 
-extern "C" int mg_mask_embed_fwd(const float* image, const float* masks, const int32_t* slot_ids, int M,
-                                 const float* table, void* out_f16, int B, int H, int W, int C, void* stream) {
-    MG_REQUIRE(image && table && out_f16 && (masks || M == 0), "mg_mask_embed_fwd: null pointer");
+static int mask_embed_fwd(const float* image, const float* masks, const int32_t* slot_ids, int M, const float* table,
+                          void* out_f16, float* out32, int B, int H, int W, int C, void* stream) {
+    MG_REQUIRE(image && table && (out_f16 || out32) && (masks || M == 0), "mg_mask_embed_fwd: null pointer");
     if (int e = check(slot_ids, M, C, "mg_mask_embed_fwd")) return e;
     if (B <= 0) return MG_OK;
     const int HW = H * W;
     const int grid = (int)std::min<size_t>(((size_t)B * HW + 255) / 256, (size_t)mg::kNumSMs * 16);
     __half* out = static_cast<__half*>(out_f16);
-    if (C == 6) MG_LAUNCH(mask_embed_fwd_kernel<6>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
-    else if (C == 8) MG_LAUNCH(mask_embed_fwd_kernel<8>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
-    else if (C == 16) MG_LAUNCH(mask_embed_fwd_kernel<16>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
-    else MG_LAUNCH(mask_embed_fwd_kernel<32>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, B, HW);
+    if (C == 6) MG_LAUNCH(mask_embed_fwd_kernel<6>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, out32, B, HW);
+    else if (C == 8) MG_LAUNCH(mask_embed_fwd_kernel<8>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, out32, B, HW);
+    else if (C == 16) MG_LAUNCH(mask_embed_fwd_kernel<16>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, out32, B, HW);
+    else MG_LAUNCH(mask_embed_fwd_kernel<32>, grid, 256, 0, stream, image, masks, slot_ids, M, table, out, out32, B, HW);
     MG_CHECK_LAUNCH("mg_mask_embed_fwd");
     return MG_OK;
+}
+
+extern "C" int mg_mask_embed_fwd(const float* image, const float* masks, const int32_t* slot_ids, int M,
+                                 const float* table, void* out_f16, int B, int H, int W, int C, void* stream) {
+    MG_REQUIRE(out_f16, "mg_mask_embed_fwd: null pointer");
+    return mask_embed_fwd(image, masks, slot_ids, M, table, out_f16, nullptr, B, H, W, C, stream);
+}
+
+extern "C" int mg_mask_embed_fwd_f32(const float* image, const float* masks, const int32_t* slot_ids, int M,
+                                     const float* table, float* out_f32, int B, int H, int W, int C, void* stream) {
+    MG_REQUIRE(out_f32, "mg_mask_embed_fwd_f32: null pointer");
+    return mask_embed_fwd(image, masks, slot_ids, M, table, nullptr, out_f32, B, H, W, C, stream);
 }
 
 extern "C" int mg_mask_embed_bwd(const void* grad_out_f16, const float* masks, const int32_t* slot_ids, int M,

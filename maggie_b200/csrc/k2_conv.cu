@@ -48,14 +48,22 @@ struct KArgs {
     const float* shift;
     const __half* res;               // optional residual, NHWC [N,Ho,Wo,Co] or [N,Ho/2,Wo/2,Co] when res_up
     int res_up;
+    // split-fp16 ("x3") mode, template parameter HP: `out` and `res` are fp32 tensors (same indexing)
+    float* out32;
+    const float* res32;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     return act == 1 ? fmaxf(v, 0.f) : (act == 2 ? (v > 0.f ? v : 0.2f * v) : v);
 }
 
+// HP ("x3", evaluation at fp32-level accuracy): every operand is an unevaluated sum of two fp16 tensors (x = x_hi + x_lo,
+// w = w_hi + w_lo, |lo| <= 2^-11 |hi|); the K loop runs three times - x_hi w_hi, x_lo w_hi, x_hi w_lo - into the same fp32
+// TMEM accumulator (the dropped x_lo w_lo term is 2^-22 relative), and the epilogue reads / writes fp32 tensors.
+template <bool HP>
 __global__ void __launch_bounds__(THREADS, 2)
-conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs a) {
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo, const KArgs a) {
     mg::pdl_launch();   // the next kernel may be scheduled; its own griddepcontrol.wait orders the memory accesses
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
@@ -78,12 +86,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ty = t % a.tiles_y, img = t / a.tiles_y;
     const int y0 = ty * a.th, x0 = tx * a.tw, n0 = blockIdx.y * a.BN;
     const int tap_first = a.phase_tap0[blockIdx.z];
-    const int nkb = (a.phase_tap0[blockIdx.z + 1] - tap_first) * a.kchunks;
+    const int nkb1 = (a.phase_tap0[blockIdx.z + 1] - tap_first) * a.kchunks;   // k-blocks of one pass over the taps
+    const int nkb = HP ? 3 * nkb1 : nkb1;
     const int oy0 = a.phase_oy0[blockIdx.z], ox0 = a.phase_ox0[blockIdx.z];
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (HP) {
+            prefetch_tmap(&tmA_lo);
+            prefetch_tmap(&tmB_lo);
+        }
         for (int s = 0; s < a.stages; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
@@ -105,10 +118,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int s = kb % a.stages, ph = (kb / a.stages) & 1;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 mbar_expect_tx(full0 + 8 * s, a_bytes + b_bytes);
-                const int tap = tap_first + kb / a.kchunks, c = kb - (kb / a.kchunks) * a.kchunks;
-                tma_load_4d(smem_u32(sA + s * a_bytes), &tmA, full0 + 8 * s, c * a.BK, x0 * a.sx + a.tap_dx[tap],
-                            y0 * a.sy + a.tap_dy[tap], img);
-                tma_load_2d(smem_u32(sB + s * b_bytes), &tmB, full0 + 8 * s, a.tap_koff[tap] + c * a.BK, n0);
+                const int term = HP ? kb / nkb1 : 0, k1 = kb - term * nkb1;
+                const int tap = tap_first + k1 / a.kchunks, c = k1 - (k1 / a.kchunks) * a.kchunks;
+                tma_load_4d(smem_u32(sA + s * a_bytes), (HP && term == 1) ? &tmA_lo : &tmA, full0 + 8 * s, c * a.BK,
+                            x0 * a.sx + a.tap_dx[tap], y0 * a.sy + a.tap_dy[tap], img);
+                tma_load_2d(smem_u32(sB + s * b_bytes), (HP && term == 2) ? &tmB_lo : &tmB, full0 + 8 * s,
+                            a.tap_koff[tap] + c * a.BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -137,11 +152,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int py = y0 + m / a.tw, px = x0 + m % a.tw;
         const bool valid = (py < a.Hg) && (px < a.Wg);
         const int oy = py * a.oys + oy0, ox = px * a.oxs + ox0;
-        __half* orow = a.out + (((size_t)img * a.Ho + oy) * a.Wo + ox) * a.Cs + a.c_off + n0;
-        const __half* rrow = nullptr;
-        if (a.res)
-            rrow = a.res + (a.res_up ? (((size_t)img * (a.Ho >> 1) + (oy >> 1)) * (a.Wo >> 1) + (ox >> 1))
-                                     : (((size_t)img * a.Ho + oy) * a.Wo + ox)) * a.Co + n0;
+        const size_t ooff = (((size_t)img * a.Ho + oy) * a.Wo + ox) * a.Cs + a.c_off + n0;
+        const size_t roff = (a.res_up ? (((size_t)img * (a.Ho >> 1) + (oy >> 1)) * (a.Wo >> 1) + (ox >> 1))
+                                      : (((size_t)img * a.Ho + oy) * a.Wo + ox)) * a.Co + n0;
+        __half* orow = HP ? nullptr : a.out + ooff;
+        const __half* rrow = (!HP && a.res) ? a.res + roff : nullptr;
+        float* orow32 = HP ? a.out32 + ooff : nullptr;
+        const float* rrow32 = (HP && a.res32) ? a.res32 + roff : nullptr;
         float* stg = s_stage + q * 32 * 17;
         float* part = s_part + q * 2 * a.BN;
         mbar_wait(tfull, 0);
@@ -180,7 +197,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(a.scale + n0 + c0 + i), __ldg(a.shift + n0 + c0 + i));
                 }
-                if (rrow) {
+                if (HP && rrow32) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 f = __ldg(reinterpret_cast<const float4*>(rrow32 + c0) + i);
+                        v[4 * i] += f.x, v[4 * i + 1] += f.y, v[4 * i + 2] += f.z, v[4 * i + 3] += f.w;
+                    }
+                }
+                if (!HP && rrow) {
                     const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rrow + c0)), r1 = __ldg(reinterpret_cast<const uint4*>(rrow + c0) + 1);
                     const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -192,6 +216,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (a.post_act) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], a.post_act);
+                }
+                if (HP) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        reinterpret_cast<float4*>(orow32 + c0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    continue;
                 }
                 uint4 o0, o1;
                 __half2 h;
@@ -236,7 +266,8 @@ int conv_halo_launch(const mg_conv_desc* d, void* stream, bool* handled);     //
 int conv_splitk_launch(const mg_conv_desc* d, void* stream, bool* handled);   // k2s_conv_splitk.cu (opt-in)
 }
 
-extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
+static int conv_launch_impl(const mg_conv_desc* d, const void* x_lo, const void* w_lo, void* stream) {
+    const bool hp = x_lo != nullptr;
     MG_REQUIRE(d && d->x && d->w && d->out, "mg_conv_fprop: null pointer");
     MG_REQUIRE(d->n_taps >= 1 && d->n_taps <= MAX_TAPS, "mg_conv_fprop: n_taps %d out of range", d->n_taps);
     MG_REQUIRE(d->Ci % 16 == 0 && d->Co % 16 == 0, "mg_conv_fprop: Ci (%d) and Co (%d) must be multiples of 16", d->Ci, d->Co);
@@ -249,13 +280,13 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
         return MG_ERR_CUDA;
     }
     MG_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "mg_conv_fprop: scale and shift go together");
-    {
+    if (!hp) {
         // high-resolution, low-channel stride-1 layers: halo-resident persistent kernel (K2b)
         bool handled = false;
         const int rc = mg::conv_halo_launch(d, stream, &handled);
         if (rc != MG_OK || handled) return rc;
     }
-    if (d->splitk_ws) {
+    if (d->splitk_ws && !hp) {
         // opt-in: layers with few CTAs split the K range of a tile over several CTAs (K2s)
         bool handled = false;
         const int rc = mg::conv_splitk_launch(d, stream, &handled);
@@ -291,56 +322,79 @@ extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) {
     }
     a.pre_act = d->pre_act, a.post_act = d->post_act, a.stats = d->stats, a.bias = d->bias;
     a.scale = d->scale, a.shift = d->shift, a.res = static_cast<const __half*>(d->res), a.res_up = d->res_up;
-    MG_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "mg_conv_fprop: scale and shift go together");
+    a.out32 = static_cast<float*>(d->out), a.res32 = static_cast<const float*>(d->res);
     MG_REQUIRE(!d->res || (d->c_off == 0 && d->Cs == d->Co), "mg_conv_fprop: residual needs a dense [N,Ho,Wo,Co] output");
 
     const int a_bytes = BM * a.BK * 2, b_bytes = a.BN * a.BK * 2;
     const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 17 * 4 + 4 * 2 * a.BN * 4;
     // this non-persistent kernel hides its prologue / epilogue behind the main loop of co-resident CTAs: keep the
-    // per-CTA footprint at <= ~100 KB so that at least two CTAs (TMEM: 2 x BN <= 512 columns) share an SM
-    // (MAGGIE_B200_CONV_SMEM_KB: experiment knob - 111 gives the 128 x 128 x 64 layers a third stage and still fits two CTAs)
-    static const int budget_kb = [] { const char* e = std::getenv("MAGGIE_B200_CONV_SMEM_KB"); const int v = e ? std::atoi(e) : 0; return v >= 64 && v <= 220 ? v : 100; }();
+    // per-CTA footprint at <= 111 KB so that two CTAs (TMEM: 2 x BN <= 512 columns) share an SM and the 128 x 128 x 64
+    // layers still get a three-stage ring (measured on the C2 step: 530.6 vs 511.2 frames/s with a 100 KB budget = two
+    // stages; MAGGIE_B200_CONV_SMEM_KB overrides, for experiments)
+    static const int budget_kb = [] { const char* e = std::getenv("MAGGIE_B200_CONV_SMEM_KB"); const int v = e ? std::atoi(e) : 0; return v >= 64 && v <= 220 ? v : 111; }();
     a.stages = std::max(2, std::min(4, (budget_kb * 1024 - fixed) / (a_bytes + b_bytes)));
     const size_t smem = (size_t)fixed + (size_t)a.stages * (a_bytes + b_bytes);
 
-    CUtensorMap tmA, tmB;
-    {
+    CUtensorMap tmA, tmB, tmA_lo, tmB_lo;
+    auto encode_a = [&](CUtensorMap* tm, const void* ptr) -> int {
         cuuint64_t dims[4] = {(cuuint64_t)d->Ci, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->N};
         cuuint64_t strides[3] = {(cuuint64_t)d->Ci * 2, (cuuint64_t)d->Wi * d->Ci * 2, (cuuint64_t)d->Hi * d->Wi * d->Ci * 2};
         cuuint32_t box[4] = {(cuuint32_t)a.BK, (cuuint32_t)(a.tw * a.sx), (cuuint32_t)(a.th * a.sy), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)a.sx, (cuuint32_t)a.sy, 1};
-        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
+        CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, mg::swz_enum(a.swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             mg::set_error("mg_conv_fprop: cuTensorMapEncodeTiled(A) failed (%d): x=%p N=%d H=%d W=%d C=%d box=%u,%u,%u", (int)r,
-                          d->x, d->N, d->Hi, d->Wi, d->Ci, box[0], box[1], box[2]);
+                          ptr, d->N, d->Hi, d->Wi, d->Ci, box[0], box[1], box[2]);
             return MG_ERR_CUDA;
         }
-    }
-    {
+        return MG_OK;
+    };
+    auto encode_b = [&](CUtensorMap* tm, const void* ptr) -> int {
         cuuint64_t dims[2] = {(cuuint64_t)d->Ktot, (cuuint64_t)d->Co};
         cuuint64_t strides[1] = {(cuuint64_t)d->Ktot * 2};
         cuuint32_t box[2] = {(cuuint32_t)a.BK, (cuuint32_t)a.BN};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
+        CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, mg::swz_enum(a.swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             mg::set_error("mg_conv_fprop: cuTensorMapEncodeTiled(W) failed (%d): Ktot=%d Co=%d", (int)r, d->Ktot, d->Co);
             return MG_ERR_CUDA;
         }
+        return MG_OK;
+    };
+    if (int e = encode_a(&tmA, d->x)) return e;
+    if (int e = encode_b(&tmB, d->w)) return e;
+    if (hp) {
+        if (int e = encode_a(&tmA_lo, x_lo)) return e;
+        if (int e = encode_b(&tmB_lo, w_lo)) return e;
+    } else {
+        tmA_lo = tmA, tmB_lo = tmB;
     }
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(conv_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
             mg::set_error("mg_conv_fprop: cannot raise dynamic shared memory limit");
             return MG_ERR_CUDA;
         }
         attr_set = true;
     }
     dim3 grid(d->N * a.tiles_y * a.tiles_x, mg::ceil_div(d->Co, a.BN), a.n_phases);
-    MG_LAUNCH(conv_tcgen05_kernel, grid, THREADS, smem, stream, tmA, tmB, a);
+    if (hp)
+        MG_LAUNCH(conv_tcgen05_kernel<true>, grid, THREADS, smem, stream, tmA, tmB, tmA_lo, tmB_lo, a);
+    else
+        MG_LAUNCH(conv_tcgen05_kernel<false>, grid, THREADS, smem, stream, tmA, tmB, tmA_lo, tmB_lo, a);
     MG_CHECK_LAUNCH("mg_conv_fprop");
     return MG_OK;
+}
+
+extern "C" int mg_conv_fprop(const mg_conv_desc* d, void* stream) { return conv_launch_impl(d, nullptr, nullptr, stream); }
+
+extern "C" int mg_conv_fprop_x3(const mg_conv_desc* d, const void* x_lo, const void* w_lo, void* stream) {
+    MG_REQUIRE(x_lo && w_lo, "mg_conv_fprop_x3: null pointer");
+    MG_REQUIRE(d && !d->stats, "mg_conv_fprop_x3: evaluation only (no BatchNorm statistics epilogue)");
+    return conv_launch_impl(d, x_lo, w_lo, stream);
 }

@@ -41,16 +41,54 @@ __device__ __forceinline__ float dot_row(const __half* row, const float* q) {
     return acc;
 }
 
+// ---- fp32 many side (evaluation at fp32-level accuracy, forward only): rows of E floats, padded to E + 4 -------------
+constexpr int ROWF = E + 4;
+
+__device__ __forceinline__ void load_tile(float (*dst)[ROWF], const float* __restrict__ src, int rows_valid) {
+    for (int i = threadIdx.x; i < TM * (E / 4); i += blockDim.x) {
+        const int r = i / (E / 4), c = i - r * (E / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_valid) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * E) + c);
+        *reinterpret_cast<float4*>(&dst[r][c * 4]) = v;
+    }
+}
+
+__device__ __forceinline__ float dot_row(const float* row, const float* q) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < E; e += 4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(row + e);
+        acc = fmaf(k4.x, q[e], acc);
+        acc = fmaf(k4.y, q[e + 1], acc);
+        acc = fmaf(k4.z, q[e + 2], acc);
+        acc = fmaf(k4.w, q[e + 3], acc);
+    }
+    return acc;
+}
+
+template <typename T> struct Tile;
+template <> struct Tile<__half> { static constexpr int ROW = ROWP; };
+template <> struct Tile<float> { static constexpr int ROW = ROWF; };
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ void from_f(__half& d, float v) { d = __float2half(v); }
+__device__ __forceinline__ void from_f(float& d, float v) { d = v; }
+// fp32 mode uses the accurate exponential (the fast one carries ~2 ulp + range-reduction error)
+template <typename T> __device__ __forceinline__ float exp_t(float x) { return __expf(x); }
+template <> __device__ __forceinline__ float exp_t<float>(float x) { return expf(x); }
+
 // ================================================================================================ tq forward
 // grid (nsplit, B), 128 threads.  partial outputs: pm/pl [B][nsplit][F], po [B][nsplit][F][E], pstat [B][nsplit][F]
+template <typename T>
 __global__ void __launch_bounds__(128)
-attn_tq_partial_kernel(const float* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V,
+attn_tq_partial_kernel(const float* __restrict__ Q, const T* __restrict__ K, const T* __restrict__ V,
                        const uint8_t* __restrict__ key_pad, const uint8_t* __restrict__ guid, int F, int S, float scale,
                        float* __restrict__ pm, float* __restrict__ pl, float* __restrict__ po, float* __restrict__ pstat) {
     mg::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
-    __half (*sK)[ROWP] = reinterpret_cast<__half (*)[ROWP]>(smem_raw);
-    __half (*sV)[ROWP] = sK + TM;
+    constexpr int ROW = Tile<T>::ROW;
+    T (*sK)[ROW] = reinterpret_cast<T (*)[ROW]>(smem_raw);
+    T (*sV)[ROW] = sK + TM;
     float* sQ = reinterpret_cast<float*>(sV + TM);   // [MAXF][E]
     float* sP = sQ + MAXF * E;                        // [MAXF][TM]
     float* sRed = sP + MAXF * TM;                     // [4]
@@ -71,7 +109,7 @@ attn_tq_partial_kernel(const float* __restrict__ Q, const __half* __restrict__ K
         __syncthreads();
         m = fmaxf(fmaxf(sRed[0], sRed[1]), fmaxf(sRed[2], sRed[3]));
         __syncthreads();
-        const float p = (live && m > -INFINITY) ? __expf(s - m) : 0.f;
+        const float p = (live && m > -INFINITY) ? exp_t<T>(s - m) : 0.f;
         sP[f * TM + t] = p;
         float l = p, st = (guid && live && guid[((size_t)b * F + f) * S + s0 + t]) ? p : 0.f;
 #pragma unroll
@@ -87,7 +125,7 @@ attn_tq_partial_kernel(const float* __restrict__ Q, const __half* __restrict__ K
     // partial output: thread = channel e
     for (int f = 0; f < F; ++f) {
         float acc = 0.f;
-        for (int k = 0; k < rows; ++k) acc = fmaf(sP[f * TM + k], __half2float(sV[k][t]), acc);
+        for (int k = 0; k < rows; ++k) acc = fmaf(sP[f * TM + k], to_f(sV[k][t]), acc);
         po[(((size_t)b * nsplit + split) * F + f) * E + t] = acc;
     }
 }
@@ -96,7 +134,7 @@ attn_tq_partial_kernel(const float* __restrict__ Q, const __half* __restrict__ K
 __global__ void __launch_bounds__(128)
 attn_tq_merge_kernel(const float* __restrict__ pm, const float* __restrict__ pl, const float* __restrict__ po,
                      const float* __restrict__ pstat, int F, int nsplit, float* __restrict__ O, float* __restrict__ stat,
-                     float* __restrict__ M, float* __restrict__ L) {
+                     float* __restrict__ M, float* __restrict__ L, int accurate) {
     mg::pdl_prologue();
     const int f = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     float m = -INFINITY;
@@ -104,7 +142,7 @@ attn_tq_merge_kernel(const float* __restrict__ pm, const float* __restrict__ pl,
     float l = 0.f, st = 0.f, acc = 0.f;
     for (int s = 0; s < nsplit; ++s) {
         const size_t o = ((size_t)b * nsplit + s) * F + f;
-        const float w = pm[o] > -INFINITY ? __expf(pm[o] - m) : 0.f;
+        const float w = pm[o] > -INFINITY ? (accurate ? expf(pm[o] - m) : __expf(pm[o] - m)) : 0.f;
         l += w * pl[o], st += w * pstat[o], acc += w * po[o * E + t];
     }
     // a fully masked row (l == 0) yields NaN exactly like softmax over an all -inf row in the reference
@@ -173,12 +211,14 @@ attn_tq_bwd_kernel(const float* __restrict__ Q, const __half* __restrict__ K, co
 
 // ================================================================================================ fq forward / backward
 // queries = many side.  grid (ceil(S/128), B), 128 threads.
+template <typename T>
 __global__ void __launch_bounds__(128)
-attn_fq_fwd_kernel(const __half* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
-                   const uint8_t* __restrict__ key_pad, int F, int S, float scale, __half* __restrict__ O) {
+attn_fq_fwd_kernel(const T* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                   const uint8_t* __restrict__ key_pad, int F, int S, float scale, T* __restrict__ O) {
     mg::pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
-    __half (*sQ)[ROWP] = reinterpret_cast<__half (*)[ROWP]>(smem_raw);
+    constexpr int ROW = Tile<T>::ROW;
+    T (*sQ)[ROW] = reinterpret_cast<T (*)[ROW]>(smem_raw);
     float* sK = reinterpret_cast<float*>(sQ + TM);   // [MAXF][E]
     float* sV = sK + MAXF * E;
     float* sP = sV + MAXF * E;                        // [TM][MAXF+1]
@@ -196,7 +236,7 @@ attn_fq_fwd_kernel(const __half* __restrict__ Q, const float* __restrict__ K, co
         }
         float l = 0.f;
 #pragma unroll
-        for (int f = 0; f < MAXF; ++f) s[f] = (s[f] > -INFINITY) ? __expf(s[f] - m) : 0.f, l += s[f];
+        for (int f = 0; f < MAXF; ++f) s[f] = (s[f] > -INFINITY) ? exp_t<T>(s[f] - m) : 0.f, l += s[f];
 #pragma unroll
         for (int f = 0; f < MAXF; ++f) sP[t * (MAXF + 1) + f] = s[f] / l;   // l == 0 (all keys padded) -> NaN as in the reference
     }
@@ -204,7 +244,7 @@ attn_fq_fwd_kernel(const __half* __restrict__ Q, const float* __restrict__ K, co
     for (int r = 0; r < rows; ++r) {
         float acc = 0.f;
         for (int f = 0; f < F; ++f) acc = fmaf(sP[r * (MAXF + 1) + f], sV[f * E + t], acc);
-        O[((size_t)b * S + s0 + r) * E + t] = __float2half(acc);
+        from_f(O[((size_t)b * S + s0 + r) * E + t], acc);
     }
 }
 
@@ -263,6 +303,8 @@ attn_fq_bwd_kernel(const __half* __restrict__ Q, const float* __restrict__ K, co
 }
 
 size_t tq_smem() { return 2 * TM * ROWP * 2 + (MAXF * E + MAXF * TM + 8) * 4; }
+size_t tq_smem_f32() { return 2 * TM * ROWF * 4 + (MAXF * E + MAXF * TM + 8) * 4; }
+size_t fq_smem_f32() { return TM * ROWF * 4 + (2 * MAXF * E + TM * (MAXF + 1)) * 4; }
 size_t tq_bwd_smem() { return 2 * TM * ROWP * 2 + (2 * MAXF * E + 2 * MAXF * TM + MAXF) * 4; }
 size_t fq_smem() { return TM * ROWP * 2 + (2 * MAXF * E + TM * (MAXF + 1)) * 4; }
 size_t fq_bwd_smem() { return 2 * TM * ROWP * 2 + (2 * MAXF * E + 2 * TM * (MAXF + 1)) * 4; }
@@ -285,9 +327,9 @@ extern "C" size_t mg_attn_tq_workspace_floats(int B, int F, int S) {
     return (size_t)B * ns * F * (3 + E);
 }
 
-extern "C" int mg_attn_tq_fwd(const float* q, const void* k, const void* v, const uint8_t* key_pad, const uint8_t* guidance,
-                              int B, int F, int S, int Edim, float* out, float* stat, float* row_max, float* row_sum,
-                              float* ws, void* stream) {
+static int attn_tq_fwd(const float* q, const void* k, const void* v, bool kv_f32, const uint8_t* key_pad, const uint8_t* guidance,
+                       int B, int F, int S, int Edim, float* out, float* stat, float* row_max, float* row_sum,
+                       float* ws, void* stream) {
     MG_REQUIRE(q && k && v && out && stat && row_max && row_sum && ws, "mg_attn_tq_fwd: null pointer");
     MG_REQUIRE(Edim == E && F >= 1 && F <= MAXF && S >= 1 && B >= 1 && B <= 65535, "mg_attn_tq_fwd: unsupported shape E=%d F=%d S=%d", Edim, F, S);
     const int ns = mg::ceil_div(S, TM);
@@ -295,14 +337,32 @@ extern "C" int mg_attn_tq_fwd(const float* q, const void* k, const void* v, cons
     float* pl = pm + (size_t)B * ns * F;
     float* pstat = pl + (size_t)B * ns * F;
     float* po = pstat + (size_t)B * ns * F;
-    static bool done = false;
-    if (int e = raise_smem(attn_tq_partial_kernel, tq_smem(), "mg_attn_tq_fwd", done)) return e;
+    static bool done = false, done32 = false;
+    if (int e = raise_smem(attn_tq_partial_kernel<__half>, tq_smem(), "mg_attn_tq_fwd", done)) return e;
+    if (int e = raise_smem(attn_tq_partial_kernel<float>, tq_smem_f32(), "mg_attn_tq_fwd", done32)) return e;
     const float scale = 1.0f / sqrtf((float)E);
-    MG_LAUNCH(attn_tq_partial_kernel, dim3(ns, B), 128, tq_smem(), stream, q, static_cast<const __half*>(k),
-              static_cast<const __half*>(v), key_pad, guidance, F, S, scale, pm, pl, po, pstat);
-    MG_LAUNCH(attn_tq_merge_kernel, dim3(F, B), 128, 0, stream, pm, pl, po, pstat, F, ns, out, stat, row_max, row_sum);
+    if (kv_f32)
+        MG_LAUNCH(attn_tq_partial_kernel<float>, dim3(ns, B), 128, tq_smem_f32(), stream, q, static_cast<const float*>(k),
+                  static_cast<const float*>(v), key_pad, guidance, F, S, scale, pm, pl, po, pstat);
+    else
+        MG_LAUNCH(attn_tq_partial_kernel<__half>, dim3(ns, B), 128, tq_smem(), stream, q, static_cast<const __half*>(k),
+                  static_cast<const __half*>(v), key_pad, guidance, F, S, scale, pm, pl, po, pstat);
+    MG_LAUNCH(attn_tq_merge_kernel, dim3(F, B), 128, 0, stream, pm, pl, po, pstat, F, ns, out, stat, row_max, row_sum,
+              kv_f32 ? 1 : 0);
     MG_CHECK_LAUNCH("mg_attn_tq_fwd");
     return MG_OK;
+}
+
+extern "C" int mg_attn_tq_fwd(const float* q, const void* k, const void* v, const uint8_t* key_pad, const uint8_t* guidance,
+                              int B, int F, int S, int Edim, float* out, float* stat, float* row_max, float* row_sum,
+                              float* ws, void* stream) {
+    return attn_tq_fwd(q, k, v, false, key_pad, guidance, B, F, S, Edim, out, stat, row_max, row_sum, ws, stream);
+}
+
+extern "C" int mg_attn_tq_fwd_f32(const float* q, const float* k, const float* v, const uint8_t* key_pad,
+                                  const uint8_t* guidance, int B, int F, int S, int Edim, float* out, float* stat,
+                                  float* row_max, float* row_sum, float* ws, void* stream) {
+    return attn_tq_fwd(q, k, v, true, key_pad, guidance, B, F, S, Edim, out, stat, row_max, row_sum, ws, stream);
 }
 
 extern "C" int mg_attn_tq_bwd(const float* q, const void* k, const void* v, const uint8_t* key_pad, const uint8_t* guidance,
@@ -326,10 +386,22 @@ extern "C" int mg_attn_fq_fwd(const void* q, const float* k, const float* v, con
     MG_REQUIRE(q && k && v && out, "mg_attn_fq_fwd: null pointer");
     MG_REQUIRE(Edim == E && F >= 1 && F <= MAXF && S >= 1 && B >= 1 && B <= 65535, "mg_attn_fq_fwd: unsupported shape");
     static bool done = false;
-    if (int e = raise_smem(attn_fq_fwd_kernel, fq_smem(), "mg_attn_fq_fwd", done)) return e;
-    MG_LAUNCH(attn_fq_fwd_kernel, dim3(mg::ceil_div(S, TM), B), 128, fq_smem(), stream, static_cast<const __half*>(q), k, v,
+    if (int e = raise_smem(attn_fq_fwd_kernel<__half>, fq_smem(), "mg_attn_fq_fwd", done)) return e;
+    MG_LAUNCH(attn_fq_fwd_kernel<__half>, dim3(mg::ceil_div(S, TM), B), 128, fq_smem(), stream, static_cast<const __half*>(q), k, v,
               key_pad, F, S, 1.0f / sqrtf((float)E), static_cast<__half*>(out));
     MG_CHECK_LAUNCH("mg_attn_fq_fwd");
+    return MG_OK;
+}
+
+extern "C" int mg_attn_fq_fwd_f32(const float* q, const float* k, const float* v, const uint8_t* key_pad, int B, int F, int S,
+                                  int Edim, float* out, void* stream) {
+    MG_REQUIRE(q && k && v && out, "mg_attn_fq_fwd_f32: null pointer");
+    MG_REQUIRE(Edim == E && F >= 1 && F <= MAXF && S >= 1 && B >= 1 && B <= 65535, "mg_attn_fq_fwd_f32: unsupported shape");
+    static bool done = false;
+    if (int e = raise_smem(attn_fq_fwd_kernel<float>, fq_smem_f32(), "mg_attn_fq_fwd_f32", done)) return e;
+    MG_LAUNCH(attn_fq_fwd_kernel<float>, dim3(mg::ceil_div(S, TM), B), 128, fq_smem_f32(), stream, q, k, v, key_pad, F, S,
+              1.0f / sqrtf((float)E), out);
+    MG_CHECK_LAUNCH("mg_attn_fq_fwd_f32");
     return MG_OK;
 }
 

@@ -73,6 +73,27 @@ def pack_weight(w, ci_pad=None):
     return p.reshape(Co, kh * kw * ci_pad).to(torch.float16).contiguous()
 
 
+def pack_weight_f32(w, ci_pad=None):
+    """[Co,Ci,kh,kw] -> fp32 [Co, kh*kw*Ci_pad] (the layout of `pack_weight`, unrounded: input of `split_f32`)."""
+    Co, Ci, kh, kw = w.shape
+    ci_pad = ci_pad or pad_channels(Ci)
+    p = w.detach().float().permute(0, 2, 3, 1)
+    if ci_pad != Ci:
+        p = F.pad(p, (0, ci_pad - Ci))
+    return p.reshape(Co, kh * kw * ci_pad).contiguous()
+
+
+def split_f32(t):
+    """fp32 tensor -> (hi, lo) fp16 tensors with t = hi + lo up to 2^-22 |t| (K17): the operand form of the fp32-accurate
+    ("x3") evaluation mode of the tensor-core kernels."""
+    _need_cuda(t)
+    t = t.contiguous()
+    assert t.dtype == torch.float32 and t.numel() % 4 == 0
+    hi, lo = torch.empty_like(t, dtype=torch.float16), torch.empty_like(t, dtype=torch.float16)
+    _lib.check(_lib.lib().mg_split_f32(_ptr(t), _ptr(hi), _ptr(lo), t.numel(), _stream()), "mg_split_f32")
+    return hi, lo
+
+
 def conv_taps(kh, kw, pad, dil, ci_pad):
     """Forward-conv tap table: [(dy, dx, koff)]."""
     return [(ky * dil - pad, kx * dil - pad, (ky * kw + kx) * ci_pad) for ky in range(kh) for kx in range(kw)]
@@ -80,12 +101,14 @@ def conv_taps(kh, kw, pad, dil, ci_pad):
 
 def conv_launch(x, w_packed, taps, *, stride=1, grid_hw=None, out=None, out_hw=None, out_map=(1, 0, 1, 0), c_off=0,
                 relu=False, stats=None, bias=None, pre_act=None, post_act=None, scale=None, shift=None, res=None,
-                res_up=False, phases=None):
+                res_up=False, phases=None, lo=None):
     """Generic launch of mg_conv_fprop.  x [N,Hi,Wi,Ci] fp16 NHWC; w_packed [Co,Ktot] fp16; taps [(dy,dx,koff)].
     grid_hw: logical output grid (defaults to ceil(Hi/stride)); out: preallocated NHWC fp16 (or None);
     out_map = (oys, oy0, oxs, ox0).
     phases: [(taps, oy0, ox0), ...] (2..4 entries, `taps` ignored): the sub-pixel phases of a stride-2 data gradient /
-    transposed conv as ONE launch; out_map supplies the common output strides (oys, _, oxs, _)."""
+    transposed conv as ONE launch; out_map supplies the common output strides (oys, _, oxs, _).
+    lo = (x_lo, w_lo): fp32-accurate "x3" mode (mg_conv_fprop_x3): x / w_packed are the hi halves of split operands, the
+    output and the residual are FP32 tensors."""
     if phases is not None:
         taps = [t for ph in phases for t in ph[0]]
     _need_cuda(x, w_packed)
@@ -93,10 +116,12 @@ def conv_launch(x, w_packed, taps, *, stride=1, grid_hw=None, out=None, out_hw=N
     N, Hi, Wi, Ci = x.shape
     Co, Ktot = w_packed.shape
     Hg, Wg = grid_hw if grid_hw is not None else ((Hi + stride - 1) // stride, (Wi + stride - 1) // stride)
+    odt = torch.float32 if lo is not None else torch.float16
     if out is None:
         Ho, Wo = out_hw if out_hw is not None else (Hg, Wg)
-        out = torch.empty((N, Ho, Wo, Co), dtype=torch.float16, device=x.device)
-    assert out.dtype == torch.float16 and out.is_contiguous()
+        out = torch.empty((N, Ho, Wo, Co), dtype=odt, device=x.device)
+    assert out.dtype == odt and out.is_contiguous()
+    assert res is None or (res.dtype == odt and res.is_contiguous())
     d = ConvDesc()
     d.x, d.N, d.Hi, d.Wi, d.Ci = x.data_ptr(), N, Hi, Wi, Ci
     d.w, d.Co, d.Ktot = w_packed.data_ptr(), Co, Ktot
@@ -122,6 +147,12 @@ def conv_launch(x, w_packed, taps, *, stride=1, grid_hw=None, out=None, out_hw=N
             d.phase_tap0[i], d.phase_oy0[i], d.phase_ox0[i] = t0, oy0, ox0
             t0 += len(ptaps)
         d.phase_tap0[len(phases)] = t0
+    if lo is not None:
+        x_lo, w_lo = lo
+        assert x_lo.shape == x.shape and x_lo.dtype == torch.float16 and x_lo.is_contiguous()
+        assert w_lo.shape == w_packed.shape and w_lo.dtype == torch.float16 and w_lo.is_contiguous() and stats is None
+        _lib.check(_lib.lib().mg_conv_fprop_x3(ctypes.byref(d), _ptr(x_lo), _ptr(w_lo), _stream()), "mg_conv_fprop_x3")
+        return out
     if SPLITK and phases is None:
         ws = _splitk_workspace(x.device)
         d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
@@ -668,6 +699,8 @@ def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="rel
     banked = _banked(w)
     _need_cuda(x, None if banked else w)
     geom = ConvGeom("convT", 4, 2, 1, 1) if transposed else ConvGeom("conv", wshape(w)[-1], stride, padding, dilation)
+    if x.dtype == torch.float32 and not training:
+        return _conv_bn_act_x3(x, w, bn, geom, act, act_first, residual, res_up)
     if x.dtype != torch.float16 or not x.permute(0, 2, 3, 1).is_contiguous():
         x = x.to(torch.float16).contiguous(memory_format=torch.channels_last)
     if residual is not None and (residual.dtype != torch.float16 or not residual.permute(0, 2, 3, 1).is_contiguous()):
@@ -694,6 +727,57 @@ def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="rel
         y = conv2d_nhwc(xn, w if banked else w.detach(), stride=stride, padding=padding, dilation=dilation, scale=scale, shift=shift, res=rn,
                         res_up=res_up, pre_act=act if act_first else None, post_act=None if act_first else act)
     return y.permute(0, 3, 1, 2)
+
+
+def _conv_bn_act_x3(x, w, bn, geom, act, act_first, residual, res_up):
+    """Eval-mode conv (+ folded BatchNorm, residual, activation) at fp32-level accuracy: fp32 activations in and out,
+    split-fp16 operands on the tensor cores (`precision="high"`, see MaGGIe.set_precision).  `w`: fp32 weight tensor."""
+    if _banked(w):
+        raise RuntimeError("the fp32-accurate evaluation mode takes fp32 weight tensors, not fp16 bank packs")
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+        raise RuntimeError("the fp32-accurate evaluation mode has no backward: run it under torch.no_grad()")
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    ci_pad = xn.shape[-1]
+    assert ci_pad % 16 == 0
+    x_hi, x_lo = split_f32(xn)
+    wd = w.detach()
+    scale = shift = None
+    if bn is not None:
+        scale, shift, _, _ = bn_finalize(None, 1, bn, False)
+    rn = residual.float().permute(0, 2, 3, 1).contiguous() if residual is not None else None
+    pre, post = (act, None) if act_first else (None, act)
+    if geom.kind == "convT":
+        N, Hi, Wi, _ = xn.shape
+        Co = wd.shape[1]
+        w_hi, w_lo = split_f32(pack_weight_f32(wd.permute(1, 0, 2, 3), ci_pad))
+        y = torch.empty((N, 2 * Hi, 2 * Wi, Co), dtype=torch.float32, device=x.device)
+        conv_launch(x_hi, w_hi, None, grid_hw=(Hi, Wi), out=y, out_map=(2, 0, 2, 0), scale=scale, shift=shift, pre_act=pre,
+                    post_act=post, phases=convT_phases(ci_pad), lo=(x_lo, w_lo))
+    else:
+        Co, _, kh, kw = wd.shape
+        w_hi, w_lo = split_f32(pack_weight_f32(wd, ci_pad))
+        Hi, Wi = xn.shape[1:3]
+        Ho, Wo = geom.out_hw(Hi, Wi)
+        y = conv_launch(x_hi, w_hi, conv_taps(kh, kw, geom.pad, geom.dil, ci_pad), stride=geom.stride, grid_hw=(Ho, Wo),
+                        scale=scale, shift=shift, res=rn, res_up=res_up, pre_act=pre, post_act=post, lo=(x_lo, w_lo))
+    return y.permute(0, 3, 1, 2)
+
+
+def linear_rows_x3(x, w, b=None):
+    """y = x W^T + b on fp32 rows [..., Cin] at fp32-level accuracy: the rows are viewed as an NHWC image and run through
+    the 1x1 case of the split-operand tensor-core conv."""
+    rows, cin = x.numel() // x.shape[-1], x.shape[-1]
+    co = w.shape[0]
+    assert cin % 16 == 0 and co % 16 == 0
+    d = 16
+    while rows % d:
+        d //= 2
+    xn = x.detach().float().reshape(1, rows // d, d, cin).contiguous()
+    x_hi, x_lo = split_f32(xn)
+    w_hi, w_lo = split_f32(w.detach().float().reshape(co, cin).contiguous())
+    bias = b.detach().float().contiguous() if b is not None else None
+    y = conv_launch(x_hi, w_hi, [(0, 0, 0)], bias=bias, lo=(x_lo, w_lo))
+    return y.reshape(*x.shape[:-1], co)
 
 
 class _ConvBias(torch.autograd.Function):

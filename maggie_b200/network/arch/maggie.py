@@ -41,6 +41,9 @@ class _DenseStage(nn.Module):
 
     def forward(self, image, masks, slot_ids, mask_os8, gt_os8, mem_feat=None):
         with ops.step_scope("dense_stage", image.device):
+            if getattr(self.encoder, "precision", "fp16") == "high" and not self.training:
+                # fp32-accurate evaluation: fp32 weights straight from the containers (per-layer spectral norm), no fp16 packs
+                return self._forward(image, masks, slot_ids, mask_os8, gt_os8, mem_feat)
             ops.prepare_weights(self.bank)  # K0: spectral norm + operand packs of every dense conv in one grouped op
             try:
                 return self._forward(image, masks, slot_ids, mask_os8, gt_os8, mem_feat)
@@ -108,6 +111,20 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
                 unsort = [order.index(j) for j in range(n_i)]
             slot_ids, n_slots = chosen, self.num_masks
         return x, masks, slot_ids, alphas, trans, chosen, n_slots, unsort, (b, n_f, n_i, h, w)
+
+    def set_precision(self, precision="fp16"):
+        """'fp16' (default): fp16 activations, fp32 accumulation - the width of the reference's autocast TRAINING
+        (engine/train.py:227).  'high': the dense stage (encoder, ASPP, dense decoder, mask-guided attention, OS8 head) of
+        an EVALUATION forward keeps fp32 activations and runs its contractions on the tensor cores with split-fp16
+        operands (x = hi + lo; three MMAs per product), i.e. at fp32-level accuracy like the reference's fp32 evaluation
+        (engine/test.py:131 has no autocast); alpha_os8 then matches the reference to ~1e-5.  The sparse refinement stage
+        stays fp16.  Image model only; training is unaffected."""
+        if precision not in ("fp16", "high"):
+            raise ValueError(f"precision must be 'fp16' or 'high' (got {precision!r})")
+        if precision == "high" and type(self) is not MaGGIe:
+            raise NotImplementedError("precision='high' is implemented for the image model")
+        self.precision = self.encoder.precision = precision
+        return self
 
     def enable_cuda_graphs(self, on=True):
         """Replay the dense stage (encoder, ASPP, dense decoder blocks, attention; forward AND backward) as CUDA graphs.
@@ -193,6 +210,10 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         it = batch.get("iter", 0)
         fea1, fea2, fea3, *dense_out = self._dense(x, masks, slot_ids, mask_os8, gt_os8,
                                                    mem_feat if torch.is_tensor(mem_feat) else None)
+        if dense_out[1].dtype == torch.float32 and dense_out[1].is_cuda:
+            # precision='high': the OS8 logits / tokens stay fp32; the sparse refinement stage below takes fp16 features
+            h16 = lambda t: t.to(torch.float16).contiguous(memory_format=torch.channels_last)
+            fea1, fea2, fea3, dense_out[1] = h16(fea1), h16(fea2), h16(fea3), h16(dense_out[1])
         with ops.step_scope("sparse_stage", x.device):
             pred = self.decoder(tuple(dense_out), (fea1, fea2, fea3), (h, w), b=b, n_f=n_f, n_i=n_i, masks=masks,
                                 iter=it, gt_alphas=alphas, spar_gt=trans, slots=chosen, n_slots=n_slots,

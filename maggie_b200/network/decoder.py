@@ -129,7 +129,7 @@ class InstanceMatteDecoder(nn.Module):
         temporal_fn (video): [b, n_f, C, h, w] -> (propagated features, hidden states); the smoothing convs then run
         on the un-propagated features (-> out_feat) and on the propagated ones (-> logits), as the reference does.
         Returns logits [b*n_f, 10, h, w] fp32, out_feat [b*n_f, 64, h, w], tokens [b, 10, 64] fp32, loss (, hidden)."""
-        if feat.is_cuda and packs.active() is not self._packs:
+        if feat.is_cuda and feat.dtype == torch.float16 and packs.active() is not self._packs:
             # operand packs of every projection that runs on the pixel rows: one grouped preparation per forward
             ws = [self.feat_proj.layers[0].weight]
             for layer in (*self.token_feat_ca_layers, *self.feat_token_ca_layers, self.final_token_feat_ca):
@@ -215,6 +215,9 @@ class MaGGIeDecoder(nn.Module):
                  warmup_mask_atten_iter=0, warmup_detail_iter=3000, detail_mask_dropout=0.2, **_):
         super().__init__()
         assert atten_head == 1, "the reference configs use one attention head"
+        if warmup_mask_atten_iter > 0:
+            # the reference's mask-attention warm-up (`use_mask_atten`) is off in both live configs and not built here
+            raise NotImplementedError("maggie_b200 implements warmup_mask_atten_iter = 0 (both live reference configs)")
         fc = final_channel
         self.max_inst = max_inst
         self.warmup_mask_atten_iter, self.warmup_detail_iter = warmup_mask_atten_iter, warmup_detail_iter

@@ -67,6 +67,9 @@ class ResMaskEmbedShortCutEncoder(nn.Module):
 
     def __init__(self, num_mask=10, num_embed=3, **_):
         super().__init__()
+        if num_mask != 10 or num_embed != 3:
+            # K1 (mask-id embedding kernel) is built for the [11, 3] table of both live reference configs
+            raise NotImplementedError(f"maggie_b200 supports num_mask=10, num_embed=3 (got {num_mask}, {num_embed})")
         self.num_embed = num_embed
         cin = 3 + num_embed
         self.conv1 = SNConv(cin, 32, 3)
@@ -98,7 +101,9 @@ class ResMaskEmbedShortCutEncoder(nn.Module):
         latency-bound trunk layers leave idle.  Autograd replays each op's backward on its forward stream, so the same
         overlap happens in the backward pass; fork and join are plain event waits (CUDA-graph capturable)."""
         t = self.training
-        x = ops.mask_embed(image, masks, self.mask_embed_layer.weight, slot_ids, self.IN_PAD)
+        hp = getattr(self, "precision", "fp16") == "high" and not t    # fp32-accurate evaluation (MaGGIe.set_precision)
+        x = ops.mask_embed(image, masks, self.mask_embed_layer.weight, slot_ids, self.IN_PAD,
+                           dtype=torch.float32 if hp else torch.float16)
         side = None
         # (with exchanged BatchNorm statistics all exchanges must stay in ONE stream order on every rank)
         if x.is_cuda and SIDE_SHORTCUTS and dense.sync_group(self.bn1) is None:

@@ -159,6 +159,19 @@ def build_sites(roi):
 
 
 # =============================================================================================== native: K1
+def _mask_embed_f32(image, masks, table, slot_ids, C):
+    """K1 with an fp32 NHWC output (fp32-accurate evaluation mode, no backward)."""
+    _need_cuda(image, masks, table, slot_ids)
+    image = image.detach().to(torch.float32).contiguous()
+    masks = masks.detach().to(torch.float32).contiguous()
+    B, _, H, W = image.shape
+    out = torch.empty((B, H, W, C), dtype=torch.float32, device=image.device)
+    tab = table.detach().to(torch.float32).contiguous()
+    _lib.check(_lib.lib().mg_mask_embed_fwd_f32(_ptr(image), _ptr(masks), _ptr(slot_ids), masks.shape[1], _ptr(tab), _ptr(out),
+                                               B, H, W, C, _stream()), "mg_mask_embed_fwd_f32")
+    return out
+
+
 class _MaskEmbed(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, masks, table, slot_ids, C):
@@ -194,11 +207,19 @@ def slot_ids_tensor(slot_ids, device):
     return _widths_tensor(tuple(int(s) for s in slot_ids), device)
 
 
-def mask_embed(image, masks, table, slot_ids, C=8):
+def mask_embed(image, masks, table, slot_ids, C=8, dtype=torch.float16):
     """image [B,3,H,W] fp32, masks [B,M,H,W] {0,1}, table [11,3], slot_ids (list or device int32 tensor [M]) ->
     packed encoder input, NCHW-shaped channels-last fp16 [B,C,H,W] (ch 0-2 image, 3-5 mean id embedding, rest 0).
+    dtype torch.float32: the fp32-accurate evaluation mode (no backward).
     Reference: arch/maggie.py:200-235 + encoder/resnet.py:211-229."""
-    return _MaskEmbed.apply(image, masks, table, slot_ids_tensor(slot_ids, image.device), C).permute(0, 3, 1, 2)
+    if tuple(table.shape) != (11, 3) or masks.shape[1] > 16:
+        # K1 keeps the 11 x 3 id table of the reference configs (num_mask = 10, num_embed = 3) in shared memory
+        raise NotImplementedError(f"mask_embed: id table must be [11, 3] and at most 16 masks per frame "
+                                  f"(got table {tuple(table.shape)}, {masks.shape[1]} masks)")
+    ids = slot_ids_tensor(slot_ids, image.device)
+    if dtype == torch.float32:
+        return _mask_embed_f32(image, masks, table, ids, C).permute(0, 3, 1, 2)
+    return _MaskEmbed.apply(image, masks, table, ids, C).permute(0, 3, 1, 2)
 
 
 # =============================================================================================== native: K12
@@ -327,6 +348,9 @@ def linear_rows(x, w, b=None):
     rows = x.numel() // x.shape[-1]
     if rows < 1024 or not x.is_cuda:
         return linear(x, w, b)
+    if x.dtype == torch.float32:      # fp32-accurate evaluation mode: split-operand tensor-core GEMM
+        from . import dense
+        return dense.linear_rows_x3(x, w, b)
     y = rows_conv(x.reshape(rows, x.shape[-1]), w, b)
     return y.reshape(*x.shape[:-1], w.shape[0]).to(x.dtype)
 
@@ -371,6 +395,17 @@ def layer_norm(x, ln, residual=None):
         if residual is not None and residual.shape != x.shape:
             residual = residual.expand_as(x)
         return _LayerNormRes.apply(x, residual, ln.weight, ln.bias, ln.eps)
+    if (x.is_cuda and x.dtype == torch.float32 and x.shape[-1] in (64, 128) and x.numel() // x.shape[-1] >= 1024
+            and not torch.is_grad_enabled()):
+        # fp32-accurate evaluation mode, pixel rows (the 10-token side stays a tiny torch op)
+        a = x.contiguous()
+        r = residual.to(torch.float32).expand_as(x).contiguous() if residual is not None else None
+        y = torch.empty_like(a)
+        E = x.shape[-1]
+        _lib.check(_lib.lib().mg_layer_norm_fwd_f32(_ptr(a), _ptr(r), _ptr(ln.weight.detach().float().contiguous()),
+                                                   _ptr(ln.bias.detach().float().contiguous()), float(ln.eps), _ptr(y),
+                                                   a.numel() // E, E, _stream()), "mg_layer_norm_fwd_f32")
+        return y
     if residual is not None:
         x = x + residual
     return F.layer_norm(x.float(), (x.shape[-1],), ln.weight, ln.bias, ln.eps).to(x.dtype)
@@ -412,6 +447,14 @@ def token_logits(tok, x, n_f):
     tok [b, q, 64] fp32; x [b*n_f, 64, h, w].  NATIVE (K13) on CUDA channels-last fp16 features; torch otherwise."""
     if x.is_cuda and x.dtype == torch.float16 and x.shape[1] == 64 and tok.shape[1] <= 16 and x.permute(0, 2, 3, 1).is_contiguous():
         return _TokenLogits.apply(tok, x, n_f)
+    if (x.is_cuda and x.dtype == torch.float32 and x.shape[1] == 64 and tok.shape[1] <= 16 and not torch.is_grad_enabled()):
+        xn = x.permute(0, 2, 3, 1).contiguous()      # fp32-accurate evaluation mode
+        BT, H, W, C = xn.shape
+        tk = tok.detach().to(torch.float32).contiguous()
+        out = torch.empty((BT, tk.shape[1], H, W), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().mg_token_logits_fwd_f32(_ptr(tk), _ptr(xn), _ptr(out), BT, n_f, tk.shape[1], H * W, C, _stream()),
+                   "mg_token_logits_fwd_f32")
+        return out
     b = tok.shape[0]
     return torch.einsum("bqc,btchw->btqhw", tok, x.float().reshape(b, n_f, *x.shape[1:])).flatten(0, 1)
 
@@ -530,11 +573,39 @@ def attention(q, k, v, key_padding=None, need_stat=None):
     key_padding [B,S] bool (True = ignore).  need_stat: optional [B,L,S] bool guidance mask; if given also returns
     stat[b,l] = sum_s guidance * A (the only thing the attention-max loss needs, instance_matte_decoder.py:101-109).
     NATIVE (K6): few-query ("tq") kernel when L <= 16, many-query ("fq") kernel when S <= 16."""
+    hp = not torch.is_grad_enabled() and (k.dtype == torch.float32 if q.shape[1] <= 16 else q.dtype == torch.float32)
+    if hp:
+        return _attention_f32(q, k, v, key_padding, need_stat)
     if q.shape[1] <= 16:
         o, stat = _AttnTQ.apply(q, k, v, key_padding, need_stat)
         return o, (stat if need_stat is not None else None)
     assert k.shape[1] <= 16 and need_stat is None, "attention: one side must have <= 16 rows"
     return _AttnFQ.apply(q, k, v, key_padding), None
+
+
+def _attention_f32(q, k, v, key_padding=None, need_stat=None):
+    """The attention cores with every operand in fp32 (fp32-accurate evaluation mode, forward only)."""
+    _need_cuda(q, k, v)
+    f = lambda t: t.detach().to(torch.float32).contiguous()
+    u8 = lambda t: t.to(torch.uint8).contiguous() if t is not None else None
+    qf, kf, vf, kp = f(q), f(k), f(v), u8(key_padding)
+    L, dev = _lib.lib(), q.device
+    if q.shape[1] <= 16:
+        B, Fq, E = qf.shape
+        S = kf.shape[1]
+        gd = u8(need_stat)
+        out = torch.empty((B, Fq, E), dtype=torch.float32, device=dev)
+        small = torch.empty((3, B, Fq), dtype=torch.float32, device=dev)
+        ws = torch.empty(L.mg_attn_tq_workspace_floats(B, Fq, S), dtype=torch.float32, device=dev)
+        _lib.check(L.mg_attn_tq_fwd_f32(_ptr(qf), _ptr(kf), _ptr(vf), _ptr(kp), _ptr(gd), B, Fq, S, E, _ptr(out), _ptr(small[0]),
+                                        _ptr(small[1]), _ptr(small[2]), _ptr(ws), _stream()), "mg_attn_tq_fwd_f32")
+        return out, (small[0] if need_stat is not None else None)
+    assert k.shape[1] <= 16 and need_stat is None, "attention: one side must have <= 16 rows"
+    B, S, E = qf.shape
+    out = torch.empty((B, S, E), dtype=torch.float32, device=dev)
+    _lib.check(L.mg_attn_fq_fwd_f32(_ptr(qf), _ptr(kf), _ptr(vf), _ptr(kp), B, kf.shape[1], S, E, _ptr(out), _stream()),
+               "mg_attn_fq_fwd_f32")
+    return out, None
 
 
 def rows_conv(src, w, bias=None, *, table=None, table_t=None, mirror=False, bn=None, mode="plain", act=None,

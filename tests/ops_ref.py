@@ -71,7 +71,7 @@ def build_sites(roi):
                           [tt(a) for a in parent], [tt(a) for a in child], shapes)
 
 
-def mask_embed(image, masks, table, slot_ids, C=8):
+def mask_embed(image, masks, table, slot_ids, C=8, dtype=None):
     """Differentiable torch restatement of K1 (encoder/resnet.py:211-229); NCHW-shaped [B,C,H,W]."""
     B, _, H, W = image.shape
     slot_ids = slot_ids.tolist() if torch.is_tensor(slot_ids) else slot_ids
@@ -80,7 +80,7 @@ def mask_embed(image, masks, table, slot_ids, C=8):
     on = (m > 0).float().unsqueeze(-1)
     emb = (table[m] * on).sum(1) / (on.sum(1) + 1e-6)
     out = torch.cat([image, emb.permute(0, 3, 1, 2), image.new_zeros(B, C - 6, H, W)], 1)
-    return out.to(ops.COMPUTE_DTYPE).contiguous(memory_format=torch.channels_last)
+    return out.to(ops.COMPUTE_DTYPE if dtype in (None, torch.float16) else dtype).contiguous(memory_format=torch.channels_last)
 
 
 def conv_bn_act(x, w, bn, training, *, stride=1, padding=1, dilation=1, act="relu", act_first=False,

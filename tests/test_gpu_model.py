@@ -20,7 +20,9 @@ from oracle import make_golden as G
 from oracle import synth
 
 pytestmark = pytest.mark.gpu
-ALPHA_TOL = 1e-3
+ALPHA_TOL = 1e-3   # north star; met by precision="high" (asserted below and in tests/test_gpu_highprec.py)
+# measured max-abs alpha_os8 error of the fp16 mode on the eval goldens (B200, bit-reproducible): asserted at 1.25x
+FP16_FLOOR = {"eval_c1_256_1inst": 7.78e-3, "eval_192x256_3inst": 8.21e-3, "eval_128_3inst_maskos8": 1.152e-2}
 
 
 def _model(training):
@@ -44,7 +46,12 @@ def test_eval_alpha_parity(case, golden):
     out = {k: v.float().cpu().numpy() for k, v in out.items()}
     assert _lib.launch_count() > 0, "native library was not used"
     d8 = np.abs(out["alpha_os8"] - z["out/alpha_os8"])
-    assert d8.max() < 2.5e-2 and d8.mean() < 1e-3, f"alpha_os8 max abs diff {d8.max()}, mean {d8.mean()}"
+    assert d8.max() <= 1.25 * FP16_FLOOR[case] and d8.mean() < 6e-4, f"alpha_os8 max abs diff {d8.max()}, mean {d8.mean()}"
+    # the stated tolerance holds in the fp32-accurate evaluation mode (same weights, same batch)
+    G.seed_all()
+    with torch.no_grad():
+        hi = m.set_precision("high")(_to_dev(synth.make_batch(**kw)), mem_feat=None)
+    assert np.abs(hi["alpha_os8"].float().cpu().numpy() - z["out/alpha_os8"]).max() <= ALPHA_TOL
     same = out["detail_mask"] == z["out/detail_mask"]
     assert same.mean() > 0.995, f"detail masks agree on {same.mean()}"
     for k in ("alpha_os4", "alpha_os1", "refined_masks"):

@@ -131,12 +131,23 @@ def _model_case(rank, world, dev):
         assert int(bn.num_batches_tracked) >= 1      # (graph capture adds its warm-up passes)
 
 
-def _worker(rank, world, port, peer):
+def _worker(rank, world, port, peer, late_s=0.0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), MAGGIE_B200_NO_PEER_EXCHANGE="0" if peer else "1")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.cuda.set_device(0)
         dev = torch.device("cuda:0")
+        if late_s:
+            # rank 1 reaches its first exchange `late_s` seconds after rank 0 (the reference engine validates on rank 0
+            # alone between steps, engine/train.py:294 with `val_dist: false`): the exchange must wait like a collective
+            from maggie_b200 import dense
+            dense.peer_window(dist.group.WORLD, dev)        # windows are set up together (a collective step)
+            if rank == 1:
+                import time
+                time.sleep(late_s)
+            _dense_case(rank, world, dev)
+            torch.cuda.synchronize()
+            return
         _dense_case(rank, world, dev)
         _rows_case(rank, world, dev)
         from maggie_b200 import dense
@@ -149,12 +160,12 @@ def _worker(rank, world, port, peer):
         dist.destroy_process_group()
 
 
-def _spawn(peer):
+def _spawn(peer, late_s=0.0):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, peer), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, peer, late_s), nprocs=2, join=True)
 
 
 def test_peer_memory_exchange_matches_full_batch():
@@ -163,3 +174,9 @@ def test_peer_memory_exchange_matches_full_batch():
 
 def test_collective_fallback_matches_full_batch():
     _spawn(False)
+
+
+def test_peer_memory_exchange_waits_for_a_late_rank():
+    """One rank shows up 22 s late (longer than the 20 s limit the first version of K15 trapped at): the in-kernel wait
+    behaves like the NCCL collective it replaces (watchdog: MAGGIE_B200_XCHG_TIMEOUT_S, default 600 s)."""
+    _spawn(True, late_s=22.0)
