@@ -171,11 +171,11 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------ GPU arm
 # (H=W of the input feature map, Cin, Cout, k, stride, dilation, transposed, count) of every dense conv of one C2 forward
 C2_CONVS = [
-    (512, 16, 32, 3, 2, 1, False, 1), (256, 32, 32, 3, 1, 1, False, 3), (256, 32, 64, 3, 2, 1, False, 1),
+    (512, 32, 32, 3, 2, 1, False, 1), (256, 32, 32, 3, 1, 1, False, 3), (256, 32, 64, 3, 2, 1, False, 1),
     (128, 64, 64, 3, 1, 1, False, 8), (128, 64, 128, 3, 2, 1, False, 1), (128, 64, 128, 2, 2, 1, False, 1),
     (64, 128, 128, 3, 1, 1, False, 14), (64, 128, 256, 3, 2, 1, False, 1), (64, 128, 256, 2, 2, 1, False, 1),
     (32, 256, 256, 3, 1, 1, False, 11), (32, 256, 512, 3, 2, 1, False, 1), (32, 256, 512, 2, 2, 1, False, 1),
-    (16, 512, 512, 3, 1, 1, False, 3), (512, 16, 32, 3, 1, 1, False, 1), (512, 32, 32, 3, 1, 1, False, 1),
+    (16, 512, 512, 3, 1, 1, False, 3), (512, 32, 32, 3, 1, 1, False, 1), (512, 32, 32, 3, 1, 1, False, 1),
     (16, 512, 256, 1, 1, 1, False, 1), (16, 512, 256, 3, 1, 2, False, 1), (16, 512, 256, 3, 1, 4, False, 1),
     (16, 512, 256, 3, 1, 8, False, 1), (1, 512, 256, 1, 1, 1, False, 1), (16, 1280, 512, 1, 1, 1, False, 1),
     (16, 512, 512, 4, 2, 1, True, 1), (32, 512, 256, 3, 1, 1, False, 1), (16, 512, 256, 1, 1, 1, False, 1),

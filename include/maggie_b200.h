@@ -141,10 +141,6 @@ typedef struct mg_conv_desc {
      * sub-pixel phases of a stride-2 data gradient or of the 4x4 stride-2 transposed conv.  Phase p uses the taps
      * [phase_tap0[p], phase_tap0[p+1]) of the table and the offsets phase_oy0[p], phase_ox0[p]; 0 or 1: plain launch. */
     int32_t n_phases, phase_tap0[5], phase_oy0[4], phase_ox0[4];
-    /* EXPERIMENTAL (NULL = off, the default): zero-initialised device workspace of splitk_ws_bytes bytes that lets layers
-     * with few CTAs split the K range of every tile over several CTAs (csrc/k2s_conv_splitk.cu).  The kernel leaves the
-     * workspace zeroed; launches that may run concurrently (different streams) need different workspaces. */
-    void* splitk_ws; int64_t splitk_ws_bytes;
 } mg_conv_desc;
 int mg_conv_fprop(const mg_conv_desc* desc, void* stream);
 /* Evaluation at fp32-level accuracy ("x3" mode; the reference evaluates in fp32: engine/test.py:131 runs without autocast).
@@ -160,6 +156,11 @@ int mg_split_f32(const float* x, void* hi_f16, void* lo_f16, size_t n, void* str
  * the weights resident in shared memory (csrc/k2b_conv_halo.cu; MAGGIE_B200_NO_HALO_CONV=1 disables the routing).
  * mg_conv_halo_launches: how many launches took that path (tests / profiling). */
 unsigned long long mg_conv_halo_launches(void);
+/* Stride-1 layers with taps within +-1 pixel, Ci a multiple of 64 (>= 128), Co a multiple of 64 and width <= 64 (the 3x3
+ * convolutions of the trunk at 64^2 / 32^2 / 16^2, of the dense decoder, and their data gradients) are routed to K2h, a
+ * persistent kernel that keeps a halo patch of a whole row slab in shared memory, streams the weights through a ring and
+ * accumulates up to five 128-pixel blocks per weight block (csrc/k2h_conv_mid.cu; MAGGIE_B200_NO_MID_CONV=1 disables it). */
+unsigned long long mg_conv_mid_launches(void);
 
 /* ---- K4: convolution weight gradient (tcgen05, split-K over pixels) ---------------------------------
  * replaces: cuDNN's wgrad behind `loss.backward()` for every conv above (engine/train.py:266).

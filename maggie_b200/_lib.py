@@ -34,6 +34,7 @@ SIGNATURES = {
     "mg_attn_fq_fwd_f32": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 2),
     "mg_conv_wgrad": (c_int, [c_void_p, c_void_p]),
     "mg_conv_halo_launches": (c_ulonglong, []),
+    "mg_conv_mid_launches": (c_ulonglong, []),
     "mg_wgrad_halo_launches": (c_ulonglong, []),
     "mg_attn_tq_workspace_floats": (c_size_t, [c_int, c_int, c_int]),
     "mg_attn_tq_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p] * 6),

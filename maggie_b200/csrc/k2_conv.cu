@@ -114,37 +114,44 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
+            int s = 0, ph = 0, term = 0, tap = tap_first, c = 0;   // counters: no run-time divisions on the issue path
+            const int tap_last = a.phase_tap0[blockIdx.z + 1];
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % a.stages, ph = (kb / a.stages) & 1;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 mbar_expect_tx(full0 + 8 * s, a_bytes + b_bytes);
-                const int term = HP ? kb / nkb1 : 0, k1 = kb - term * nkb1;
-                const int tap = tap_first + k1 / a.kchunks, c = k1 - (k1 / a.kchunks) * a.kchunks;
                 tma_load_4d(smem_u32(sA + s * a_bytes), (HP && term == 1) ? &tmA_lo : &tmA, full0 + 8 * s, c * a.BK,
                             x0 * a.sx + a.tap_dx[tap], y0 * a.sy + a.tap_dy[tap], img);
                 tma_load_2d(smem_u32(sB + s * b_bytes), (HP && term == 2) ? &tmB_lo : &tmB, full0 + 8 * s,
                             a.tap_koff[tap] + c * a.BK, n0);
+                if (++s == a.stages) s = 0, ph ^= 1;
+                if (++c == a.kchunks) {
+                    c = 0;
+                    if (++tap == tap_last) tap = tap_first, ++term;
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = instr_desc_f16(BM, a.BN, 0, 0);
-            const uint32_t layout = swizzle_layout(a.swizzle), sbo = 8 * a.swizzle;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % a.stages, ph = (kb / a.stages) & 1;
-                mbar_wait(full0 + 8 * s, ph);
-                tc_fence_after();
-                const uint32_t abase = smem_u32(sA + s * a_bytes), bbase = smem_u32(sB + s * b_bytes);
-                for (int k = 0; k < a.BK / 16; ++k) {
-                    const uint64_t da = smem_desc(abase + k * 32, 0, sbo, layout);
-                    const uint64_t db = smem_desc(bbase + k * 32, 0, sbo, layout);
-                    mma_f16(tmem_base, da, db, idesc, (kb | k) != 0);
-                }
+        // ===== MMA issuer: the whole warp runs the loop (all operands provably warp-uniform -> uniform registers, no
+        // elect / R2UR waterfall around every tcgen05.mma), one elected lane issues =====
+        const uint32_t tmem_u = uniform_u32(tmem_base);
+        const uint32_t idesc = instr_desc_f16(BM, a.BN, 0, 0);
+        const uint32_t layout = swizzle_layout(a.swizzle), sbo = 8 * a.swizzle;
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        const int ksteps = a.BK / 16;
+        int s = 0, ph = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(full0 + 8 * s, ph);
+            tc_fence_after();
+            const uint64_t da = smem_desc(sA_u + s * a_bytes, 0, sbo, layout);
+            const uint64_t db = smem_desc(sB_u + s * b_bytes, 0, sbo, layout);
+            if (elect_one()) {
+                mma_f16(tmem_u, da, db, idesc, kb != 0);
+                for (int k = 1; k < ksteps; ++k) mma_f16(tmem_u, da + 2 * k, db + 2 * k, idesc, 1u);
                 mma_commit(empty0 + 8 * s);  // frees the smem slot when these MMAs retire
             }
-            mma_commit(tfull);               // accumulator complete
+            if (++s == a.stages) s = 0, ph ^= 1;
         }
+        if (elect_one()) mma_commit(tfull);  // accumulator complete
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
@@ -263,7 +270,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 namespace mg {
 int conv_halo_launch(const mg_conv_desc* d, void* stream, bool* handled);     // k2b_conv_halo.cu
-int conv_splitk_launch(const mg_conv_desc* d, void* stream, bool* handled);   // k2s_conv_splitk.cu (opt-in)
+int conv_mid_launch(const mg_conv_desc* d, void* stream, bool* handled);      // k2h_conv_mid.cu
 }
 
 static int conv_launch_impl(const mg_conv_desc* d, const void* x_lo, const void* w_lo, void* stream) {
@@ -286,10 +293,10 @@ static int conv_launch_impl(const mg_conv_desc* d, const void* x_lo, const void*
         const int rc = mg::conv_halo_launch(d, stream, &handled);
         if (rc != MG_OK || handled) return rc;
     }
-    if (d->splitk_ws && !hp) {
-        // opt-in: layers with few CTAs split the K range of a tile over several CTAs (K2s)
+    if (!hp) {
+        // mid-resolution stride-1 3x3 layers with >= 128 input channels: halo-patch / weight-streaming kernel (K2h)
         bool handled = false;
-        const int rc = mg::conv_splitk_launch(d, stream, &handled);
+        const int rc = mg::conv_mid_launch(d, stream, &handled);
         if (rc != MG_OK || handled) return rc;
     }
     KArgs a;

@@ -119,42 +119,43 @@ conv_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = instr_desc_f16(128, a.Co, 0, 0);
-            const uint32_t lay = swizzle_layout(a.row_bytes), sbo = 8 * a.row_bytes;   // A and B rows are both C*2 bytes
-            // per-tap constants: A start offset in 16-byte units (relative to the patch, may be -row), B descriptor
-            int a_off[9];
-            uint64_t b_desc[9];
-            const int ntap = (a.debug & 1) ? 1 : a.n_taps;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                a_off[t] = t < a.n_taps ? (((1 + a.tap_dy[t]) * a.P + a.tap_dx[t]) * a.row_bytes) >> 4 : 0;
-                b_desc[t] = smem_desc(smem_u32(sB + (t < a.n_taps ? t : 0) * a.b_tap_bytes), 0, sbo, lay);
-            }
-            const uint32_t mb_step = (128 * a.row_bytes) >> 4;
-            mbar_wait(b_full, 0);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1, ph = (it >> 1) & 1;   // halo buffer and accumulator set alternate together
-                mbar_wait(t_empty + 8 * buf, ph ^ 1);
-                mbar_wait(a_full + 8 * buf, ph);
-                tc_fence_after();
-                uint64_t a_desc = smem_desc(smem_u32(sA + buf * a_al), 0, sbo, lay);
-                uint32_t d_tmem = tmem_base + buf * a.set_cols;
+        // ===== MMA issuer: the whole warp runs the loop with warp-uniform operands (uniform registers; otherwise ptxas wraps
+        // EVERY tcgen05.mma in an elect / R2UR.BROADCAST waterfall of ~100 cycles - 2-3x the tensor time of these small
+        // MMAs, measured with tools/mma_bench.cu), one elected lane issues =====
+        const uint32_t tmem_u = uniform_u32(tmem_base);
+        const uint32_t idesc = instr_desc_f16(128, a.Co, 0, 0);
+        const uint32_t lay = swizzle_layout(a.row_bytes), sbo = 8 * a.row_bytes;   // A and B rows are both C*2 bytes
+        const int ntap = (a.debug & 1) ? 1 : a.n_taps;
+        const uint32_t mb_step = (128 * a.row_bytes) >> 4;
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        mbar_wait(b_full, 0);
+        int buf = 0, ph = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            mbar_wait(t_empty + 8 * buf, ph ^ 1);   // halo buffer and accumulator set alternate together
+            mbar_wait(a_full + 8 * buf, ph);
+            tc_fence_after();
+            if (elect_one()) {
+                uint64_t a_desc = smem_desc(sA_u + buf * a_al, 0, sbo, lay);
+                uint32_t d_tmem = tmem_u + buf * a.set_cols;
                 for (int mb = 0; mb < a.mblocks; ++mb, a_desc += mb_step, d_tmem += a.acc_cols) {
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         if (t < ntap) {
-                            const uint64_t da = a_desc + (int64_t)a_off[t];
+                            // per-tap constants straight from the kernel parameters (compile-time indices): A start offset
+                            // in 16-byte units relative to the patch (may be -1 pixel), B descriptor of the resident tap
+                            const int a_off = (((1 + a.tap_dy[t]) * a.P + a.tap_dx[t]) * a.row_bytes) >> 4;
+                            const uint64_t da = a_desc + (int64_t)a_off;
+                            const uint64_t db = smem_desc(sB_u + t * a.b_tap_bytes, 0, sbo, lay);
 #pragma unroll
-                            for (int k = 0; k < KS; ++k) mma_f16(d_tmem, da + 2 * k, b_desc[t] + 2 * k, idesc, (t | k) != 0);
+                            for (int k = 0; k < KS; ++k) mma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (t | k) != 0);
                         }
                     }
                 }
                 mma_commit(t_full + 8 * buf);    // the whole tile's accumulators are complete ...
                 mma_commit(a_empty + 8 * buf);   // ... and its halo patch can be overwritten
             }
+            if (buf) ph ^= 1;
+            buf ^= 1;
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====

@@ -100,30 +100,33 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
-                const uint32_t idesc = instr_desc_f16(128, a.BN, 1, 1);  // both operands MN-major
-                const uint32_t layB = swizzle_layout(a.swz_b);
-                const uint32_t zbase = smem_u32(sZ);
-                for (int i = 0; i < nk; ++i) {
-                    const int s = i % a.stages, ph = (i / a.stages) & 1;
-                    mbar_wait(full0 + 8 * s, ph);
-                    tc_fence_after();
-                    const uint32_t abase = smem_u32(sA + s * a_bytes);
-                    const uint32_t lbo_a = a.a_atoms == 2 ? (uint32_t)atom_bytes : zbase - abase;
+            // whole warp, warp-uniform operands, one elected lane issues (no elect / R2UR waterfall per tcgen05.mma)
+            const uint32_t tmem_u = uniform_u32(tmem_base);
+            const uint32_t idesc = instr_desc_f16(128, a.BN, 1, 1);  // both operands MN-major
+            const uint32_t layB = swizzle_layout(a.swz_b);
+            const uint32_t zbase = smem_u32(sZ), sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            int s = 0, ph = 0;
+            for (int i = 0; i < nk; ++i) {
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t abase = sA_u + s * a_bytes;
+                const uint32_t lbo_a = a.a_atoms == 2 ? (uint32_t)atom_bytes : zbase - abase;
+                if (elect_one()) {
                     // tap outer, k inner (measured: switching accumulator / B tile on every MMA is ~25 % slower)
                     for (int tt = 0; tt < nt; ++tt) {
-                        const uint32_t bbase = smem_u32(sB + s * b_bytes + tt * b_tile);
+                        const uint32_t bbase = sB_u + s * b_bytes + tt * b_tile;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {  // 128 pixels = 8 x UMMA_K(16)
                             const uint64_t da = smem_desc(abase + k * 16 * 128, lbo_a, 8 * 128, 2);
                             const uint64_t db = smem_desc(bbase + k * 16 * a.swz_b, b_atom_bytes, 8 * a.swz_b, layB);
-                            mma_f16(tmem_base + tt * a.BN, da, db, idesc, (i | k) != 0);
+                            mma_f16(tmem_u + tt * a.BN, da, db, idesc, (i | k) != 0);
                         }
                     }
                     mma_commit(empty0 + 8 * s);
                 }
-                mma_commit(tfull);
+                if (++s == a.stages) s = 0, ph ^= 1;
             }
+            if (elect_one()) mma_commit(tfull);
         } else {
             const int q = warp & 3;
             const int co = co0 + q * 32 + lane;

@@ -85,33 +85,36 @@ wgrad_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc96 = instr_desc_f16(128, 96, 1, 1), idesc32 = instr_desc_f16(128, 32, 1, 1);
-            const uint32_t zbase = smem_u32(sZ);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1, ph = (it >> 1) & 1;
-                mbar_wait(full + 8 * buf, ph);
-                tc_fence_after();
-                const uint32_t xbase = smem_u32(sX + buf * x_al), ybase = smem_u32(sY + buf * y_al);
+        // whole warp, warp-uniform operands, one elected lane issues (no elect / R2UR waterfall per tcgen05.mma)
+        const uint32_t tmem_u = uniform_u32(tmem_base);
+        const uint32_t idesc96 = instr_desc_f16(128, 96, 1, 1), idesc32 = instr_desc_f16(128, 32, 1, 1);
+        const uint32_t zbase = smem_u32(sZ), sX_u = smem_u32(sX), sY_u = smem_u32(sY);
+        int buf = 0, ph = 0;
+        bool first = true;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            mbar_wait(full + 8 * buf, ph);
+            tc_fence_after();
+            const uint32_t xbase = sX_u + buf * x_al, ybase = sY_u + buf * y_al;
+            if (elect_one()) {
                 for (int r = 0; r < a.R; ++r) {
                     const uint32_t arow = ybase + r * 128 * YROW;
                     const uint32_t lbo_a = zbase - arow;                 // atom 1 of M = 128: the shared zero region
+#pragma unroll
                     for (int dyi = 0; dyi < 3; ++dyi) {
                         const uint32_t brow = xbase + ((r + dyi) * P) * XROW;   // patch row r + 1 + dy, dx = -1 is pixel 0
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const uint64_t da = smem_desc(arow + k * 16 * YROW, lbo_a, 8 * YROW, 2);
-                            const uint32_t acc = (it | r | k) != 0;
+                            const uint32_t acc = (first && r == 0 && k == 0) ? 0u : 1u;
                             if (a.mode == 0) {
                                 // N = 96: atoms 0..2 = the patch shifted by 0 / 1 / 2 pixels (dx = -1, 0, +1)
                                 const uint64_t db = smem_desc(brow + k * 16 * XROW, XROW, 8 * XROW, 4);
-                                mma_f16(tmem_base + dyi * 96, da, db, idesc96, acc);
+                                mma_f16(tmem_u + dyi * 96, da, db, idesc96, acc);
                             } else {
 #pragma unroll
                                 for (int dxi = 0; dxi < 3; ++dxi) {
                                     const uint64_t db = smem_desc(brow + dxi * XROW + k * 16 * XROW, 128 * XROW, 8 * XROW, 4);
-                                    mma_f16(tmem_base + dyi * 96 + dxi * 32, da, db, idesc32, acc);
+                                    mma_f16(tmem_u + dyi * 96 + dxi * 32, da, db, idesc32, acc);
                                 }
                             }
                         }
@@ -119,8 +122,11 @@ wgrad_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
                 }
                 mma_commit(empty + 8 * buf);
             }
-            if (any) mma_commit(tfull);
+            first = false;
+            if (buf) ph ^= 1;
+            buf ^= 1;
         }
+        if (any && elect_one()) mma_commit(tfull);
     } else if (any) {
         // final epilogue: accumulator row = output channel (TMEM lane), 288 columns = (dy, dx, ci)
         const int q = warp & 3, co = q * 32 + lane;

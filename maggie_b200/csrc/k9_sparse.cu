@@ -291,21 +291,27 @@ sparse_conv_kernel(const SArgs a) {
                 }
             }
         }
-    } else if (lane == 0) {
-        // ===== MMA issuer =====
+    } else {
+        // ===== MMA issuer: whole warp, warp-uniform operands (uniform registers, no elect / R2UR waterfall per
+        // tcgen05.mma), one elected lane issues =====
+        const uint32_t tmem_u = uniform_u32(tmem_base);
         const uint32_t idesc = instr_desc_f16(128, a.Cout, 0, 0);
         const uint32_t layout = swizzle_layout(a.rowb), sbo = 8 * a.rowb;
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        const int ksteps = a.BK / 16;
+        int s = 0, ph = 0;
         for (int st = 0; st < steps; ++st) {
-            const int s = st % a.stages, ph = (st / a.stages) & 1;
             mbar_wait(full0 + 8 * s, ph);
             tc_fence_after();
-            const uint32_t abase = smem_u32(sA + (size_t)s * a_tile), bbase = smem_u32(sB + (size_t)st * b_tile);
-            for (int k = 0; k < a.BK / 16; ++k)
-                mma_f16(tmem_base, smem_desc(abase + k * 32, 0, sbo, layout), smem_desc(bbase + k * 32, 0, sbo, layout), idesc,
-                        (st | k) != 0);
-            mma_commit(empty0 + 8 * s);
+            const uint64_t da = smem_desc(sA_u + s * a_tile, 0, sbo, layout), db = smem_desc(sB_u + st * b_tile, 0, sbo, layout);
+            if (elect_one()) {
+                mma_f16(tmem_u, da, db, idesc, st != 0);
+                for (int k = 1; k < ksteps; ++k) mma_f16(tmem_u, da + 2 * k, db + 2 * k, idesc, 1u);
+                mma_commit(empty0 + 8 * s);
+            }
+            if (++s == a.stages) s = 0, ph ^= 1;
         }
-        mma_commit(tfull);
+        if (elect_one()) mma_commit(tfull);
     }
     tc_fence_before();
     __syncthreads();
@@ -454,26 +460,32 @@ sparse_wgrad_kernel(const SWArgs a) {
                                    __uint_as_float(r[i + 3]));
                 }
             }
-        } else if (lane == 0) {
+        } else {
+            // whole warp, warp-uniform operands, one elected lane issues
+            const uint32_t tmem_u = uniform_u32(tmem_base);
             const uint32_t idesc = instr_desc_f16(128, a.Cin, 1, 1);
             const uint32_t layA = swizzle_layout(a.rowb_a), layB = swizzle_layout(a.rowb_b);
+            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            int s = 0, ph = 0;
             for (int i = 0; i < nk; ++i) {
-                const int s = i % STAGES, ph = (i / STAGES) & 1;
                 mbar_wait(full0 + 8 * s, ph);
                 tc_fence_after();
-                const uint32_t abase = smem_u32(sA + (size_t)s * a_tile);
-                for (int tt = 0; tt < nt; ++tt) {
-                    const uint32_t bbase = smem_u32(sB + (size_t)(s * a.taps_per_cta + tt) * b_tile);
+                const uint32_t abase = sA_u + s * a_tile;
+                if (elect_one()) {
+                    for (int tt = 0; tt < nt; ++tt) {
+                        const uint32_t bbase = sB_u + (s * a.taps_per_cta + tt) * b_tile;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint64_t da = smem_desc(abase + k * 16 * a.rowb_a, a_atom, 8 * a.rowb_a, layA);
-                        const uint64_t db = smem_desc(bbase + k * 16 * a.rowb_b, b_atom, 8 * a.rowb_b, layB);
-                        mma_f16(tmem_base + tt * a.Cin, da, db, idesc, (i | k) != 0);
+                        for (int k = 0; k < 8; ++k) {
+                            const uint64_t da = smem_desc(abase + k * 16 * a.rowb_a, a_atom, 8 * a.rowb_a, layA);
+                            const uint64_t db = smem_desc(bbase + k * 16 * a.rowb_b, b_atom, 8 * a.rowb_b, layB);
+                            mma_f16(tmem_u + tt * a.Cin, da, db, idesc, (i | k) != 0);
+                        }
                     }
+                    mma_commit(empty0 + 8 * s);
                 }
-                mma_commit(empty0 + 8 * s);
+                if (++s == STAGES) s = 0, ph ^= 1;
             }
-            mma_commit(tfull);
+            if (elect_one()) mma_commit(tfull);
         }
     }
     tc_fence_before();

@@ -123,26 +123,29 @@ sparse_conv_persistent_kernel(const PArgs a) {
             mbar_arrive(a_full + 8 * buf);
         }
     } else if (warp == 4) {
-        if (lane == 0) {
-            // ===== MMA issuer: T taps x 2 K steps per tile, one commit per tile =====
-            const uint32_t idesc = instr_desc_f16(128, a.Cout, 0, 0);
-            const uint32_t lay = swizzle_layout(ROWB), sbo = 8 * ROWB;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1, ph = (it >> 1) & 1;
-                mbar_wait(t_empty + 8 * buf, ph ^ 1);
-                mbar_wait(a_full + 8 * buf, ph);
-                tc_fence_after();
-                const uint32_t abase = smem_u32(sA + (size_t)buf * a_buf), d_tmem = tmem_base + buf * a.acc_cols;
+        // ===== MMA issuer: T taps x 2 K steps per tile, one commit per tile.  Whole warp with warp-uniform operands (no
+        // elect / R2UR waterfall per tcgen05.mma), one elected lane issues =====
+        const uint32_t tmem_u = uniform_u32(tmem_base);
+        const uint32_t idesc = instr_desc_f16(128, a.Cout, 0, 0);
+        const uint32_t lay = swizzle_layout(ROWB), sbo = 8 * ROWB;
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        int buf = 0, ph = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            mbar_wait(t_empty + 8 * buf, ph ^ 1);
+            mbar_wait(a_full + 8 * buf, ph);
+            tc_fence_after();
+            const uint32_t abase = sA_u + buf * a_buf, d_tmem = tmem_u + buf * a.acc_cols;
+            if (elect_one()) {
                 for (int t = 0; t < a.T; ++t) {
-                    const uint32_t at = abase + t * a_tile, bt = smem_u32(sB + (size_t)t * a.b_tile);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        mma_f16(d_tmem, smem_desc(at + k * 32, 0, sbo, lay), smem_desc(bt + k * 32, 0, sbo, lay), idesc, (t | k) != 0);
+                    const uint64_t da = smem_desc(abase + t * a_tile, 0, sbo, lay), db = smem_desc(sB_u + t * a.b_tile, 0, sbo, lay);
+                    mma_f16(d_tmem, da, db, idesc, t != 0);
+                    mma_f16(d_tmem, da + 2, db + 2, idesc, 1u);
                 }
                 mma_commit(t_full + 8 * buf);
                 mma_commit(a_empty + 8 * buf);
             }
+            if (buf) ph ^= 1;
+            buf ^= 1;
         }
     } else {
         // ===== epilogue: warps 5..12; warpgroup g takes the tiles with (it & 1) == g =====
@@ -379,26 +382,34 @@ sparse_wgrad_persistent_kernel(const GArgs a) {
                 }
             }
         }
-    } else if (lane == 0) {
+    } else {
+        // whole warp, warp-uniform operands, one elected lane issues
+        const uint32_t tmem_u = uniform_u32(tmem_base);
         const uint32_t idesc = instr_desc_f16(128, 32, 1, 1);   // both operands MN-major
         const uint32_t lay = swizzle_layout(ROWB);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1, ph = (it >> 1) & 1;
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        int buf = 0, ph = 0;
+        bool first = true;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             mbar_wait(full + 8 * buf, ph);
             tc_fence_after();
-            const uint32_t abase = smem_u32(sA + (size_t)buf * a_buf), bbase = smem_u32(sB + (size_t)buf * b_buf);
-            for (int t = 0; t < a.T; ++t) {
+            const uint32_t abase = sA_u + buf * a_buf, bbase = sB_u + buf * b_buf;
+            if (elect_one()) {
+                for (int t = 0; t < a.T; ++t) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {   // 128 sites = 8 x UMMA_K(16)
-                    const uint64_t da = smem_desc(abase + k * 16 * ROWB, atom, 8 * ROWB, lay);
-                    const uint64_t db = smem_desc(bbase + t * atom + k * 16 * ROWB, atom, 8 * ROWB, lay);
-                    mma_f16(tmem_base + t * 32, da, db, idesc, (it | k) != 0);
+                    for (int k = 0; k < 8; ++k) {   // 128 sites = 8 x UMMA_K(16)
+                        const uint64_t da = smem_desc(abase + k * 16 * ROWB, atom, 8 * ROWB, lay);
+                        const uint64_t db = smem_desc(bbase + t * atom + k * 16 * ROWB, atom, 8 * ROWB, lay);
+                        mma_f16(tmem_u + t * 32, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                    }
                 }
+                mma_commit(empty + 8 * buf);
             }
-            mma_commit(empty + 8 * buf);
+            first = false;
+            if (buf) ph ^= 1;
+            buf ^= 1;
         }
-        if (my_tiles > 0) mma_commit(tfull);
+        if (my_tiles > 0 && elect_one()) mma_commit(tfull);
     }
     tc_fence_before();
     __syncthreads();

@@ -31,6 +31,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
+// One lane of a fully converged warp (elect.sync): the others fall through.  Code that issues tcgen05.mma should run with
+// the WHOLE warp executing the surrounding loop (so that ptxas can prove every operand warp-uniform and keep it in uniform
+// registers) and only the instruction itself under this predicate.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+// A value that is equal in all lanes, made uniform for the compiler (REDUX writes a uniform register).
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+
 // ---- TMA ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -39,25 +39,9 @@ class ConvDesc(ctypes.Structure):
         ("pre_act", c_int32), ("post_act", c_int32), ("stats", c_void_p), ("bias", c_void_p),
         ("scale", c_void_p), ("shift", c_void_p), ("res", c_void_p), ("res_up", c_int32),
         ("n_phases", c_int32), ("phase_tap0", c_int32 * 5), ("phase_oy0", c_int32 * 4), ("phase_ox0", c_int32 * 4),
-        ("splitk_ws", c_void_p), ("splitk_ws_bytes", ctypes.c_int64),
     ]
 
 ACT = {None: 0, "relu": 1, "lrelu": 2}
-
-# EXPERIMENTAL, off by default (not yet validated on hardware): split-K variant K2s for the layers with few CTAs
-# (csrc/k2s_conv_splitk.cu).  One zeroed workspace per (device, stream): launches on different streams may overlap.
-SPLITK = os.environ.get("MAGGIE_B200_CONV_SPLITK", "0") == "1"
-_SPLITK_WS = {}
-_SPLITK_WS_BYTES = 16 * 1024 + 16 * 1024 * 1024
-
-
-def _splitk_workspace(device):
-    key = (device.index, torch._C._cuda_getCurrentRawStream(device.index))
-    ws = _SPLITK_WS.get(key)
-    if ws is None:
-        ws = _SPLITK_WS[key] = torch.zeros(_SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
-    return ws
-
 
 def pad_channels(c):
     return (c + 15) // 16 * 16
@@ -153,9 +137,6 @@ def conv_launch(x, w_packed, taps, *, stride=1, grid_hw=None, out=None, out_hw=N
         assert w_lo.shape == w_packed.shape and w_lo.dtype == torch.float16 and w_lo.is_contiguous() and stats is None
         _lib.check(_lib.lib().mg_conv_fprop_x3(ctypes.byref(d), _ptr(x_lo), _ptr(w_lo), _stream()), "mg_conv_fprop_x3")
         return out
-    if SPLITK and phases is None:
-        ws = _splitk_workspace(x.device)
-        d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     _lib.check(_lib.lib().mg_conv_fprop(ctypes.byref(d), _stream()), "mg_conv_fprop")
     return out
 
