@@ -313,7 +313,8 @@ def run_gpu(args):
     model.enable_cuda_graphs(not args.no_graphs)
     flat = FlatGradAllReduce(model.parameters())
 
-    host = synth.make_batch(b=FRAMES_PER_GPU, n_f=1, n_i=N_INST, H=H, W=W, edge_px=EDGE_PX, seed=1234 + rank, train=True, it=1)
+    host = synth.make_batch(b=FRAMES_PER_GPU, n_f=1, n_i=N_INST, H=H, W=W, edge_px=EDGE_PX, seed=1234 + rank, train=True,
+                            it=args.iter)
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items() if k not in ("fg", "bg")}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
     copy_stream = torch.cuda.Stream(device=dev)
@@ -430,10 +431,49 @@ def run_gpu(args):
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     pending[-1][0].synchronize()
+    counts_main = list(model.last_site_counts)
+
+    # the other training regime: iter >= 9000 - the predicted OS8 alpha guides the detail stage, the uncertain
+    # region is known only after the dense stage (one host read of the status word in the middle of the step)
+    post = None
+    if not args.no_post_warmup:
+        other_iter = 100000 if args.iter < 9000 else 1
+        alt = dict(resident)
+        alt["iter"] = other_iter
+        for _ in range(3):
+            step(alt)
+        n_alt = max(10, args.steps // 3)
+        ms_alt = timed(lambda: step(alt), n_alt)
+        post = {"iter": other_iter, "value": FRAMES_PER_GPU * world / (ms_alt * 1e-3), "unit": "frames/s", "ms_per_step": ms_alt,
+                "steps": n_alt, "active_sites_os1_os2_os4_os8": list(model.last_site_counts),
+                "note": "same model / batch, inputs resident; iter >= 3 * warmup_detail_iter: uncertain region from the "
+                        "predicted alpha (device-side switch), one 32-byte host read per step after the dense stage.  With "
+                        "RANDOM weights the predicted alpha is uncertain everywhere, so this is also the 100 %-active stress "
+                        "case of the sparse stage (compare the site counts)"}
+        if other_iter > 1:
+            # the same control flow at EQUAL work: the OS8 head's output is replaced by the ground-truth alpha (benchmark-only
+            # substitution), so the uncertain region is the warm-up regime's while the switch, the mask, the site tables
+            # and the host read all happen after the dense stage as in a trained model's late iterations
+            dec = model.decoder
+            orig = dec._os8_alpha
+            gt_dev = alt["alpha"][:, 0].float()
+            dec._os8_alpha = lambda logits, masks, n_i, Hh, Ww, slots=None, status=None: (
+                orig(logits, masks, n_i, Hh, Ww, slots, status) * 0.0 + gt_dev)
+            try:
+                for _ in range(3):
+                    step(alt)
+                ms_eq = timed(lambda: step(alt), n_alt)
+            finally:
+                dec._os8_alpha = orig
+            post["equal_work"] = {"value": FRAMES_PER_GPU * world / (ms_eq * 1e-3), "ms_per_step": ms_eq,
+                                  "active_sites_os1_os2_os4_os8": list(model.last_site_counts),
+                                  "note": "OS8 alpha replaced by the ground truth (benchmark-only): post-warm-up control flow "
+                                          "(device-side switch, mask + site tables + host read after the dense stage) at the "
+                                          "warm-up regime's active fraction"}
     last_loss = float(loss_host[pending[-1][1]])
     assert last_loss == last_loss, "loss is NaN"
     clocks = sampler.stop() if rank == 0 else None
-    counts = model.last_site_counts
+    counts = counts_main
     if sync_bn:
         from maggie_b200 import dense as _dense
         sync_bn_path = ("peer-memory kernel (K15), 2 per BatchNorm per step" if all(w is not None for w in _dense._WINDOWS.values())
@@ -454,7 +494,7 @@ def run_gpu(args):
         "metric": "frames_per_sec_fwd_bwd", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd per GPU (iter=1, edge {EDGE_PX}px)",
+        "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd per GPU (iter={args.iter}, edge {EDGE_PX}px)",
                    "frames_per_gpu": FRAMES_PER_GPU, "active_sites_os1_os2_os4_os8": counts,
                    "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
                    "loss_scale": LOSS_SCALE, "host_run_ahead_steps": 2 if throttle else "unbounded", "sync_bn": sync_bn, "cuda_graphs_dense_stage": bool(model._graphs),
@@ -470,6 +510,8 @@ def run_gpu(args):
                           "peak_tflops_sustained": peaks["tf_sustained"],
                           "frac": f_step / (ms * 1e-3) / 1e12 / peaks["tf_sustained"], "peak_source": peaks["src"]},
     }
+    if post is not None:
+        line["other_regime"] = post
     if world == 1 and not args.no_cpu_baseline:
         cstep, cframes = cpu_step_fn(2)
         cstep()
@@ -492,6 +534,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="run the dense stage eagerly instead of as CUDA graphs")
     ap.add_argument("--sync-bn", action="store_true", help="N>1: exchange BatchNorm statistics across ranks (model.sync_bn true)")
+    ap.add_argument("--iter", type=int, default=1, help="training iteration of the headline number (1: warm-up regime of the "
+                    "first 3000 iterations; >= 9000: the predicted OS8 alpha guides the detail stage)")
+    ap.add_argument("--no-post-warmup", action="store_true", help="skip the extra iter=100000 measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -47,6 +47,12 @@ void mg_reset_launch_count(void);
  *           of word x/32.  At least one output must be given.  Bit-exact.                              */
 int mg_unknown_mask(const float* alpha, int slices, int H, int W, const int32_t* widths,
                     const uint8_t* and_mask, uint8_t* out_u8, uint32_t* out_bits, void* stream);
+/* the same, reading the slices from `alt` instead of `alpha` when the DEVICE flag *use_alt != 0: the warm-up switch of
+ * decoder/resnet_inst_matt_spconv.py:311-316 ("guide with the ground truth when the predicted alpha is all zero") decided
+ * on the device, no host read. */
+int mg_unknown_mask_select(const float* alpha, const float* alt, const int32_t* use_alt, int slices, int H, int W,
+                           const int32_t* widths, const uint8_t* and_mask, uint8_t* out_u8, uint32_t* out_bits,
+                           void* stream);
 
 /* ---- K8b: active-site lists for the sparse refinement ---------------------------------------------
  * replaces: decoder/resnet_inst_matt_spconv.py:203-218 (torch.nonzero + spconv `dummy_downscale`, whose only
@@ -325,8 +331,10 @@ int mg_token_logits_bwd(const float* tok, const void* x, const float* g, void* d
  *           alpha scales (decoder/resnet_inst_matt_spconv.py:302-309, 357-362) and their autograd backward.
  * logits fp32 [planes,h,w]; out / g fp32 [planes,h*S,w*S]; S in {1,2,4,8}; plane_scale optional fp32 [planes].
  * fwd: out = (tanh(bilerp(logits)) + 1) / 2 * plane_scale.   bwd: glogits = d out / d logits applied to g (gather form). */
+/* all_zero (optional, device int32, preset to 1 by the caller): cleared when some output value is non-zero - the device-side
+ * form of the reference's `x_os8.sum() == 0` host test (decoder/resnet_inst_matt_spconv.py:314). */
 int mg_upsample_tanh_fwd(const float* logits, const float* plane_scale, float* out, int planes, int h, int w, int S,
-                         void* stream);
+                         int32_t* all_zero, void* stream);
 int mg_upsample_tanh_bwd(const float* logits, const float* plane_scale, const float* g, float* glogits, int planes, int h,
                          int w, int S, void* stream);
 

@@ -20,6 +20,8 @@ SIGNATURES = {
     "mg_launch_count": (c_ulonglong, []),
     "mg_reset_launch_count": (None, []),
     "mg_unknown_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mg_unknown_mask_select": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
     "mg_sites_workspace": (c_size_t, [c_int, c_int, c_int]),
     "mg_sites_count": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mg_sites_tables": (c_int, [c_void_p, c_int, c_int, c_int, _I32P, _PP, _PP, _PP, _PP, c_void_p]),
@@ -68,7 +70,7 @@ SIGNATURES = {
     "mg_wprep_bwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5),
     "mg_optim_adamw_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
                             + [c_float] * 7 + [c_void_p]),
-    "mg_upsample_tanh_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mg_upsample_tanh_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mg_upsample_tanh_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_layer_norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_void_p]),

@@ -25,8 +25,9 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ p, int w, int 
 
 __global__ void __launch_bounds__(256)
 upsample_tanh_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ plane_scale, float* __restrict__ out,
-                         int planes, int h, int w, int S) {
+                         int planes, int h, int w, int S, int32_t* __restrict__ all_zero) {
     mg::pdl_prologue();
+    bool nz = false;
     const int H = h * S, W = w * S;
     const float rs = 1.f / (float)S;
     const size_t total = (size_t)planes * H * W;
@@ -46,7 +47,10 @@ upsample_tanh_fwd_kernel(const float* __restrict__ logits, const float* __restri
         float a = (tanhf(v) + 1.0f) * 0.5f;
         if (plane_scale) a *= __ldg(plane_scale + pl);
         out[i] = a;
+        nz |= a != 0.f;
     }
+    // device-side form of the reference's `x_os8.sum() == 0` test (decoder/resnet_inst_matt_spconv.py:314): no host read
+    if (all_zero && __any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0) *all_zero = 0;
 }
 
 // grid (w / TC, h / TC, planes), block 256;  TC = coarse tile edge, footprint edge F = S * TC + S
@@ -129,13 +133,13 @@ tanh_head_bwd_kernel(const float* __restrict__ logits, const float* __restrict__
 }  // namespace
 
 extern "C" int mg_upsample_tanh_fwd(const float* logits, const float* plane_scale, float* out, int planes, int h, int w, int S,
-                                    void* stream) {
+                                    int32_t* all_zero, void* stream) {
     MG_REQUIRE(S == 1 || S == 2 || S == 4 || S == 8, "mg_upsample_tanh_fwd: scale must be 1, 2, 4 or 8 (got %d)", S);
     if (planes <= 0 || h <= 0 || w <= 0) return MG_OK;
     MG_REQUIRE(logits && out, "mg_upsample_tanh_fwd: null pointer");
     const size_t total = (size_t)planes * h * S * w * S;
     const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)mg::kNumSMs * 16);
-    MG_LAUNCH(upsample_tanh_fwd_kernel, grid, 256, 0, stream, logits, plane_scale, out, planes, h, w, S);
+    MG_LAUNCH(upsample_tanh_fwd_kernel, grid, 256, 0, stream, logits, plane_scale, out, planes, h, w, S, all_zero);
     MG_CHECK_LAUNCH("mg_upsample_tanh_fwd");
     return MG_OK;
 }

@@ -41,11 +41,15 @@ __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) {
     return (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
 }
 
+// alt / use_alt (optional): when *use_alt != 0 the slices are read from `alt` instead of `alpha` - the device-side form of
+// the reference's warm-up switch "guide the detail stage with the ground truth when the predicted alpha is all zero"
+// (decoder/resnet_inst_matt_spconv.py:311-316) without a host read of the sum.
 __global__ void __launch_bounds__(THREADS)
-unknown_mask_kernel(const float* __restrict__ alpha, int H, int W, const int32_t* __restrict__ widths,
-                    const uint8_t* __restrict__ and_mask, uint8_t* __restrict__ out_u8,
-                    uint32_t* __restrict__ out_bits) {
+unknown_mask_kernel(const float* __restrict__ alpha, const float* __restrict__ alt, const int32_t* __restrict__ use_alt,
+                    int H, int W, const int32_t* __restrict__ widths, const uint8_t* __restrict__ and_mask,
+                    uint8_t* __restrict__ out_u8, uint32_t* __restrict__ out_bits) {
     mg::pdl_prologue();
+    if (alt && use_alt && *use_alt != 0) alpha = alt;
     extern __shared__ uint32_t sbits[];  // [TH + MAXK - 1][Wd + 2]
     __shared__ int s_lo[MAXK], s_w[MAXK];
 
@@ -65,6 +69,35 @@ unknown_mask_kernel(const float* __restrict__ alpha, int H, int W, const int32_t
     }
     const float lower = 1.0f / 255.0f, upper = 254.0f / 255.0f;  // fp32-rounded, as torch compares
     const float* aslice = alpha + (size_t)s * H * W;
+    if ((W & 31) == 0) {
+        // vectorised threshold: a thread owns 8 consecutive pixels (two 16-byte loads in flight per item, items of
+        // several rows interleaved), four neighbouring lanes assemble one 32-pixel word with two shuffles
+        const int per_row = Wd * 4, total = R * per_row;
+        for (int base = warp * 32; base < total; base += THREADS) {
+            const int idx = base + lane;
+            uint32_t m = 0u;
+            int r = 0, q = 0;
+            if (idx < total) {
+                r = idx / per_row, q = idx - r * per_row;
+                const int gy = y0 - a + r;
+                if (gy >= 0 && gy < H) {
+                    const float4* p = reinterpret_cast<const float4*>(aslice + (size_t)gy * W + q * 8);
+                    const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+                    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) m |= (uint32_t)((v[i] > lower) && (v[i] < upper)) << i;
+                }
+                m <<= 8 * (q & 3);
+            }
+            m |= __shfl_xor_sync(0xffffffffu, m, 1);
+            m |= __shfl_xor_sync(0xffffffffu, m, 2);
+            if (idx < total) {
+                uint32_t* row = sbits + r * RW;
+                if ((q & 3) == 0) row[1 + (q >> 2)] = m;
+                if (q == 0) row[0] = 0u, row[Wd + 1] = 0u;
+            }
+        }
+    } else
     for (int r = warp; r < R; r += THREADS / 32) {
         const int gy = y0 - a + r;
         uint32_t* row = sbits + r * RW;
@@ -130,8 +163,8 @@ unknown_mask_kernel(const float* __restrict__ alpha, int H, int W, const int32_t
 
 }  // namespace
 
-extern "C" int mg_unknown_mask(const float* alpha, int slices, int H, int W, const int32_t* widths,
-                               const uint8_t* and_mask, uint8_t* out_u8, uint32_t* out_bits, void* stream) {
+static int unknown_mask(const float* alpha, const float* alt, const int32_t* use_alt, int slices, int H, int W,
+                        const int32_t* widths, const uint8_t* and_mask, uint8_t* out_u8, uint32_t* out_bits, void* stream) {
     MG_REQUIRE(alpha && widths && (out_u8 || out_bits), "mg_unknown_mask: null pointer");
     MG_REQUIRE(slices >= 0 && H > 0 && W > 0 && W <= 4096, "mg_unknown_mask: bad shape %d x %d x %d", slices, H, W);
     if (slices == 0) return MG_OK;
@@ -139,7 +172,19 @@ extern "C" int mg_unknown_mask(const float* alpha, int slices, int H, int W, con
     const int Wd = (W + 31) / 32;
     const size_t smem = (size_t)(TH + MAXK - 1) * (Wd + 2) * sizeof(uint32_t);
     dim3 grid(mg::ceil_div(H, TH), slices);
-    MG_LAUNCH(unknown_mask_kernel, grid, THREADS, smem, stream, alpha, H, W, widths, and_mask, out_u8, out_bits);
+    MG_LAUNCH(unknown_mask_kernel, grid, THREADS, smem, stream, alpha, alt, use_alt, H, W, widths, and_mask, out_u8, out_bits);
     MG_CHECK_LAUNCH("mg_unknown_mask");
     return MG_OK;
+}
+
+extern "C" int mg_unknown_mask(const float* alpha, int slices, int H, int W, const int32_t* widths,
+                               const uint8_t* and_mask, uint8_t* out_u8, uint32_t* out_bits, void* stream) {
+    return unknown_mask(alpha, nullptr, nullptr, slices, H, W, widths, and_mask, out_u8, out_bits, stream);
+}
+
+extern "C" int mg_unknown_mask_select(const float* alpha, const float* alt, const int32_t* use_alt, int slices, int H, int W,
+                                      const int32_t* widths, const uint8_t* and_mask, uint8_t* out_u8, uint32_t* out_bits,
+                                      void* stream) {
+    MG_REQUIRE(alt && use_alt, "mg_unknown_mask_select: null pointer");
+    return unknown_mask(alpha, alt, use_alt, slices, H, W, widths, and_mask, out_u8, out_bits, stream);
 }

@@ -172,8 +172,15 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         prep = self._prepare(batch)
         x, masks, slot_ids, alphas, trans, chosen, n_slots, unsort, (b, n_f, n_i, h, w) = prep
         mask_os8, gt_os8 = self.decoder.pooled_masks(masks, alphas, b, n_f, n_i, h, w, self.training, chosen, n_slots)
-        roi_plan = self.decoder.plan_roi(alphas, batch.get("iter", 0))
-        return prep, mask_os8, gt_os8, roi_plan
+        # the step's status word (site counts + device-side flags, ONE host read per step, see ops.new_status); the
+        # "some sample has no mask at all" flag stands in for the reference's per-layer NaN check + ValueError
+        # (module/mask_attention.py:95-98, five host synchronisations per forward there)
+        status = ops.new_status(x.device) if x.is_cuda else None
+        if status is not None:
+            empty = ~mask_os8.flatten(1).any(1)                       # [b]: no mask pixel in any frame / slot of the sample
+            status[ops.STATUS_EMPTY_MASK:ops.STATUS_EMPTY_MASK + 1].copy_(empty.any().to(torch.int32))
+        roi_plan = self.decoder.plan_roi(alphas, batch.get("iter", 0), status)
+        return prep, mask_os8, gt_os8, roi_plan, status
 
     def _input_stage_async(self, batch, ready_event):
         """`batch['ready_event']` (optional, a `torch.cuda.Event`): the caller produced the inputs on another stream (a
@@ -202,9 +209,9 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
     def forward(self, batch, **kwargs):
         ev = batch.get("ready_event")
         if ev is not None and batch["image"].is_cuda:
-            prep, mask_os8, gt_os8, roi_plan = self._input_stage_async(batch, ev)
+            prep, mask_os8, gt_os8, roi_plan, status = self._input_stage_async(batch, ev)
         else:
-            prep, mask_os8, gt_os8, roi_plan = self._input_stage(batch)
+            prep, mask_os8, gt_os8, roi_plan, status = self._input_stage(batch)
         x, masks, slot_ids, alphas, trans, chosen, n_slots, unsort, (b, n_f, n_i, h, w) = prep
         mem_feat = kwargs.pop("mem_feat", None)
         it = batch.get("iter", 0)
@@ -217,7 +224,7 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         with ops.step_scope("sparse_stage", x.device):
             pred = self.decoder(tuple(dense_out), (fea1, fea2, fea3), (h, w), b=b, n_f=n_f, n_i=n_i, masks=masks,
                                 iter=it, gt_alphas=alphas, spar_gt=trans, slots=chosen, n_slots=n_slots,
-                                roi_plan=roi_plan, **kwargs)
+                                roi_plan=roi_plan, status=status, **kwargs)
         self.last_site_counts = pred.pop("site_counts", None)
 
         alpha_pred = pred.pop("refined_masks")

@@ -316,36 +316,55 @@ class MaGGIeDecoder(nn.Module):
             gt_os8 = place(F.max_pool2d((gt_alphas > 0).float(), 8, 8).reshape(b, n_f, n_i, H // 8, W // 8) > 0)
         return mask_os8, gt_os8
 
-    def _os8_alpha(self, os8_logits, masks, n_i, H, W, slots=None):
+    def _os8_alpha(self, os8_logits, masks, n_i, H, W, slots=None, status=None):
         if slots is not None:       # compact training planes: only the slots that hold an instance are upsampled
             os8_logits = ops.take(os8_logits, 1, slots)
         if self.training:
             valid = (masks.flatten(2).sum(2) > 0).float()          # [B, planes]: alpha of a plane without a mask is zeroed
-            return ops.upsample_tanh(os8_logits, size=(H, W), plane_scale=valid)
+            flag = status[ops.STATUS_ALL_ZERO:ops.STATUS_ALL_ZERO + 1] if status is not None else None
+            return ops.upsample_tanh(os8_logits, size=(H, W), plane_scale=valid, all_zero=flag)
         return ops.upsample_tanh(os8_logits, size=(H, W))[:, :n_i]
 
-    def _choose_guidance(self, a8, gt_alphas, iter):
-        """Warm-up switch of resnet_inst_matt_spconv.py:311-316 (same python RNG draw)."""
+    def _choose_guidance(self, iter):
+        """The host part of the warm-up switch of resnet_inst_matt_spconv.py:311-316 (same python RNG draw for
+        `iter < 3 * warmup`).  The third condition of the reference, `x_os8.sum() == 0`, is decided on the DEVICE (flag
+        STATUS_ALL_ZERO of the step's status word, written by the OS8 head kernel): no host read in the middle of the
+        step.  (In that degenerate case the reference skips the RNG draw; here it has already been made.)"""
         wd = self.warmup_detail_iter
-        if self.training and (iter < wd or float(a8.sum()) == 0 or (iter < wd * 3 and random.random() < 0.5)):
-            return gt_alphas, True
-        return a8, False
+        return self.training and (iter < wd or (iter < wd * 3 and random.random() < 0.5))
 
-    def plan_roi(self, gt_alphas, iter):
+    def plan_roi(self, gt_alphas, iter, status=None):
         """Warm-up iterations take the uncertain region from the ground-truth alphas (resnet_inst_matt_spconv.py:311-316),
         i.e. from an INPUT: its mask and site tables can then be built before the dense stage is even launched, and the
-        one host read of the site counts no longer stalls the middle of the step.  Returns (unk, site tables) or None."""
+        one host read of the step (site counts + status flags) no longer stalls the middle of the step.
+        Returns (unk, site tables) or None."""
         if not (self.training and iter < self.warmup_detail_iter and gt_alphas is not None):
             return None
         unk = ops.unknown_mask(gt_alphas, _draw_widths(gt_alphas.shape[0] * gt_alphas.shape[1], 30, False))
-        T = ops.build_sites(unk.reshape(-1, *unk.shape[-2:]))
+        T = ops.build_sites(unk.reshape(-1, *unk.shape[-2:]), status)
         return (unk, T) if T.counts[0] > 0 else None   # empty set: the regular path handles the degenerate batch
 
-    def _guidance_and_roi(self, a8, gt_alphas, iter, roi_plan):
+    def _guidance_and_roi(self, a8, gt_alphas, iter, roi_plan, status=None):
+        """-> (use_gt, uncertain-region mask, site tables).  Exactly one host read per step: the status word (site counts +
+        flags), issued by the `build_sites` call below unless the input stage has already done it (`roi_plan`)."""
         if roi_plan is not None:
             return True, roi_plan[0], roi_plan[1]
-        guided, use_gt = self._choose_guidance(a8, gt_alphas, iter)
-        return use_gt, ops.unknown_mask(guided, _draw_widths(guided.shape[0] * guided.shape[1], 30, False)), None
+        widths = _draw_widths(a8.shape[0] * a8.shape[1], 30, False)
+        if self._choose_guidance(iter):
+            unk, use_gt = ops.unknown_mask(gt_alphas, widths), True
+            T = ops.build_sites(unk.reshape(-1, *unk.shape[-2:]), status)
+        elif self.training and status is not None:
+            # predicted alpha guides - unless it is all zero, which the device decides (no host read before the mask)
+            flag = status[ops.STATUS_ALL_ZERO:ops.STATUS_ALL_ZERO + 1]
+            unk = ops.unknown_mask(a8, widths, alt=gt_alphas, use_alt=flag)
+            T = ops.build_sites(unk.reshape(-1, *unk.shape[-2:]), status)
+            use_gt = bool(T.flags[ops.STATUS_ALL_ZERO - 4])
+        else:
+            # eval, or the host-side golden tests (CPU tensors, no status word: the reference's host test as it is)
+            use_gt = bool(self.training and status is None and float(a8.sum()) == 0)
+            unk = ops.unknown_mask(gt_alphas if use_gt else a8, widths)
+            T = ops.build_sites(unk.reshape(-1, *unk.shape[-2:]), status)
+        return use_gt, unk, T
 
     def _refine_and_fuse(self, x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W, slots=None, n_slots=None, T=None):
         """process_os4_os1 + fuse (resnet_inst_matt_spconv.py:346-366, 272-290, 333-340).  `slots`: the planes are
@@ -356,7 +375,7 @@ class MaGGIeDecoder(nn.Module):
         B = a8.shape[0]
         n_ref = n_slots if slots is not None else a8.shape[1]
         if T is None:
-            T = ops.build_sites(unk.reshape(-1, H, W))   # the one host read of the step: the four site counts
+            T = ops.build_sites(unk.reshape(-1, H, W))   # (callers normally pass the tables: see _guidance_and_roi)
         if t and T.counts[0] == 0:
             if slots is not None:
                 # degenerate batch: the reference paints the dummy patch into EVERY slot, the empty ones included
@@ -398,13 +417,14 @@ class MaGGIeDecoder(nn.Module):
         return ret
 
     def forward(self, dense_out, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, slots=None, n_slots=None,
-                roi_plan=None, **_):
+                roi_plan=None, status=None, **_):
         """dense_out: (os8_logits, os8_feat, queries, loss_atten) from `dense_stage`; fea: (fea1, fea2, fea3);
-        masks [b*n_f, n_i, H, W] fp32 {0,1}; gt_alphas [b*n_f, n_i, H, W]; slots / n_slots: see `_refine_and_fuse`."""
+        masks [b*n_f, n_i, H, W] fp32 {0,1}; gt_alphas [b*n_f, n_i, H, W]; slots / n_slots: see `_refine_and_fuse`;
+        status: the step's device status word (`ops.new_status`)."""
         H, W = image_hw
         os8_logits, x, queries, loss_atten = dense_out
-        a8 = self._os8_alpha(os8_logits, masks, n_i, H, W, slots)
-        use_gt, unk, T = self._guidance_and_roi(a8, gt_alphas, iter, roi_plan)
+        a8 = self._os8_alpha(os8_logits, masks, n_i, H, W, slots, status if roi_plan is None else None)
+        use_gt, unk, T = self._guidance_and_roi(a8, gt_alphas, iter, roi_plan, status)
         ret = self._refine_and_fuse(x, queries, fea, a8, unk, use_gt, gt_alphas, b, n_f, H, W, slots, n_slots, T)
         if self.training and iter >= self.warmup_mask_atten_iter:
             ret["loss_max_atten"] = loss_atten
@@ -512,15 +532,15 @@ class MaGGIeTempDecoder(MaGGIeDecoder):
         return diff.sum() / (torch.sum(mask[:, 1:]) + 1e-6 * pad_ratio * mask[:, 1:].numel())
 
     def forward(self, dense_out, fea, image_hw, b, n_f, n_i, masks, iter, gt_alphas, spar_gt=None, slots=None,
-                n_slots=None, roi_plan=None, **_):
+                n_slots=None, roi_plan=None, status=None, **_):
         H, W = image_hw
         t = self.training
         os8_logits, x, queries, loss_atten, hidden = dense_out
         feat_os8 = x.reshape(b, n_f, *x.shape[1:]).detach()
-        a8 = self._os8_alpha(os8_logits, masks, n_i, H, W, slots)
+        a8 = self._os8_alpha(os8_logits, masks, n_i, H, W, slots, status if (t and roi_plan is None) else None)
         T = None
         if t:
-            use_gt, unk, T = self._guidance_and_roi(a8, gt_alphas, iter, roi_plan)
+            use_gt, unk, T = self._guidance_and_roi(a8, gt_alphas, iter, roi_plan, status)
         else:
             use_gt = False
             a8 = torch.where(a8 >= 0.95, torch.ones_like(a8), a8)

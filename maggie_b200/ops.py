@@ -109,10 +109,13 @@ class _IntStager:
 _STAGERS = {}
 
 
-def unknown_mask(alpha, widths, and_mask=None):
+def unknown_mask(alpha, widths, and_mask=None, alt=None, use_alt=None):
     """uint8 {0,1} mask of the dilated uncertain region (reference: utils/utils.py:28-55 compute_unknown).
-    alpha [..., H, W] fp32; widths: one ellipse size (1..29) per [H, W] slice; and_mask optional uint8."""
-    _need_cuda(alpha, and_mask)
+    alpha [..., H, W] fp32; widths: one ellipse size (1..29) per [H, W] slice; and_mask optional uint8.
+    alt / use_alt (optional): `use_alt` is a DEVICE int32 scalar; when it is non-zero the mask is computed from `alt`
+    (same shape as alpha) instead - the reference's "guide with the ground truth when the predicted alpha is all zero"
+    switch (decoder/resnet_inst_matt_spconv.py:311-316) without a host read."""
+    _need_cuda(alpha, and_mask, alt, use_alt)
     a = alpha.detach().to(torch.float32).contiguous()
     H, W = a.shape[-2:]
     slices = a.numel() // (H * W) if a.numel() else 0
@@ -125,27 +128,51 @@ def unknown_mask(alpha, widths, and_mask=None):
     if and_mask is not None:
         and_mask = and_mask.to(torch.uint8).contiguous()
         assert and_mask.shape == a.shape
+    if alt is not None:
+        b = alt.detach().to(torch.float32).contiguous()
+        assert b.shape == a.shape and use_alt.dtype == torch.int32
+        _lib.check(_lib.lib().mg_unknown_mask_select(_ptr(a), _ptr(b), _ptr(use_alt), slices, H, W, _ptr(w), _ptr(and_mask),
+                                                    _ptr(out), None, _stream()), "mg_unknown_mask_select")
+        return out
     _lib.check(_lib.lib().mg_unknown_mask(_ptr(a), slices, H, W, _ptr(w), _ptr(and_mask), _ptr(out), None, _stream()),
                "mg_unknown_mask")
     return out
 
 
 # =============================================================================================== native: K8b
-SiteTables = namedtuple("SiteTables", "counts coords nbr parent child shapes")
+SiteTables = namedtuple("SiteTables", "counts coords nbr parent child shapes flags", defaults=(None,))
+
+# The step's status word: int32[8] on the device = four site counts + device-side flags, read by the host in ONE 32-byte
+# copy (the step's only host read): [4] the predicted OS8 alpha is all zero (`x_os8.sum() == 0`,
+# decoder/resnet_inst_matt_spconv.py:314), [5] some sample has no mask at all (the reference raises "Mask is empty",
+# module/mask_attention.py:95-98).
+STATUS_ALL_ZERO, STATUS_EMPTY_MASK = 4, 5
+_STATUS_INIT = {}
 
 
-def build_sites(roi):
+def new_status(device):
+    t = _STATUS_INIT.get(str(device))
+    if t is None:
+        t = _STATUS_INIT[str(device)] = torch.tensor([0, 0, 0, 0, 1, 0, 0, 0], dtype=torch.int32, device=device)
+    return t.clone()
+
+
+def build_sites(roi, status=None):
     """Active-site lists and rulebook tables of the 4 sparse levels (reference:
     decoder/resnet_inst_matt_spconv.py:203-218: nonzero + spconv dummy_downscale index generation).
-    roi uint8 [slots, H, W].  One 16-byte D2H read of the four counts."""
-    _need_cuda(roi)
+    roi uint8 [slots, H, W].  One small D2H read: the four counts (+ the flags of `status`, see `new_status`, which then
+    come back as `.flags`)."""
+    _need_cuda(roi, status)
     roi = roi.to(torch.uint8).contiguous()
     S, H, W = roi.shape
     L = _lib.lib()
     ws = torch.empty(L.mg_sites_workspace(S, H, W), dtype=torch.uint8, device=roi.device)
-    counts_d = torch.zeros(4, dtype=torch.int32, device=roi.device)
+    counts_d = status if status is not None else torch.zeros(4, dtype=torch.int32, device=roi.device)
     _lib.check(L.mg_sites_count(_ptr(roi), S, H, W, _ptr(ws), _ptr(counts_d), _stream()), "mg_sites_count")
-    counts = [int(c) for c in counts_d.cpu()]
+    host = [int(c) for c in counts_d.cpu()]
+    counts, flags = host[:4], (host[4:] if status is not None else None)
+    if flags is not None and flags[STATUS_EMPTY_MASK - 4]:
+        raise ValueError("Mask is empty")      # module/mask_attention.py:95-98
     mk = lambda n, k: torch.empty((n, k), dtype=torch.int32, device=roi.device)
     coords = [mk(n, 3) for n in counts]
     nbr = [mk(counts[0], 9), None, mk(counts[2], 9), None]
@@ -155,7 +182,7 @@ def build_sites(roi):
     _lib.check(L.mg_sites_tables(_ptr(ws), S, H, W, _lib.i32_array(counts), pa(coords), pa(nbr), pa(parent), pa(child),
                                  _stream()), "mg_sites_tables")
     shapes = [(H >> l, W >> l) for l in range(4)]
-    return SiteTables(counts, coords, nbr, parent, child, shapes)
+    return SiteTables(counts, coords, nbr, parent, child, shapes, flags)
 
 
 # =============================================================================================== native: K1
@@ -636,13 +663,14 @@ class _UpsampleTanh(torch.autograd.Function):
     """(tanh(bilinear_upsample(logits)) + 1) / 2 * plane_scale, fp32 (K7)."""
 
     @staticmethod
-    def forward(ctx, logits, plane_scale, S):
+    def forward(ctx, logits, plane_scale, S, all_zero=None):
         x = logits.detach().to(torch.float32).contiguous()
         h, w = x.shape[-2:]
         planes = x.numel() // (h * w) if x.numel() else 0
         ps = plane_scale.detach().to(torch.float32).contiguous() if plane_scale is not None else None
         out = torch.empty(x.shape[:-2] + (h * S, w * S), dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib().mg_upsample_tanh_fwd(_ptr(x), _ptr(ps), _ptr(out), planes, h, w, S, _stream()), "mg_upsample_tanh_fwd")
+        _lib.check(_lib.lib().mg_upsample_tanh_fwd(_ptr(x), _ptr(ps), _ptr(out), planes, h, w, S, _ptr(all_zero), _stream()),
+                   "mg_upsample_tanh_fwd")
         ctx.save_for_backward(x, ps)
         ctx.meta = (planes, h, w, S, logits.dtype)
         return out
@@ -654,23 +682,26 @@ class _UpsampleTanh(torch.autograd.Function):
         gl = torch.empty_like(x)
         _lib.check(_lib.lib().mg_upsample_tanh_bwd(_ptr(x), _ptr(ps), _ptr(g.to(torch.float32).contiguous()), _ptr(gl), planes, h, w,
                                                   S, _stream()), "mg_upsample_tanh_bwd")
-        return gl.to(dt), None, None
+        return gl.to(dt), None, None, None
 
 
-def upsample_tanh(logits, size=None, scale=None, plane_scale=None):
+def upsample_tanh(logits, size=None, scale=None, plane_scale=None, all_zero=None):
     """bilinear (align_corners=False) -> (tanh+1)/2 (-> * plane_scale [planes]) in fp32.  NATIVE (K7) on CUDA for the integer
-    scales 1 / 2 / 4 / 8 the path uses; torch composition otherwise (host goldens)."""
+    scales 1 / 2 / 4 / 8 the path uses; torch composition otherwise (host goldens).
+    all_zero (optional): device int32 scalar preset to 1, cleared by the kernel when some output is non-zero."""
     S = 1
     if size is not None:
         S = size[-1] // logits.shape[-1] if size[-1] % logits.shape[-1] == 0 and size[-2] == logits.shape[-2] * (size[-1] // logits.shape[-1]) else 0
     elif scale is not None:
         S = int(scale) if float(scale) == int(scale) else 0
     if logits.is_cuda and S in (1, 2, 4, 8) and logits.shape[-3:].numel() > 0:
-        return _UpsampleTanh.apply(logits, plane_scale, S)
+        return _UpsampleTanh.apply(logits, plane_scale, S, all_zero)
     x = logits.float()
     if size is not None or scale is not None:
         x = F.interpolate(x, size=size, scale_factor=scale, mode="bilinear", align_corners=False)
     a = (torch.tanh(x) + 1.0) / 2.0
     if plane_scale is not None:
         a = a * plane_scale.reshape(a.shape[:-2] + (1, 1)).to(a.dtype)
+    if all_zero is not None:
+        all_zero.copy_((a.detach().amax() == 0).to(all_zero.dtype))
     return a

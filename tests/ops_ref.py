@@ -11,7 +11,9 @@ from maggie_b200 import ops
 from oracle import unknown as U
 
 
-def unknown_mask(alpha, widths, and_mask=None):
+def unknown_mask(alpha, widths, and_mask=None, alt=None, use_alt=None):
+    if alt is not None and int(use_alt) != 0:
+        alpha = alt
     out = U.compute_unknown(alpha.detach().cpu().float().numpy(), list(widths))
     if and_mask is not None:
         out = out * (and_mask.cpu().numpy() != 0)
@@ -62,13 +64,18 @@ def sites_tables_ref(roi):
     return coords, nbr, parent, child, shapes
 
 
-def build_sites(roi):
+def build_sites(roi, status=None):
     dev = roi.device
+    flags = None
+    if status is not None:
+        flags = [int(v) for v in status[4:].cpu()]
+        if flags[ops.STATUS_EMPTY_MASK - 4]:
+            raise ValueError("Mask is empty")
     coords, nbr, parent, child, shapes = sites_tables_ref(roi.cpu().numpy().astype(np.uint8))
     tt = lambda a: None if a is None else torch.from_numpy(
         np.ascontiguousarray(a).astype(np.int32).reshape(len(a), a.shape[1] if a.ndim > 1 else -1)).to(dev)
     return ops.SiteTables([len(c) for c in coords], [tt(c) for c in coords], [tt(a) for a in nbr],
-                          [tt(a) for a in parent], [tt(a) for a in child], shapes)
+                          [tt(a) for a in parent], [tt(a) for a in child], shapes, flags)
 
 
 def mask_embed(image, masks, table, slot_ids, C=8, dtype=None):

@@ -146,3 +146,32 @@ def test_upsample_tanh_fwd_bwd_matches_torch(dev, planes, h, w, S, with_scale):
     ref.backward(g)
     assert y.shape == ref.shape and (y - ref).abs().max() < 1e-6
     assert (got - x2.grad).abs().max() < 1e-5 * max(1.0, float(x2.grad.abs().max()))
+
+
+def test_unknown_mask_device_side_source_select():
+    """`use_alt` (a device flag) switches the source to `alt` without a host read (the reference's warm-up switch)."""
+    from maggie_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    a = torch.rand(3, 2, 96, 128, generator=g).cuda()
+    b = torch.rand(3, 2, 96, 128, generator=g).cuda()
+    widths = [5, 9, 15, 3, 29, 1]
+    for flag in (0, 1):
+        f = torch.tensor([flag], dtype=torch.int32, device="cuda")
+        got = ops.unknown_mask(a, widths, alt=b, use_alt=f)
+        want = ops.unknown_mask(b if flag else a, widths)
+        assert torch.equal(got, want)
+
+
+def test_upsample_tanh_all_zero_flag():
+    from maggie_b200 import ops
+    x = torch.full((2, 3, 8, 8), -40.0, device="cuda")          # tanh == -1 exactly: alpha == 0 everywhere
+    flag = torch.ones(1, dtype=torch.int32, device="cuda")
+    ops.upsample_tanh(x, scale=8.0, all_zero=flag)
+    assert int(flag) == 1
+    x[1, 2, 3, 3] = 0.5
+    ops.upsample_tanh(x, scale=8.0, all_zero=flag)
+    assert int(flag) == 0
+    # a zero plane factor keeps the flag set whatever the logits are
+    flag.fill_(1)
+    ops.upsample_tanh(x, scale=8.0, plane_scale=torch.zeros(2, 3, device="cuda"), all_zero=flag)
+    assert int(flag) == 1

@@ -88,6 +88,50 @@ def test_train_loss_and_gradient_parity(case, golden):
     assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
 
 
+def test_empty_mask_raises_like_the_reference():
+    """A sample without any mask pixel: the reference raises ValueError("Mask is empty") from its NaN checks
+    (module/mask_attention.py:95-98); here a device-side flag travels with the step's one host read."""
+    for training in (False, True):
+        m = _model(training)
+        batch = _to_dev(synth.make_batch(b=2, n_f=1, n_i=2, H=128, W=128, edge_px=4.0, seed=8, train=training, it=1))
+        batch["mask"][1] = 0
+        G.seed_all()
+        with pytest.raises(ValueError, match="Mask is empty"):
+            with torch.set_grad_enabled(training):
+                m(batch, mem_feat=None)
+
+
+def test_post_warmup_step_reads_the_host_once():
+    """iter >= 3 * warmup_detail_iter: the predicted OS8 alpha guides the detail stage (resnet_inst_matt_spconv.py:311-316).
+    The reference tests `x_os8.sum() == 0` on the host; here the switch is a device flag and the step's only synchronising
+    call is the 32-byte read of the status word (site counts + flags)."""
+    import warnings
+    m = _model(True)
+    m.decoder.inst_spec_layer.dropout.p = 0.0
+    batch = _to_dev(synth.make_batch(b=2, n_f=1, n_i=2, H=128, W=128, edge_px=4.0, seed=3, train=True, it=100000))
+    for _ in range(2):      # caches (index tensors, pinned staging) are filled by the first steps
+        G.seed_all()
+        _, loss = m(batch, mem_feat=None)
+        (loss["total"] * 64.0).backward()
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("warn")
+    try:
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter("always")
+            G.seed_all()
+            out, loss = m(batch, mem_feat=None)
+            (loss["total"] * 64.0).backward()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    syncs = [w for w in rec if "synchroniz" in str(w.message).lower()]
+    assert len(syncs) == 1, [str(w.message) for w in syncs]
+    assert np.isfinite(float(loss["total"]))
+    # an all-zero prediction switches to the ground truth on the device (and the host learns it from the same read)
+    use_gt, unk, T = m.decoder._guidance_and_roi(torch.zeros_like(batch["alpha"][:, 0]), batch["alpha"][:, 0].float(), 100000, None,
+                                                 __import__("maggie_b200").ops.new_status(batch["alpha"].device))
+    assert use_gt and T.counts[0] > 0
+
+
 def test_full_size_c2_properties():
     """BASELINE config C2 (8 x 512 x 512 x 3 instances, training): size-independent properties."""
     m = _model(True)
