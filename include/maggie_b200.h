@@ -54,6 +54,14 @@ int mg_unknown_mask_select(const float* alpha, const float* alt, const int32_t* 
                            const int32_t* widths, const uint8_t* and_mask, uint8_t* out_u8, uint32_t* out_bits,
                            void* stream);
 
+/* ---- K10: one stage of the progressive fusion -----------------------------------------------------------------
+ * replaces: fuse() of decoder/resnet_inst_matt_spconv.py:272-290 (compute_unknown on the CPU + two full-size blend passes
+ *           per stage): w = dilate(1/255 < src < 254/255, ellipse(width)) AND and_mask;  out_alpha = w ? finer : coarser
+ *           (`finer * w + coarser * (1 - w)` with w in {0,1}).  src / finer / coarser / out_alpha fp32 [slices,H,W]
+ *           (out_alpha may not alias src: neighbouring CTAs still read its halo rows), out_w_u8 the {0,1} mask.  Bit-exact. */
+int mg_fuse_stage(const float* src, const float* finer, const float* coarser, int slices, int H, int W,
+                  const int32_t* widths, const uint8_t* and_mask, uint8_t* out_w_u8, float* out_alpha, void* stream);
+
 /* ---- K8b: active-site lists for the sparse refinement ---------------------------------------------
  * replaces: decoder/resnet_inst_matt_spconv.py:203-218 (torch.nonzero + spconv `dummy_downscale`, whose only
  *           live product is the OS1/OS2/OS4/OS8 index sets and the (in,out,tap) pair tables).
@@ -249,14 +257,15 @@ int mg_sparse_wgrad(const void* dout, int dout_stride, int Cout, const void* src
  * parameter's address; items[k] = (tensor index, element offset) work items of <= 16384 elements.
  * acc [2] (zero before the first call; the call leaves it zeroed), step [1] (number of updates applied so far, advanced on
  * the device unless a gradient was inf / nan, in which case nothing is updated), report [2] = (unscaled gradient norm,
- * found_inf) of this call.  inv_scale = 1 / loss scale. */
+ * found_inf) of this call.  inv_scale = 1 / loss scale.  skip (optional, uint8 per tensor): tensors that received no gradient
+ * this step are left untouched (no weight decay, no moment decay), as torch.optim.AdamW does for `grad is None`. */
 typedef struct mg_optim_tensor {
     float* param;
     int64_t flat_off, numel;
 } mg_optim_tensor;
 int mg_optim_adamw_step(const mg_optim_tensor* tensors, const int32_t* items, int n_items, const float* grad, size_t n_flat,
                         float* m, float* v, float* acc, float* step, float* report, float lr, float beta1, float beta2,
-                        float eps, float weight_decay, float max_norm, float inv_scale, void* stream);
+                        float eps, float weight_decay, float max_norm, float inv_scale, const uint8_t* skip, void* stream);
 
 /* ---- K16: loader / evaluator ends of the path ------------------------------------------------------------------
  * mg_input_stage    replaces ToTensor + Normalize (dataloader/transforms.py:720-783) and the dataset's scaling / nearest 1/8

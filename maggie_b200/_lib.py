@@ -22,6 +22,7 @@ SIGNATURES = {
     "mg_unknown_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mg_unknown_mask_select": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
+    "mg_fuse_stage": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mg_sites_workspace": (c_size_t, [c_int, c_int, c_int]),
     "mg_sites_count": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mg_sites_tables": (c_int, [c_void_p, c_int, c_int, c_int, _I32P, _PP, _PP, _PP, _PP, c_void_p]),
@@ -69,7 +70,7 @@ SIGNATURES = {
     "mg_wprep_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int] + [c_void_p] * 5),
     "mg_wprep_bwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5),
     "mg_optim_adamw_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
-                            + [c_float] * 7 + [c_void_p]),
+                            + [c_float] * 7 + [c_void_p, c_void_p]),
     "mg_upsample_tanh_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mg_upsample_tanh_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mg_layer_norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -43,10 +43,11 @@ struct OptimHyper {
 __global__ void __launch_bounds__(256)
 optim_adamw_kernel(const mg_optim_tensor* __restrict__ tensors, const int2* __restrict__ items, const float* __restrict__ grad,
                    float* __restrict__ m, float* __restrict__ v, const float* __restrict__ acc, float* __restrict__ step,
-                   OptimHyper h) {
+                   const uint8_t* __restrict__ skip, OptimHyper h) {
     mg::pdl_prologue();
     if (acc[1] != 0.f) return;                          // a gradient was inf / nan: the whole step is skipped
     const int2 it = items[blockIdx.x];
+    if (skip && skip[it.x]) return;                     // no gradient this step: torch.optim.AdamW leaves the tensor alone
     const mg_optim_tensor T = tensors[it.x];
     const float total_norm = sqrtf(acc[0]);
     const float clip = fminf(1.f, h.max_norm / (total_norm + 1e-6f)) * h.inv_scale;   // torch: clamp(max_norm / (norm + 1e-6), max=1)
@@ -80,14 +81,14 @@ __global__ void optim_finish_kernel(float* __restrict__ acc, float* __restrict__
 extern "C" int mg_optim_adamw_step(const mg_optim_tensor* tensors, const int32_t* items, int n_items, const float* grad,
                                    size_t n_flat, float* m, float* v, float* acc, float* step, float* report, float lr,
                                    float beta1, float beta2, float eps, float weight_decay, float max_norm, float inv_scale,
-                                   void* stream) {
+                                   const uint8_t* skip, void* stream) {
     MG_REQUIRE(tensors && items && grad && m && v && acc && step && report, "mg_optim_adamw_step: null pointer");
     MG_REQUIRE(n_items > 0 && n_flat > 0, "mg_optim_adamw_step: no work");
     const int grid = (int)std::min<size_t>((n_flat + 255) / 256, (size_t)mg::kNumSMs * 8);
     MG_LAUNCH(optim_norm_kernel, grid, 256, 0, stream, grad, n_flat, inv_scale, acc);
     OptimHyper h{lr, beta1, beta2, eps, weight_decay, max_norm, inv_scale};
     MG_LAUNCH(optim_adamw_kernel, n_items, 256, 0, stream, tensors, reinterpret_cast<const int2*>(items), grad, m, v,
-              const_cast<const float*>(acc), step, h);
+              const_cast<const float*>(acc), step, skip, h);
     MG_LAUNCH(optim_finish_kernel, 1, 32, 0, stream, acc, step, report);
     MG_CHECK_LAUNCH("mg_optim_adamw_step");
     return MG_OK;

@@ -47,7 +47,8 @@ __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) {
 __global__ void __launch_bounds__(THREADS)
 unknown_mask_kernel(const float* __restrict__ alpha, const float* __restrict__ alt, const int32_t* __restrict__ use_alt,
                     int H, int W, const int32_t* __restrict__ widths, const uint8_t* __restrict__ and_mask,
-                    uint8_t* __restrict__ out_u8, uint32_t* __restrict__ out_bits) {
+                    uint8_t* __restrict__ out_u8, uint32_t* __restrict__ out_bits, const float* __restrict__ blend_x,
+                    const float* __restrict__ blend_y, float* __restrict__ blend_out) {
     mg::pdl_prologue();
     if (alt && use_alt && *use_alt != 0) alpha = alt;
     extern __shared__ uint32_t sbits[];  // [TH + MAXK - 1][Wd + 2]
@@ -146,6 +147,22 @@ unknown_mask_kernel(const float* __restrict__ alpha, const float* __restrict__ a
             acc &= m;
         }
         if (out_bits) out_bits[((size_t)s * H + (y0 + r)) * Wd + j] = acc;
+        if (blend_out) {
+            // K10 (progressive fusion, decoder/resnet_inst_matt_spconv.py:272-290): the {0,1} mask selects between the finer
+            // and the coarser alpha - `x * w + y * (1 - w)` of the reference - in the kernel that produces the mask
+            if (vec) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 xv = __ldg(reinterpret_cast<const float4*>(blend_x + off) + q);
+                    const float4 yv = __ldg(reinterpret_cast<const float4*>(blend_y + off) + q);
+                    const uint32_t b = acc >> (4 * q);
+                    reinterpret_cast<float4*>(blend_out + off)[q] =
+                        make_float4((b & 1u) ? xv.x : yv.x, (b & 2u) ? xv.y : yv.y, (b & 4u) ? xv.z : yv.z, (b & 8u) ? xv.w : yv.w);
+                }
+            } else {
+                for (int b = 0; b < 32 && x0 + b < W; ++b) blend_out[off + b] = ((acc >> b) & 1u) ? blend_x[off + b] : blend_y[off + b];
+            }
+        }
         if (out_u8) {
             if (vec) {
                 uint4 o0, o1;
@@ -164,7 +181,8 @@ unknown_mask_kernel(const float* __restrict__ alpha, const float* __restrict__ a
 }  // namespace
 
 static int unknown_mask(const float* alpha, const float* alt, const int32_t* use_alt, int slices, int H, int W,
-                        const int32_t* widths, const uint8_t* and_mask, uint8_t* out_u8, uint32_t* out_bits, void* stream) {
+                        const int32_t* widths, const uint8_t* and_mask, uint8_t* out_u8, uint32_t* out_bits, void* stream,
+                        const float* blend_x = nullptr, const float* blend_y = nullptr, float* blend_out = nullptr) {
     MG_REQUIRE(alpha && widths && (out_u8 || out_bits), "mg_unknown_mask: null pointer");
     MG_REQUIRE(slices >= 0 && H > 0 && W > 0 && W <= 4096, "mg_unknown_mask: bad shape %d x %d x %d", slices, H, W);
     if (slices == 0) return MG_OK;
@@ -172,7 +190,8 @@ static int unknown_mask(const float* alpha, const float* alt, const int32_t* use
     const int Wd = (W + 31) / 32;
     const size_t smem = (size_t)(TH + MAXK - 1) * (Wd + 2) * sizeof(uint32_t);
     dim3 grid(mg::ceil_div(H, TH), slices);
-    MG_LAUNCH(unknown_mask_kernel, grid, THREADS, smem, stream, alpha, alt, use_alt, H, W, widths, and_mask, out_u8, out_bits);
+    MG_LAUNCH(unknown_mask_kernel, grid, THREADS, smem, stream, alpha, alt, use_alt, H, W, widths, and_mask, out_u8, out_bits,
+              blend_x, blend_y, blend_out);
     MG_CHECK_LAUNCH("mg_unknown_mask");
     return MG_OK;
 }
@@ -187,4 +206,11 @@ extern "C" int mg_unknown_mask_select(const float* alpha, const float* alt, cons
                                       void* stream) {
     MG_REQUIRE(alt && use_alt, "mg_unknown_mask_select: null pointer");
     return unknown_mask(alpha, alt, use_alt, slices, H, W, widths, and_mask, out_u8, out_bits, stream);
+}
+
+extern "C" int mg_fuse_stage(const float* src, const float* finer, const float* coarser, int slices, int H, int W,
+                             const int32_t* widths, const uint8_t* and_mask, uint8_t* out_w_u8, float* out_alpha, void* stream) {
+    MG_REQUIRE(finer && coarser && out_alpha && out_w_u8, "mg_fuse_stage: null pointer");
+    return unknown_mask(src, nullptr, nullptr, slices, H, W, widths, and_mask, out_w_u8, nullptr, stream, finer, coarser,
+                        out_alpha);
 }

@@ -228,10 +228,39 @@ class step_scope:
         return False
 
 
+# Backward passes run outside any scope (the autograd engine calls them).  `arm_backward_pool`, called at the end of a
+# training forward, zeroes ONE pool (sized from the previous backward) that the backward's small zero-initialised buffers
+# (atomic accumulators of bias / gamma / beta / token gradients, sparse weight gradients) are carved from, instead of one
+# fill launch each (135 fills per C2 step before).  Slices are handed out once per arming, so they are always zero.
+_BWD_POOL = {}
+
+
+def arm_backward_pool(device):
+    st = _BWD_POOL.setdefault(str(device), {"buf": None, "used": 0, "asked": 0})
+    need = max(st["asked"], st["used"])
+    if st["buf"] is None or st["buf"].numel() < need:
+        st["buf"] = torch.zeros(int(need * 1.25) + 4096, dtype=torch.float32, device=device)
+    elif st["used"]:
+        st["buf"][:st["used"]].zero_()
+    st["used"] = st["asked"] = 0
+
+
 def zeros_f32(n, device):
-    """Zeroed fp32 scratch of n elements (from the enclosing scope's pool when there is one)."""
+    """Zeroed fp32 scratch of n elements (from the enclosing scope's pool, or the armed backward pool, when there is one)."""
     if _SCOPES:
         return _SCOPES[-1].take(n, device)
+    st = _BWD_POOL.get(str(device))
+    if st is not None and torch.cuda.is_current_stream_capturing():
+        st = None       # a captured graph must own its fills: the pool is re-zeroed by eager code only
+    if st is not None and st["buf"] is not None:
+        n_al = (n + 31) // 32 * 32
+        st["asked"] += n_al
+        if st["used"] + n_al <= st["buf"].numel():
+            out = st["buf"][st["used"]:st["used"] + n]
+            st["used"] += n_al
+            return out
+    elif st is not None:
+        st["asked"] += (n + 31) // 32 * 32
     return torch.zeros(n, dtype=torch.float32, device=device)
 
 
@@ -646,7 +675,7 @@ class _ConvBNAct(torch.autograd.Function):
         L = _lib.lib()
         sums, ctx.sums = ctx.sums, None
         if sums is None:
-            sums = torch.zeros((2, Co), dtype=torch.float32, device=r.device)
+            sums = zeros_f32(2 * Co, r.device).view(2, Co)
         a_post = 0 if act_first else ACT[act]
         _lib.check(L.mg_bn_bwd_reduce(_ptr(dy), _ptr(y), _ptr(r), _ptr(mean), _ptr(invstd), _ptr(sums), N, Ho, Wo, Co, a_post,
                                       _stream()), "mg_bn_bwd_reduce")

@@ -18,6 +18,7 @@ class FlatGradAllReduce:
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=dtype, device=dev)
+        self.no_grad = ()
         self.views, off = [], 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
@@ -29,6 +30,8 @@ class FlatGradAllReduce:
 
     def pack(self):
         """Gradients -> flat buffer (parameters without a gradient contribute zeros); p.grad becomes the view."""
+        # (indices of the parameters that received no gradient this step: the optimizer leaves them alone, as torch does)
+        self.no_grad = tuple(i for i, p in enumerate(self.params) if p.grad is None)
         have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
         if len(have) != len(self.params):
             for v, p in zip(self.views, self.params):

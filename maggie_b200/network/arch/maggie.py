@@ -256,6 +256,8 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
             self._extra_decoder_losses(pred, loss_dict)
             if unsort is not None:
                 output = {k: ops.take(v, 2, unsort) for k, v in output.items()}
+            if x.is_cuda and torch.is_grad_enabled():
+                dense.arm_backward_pool(x.device)   # one memset for the backward's small zeroed accumulators
             return output, loss_dict
 
         for k in pred:

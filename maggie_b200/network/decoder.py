@@ -402,10 +402,9 @@ class MaGGIeDecoder(nn.Module):
             a1 = torch.zeros_like(a8)
         ret = dict(alpha_os1=a1, alpha_os4=a4, alpha_os8=a8)
         # progressive fusion (fuse(), :272-290): the weights are {0,1} masks, so `x*w + y*(1-w)` is a select
-        w4 = ops.unknown_mask(a8, widths(27), and_mask=unk)
-        a = torch.where(w4 != 0, a4, a8)
-        w1 = ops.unknown_mask(a, widths(15), and_mask=unk)
-        a = torch.where(w1 != 0, a1, a)
+        # (K10: mask + blend of a stage in one kernel)
+        a, w4 = ops.fuse_stage(a8, a4, a8, widths(27), unk)
+        a, w1 = ops.fuse_stage(a, a1, a, widths(15), unk)
         ret["refined_masks"] = a
         if not use_gt:
             w4, w1 = w4.to(a8.dtype), w1.to(a8.dtype)

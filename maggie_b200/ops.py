@@ -139,6 +139,30 @@ def unknown_mask(alpha, widths, and_mask=None, alt=None, use_alt=None):
     return out
 
 
+def fuse_stage(src, finer, coarser, widths, and_mask):
+    """One stage of the progressive fusion (reference: decoder/resnet_inst_matt_spconv.py:272-290 fuse()):
+    w = unknown_mask(src, widths) & and_mask;  alpha = where(w, finer, coarser).  Returns (alpha fp32, w uint8).
+    NATIVE (K10: the blend runs in the mask kernel's epilogue); no gradient flows through the fused alpha (the losses
+    take the three scales separately), as in the reference's detached use."""
+    _need_cuda(src, finer, coarser, and_mask)
+    f = lambda t: t.detach().to(torch.float32).contiguous()
+    s_, x, y = f(src), f(finer), f(coarser)
+    H, W = s_.shape[-2:]
+    slices = s_.numel() // (H * W) if s_.numel() else 0
+    w_out = torch.empty(s_.shape, dtype=torch.uint8, device=s_.device)
+    a_out = torch.empty_like(s_)
+    if slices == 0:
+        return a_out, w_out
+    if len(widths) != slices:
+        raise ValueError(f"fuse_stage: {len(widths)} widths for {slices} slices")
+    wd = _widths_tensor(tuple(int(v) for v in widths), s_.device)
+    am = and_mask.to(torch.uint8).contiguous()
+    assert am.shape == s_.shape and x.shape == s_.shape and y.shape == s_.shape
+    _lib.check(_lib.lib().mg_fuse_stage(_ptr(s_), _ptr(x), _ptr(y), slices, H, W, _ptr(wd), _ptr(am), _ptr(w_out), _ptr(a_out),
+                                       _stream()), "mg_fuse_stage")
+    return a_out, w_out
+
+
 # =============================================================================================== native: K8b
 SiteTables = namedtuple("SiteTables", "counts coords nbr parent child shapes flags", defaults=(None,))
 
@@ -264,7 +288,8 @@ class _MatteLossSums(torch.autograd.Function):
         ws = torch.empty(L.mg_loss_workspace_floats(S, H, W), dtype=torch.float32, device=a1.device)
         n0 = 3 * S * H * W
         sg = torch.empty(n0 + n0 // 4 + n0 // 16, dtype=torch.float16, device=a1.device)
-        sums = torch.zeros((32, 3, 8), dtype=torch.float32, device=a1.device)
+        from . import dense
+        sums = dense.zeros_f32(32 * 3 * 8, a1.device).view(32, 3, 8)
         _lib.check(L.mg_loss_fwd(_ptr(a1d), _ptr(a4d), _ptr(a8d), _ptr(td), _ptr(w1d), _ptr(w4d), _ptr(w8d), _ptr(psd), S, H, W,
                                  _ptr(ws), _ptr(sg), _ptr(sums), _stream()), "mg_loss_fwd")
         ctx.save_for_backward(a1d, a4d, a8d, td, w1d, w4d, w8d, ws, sg, psd)
@@ -463,7 +488,8 @@ class _TokenLogits(torch.autograd.Function):
         Q = tk.shape[1]
         gc = g.to(torch.float32).contiguous()
         dx = torch.empty_like(xn) if ctx.needs_input_grad[1] else None
-        dtok = torch.zeros_like(tk) if ctx.needs_input_grad[0] else None
+        from . import dense
+        dtok = dense.zeros_f32(tk.numel(), tk.device).view(tk.shape) if ctx.needs_input_grad[0] else None
         _lib.check(_lib.lib().mg_token_logits_bwd(_ptr(tk), _ptr(xn), _ptr(gc), _ptr(dx), _ptr(dtok), BT, n_f, Q, H * W, C,
                                                  _stream()), "mg_token_logits_bwd")
         return (dtok.to(tdt) if dtok is not None else None), (dx.permute(0, 3, 1, 2) if dx is not None else None), None
@@ -554,7 +580,8 @@ class _AttnTQ(torch.autograd.Function):
         S = kh.shape[1]
         go = g_out.to(torch.float32).contiguous()
         gs = g_stat.to(torch.float32).contiguous() if (g_stat is not None and gd is not None) else None
-        dq = torch.zeros_like(qf)
+        from . import dense
+        dq = dense.zeros_f32(qf.numel(), qf.device).view(qf.shape)
         dk, dv = torch.empty_like(kh), torch.empty_like(vh)
         _lib.check(_lib.lib().mg_attn_tq_bwd(_ptr(qf), _ptr(kh), _ptr(vh), _ptr(kp), _ptr(gd), _ptr(out), _ptr(small[0]),
                                             _ptr(small[1]), _ptr(small[2]), _ptr(go), _ptr(gs), B, Fq, S, E, _ptr(dq),
@@ -588,7 +615,9 @@ class _AttnFQ(torch.autograd.Function):
         Fk = kf.shape[1]
         go = g_out.to(torch.float16).contiguous()
         dq = torch.empty_like(qh)
-        dk, dv = torch.zeros_like(kf), torch.zeros_like(vf)
+        from . import dense
+        dk = dense.zeros_f32(kf.numel(), kf.device).view(kf.shape)
+        dv = dense.zeros_f32(vf.numel(), vf.device).view(vf.shape)
         _lib.check(_lib.lib().mg_attn_fq_bwd(_ptr(qh), _ptr(kf), _ptr(vf), _ptr(kp), _ptr(go), B, Fk, S, E, _ptr(dq), _ptr(dk),
                                             _ptr(dv), _stream()), "mg_attn_fq_bwd")
         qd, kd, vd = ctx.dt

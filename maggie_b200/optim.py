@@ -49,6 +49,7 @@ class FusedAdamW:
         self.tensors = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         self.items = torch.from_numpy(np.asarray(items, dtype=np.int32)).to(dev)
         self.n_items = len(items)
+        self._skip_key, self._skip = (), None               # device mask of the tensors without a gradient (rarely changes)
 
     def zero_grad(self, set_to_none=True):
         self.flat.zero()
@@ -60,17 +61,53 @@ class FusedAdamW:
         if self._sig != tuple(p.data_ptr() for p in self.flat.params):
             raise RuntimeError("FusedAdamW: parameter storage moved after construction (.to() / load into new tensors)")
         grad = self.flat.pack()
+        if self.flat.no_grad != self._skip_key:
+            # e.g. the four `dummy_downscale` weights: trainable flag set, never part of the graph.  torch.optim.AdamW
+            # skips `grad is None` parameters entirely (no weight decay, no moment decay): so does the kernel.
+            self._skip_key = self.flat.no_grad
+            mask = torch.zeros(len(self.flat.params), dtype=torch.uint8)
+            mask[list(self._skip_key)] = 1
+            self._skip = mask.to(grad.device) if self._skip_key else None
         g = self.param_groups[0]
         _lib.check(_lib.lib().mg_optim_adamw_step(
             _lib.tensor_ptr(self.tensors), _lib.tensor_ptr(self.items), self.n_items, _lib.tensor_ptr(grad), grad.numel(),
             _lib.tensor_ptr(self.m), _lib.tensor_ptr(self.v), _lib.tensor_ptr(self.acc), _lib.tensor_ptr(self.step_count),
             _lib.tensor_ptr(self.report), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-            float(g["weight_decay"]), float(self.clip_norm), 1.0 / float(grad_scale), _lib.stream_ptr()), "mg_optim_adamw_step")
+            float(g["weight_decay"]), float(self.clip_norm), 1.0 / float(grad_scale), _lib.tensor_ptr(self._skip),
+            _lib.stream_ptr()), "mg_optim_adamw_step")
         return self.report
 
     def state_dict(self):
-        return dict(m=self.m, v=self.v, step=self.step_count, param_groups=[{k: v for k, v in self.param_groups[0].items() if k != "params"}])
+        """The layout `torch.optim.AdamW.state_dict()` writes (what the reference engine saves to / resumes from
+        `last_opt.pth`, engine/train.py): per-parameter `step` / `exp_avg` / `exp_avg_sq`, parameters numbered in order.
+        Parameters that never received a gradient have no state entry, as in torch."""
+        state, off = {}, 0
+        never = set(self._skip_key)
+        for i, p in enumerate(self.flat.params):
+            n = p.numel()
+            if i not in never:
+                state[i] = dict(step=self.step_count.clone().reshape(()), exp_avg=self.m[off:off + n].view_as(p).clone(),
+                                exp_avg_sq=self.v[off:off + n].view_as(p).clone())
+            off += n
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group.update(params=list(range(len(self.flat.params))), amsgrad=False, maximize=False, foreach=None, capturable=False,
+                     differentiable=False, fused=None)
+        return dict(state=state, param_groups=[group])
 
     def load_state_dict(self, sd):
-        self.m.copy_(sd["m"]), self.v.copy_(sd["v"]), self.step_count.copy_(sd["step"])
-        self.param_groups[0].update(sd["param_groups"][0])
+        """Accepts a `torch.optim.AdamW` state dict over the same parameter list (or this class's own)."""
+        off, steps = 0, []
+        for i, p in enumerate(self.flat.params):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.m[off:off + n].copy_(st["exp_avg"].reshape(-1)), self.v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.append(float(st["step"]))
+            else:
+                self.m[off:off + n].zero_(), self.v[off:off + n].zero_()
+            off += n
+        if steps:
+            self.step_count.fill_(max(steps))     # one shared step counter: every parameter with state is stepped together
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in sd["param_groups"][0]:
+                self.param_groups[0][k] = sd["param_groups"][0][k]

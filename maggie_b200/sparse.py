@@ -109,7 +109,8 @@ def _f16rows(t):
 
 
 def _wgrad(dout, cout, src, cin, table, T):
-    dw = torch.zeros((cout, T * cin), dtype=torch.float32, device=src.device)
+    from . import dense
+    dw = dense.zeros_f32(cout * T * cin, src.device).view(cout, T * cin)
     No = dout.shape[0]
     _lib.check(_lib.lib().mg_sparse_wgrad(_ptr(dout), dout.stride(0), cout, _ptr(src), src.stride(0), cin,
                                          _ptr(table) if table is not None else None, T, No, _ptr(dw), _stream()),

@@ -20,6 +20,11 @@ def unknown_mask(alpha, widths, and_mask=None, alt=None, use_alt=None):
     return torch.from_numpy(out.astype(np.uint8)).to(alpha.device)
 
 
+def fuse_stage(src, finer, coarser, widths, and_mask):
+    w = unknown_mask(src, widths, and_mask=and_mask)
+    return torch.where(w != 0, finer.detach().float(), coarser.detach().float()), w
+
+
 def _imap(coords, slots, H, W):
     m = np.full((slots, H, W), -1, np.int64)
     if len(coords):
@@ -242,10 +247,11 @@ def conv_bias(x, w, bias=None, *, padding=1):
 def injected(dtype=torch.float32):
     """Swap the native ops for the references above (CPU container only)."""
     names = ("unknown_mask", "build_sites", "mask_embed", "conv_bn_act", "rows_conv", "rows_head", "gather_dense",
-             "matte_loss_sums", "attention", "conv_bias", "prepare_weights", "COMPUTE_DTYPE")
+             "matte_loss_sums", "attention", "conv_bias", "prepare_weights", "COMPUTE_DTYPE", "fuse_stage")
     saved = {n: getattr(ops, n) for n in names}
     ops.unknown_mask, ops.build_sites, ops.mask_embed, ops.conv_bn_act, ops.COMPUTE_DTYPE = \
         unknown_mask, build_sites, mask_embed, conv_bn_act, dtype
+    ops.fuse_stage = fuse_stage
     ops.rows_conv, ops.rows_head, ops.gather_dense = rows_conv, rows_head, gather_dense
     ops.matte_loss_sums, ops.attention, ops.conv_bias = matte_loss_sums, attention, conv_bias
     ops.prepare_weights = lambda bank: None  # layers then use the per-layer torch composition (ops.spectral_weight)

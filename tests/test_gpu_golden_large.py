@@ -1,0 +1,124 @@
+"""-m gpu: parity at the BASELINE.json config sizes against goldens of the UNMODIFIED reference (oracle/make_golden_large.py,
+stored compactly), and a 20-step training curve against the reference engine's update rule.
+
+  C2 (8 x 512 x 512 x 3 instances): evaluation forward in both precisions, one training step (iter = 1);
+  C5 (1024 x 1024 x 8 instances): evaluation forward;
+  loss curve: 20 steps (backward, clip_grad_norm_, AdamW) on a cycle of four 8 x 128 x 128 batches, iter = 100000.
+Tolerances are stated next to each assert; measured values are printed with `-s`."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from maggie_b200.config import CfgNode
+from maggie_b200.network import build_model
+from oracle import make_golden as G
+from oracle import make_golden_large as GL
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+ALPHA_TOL = 1e-3          # north star: alpha within 1e-3 max abs (met by precision="high", the reference evaluates in fp32)
+
+
+def _model(training, precision="fp16"):
+    m, _ = build_model(CfgNode(synth.model_cfg()))
+    m.load_state_dict(synth.synth_state_dict(m.state_dict()), strict=True)
+    m.decoder.inst_spec_layer.dropout.p = 0.0
+    return m.cuda().train(training).set_precision(precision)
+
+
+def _dev(batch):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def _detail(z):
+    shape = tuple(int(v) for v in z["out_shape/detail_mask"])
+    return np.unpackbits(z["out_bits/detail_mask"])[:int(np.prod(shape))].reshape(shape).astype(bool)
+
+
+@pytest.mark.parametrize("case", ["c2_eval_8x512_3inst", "c5_eval_1024_8inst"])
+def test_eval_at_baseline_config_size(case, golden):
+    kw, _, sub = GL.LARGE[case]
+    z = golden(case)
+    res = {}
+    for precision in ("high", "fp16"):
+        m = _model(False, precision)
+        grabbed = {}
+        imd = m.decoder.refine_OS8.forward
+        m.decoder.refine_OS8.forward = lambda *a, **k: grabbed.setdefault("out", imd(*a, **k))
+        G.seed_all()
+        with torch.no_grad():
+            out = m(_dev(synth.make_batch(**kw)), mem_feat=None)
+        a8 = out["alpha_os8"].float().cpu().numpy()[..., ::sub, ::sub]
+        lg = grabbed["out"][0].float().cpu().numpy()
+        res[precision] = (float(np.abs(a8 - z["out_sub/alpha_os8"]).max()), float(np.abs(lg - z["stage/os8_logits"]).max()),
+                          float((out["detail_mask"].cpu().numpy().astype(bool) == _detail(z)).mean()))
+        del m, out
+        torch.cuda.empty_cache()
+    print(f"\n{case}: max|alpha_os8 - ref| (every {sub}th pixel), max|os8 logits - ref|, detail-mask agreement")
+    for k, v in res.items():
+        print(f"  {k:5s} {v[0]:.3e}  {v[1]:.3e}  {v[2]:.6f}")
+    assert res["high"][0] <= ALPHA_TOL, res
+    assert res["high"][2] >= 0.9995
+    assert res["fp16"][0] <= 2.5e-2          # fp16 storage floor at this size (measured ~1e-2; noise realisation dependent)
+    assert res["fp16"][0] > 5 * res["high"][0]
+
+
+def test_c2_training_step_matches_the_reference(golden):
+    """BASELINE config C2, one training step at iter = 1: losses, active sites, gradient norms (fp16 autocast width)."""
+    case = "c2_train_8x512_3inst_iter1"
+    kw, _, sub = GL.LARGE[case]
+    z = golden(case)
+    m = _model(True)
+    G.seed_all()
+    out, loss = m(_dev(synth.make_batch(**kw)), mem_feat=None)
+    (loss["total"] * 64.0).backward()
+    assert int(out["detail_mask"].sum()) == int(z["detail_count"])      # the uncertain region comes from the GT: bit exact
+    assert bool((out["detail_mask"].cpu().numpy().astype(bool) == _detail(z)).all())
+    print()
+    for k in sorted(k[5:] for k in z if k.startswith("loss/")):
+        ref, got = float(z["loss/" + k]), float(loss[k])
+        print(f"  {k:16s} ref {ref:.5f} ours {got:.5f}  rel {abs(got - ref) / max(abs(ref), 1e-9):.2e}")
+        assert abs(got - ref) <= 0.03 * max(1.0, abs(ref)), (k, got, ref)   # 3 %: fp16 activations vs the fp32 reference
+    a8 = out["alpha_os8"].detach().float().cpu().numpy()[..., ::sub, ::sub]
+    assert float(np.abs(a8 - z["out_sub/alpha_os8"]).mean()) < 5e-3
+    rel = []
+    for n, p in m.named_parameters():
+        key = "gradnorm/" + n
+        if key in z and p.grad is not None and float(z[key]) > 1e-4:
+            rel.append(abs(float((p.grad.double() / 64.0).norm()) - float(z[key])) / float(z[key]))
+    rel = np.array(rel)
+    print(f"  gradient norms of {len(rel)} parameters: median rel err {np.median(rel):.3e}, 90th pct {np.percentile(rel, 90):.3e}")
+    assert len(rel) > 250 and np.median(rel) < 0.05 and np.percentile(rel, 90) < 0.25
+
+
+def test_loss_curve_tracks_the_reference(golden):
+    """20 optimizer steps with the fused optimizer tail (K14) on the flat gradient buffer against the reference model under
+    torch's clip_grad_norm_ + AdamW (fp32, CPU): the loss curve must track within the stated tolerance."""
+    from maggie_b200.dp import FlatGradAllReduce
+    from maggie_b200.optim import FusedAdamW
+    z = golden(GL.CURVE)
+    keys = [str(k) for k in z["keys"]]
+    ref = z["losses"][:, keys.index("total")]
+    m = _model(True)
+    flat = FlatGradAllReduce(m.parameters())
+    opt = FusedAdamW(flat, lr=float(z["lr"]), betas=(0.9, 0.999), weight_decay=0.01, clip_norm=float(z["clip"]))
+    batches = [_dev(b) for b in GL.curve_batches()]
+    scale, ours, norms = 256.0, [], []
+    for step in range(GL.CURVE_STEPS):
+        G.seed_all(G.RNG_SEED + step)
+        flat.zero()
+        _, loss = m(batches[step % GL.CURVE_BATCHES], mem_feat=None)
+        (loss["total"] * scale).backward()
+        rep = opt.step(grad_scale=scale)
+        ours.append(float(loss["total"]))
+        norms.append(float(rep[0]))
+    ours, norms = np.array(ours), np.array(norms)
+    rel = np.abs(ours - ref) / ref
+    print("\n  step   reference   ours      rel.err   |grad| ref / ours")
+    for i in range(GL.CURVE_STEPS):
+        print(f"  {i:3d}   {ref[i]:9.5f}  {ours[i]:9.5f}  {rel[i]:.3e}   {z['grad_norm'][i]:.3f} / {norms[i]:.3f}")
+    # stated tolerance: every step within 10 % of the reference curve, 3 % on average, and the same overall descent
+    assert rel.max() < 0.10 and rel.mean() < 0.03, (rel.max(), rel.mean())
+    assert abs((ours[-4:].mean() / ours[:4].mean()) - (ref[-4:].mean() / ref[:4].mean())) < 0.05

@@ -175,3 +175,18 @@ def test_upsample_tanh_all_zero_flag():
     flag.fill_(1)
     ops.upsample_tanh(x, scale=8.0, plane_scale=torch.zeros(2, 3, device="cuda"), all_zero=flag)
     assert int(flag) == 1
+
+
+def test_fuse_stage_bit_exact_against_mask_then_blend():
+    """K10: mask + blend of one progressive-fusion stage in one kernel == unknown_mask followed by torch.where."""
+    from maggie_b200 import ops
+    g = torch.Generator().manual_seed(33)
+    for shape in ((4, 3, 128, 160), (2, 2, 72, 100)):              # vectorised (W % 32 == 0) and scalar tails
+        src = torch.rand(*shape, generator=g).cuda()
+        src[src < 0.5] = 0.0
+        fine, roi = torch.rand(*shape, generator=g).cuda(), (torch.rand(*shape, generator=g) > 0.3).to(torch.uint8).cuda()
+        widths = [int(v) for v in torch.randint(1, 28, (shape[0] * shape[1],), generator=g)]
+        a, w = ops.fuse_stage(src, fine, src, widths, roi)
+        w_ref = ops.unknown_mask(src, widths, and_mask=roi)
+        assert torch.equal(w, w_ref)
+        assert torch.equal(a, torch.where(w_ref != 0, fine, src))
