@@ -184,45 +184,99 @@ C2_CONVS = [
 ]
 
 
+def _traffic_table():
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels below from the committed
+    `ncu --set full` captures (profiles/r2_ncu_traffic.json, written by tools/ncu_kernels.py); {} when absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def kernel_probes(torch, dev, peaks):
-    """Live CUDA-event timing of this repo's own kernels at the C2 shapes (L2 flushed between launches).
-    The conv family is timed layer by layer over the whole C2 layer table (forward, data gradient, weight gradient);
-    achieved = sum of algorithmic FLOPs / sum of launch durations."""
-    from maggie_b200 import dense, ops
+    """Live CUDA-event timing of this repo's own kernels at the C2 shapes.  Every entry is the AVERAGE launch duration over a
+    timed region of back-to-back launches on rotating operand sets (more than the 126 MB L2 in total), replayed from a CUDA
+    graph so that no host launch overhead sits between the events.  The conv family is timed layer by layer over the whole
+    C2 layer table (forward, data gradient, weight gradient); achieved = sum of algorithmic FLOPs (or bytes) / sum of
+    average launch durations x launches per step."""
+    from maggie_b200 import _lib, dense, ops, sparse
     from oracle import synth
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+    traffic = _traffic_table()
 
-    def timeit(fn, n=5):
-        for _ in range(2):
-            fn()
+    def burst(fn, nsets, rounds=3):
+        for i in range(nsets):
+            fn(i)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(rounds):
+                    for i in range(nsets):
+                        fn(i)
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()
         ts = []
-        for _ in range(n):
-            flush.fill_(1)
+        for _ in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            g.replay()
             e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e-3)
-        return sorted(ts)[len(ts) // 2]
+            ts.append(e0.elapsed_time(e1) * 1e-3 / (rounds * nsets))
+        return sorted(ts)[1]
+
+    def nsets_for(nbytes):
+        return int(max(2, min(12, (300 << 20) // max(int(nbytes), 1) + 1)))
 
     out = {}
-    al = torch.stack([synth.soft_ellipse_alphas(1, 10, H, W, EDGE_PX, seed=s)[0] for s in range(FRAMES_PER_GPU)]).to(dev)
+
+    def hbm_entry(name, t, nbytes, note=None, launches=1):
+        out[name] = dict(bound="hbm", achieved=nbytes / t / 1e9, peak=peaks["hbm"], unit="GB/s", frac=nbytes / t / 1e9 / peaks["hbm"],
+                         traffic=traffic.get(name), us_per_launch=t * 1e6, algorithmic_bytes=nbytes, launches_per_step=launches)
+        if note:
+            out[name]["note"] = note
+
+    # ---- bandwidth kernels
+    als = [torch.stack([synth.soft_ellipse_alphas(1, 10, H, W, EDGE_PX, seed=s + 10 * k)[0] for s in range(FRAMES_PER_GPU)]).to(dev)
+           for k in range(3)]
     widths = [15] * (FRAMES_PER_GPU * 10)
-    img = torch.randn(FRAMES_PER_GPU, 3, H, W, device=dev)
-    msk = (al[:, :3] > 0.5).float().contiguous()
+    hbm_entry("unknown_mask_kernel", burst(lambda i: ops.unknown_mask(als[i], widths), 3), als[0].numel() * 5.0,
+              "threshold + elliptical dilation of 80 planes of 512^2: 4 B read + 1 B written per pixel", launches=5)
+    imgs = [torch.randn(FRAMES_PER_GPU, 3, H, W, device=dev) for _ in range(3)]
+    msk = (als[0][:, :3] > 0.5).float().contiguous()
     tab = torch.randn(11, 3, device=dev)
-    for name, fn, nbytes in (("unknown_mask_kernel", lambda: ops.unknown_mask(al, widths), al.numel() * 5.0),
-                             ("mask_embed_fwd_kernel", lambda: ops.mask_embed(img, msk, tab, [0, 1, 2], 16),
-                              img.shape[0] * H * W * (6 * 4 + 32.0))):
-        t = timeit(fn, 10)
-        out[name] = dict(bound="hbm", achieved=nbytes / t / 1e9, peak=peaks["hbm"], unit="GB/s",
-                         frac=nbytes / t / 1e9 / peaks["hbm"], traffic=None, us_per_step=t * 1e6, algorithmic_bytes=nbytes)
-    # conv family: every layer of the C2 table, forward / data gradient / weight gradient, weight packs prepared outside
-    # the timed region (in the step they come from the grouped K0 kernel).  Launches that mg_conv_fprop routes to the
-    # halo-resident kernel K2b (high-resolution, <= 64 channels: HBM-bound) are accounted separately, in bytes.
-    from maggie_b200 import _lib
+    with torch.no_grad():
+        hbm_entry("mask_embed_fwd_kernel", burst(lambda i: ops.mask_embed(imgs[i], msk, tab, [0, 1, 2], 32), 3),
+                  FRAMES_PER_GPU * H * W * (6 * 4 + 64.0), "3 image + 3 mask planes fp32 read, 32 fp16 channels written per pixel")
+
+    # ---- sparse refinement kernels (K9b / K9c) on a C2-sized OS1 site list: 3x3 SubM 32 -> 32
+    roi = (als[0][:, :N_INST] > 1.0 / 255) & (als[0][:, :N_INST] < 254.0 / 255)
+    T = ops.build_sites(ops.unknown_mask(als[0][:, :N_INST].contiguous(), [15] * (FRAMES_PER_GPU * N_INST)).reshape(-1, H, W))
+    n1 = T.counts[0]
+    srcs = [torch.randn(n1, 32, device=dev).half() for _ in range(6)]
+    gys = [torch.randn(n1, 32, device=dev).half() for _ in range(6)]
+    w9 = torch.randn(32, 3, 3, 32, device=dev) / 17.0
+    wp = sparse.pack_fwd(w9)
+    t = burst(lambda i: sparse.sparse_conv_launch(srcs[i], wp, 9, 32, 32, table=T.nbr[0]), 6)
+    rows_bytes = n1 * (32 * 2 * 2 + 9 * 4.0)          # rows read once + written once (gathers hit L2) + the rulebook
+    hbm_entry("sparse_conv_persistent_kernel", t, rows_bytes,
+              f"SubM 3x3 32->32 on {n1} active sites: rows in + rows out + 36 B of rulebook per site (SURVEY 8d byte model)", launches=12)
+    out["sparse_conv_persistent_kernel"]["tflops"] = 2.0 * n1 * 9 * 32 * 32 / t / 1e12
+    t = burst(lambda i: sparse._wgrad(gys[i], 32, srcs[i], 32, T.nbr[0], 9), 6)
+    hbm_entry("sparse_wgrad_persistent_kernel", t, rows_bytes,
+              f"weight gradient of the same layer: d_out rows + gathered source rows + rulebook", launches=5)
+    del srcs, gys
+
+    # ---- conv family: every layer of the C2 table, forward / data gradient / weight gradient, weight packs prepared outside
+    # the timed region (in the step they come from the grouped K0 kernel).  Launches are accounted to the kernel
+    # mg_conv_fprop / mg_conv_wgrad routed them to: K2 (generic), K2b / K4b (halo, <= 64 channels: HBM-bound, in bytes),
+    # K2h (mid-resolution 3x3 layers).
     orig_pack, memo = dense.pack_weight, {}
 
     def cached_pack(w, ci_pad=None):
@@ -232,37 +286,43 @@ def kernel_probes(torch, dev, peaks):
         return memo[key][0]
 
     dense.pack_weight = cached_pack
-    tot = {"conv_tcgen05_kernel[fprop]": [0.0, 0.0, 0], "conv_tcgen05_kernel[dgrad]": [0.0, 0.0, 0],
-           "wgrad_tcgen05_kernel": [0.0, 0.0, 0], "conv_halo_tcgen05_kernel": [0.0, 0.0, 0],
-           "wgrad_halo_tcgen05_kernel": [0.0, 0.0, 0]}
+    names = ["conv_tcgen05_kernel[fprop]", "conv_tcgen05_kernel[dgrad]", "conv_mid_tcgen05_kernel[fprop]",
+             "conv_mid_tcgen05_kernel[dgrad]", "wgrad_tcgen05_kernel", "conv_halo_tcgen05_kernel", "wgrad_halo_tcgen05_kernel"]
+    tot = {k: [0.0, 0.0, 0] for k in names}
     try:
         for (hw, ci, co, k, s, d, tr, cnt) in C2_CONVS:
             N = FRAMES_PER_GPU
-            x = torch.randn(N, hw, hw, ci, device=dev).half()
             w = torch.randn((ci, co, k, k) if tr else (co, ci, k, k), device=dev) / (ci * k * k) ** 0.5
             g = dense.ConvGeom("convT", 4, 2, 1, 1) if tr else dense.ConvGeom("conv", k, s, d * (k // 2) if k > 1 else 0, d)
             if not tr and k == 2:
                 g = dense.ConvGeom("conv", 2, 2, 0, 1)
-            y = g.fwd(x, w)
-            flops = 2.0 * y.shape[0] * y.shape[1] * y.shape[2] * co * ci * (4 if tr else k * k)
-            nbytes = 2.0 * (x.numel() + y.numel())
+            x0 = torch.randn(N, hw, hw, ci, device=dev).half()
+            y0 = g.fwd(x0, w)
+            nbytes = 2.0 * (x0.numel() + y0.numel())
+            ns = nsets_for(nbytes)
+            xs = [x0] + [torch.randn_like(x0) for _ in range(ns - 1)]
+            ys = [y0] + [torch.randn_like(y0) for _ in range(ns - 1)]
+            flops = 2.0 * y0.shape[0] * y0.shape[1] * y0.shape[2] * co * ci * (4 if tr else k * k)
             dwp = torch.zeros_like(dense.pack_weight(w.permute(1, 0, 2, 3) if tr else w, ci), dtype=torch.float32)
 
             class Bank:   # accumulate into a pre-zeroed pack as the weight bank does (no fill inside the timing)
                 G = dwp
 
-            for key, fn, nl in (("conv_tcgen05_kernel[fprop]", lambda: g.fwd(x, w), 1),       # sub-pixel phases: one launch
-                                ("conv_tcgen05_kernel[dgrad]", lambda: g.dgrad(y, w, x.shape), 1),
-                                ("wgrad_tcgen05_kernel", lambda: g.wgrad(y, x, w.shape, bank=Bank), 4 if tr else 1)):
-                h0, w0 = _lib.lib().mg_conv_halo_launches(), _lib.lib().mg_wgrad_halo_launches()
-                fn()
-                halo = _lib.lib().mg_conv_halo_launches() > h0 or _lib.lib().mg_wgrad_halo_launches() > w0
-                t = timeit(fn, 3)
-                if halo:
-                    key = "wgrad_halo_tcgen05_kernel" if key == "wgrad_tcgen05_kernel" else "conv_halo_tcgen05_kernel"
+            for kind, fn, nl in (("fprop", lambda i: g.fwd(xs[i], w), 1), ("dgrad", lambda i: g.dgrad(ys[i], w, x0.shape), 1),
+                                 ("wgrad", lambda i: g.wgrad(ys[i], xs[i], w.shape, bank=Bank), 4 if tr else 1)):
+                h0, m0, w0 = L.mg_conv_halo_launches(), L.mg_conv_mid_launches(), L.mg_wgrad_halo_launches()
+                fn(0)
+                halo = L.mg_conv_halo_launches() > h0 or L.mg_wgrad_halo_launches() > w0
+                mid = L.mg_conv_mid_launches() > m0
+                t = burst(fn, ns)
+                if kind == "wgrad":
+                    key = "wgrad_halo_tcgen05_kernel" if halo else "wgrad_tcgen05_kernel"
+                else:
+                    key = "conv_halo_tcgen05_kernel" if halo else (f"conv_mid_tcgen05_kernel[{kind}]" if mid else f"conv_tcgen05_kernel[{kind}]")
                 tot[key][0] += (nbytes if halo else flops) * cnt
                 tot[key][1] += t * cnt
                 tot[key][2] += nl * cnt
+            del xs, ys
     finally:
         dense.pack_weight = orig_pack
     for key, (work, t, nl) in tot.items():
@@ -270,16 +330,98 @@ def kernel_probes(torch, dev, peaks):
             continue
         if key in ("conv_halo_tcgen05_kernel", "wgrad_halo_tcgen05_kernel"):
             out[key] = dict(bound="hbm", achieved=work / t / 1e9, peak=peaks["hbm"], unit="GB/s",
-                            frac=work / t / 1e9 / peaks["hbm"], traffic=None, us_per_step=t * 1e6, algorithmic_bytes_per_step=work,
-                            launches_per_step=nl,
+                            frac=work / t / 1e9 / peaks["hbm"], traffic=traffic.get(key), us_per_step=t * 1e6,
+                            algorithmic_bytes_per_step=work, launches_per_step=nl,
                             note="K2b / K4b launches of the C2 layer table (stride-1 3x3 layers with <= 64 channels at >= 128-wide "
-                                 "resolutions); bytes = the two activation tensors the kernel streams, L2 flushed")
+                                 "resolutions); bytes = the two activation tensors the kernel streams")
         else:
             out[key] = dict(bound="tensor", achieved=work / t / 1e12, peak=peaks["tf_sustained"], unit="TFLOP/s",
-                            frac=work / t / 1e12 / peaks["tf_sustained"], traffic=None, us_per_step=t * 1e6,
+                            frac=work / t / 1e12 / peaks["tf_sustained"], traffic=traffic.get(key.split("[")[0]), us_per_step=t * 1e6,
                             algorithmic_flops_per_step=work, launches_per_step=nl,
-                            note="sum over the C2 conv layers served by this kernel; each launch timed with CUDA events, L2 flushed")
+                            note="sum over the C2 conv layers routed to this kernel")
+    for k2 in ("unknown_mask_kernel", "mask_embed_fwd_kernel", "sparse_conv_persistent_kernel", "sparse_wgrad_persistent_kernel"):
+        out[k2]["us_per_step"] = out[k2]["us_per_launch"] * out[k2]["launches_per_step"]
     return out
+
+
+def other_configs(torch, dev):
+    """The remaining BASELINE.json configs on one GPU, each a short measurement (CUDA events, inputs resident, 3 warm-up +
+    median of >= 5): C1 = eval forward of one 256 x 256 image with one instance (both precisions); C4 = video model, one
+    5-frame 480 x 832 clip with 2 instances, training step; C5 = 1024 x 1024 x 8 instances, training step at three widths
+    of the alpha transition band (= three active-site fractions of the sparse refinement)."""
+    import numpy as np
+    import random
+
+    from maggie_b200.config import CfgNode
+    from maggie_b200.network import build_model
+    from oracle import synth
+
+    def med(fn, n=5, warm=3):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(n):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    to_dev = lambda b: {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items() if k not in ("fg", "bg")}
+    res = {}
+    torch.manual_seed(1234)
+    model, _ = build_model(CfgNode(synth.model_cfg()))
+    model.to(dev)
+
+    def train_step(m, batch):
+        np.random.seed(7), random.seed(7)
+        for p in m.parameters():
+            p.grad = None
+        _, loss = m(batch, mem_feat=None)
+        (loss["total"] * LOSS_SCALE).backward()
+
+    # C1
+    model.eval()
+    b1 = to_dev(synth.make_batch(b=1, n_f=1, n_i=1, H=256, W=256, edge_px=6.0))
+    c1 = {}
+    with torch.no_grad():
+        for prec in ("fp16", "high"):
+            model.set_precision(prec)
+            ms = med(lambda: model(b1, mem_feat=None), n=9)
+            c1[prec] = {"ms": ms, "frames_per_sec": 1e3 / ms}
+    model.set_precision("fp16")
+    res["c1_eval_256_1inst"] = dict(c1, note="eval forward incl. the one host read of the status word; 'high' = fp32-accurate mode")
+    # C5 sweep
+    model.train()
+    sweep = []
+    for edge in (3.0, 8.0, 24.0):
+        b5 = to_dev(synth.make_batch(b=1, n_f=1, n_i=8, H=1024, W=1024, edge_px=edge, seed=77, train=True, it=1))
+        ms = med(lambda: train_step(model, b5), n=5)
+        n1 = model.last_site_counts[0]
+        sweep.append({"edge_px": edge, "active_fraction": n1 / (8 * 1024 * 1024), "active_sites_os1": n1, "ms_per_step": ms,
+                      "frames_per_sec": 1e3 / ms})
+        del b5
+    res["c5_train_1024_8inst_sweep"] = sweep
+    del model
+    torch.cuda.empty_cache()
+    # C4
+    vmodel, _ = build_model(CfgNode(synth.video_cfg()))
+    vmodel.to(dev).train()
+    b4 = to_dev(synth.make_batch(b=1, n_f=5, n_i=2, H=480, W=832, edge_px=6.0, seed=9, train=True, it=1))
+    ms = med(lambda: train_step(vmodel, b4), n=5)
+    res["c4_video_train_5x480x832_2inst"] = {"ms_per_clip": ms, "clips_per_sec": 1e3 / ms, "frames_per_sec": 5e3 / ms,
+                                             "active_sites_os1": vmodel.last_site_counts[0]}
+    vmodel.eval()
+    b4e = to_dev(synth.make_batch(b=1, n_f=3, n_i=2, H=480, W=832, edge_px=6.0, seed=9))
+    with torch.no_grad():
+        ms = med(lambda: vmodel(b4e, mem_feat=None), n=5)
+    res["c4_video_eval_window_3x480x832_2inst"] = {"ms_per_window": ms, "windows_per_sec": 1e3 / ms}
+    del vmodel
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_gpu(args):
@@ -376,22 +518,25 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    last_median = [None]
+
     def timed(fn, n):
+        """Mean over exactly n steps between two events (barrier + synchronize on both sides, max over ranks); the median
+        of the per-step intervals (one event per step, read after the region) is kept in `last_median`."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = []
         e0.record()
         for i in range(n):
             fn()
-            if (i + 1) % 10 == 0 and i + 1 < n:      # diagnostic split of the same region (stderr only)
+            if i + 1 < n:
                 marks.append(torch.cuda.Event(enable_timing=True))
                 marks[-1].record()
         e1.record()
         barrier()
-        if rank == 0 and marks:
-            pts = [e0] + marks + [e1]
-            print("timed region, ms per 10-step chunk:", [round(a.elapsed_time(b), 1) for a, b in zip(pts, pts[1:])],
-                  file=sys.stderr)
+        pts = [e0] + marks + [e1]
+        per = sorted(a.elapsed_time(b) for a, b in zip(pts, pts[1:]))
+        last_median[0] = per[len(per) // 2]
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -404,6 +549,7 @@ def run_gpu(args):
     _lib.reset_launch_count()
     replayed0 = model.replayed_native_launches
     ms = timed(lambda: step(resident), args.steps)
+    ms_median = last_median[0]
     launches = _lib.launch_count() + (model.replayed_native_launches - replayed0)
 
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
@@ -492,7 +638,7 @@ def run_gpu(args):
     roof = dict(probes[top], kernel=top, peak_source=peaks["src"])
     line = {
         "metric": "frames_per_sec_fwd_bwd", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "ms_per_step_median": ms_median, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd per GPU (iter={args.iter}, edge {EDGE_PX}px)",
                    "frames_per_gpu": FRAMES_PER_GPU, "active_sites_os1_os2_os4_os8": counts,
@@ -512,6 +658,10 @@ def run_gpu(args):
     }
     if post is not None:
         line["other_regime"] = post
+    if world == 1 and not args.no_extras:
+        del model, flat
+        torch.cuda.empty_cache()
+        line["other_configs"] = other_configs(torch, dev)
     if world == 1 and not args.no_cpu_baseline:
         cstep, cframes = cpu_step_fn(2)
         cstep()
@@ -528,7 +678,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -537,6 +687,7 @@ def main():
     ap.add_argument("--iter", type=int, default=1, help="training iteration of the headline number (1: warm-up regime of the "
                     "first 3000 iterations; >= 9000: the predicted OS8 alpha guides the detail stage)")
     ap.add_argument("--no-post-warmup", action="store_true", help="skip the extra iter=100000 measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1 / C4 / C5 measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

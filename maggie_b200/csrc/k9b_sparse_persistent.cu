@@ -27,7 +27,8 @@ constexpr int ROWB = 64;                                   // 32 fp16 channels p
 
 struct PArgs {
     const __half* src; int src_stride;
-    const int32_t* table; int T, No, Cout;             // Cin = 32; Cout multiple of 16, <= 64
+    const int32_t* table; int T, No, Cout;             // T = VIRTUAL taps = table taps x (Cin / 32); Cout multiple of 16, <= 64
+    int Tt, cl;                                         // table taps, log2(Cin / 32): virtual tap vt = (tap vt >> cl, channels (vt & mask) * 32 ..)
     const __half* w;                                    // [Cout][T*32]
     const float* bias;
     __half* out; int out_stride, c_off;
@@ -102,17 +103,18 @@ sparse_conv_persistent_kernel(const PArgs a) {
                 for (int i = 0; i < 4; ++i) {
                     const int p = tile0 + rr + i * 32;
                     idx[t][i] = -1;
-                    if (t < a.T && p < a.No) idx[t][i] = a.table ? __ldg(a.table + (size_t)p * a.T + t) : p;
+                    if (t < a.T && p < a.No) idx[t][i] = a.table ? __ldg(a.table + (size_t)p * a.Tt + (t >> a.cl)) : p;
                 }
             mbar_wait(a_empty + 8 * buf, ph ^ 1);
             const uint32_t base = smem_u32(sA + (size_t)buf * a_buf);
+            const int cmask = (1 << a.cl) - 1;
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 if (t < a.T) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = rr + i * 32;
-                        const __half* srcp = idx[t][i] >= 0 ? a.src + (size_t)idx[t][i] * a.src_stride + sub * 8 : a.src;
+                        const __half* srcp = idx[t][i] >= 0 ? a.src + (size_t)idx[t][i] * a.src_stride + (t & cmask) * 32 + sub * 8 : a.src;
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + t * a_tile + r * ROWB + swz64(r, sub) * 16),
                                      "l"(srcp), "r"(idx[t][i] >= 0 ? 16u : 0u) : "memory");
                     }
@@ -239,12 +241,16 @@ int sparse_conv_persistent_launch(const mg_sparse_conv_desc* d, void* stream, bo
     const char* e = std::getenv("MAGGIE_B200_NO_PERSISTENT_SPARSE");
     if (e && e[0] == '1') return MG_OK;
     const int cout_pad = (d->Cout + 15) / 16 * 16;     // the caller packs the weights with rows padded to 16
-    if (d->Cin != 32 || cout_pad > 64 || d->T > 9 || (!d->map && d->Cout % 16) || (d->map && d->stats)) return MG_OK;
+    // 32 or 64 input channels: a 64-channel row is two "virtual taps" of 32 channels (the weight pack is already laid out
+    // that way: K index = tap * Cin + ci)
+    if ((d->Cin != 32 && d->Cin != 64) || cout_pad > 64 || (!d->map && d->Cout % 16) || (d->map && d->stats)) return MG_OK;
+    const int cl = d->Cin == 64 ? 1 : 0, VT = d->T << cl;
+    if (VT > 9) return MG_OK;
     const int n_tiles = ceil_div(d->No, 128);
     if (n_tiles < 2 * kNumSMs) return MG_OK;              // small site lists: the one-tile-per-CTA kernel has more parallelism
     PArgs a;
     a.src = static_cast<const __half*>(d->src), a.src_stride = d->src_stride;
-    a.table = d->table, a.T = d->T, a.No = d->No, a.Cout = cout_pad, a.Cout_real = d->Cout;
+    a.table = d->table, a.T = VT, a.Tt = d->T, a.cl = cl, a.No = d->No, a.Cout = cout_pad, a.Cout_real = d->Cout;
     a.map = d->map, a.coords = d->coords, a.mapH = d->mapH, a.mapW = d->mapW;
     a.w = static_cast<const __half*>(d->w), a.bias = d->bias;
     a.out = static_cast<__half*>(d->out), a.out_stride = d->out_stride, a.c_off = d->c_off;
@@ -252,7 +258,7 @@ int sparse_conv_persistent_launch(const mg_sparse_conv_desc* d, void* stream, bo
     a.b_tile = ((cout_pad * ROWB + 1023) / 1024) * 1024;
     a.acc_cols = cout_pad < 32 ? 32 : cout_pad;
     a.tmem_cols = 2 * a.acc_cols;                          // 64 or 128
-    const size_t smem = 1024 + (size_t)d->T * a.b_tile + 2 * (size_t)d->T * 128 * ROWB + 256 + EPI_WARPS * 16 * 36 * 4 +
+    const size_t smem = 1024 + (size_t)VT * a.b_tile + 2 * (size_t)VT * 128 * ROWB + 256 + EPI_WARPS * 16 * 36 * 4 +
                         EPI_WARPS * 2 * cout_pad * 4;
     if (smem > 224 * 1024) return MG_OK;
     static bool attr_set = false;
@@ -284,6 +290,7 @@ struct GArgs {
     const int32_t* table; int T, No, n_tiles;
     float* dw;                                             // [Cout][T*32]
     int tmem_cols;
+    int Tt, cl;          // table taps, log2(Cin / 32): T counts VIRTUAL taps (see PArgs)
 };
 
 constexpr int G_THREADS = PRODUCERS + 32;   // warps 0..3 gather (+ epilogue at the end), warp 4 MMA
@@ -329,9 +336,10 @@ sparse_wgrad_persistent_kernel(const GArgs a) {
                 for (int i = 0; i < 4; ++i) {
                     const int p = tile0 + rr + i * 32;
                     idx[t][i] = -1;
-                    if (t < a.T && p < a.No) idx[t][i] = a.table ? __ldg(a.table + (size_t)p * a.T + t) : p;
+                    if (t < a.T && p < a.No) idx[t][i] = a.table ? __ldg(a.table + (size_t)p * a.Tt + (t >> a.cl)) : p;
                 }
             mbar_wait(empty + 8 * buf, ph ^ 1);
+            const int cmask = (1 << a.cl) - 1;
             // A: d_out rows, one 32-channel atom per 64 bytes of a row
             const uint32_t abase = smem_u32(sA + (size_t)buf * a_buf);
 #pragma unroll
@@ -352,7 +360,7 @@ sparse_wgrad_persistent_kernel(const GArgs a) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = rr + i * 32;
-                        const __half* srcp = idx[t][i] >= 0 ? a.src + (size_t)idx[t][i] * a.src_stride + sub * 8 : a.src;
+                        const __half* srcp = idx[t][i] >= 0 ? a.src + (size_t)idx[t][i] * a.src_stride + (t & cmask) * 32 + sub * 8 : a.src;
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(bbase + t * atom + r * ROWB + swz64(r, sub) * 16),
                                      "l"(srcp), "r"(idx[t][i] >= 0 ? 16u : 0u) : "memory");
                     }
@@ -429,16 +437,18 @@ int sparse_wgrad_persistent_launch(const void* dout, int dout_stride, int Cout, 
     const char* e = std::getenv("MAGGIE_B200_NO_PERSISTENT_SPARSE");
     if (e && e[0] == '1') return MG_OK;
     const int cout_eff = (Cout + 31) / 32 * 32;
-    if (Cin != 32 || cout_eff > 128 || dout_stride < cout_eff || T > 9) return MG_OK;
+    if ((Cin != 32 && Cin != 64) || cout_eff > 128 || dout_stride < cout_eff) return MG_OK;
+    const int cl = Cin == 64 ? 1 : 0, VT = T << cl;       // virtual taps of 32 channels (dw column = vt * 32 + ci)
+    if (VT > 9) return MG_OK;
     const int n_tiles = ceil_div(No, 128);
     if (n_tiles < 2 * kNumSMs) return MG_OK;
     GArgs a;
     a.dout = static_cast<const __half*>(dout), a.dout_stride = dout_stride, a.Cout = Cout, a.cout_eff = cout_eff;
     a.src = static_cast<const __half*>(src), a.src_stride = src_stride;
-    a.table = table, a.T = T, a.No = No, a.n_tiles = n_tiles, a.dw = dw;
+    a.table = table, a.T = VT, a.Tt = T, a.cl = cl, a.No = No, a.n_tiles = n_tiles, a.dw = dw;
     a.tmem_cols = 32;
-    while (a.tmem_cols < T * 32) a.tmem_cols <<= 1;
-    const size_t smem = 1024 + 2 * (size_t)(4 + T) * 128 * ROWB + 256;
+    while (a.tmem_cols < VT * 32) a.tmem_cols <<= 1;
+    const size_t smem = 1024 + 2 * (size_t)(4 + VT) * 128 * ROWB + 256;
     if (smem > 224 * 1024) return MG_OK;
     static bool attr_set = false;
     if (!attr_set) {

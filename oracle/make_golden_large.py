@@ -24,7 +24,10 @@ LARGE = {
     "c5_eval_1024_8inst": (dict(b=1, n_f=1, n_i=8, H=1024, W=1024, edge_px=8.0, seed=2003), False, 8),
 }
 CURVE = "curve_b8_128_2inst_20steps"
-CURVE_STEPS, CURVE_LR, CURVE_CLIP, CURVE_BATCHES = 20, 1e-3, 0.1, 4
+# the published recipe's update rule (configs/maggie_image.yaml: AdamW lr 1.5e-4, betas (0.9, 0.999); engine/train.py:274 clips
+# the global gradient norm at 0.01).  (A first version used lr 1e-3 / clip 0.1: at that step size the 8-sample BatchNorm
+# dynamics are chaotic and an fp16 run separates from an fp32 one by tens of per cent within ten steps.)
+CURVE_STEPS, CURVE_LR, CURVE_CLIP, CURVE_BATCHES = 20, 1.5e-4, 0.01, 4
 
 
 def _reference(training):
