@@ -175,6 +175,8 @@ unsigned long long mg_conv_halo_launches(void);
  * persistent kernel that keeps a halo patch of a whole row slab in shared memory, streams the weights through a ring and
  * accumulates up to five 128-pixel blocks per weight block (csrc/k2h_conv_mid.cu; MAGGIE_B200_NO_MID_CONV=1 disables it). */
 unsigned long long mg_conv_mid_launches(void);
+/* profiling aid: K2h launches write 8 globaltimer stamps per CTA into buf (device, >= 148 * 8 uint64; NULL = off) */
+void mg_conv_mid_trace(unsigned long long* buf);
 
 /* ---- K4: convolution weight gradient (tcgen05, split-K over pixels) ---------------------------------
  * replaces: cuDNN's wgrad behind `loss.backward()` for every conv above (engine/train.py:266).

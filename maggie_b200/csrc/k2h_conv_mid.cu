@@ -47,7 +47,18 @@ struct MArgs {
     float* stats;
     const float *bias, *scale, *shift;
     const __half* res;
+    unsigned long long* trace;   // profiling only (mg_conv_mid_trace): per CTA 8 globaltimer stamps, see the kernel
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define MID_STAMP(slot)                                                          \
+    do {                                                                         \
+        if (a.trace && lane == 0) a.trace[blockIdx.x * 8 + (slot)] = gtime();    \
+    } while (0)
 
 __device__ __forceinline__ float act_apply(float v, int act) {
     return act == 1 ? fmaxf(v, 0.f) : (act == 2 ? (v > 0.f ? v : 0.2f * v) : v);
@@ -65,6 +76,7 @@ template <int KS, int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_mid_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const MArgs a) {
     mg::pdl_launch();
+    if (a.trace && threadIdx.x == 32) a.trace[blockIdx.x * 8 + 0] = gtime();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // [1 KB guard][A ring][B ring][barriers][tmem slot][epilogue staging][stat partials]
@@ -97,6 +109,7 @@ conv_mid_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     tc_fence_after();
     mg::pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 1) MID_STAMP(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -150,12 +163,14 @@ conv_mid_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int c = 0; c < a.chunks; ++c) {
                 mbar_wait(a_full + 8 * sa, pa);
                 tc_fence_after();
+                if (item == (int)blockIdx.x && c == 0) MID_STAMP(2);
                 const uint64_t a_desc0 = smem_desc(sA_u + sa * a.a_al, 0, sbo, lay);
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
                     if (t < a.n_taps) {
                         mbar_wait(b_full + 8 * sb, pb);
                         tc_fence_after();
+                        if (item == (int)blockIdx.x && c == 0 && t == 0) MID_STAMP(3);
                         const int a_off = (((1 + a.tap_dy[t]) * a.P + a.tap_dx[t]) * a.row_bytes) >> 4;
                         const uint64_t b_desc = smem_desc(sB_u + sb * a.b_bytes, 0, sbo, lay);
                         uint64_t da = a_desc0 + (int64_t)a_off;
@@ -175,6 +190,7 @@ conv_mid_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 if (++sa == a.NA) sa = 0, pa ^= 1;
             }
             if (elect_one()) mma_commit(t_full + 8 * set);               // all accumulators of the item are complete
+            if (item == (int)blockIdx.x) MID_STAMP(4);
             if (a.sets == 2) {
                 if (set) tph ^= 1;
                 set ^= 1;
@@ -197,6 +213,7 @@ conv_mid_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const int tph = a.sets == 2 ? ((it >> 1) & 1) : (it & 1);
             mbar_wait(t_full + 8 * set, tph);
             tc_fence_after();
+            if (item == (int)blockIdx.x && warp == FIRST_EPI_WARP) MID_STAMP(5);
             for (int mb = grp; mb < a.mblocks; mb += EPI_GROUPS) {
                 const int m = mb * 128 + q * 32 + lane;
                 const int row = m / a.P, j = m - row * a.P;
@@ -272,6 +289,7 @@ conv_mid_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             }
             tc_fence_before();
             __syncwarp();
+            if (item == (int)blockIdx.x && warp == FIRST_EPI_WARP) MID_STAMP(6);
             if (lane == 0) mbar_arrive(t_empty + 8 * set);
             if (a.stats && a.n_ntiles > 1) {
                 // the partial sums belong to this item's channel tile: flush them before the next item changes n0
@@ -305,10 +323,12 @@ conv_mid_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, a.tmem_cols);
+        MID_STAMP(7);
     }
 }
 
 std::atomic<unsigned long long> g_mid_launches{0};
+unsigned long long* g_mid_trace = nullptr;    // device buffer [148][8] set by mg_conv_mid_trace (profiling only)
 
 bool mid_disabled() {
     const char* e = std::getenv("MAGGIE_B200_NO_MID_CONV");
@@ -386,6 +406,7 @@ int conv_mid_launch(const mg_conv_desc* d, void* stream, bool* handled) {
     a.Cs = d->Cs, a.c_off = d->c_off;
     a.pre_act = d->pre_act, a.post_act = d->post_act, a.stats = d->stats, a.bias = d->bias;
     a.scale = d->scale, a.shift = d->shift, a.res = static_cast<const __half*>(d->res);
+    a.trace = g_mid_trace;
 
     CUtensorMap tmA, tmB;
     {
@@ -437,3 +458,8 @@ int conv_mid_launch(const mg_conv_desc* d, void* stream, bool* handled) {
 }  // namespace mg
 
 extern "C" unsigned long long mg_conv_mid_launches(void) { return g_mid_launches.load(); }
+
+// Profiling aid (tools/mid_probe.py): K2h launches write 8 globaltimer stamps per CTA into `buf` (device, >= 148 * 8
+// uint64): kernel entry, after griddepcontrol.wait, first patch landed, first weight block landed, all MMAs of the first
+// item issued, accumulators complete, epilogue of the first item done, kernel exit.  NULL switches it off.
+extern "C" void mg_conv_mid_trace(unsigned long long* buf) { g_mid_trace = buf; }

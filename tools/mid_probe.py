@@ -51,3 +51,29 @@ for (hw, ci, co) in shapes:
         ts = timeit(lambda: dense.conv_launch(x, wp, taps, grid_hw=(hw, hw), stats=stats, pre_act="relu"))
         row.append(f"{name}{'*' if used else ''}: {t:6.1f} us ({flops / t / 1e6:4.0f} TF/s) burst {tb:6.1f} us ({flops / tb / 1e6:4.0f}) +stats {ts:6.1f}{err}")
     print("\n    ".join(row), flush=True)
+
+# ---- timeline of one K2h launch (globaltimer stamps per CTA, see mg_conv_mid_trace)
+import numpy as np
+for k in ("MAGGIE_B200_NO_MID_CONV", "MAGGIE_B200_MID_CH", "MAGGIE_B200_MID_BLOCKS"):
+    os.environ.pop(k, None)
+names = ["entry", "pdl_wait done", "first patch", "first weights", "MMAs issued", "accum complete", "epilogue done", "exit"]
+for (hw, ci, co) in ((64, 128, 128), (32, 256, 256)):
+    x = torch.randn(8, hw, hw, ci, device="cuda").half()
+    w = torch.randn(co, ci, 3, 3, device="cuda") / (ci * 9) ** 0.5
+    wp, taps = dense.pack_weight(w, ci), dense.conv_taps(3, 3, 1, 1, ci)
+    buf = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+    for warm in (True, False):
+        if not warm:
+            flush.fill_(1)
+        torch.cuda.synchronize()
+        _lib.lib().mg_conv_mid_trace(buf.data_ptr())
+        dense.conv_launch(x, wp, taps, grid_hw=(hw, hw))
+        torch.cuda.synchronize()
+        _lib.lib().mg_conv_mid_trace(None)
+        t = buf.cpu().numpy().reshape(148, 8).astype(np.float64)
+        t = t[t[:, 0] > 0]
+        t0 = t[:, 0].min()
+        rel = (t - t0) / 1e3
+        print(f"{hw}^2 {ci}->{co} ({'L2-warm' if warm else 'L2 flushed'}): {len(t)} CTAs; us since first CTA entry: median (min .. max)")
+        for j, n in enumerate(names):
+            print(f"    {n:16s} {np.median(rel[:, j]):7.2f}  ({rel[:, j].min():6.2f} .. {rel[:, j].max():6.2f})")
