@@ -43,7 +43,7 @@ __device__ __forceinline__ void block_accumulate(float* vals, int n, float* dst)
 // grid (W/32, H/32, 3*S), block 16x16; each thread owns a 2x2 pixel quad and one d1 output.
 __global__ void __launch_bounds__(256)
 loss_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const float* __restrict__ plane_scale, float* __restrict__ D1,
-                   float* __restrict__ sums, int S, int H, int W) {
+                   float* __restrict__ sums, uint8_t* __restrict__ tile_raw, int S, int H, int W) {
     mg::pdl_prologue();
     __shared__ float s_d[36][37], s_pw[34][35], s_tw[34][35];
     const int scale = blockIdx.z / S, sl = blockIdx.z - scale * S;
@@ -68,6 +68,8 @@ loss_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const float* __
     }
     // tiles without any weight (most of the OS1 / OS4 scales) contribute nothing to the weighted-L1 / Sobel / weight sums
     const bool weighted = __syncthreads_or(any_w) != 0;
+    // tile map for the later passes: 1 = some weight inside this 32 x 32 tile (+ 1 pixel of halo)
+    if (tid == 0) tile_raw[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = weighted ? 1 : 0;
     float acc[3] = {0.f, 0.f, 0.f};  // rec, sobel, wsum
 #pragma unroll
     for (int qy = 0; qy < 2; ++qy)
@@ -110,6 +112,32 @@ loss_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const float* __
     block_accumulate(&out3[0], 1, dst + 0);
     block_accumulate(&out3[1], 1, dst + 4);
     block_accumulate(&out3[2], 1, dst + 5);
+}
+
+// ---- tile map: near[tile] = some weight within the 3 x 3 tile neighbourhood (+-32 pixels).  The Laplacian terms, their
+// stored signs and every level of the adjoint pyramid are EXACTLY zero at pixels of tiles that are not `near` (the reach
+// of the three pyramid levels is 2 + 4 + 8 + 12 = 26 fine pixels), and the OS1 / OS4 weights are ~5 % wide bands: the
+// passes below skip such tiles (forward: nothing to add, nothing stored; backward: zeros written, nothing read).
+__global__ void __launch_bounds__(256)
+loss_tiles_near_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ near, int planes, int TY, int TX) {
+    mg::pdl_prologue();
+    const int total = planes * TY * TX;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tx = i % TX, ty = (i / TX) % TY;
+        const uint8_t* base = raw + (size_t)(i / (TX * TY)) * TY * TX;
+        uint8_t v = 0;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = ty + dy, xx = tx + dx;
+                if (yy >= 0 && yy < TY && xx >= 0 && xx < TX) v |= base[yy * TX + xx];
+            }
+        near[i] = v;
+    }
+}
+
+// near-flag of the tile holding level-`level` pixel (y, x) of plane `plane` (= scale * S + slice)
+__device__ __forceinline__ bool tile_near(const uint8_t* __restrict__ near, size_t plane, int y, int x, int level, int TY, int TX) {
+    return near[(plane * TY + ((y << level) >> 5)) * TX + ((x << level) >> 5)] != 0;
 }
 
 // ---- F2: d_{k+1} = D G d_k on the small levels (one thread per output) ----------------------------------------
@@ -161,8 +189,8 @@ __device__ __forceinline__ float upsample_at(const float* __restrict__ dc, int h
 // level 0: d_0 = p - t on the fly (dk == nullptr).  wstep = 2^k (sub-sampling of the full-resolution weight).
 __global__ void __launch_bounds__(256)
 loss_lap_kernel(Ptr3 P, const float* __restrict__ T, const float* __restrict__ dk, const float* __restrict__ dk1, Ptr3 Wt,
-                const float* __restrict__ plane_scale, __half* __restrict__ sg, float* __restrict__ sums, int S, int H, int W,
-                int level) {
+                const float* __restrict__ plane_scale, __half* __restrict__ sg, float* __restrict__ sums,
+                const uint8_t* __restrict__ near, int TY, int TX, int S, int H, int W, int level) {
     mg::pdl_prologue();
     const int h = H >> level, w = W >> level, hc = h >> 1, wc = w >> 1, wstep = 1 << level;
     const int scale = blockIdx.y;                                   // one scale per grid row: partial sums never mix
@@ -170,6 +198,10 @@ loss_lap_kernel(Ptr3 P, const float* __restrict__ T, const float* __restrict__ d
     float acc[2] = {0.f, 0.f};
     for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < per_scale; r += (size_t)gridDim.x * blockDim.x) {
         const int x = (int)(r % w), y = (int)((r / w) % h), sl = (int)(r / ((size_t)w * h));
+        if (!tile_near(near, (size_t)scale * S + sl, y, x, level, TY, TX)) {
+            sg[base + r] = __float2half(0.f);   // nothing to add, nothing read; (the adjoint's taps may reach into this tile)
+            continue;
+        }
         // the Laplacian value only matters under a non-zero weight (the OS1 / OS4 weights are the ~5 % wide refinement
         // bands): everywhere else the term and its stored sign are exactly zero, and neither the difference image nor the
         // 3x3 coarse neighbourhood is read
@@ -289,13 +321,18 @@ __device__ __forceinline__ float bwd_level_value(const __half* __restrict__ sg_k
 // coefficient layout: coef[scale][5] = upstream gradient of (rec, lap0, lap1, lap2, sobel) numerators
 __global__ void __launch_bounds__(256)
 loss_bwd_small_kernel(const __half* __restrict__ sg_k, const float* __restrict__ g_k1, const __half* __restrict__ sg_km1,
-                      const float* __restrict__ coef, float* __restrict__ g_out, int S, int h, int w, int level) {
+                      const float* __restrict__ coef, float* __restrict__ g_out, const uint8_t* __restrict__ near, int TY, int TX,
+                      int S, int h, int w, int level) {
     mg::pdl_prologue();
     const size_t per_scale = (size_t)S * h * w, total = 3 * per_scale;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int scale = (int)(i / per_scale);
         const int x = (int)(i % w), y = (int)((i / w) % h);
         const size_t img = i / ((size_t)w * h);
+        if (!tile_near(near, img, y, x, level, TY, TX)) {     // exactly zero there (see loss_tiles_near_kernel)
+            g_out[i] = 0.f;
+            continue;
+        }
         const float c_k = level <= 2 ? coef[scale * 5 + 1 + level] : 0.f;
         const float c_km1 = coef[scale * 5 + level];  // level >= 1 here: lap_{level-1}
         g_out[i] = bwd_level_value(sg_k, c_k, g_k1, sg_km1, c_km1, img, y, x, h, w);
@@ -306,11 +343,20 @@ loss_bwd_small_kernel(const __half* __restrict__ sg_k, const float* __restrict__
 // grid (W/32, H/32, 3*S), block 32x8 (each thread 4 rows).
 __global__ void __launch_bounds__(256)
 loss_bwd_level0_kernel(Ptr3 P, const float* __restrict__ T, Ptr3 Wt, const float* __restrict__ plane_scale,
-                       const __half* __restrict__ sg0, const float* __restrict__ g1, const float* __restrict__ coef, MPtr3 G, int S,
-                       int H, int W) {
+                       const __half* __restrict__ sg0, const float* __restrict__ g1, const float* __restrict__ coef, MPtr3 G,
+                       const uint8_t* __restrict__ near, int S, int H, int W) {
     mg::pdl_prologue();
     __shared__ float s_pw[36][37], s_tw[36][37], s_gx[34][35], s_gy[34][35];
     const int scale = blockIdx.z / S, sl = blockIdx.z - scale * S;
+    if (!near[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) {
+        // no weight within 32 pixels: every term of the gradient is exactly zero here
+        float* gp = G.p[scale] + (size_t)sl * H * W;
+        for (int row = threadIdx.y; row < 32; row += 8) {
+            const int y = blockIdx.y * 32 + row, x = blockIdx.x * 32 + threadIdx.x;
+            if (y < H && x < W) gp[(size_t)y * W + x] = 0.f;
+        }
+        return;
+    }
     const float* p = P.p[scale] + (size_t)sl * H * W;
     const float* t = T + (size_t)sl * H * W;
     const float* w = Wt.p[scale] + (size_t)sl * H * W;
@@ -411,7 +457,15 @@ int small_grid(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t
 extern "C" size_t mg_loss_workspace_floats(int S, int H, int W) {
     // d1, d2, d3 (fp32) + g1, g2, g3 (fp32) for three scales
     const size_t l1 = (size_t)3 * S * (H / 2) * (W / 2), l2 = l1 / 4, l3 = l2 / 4;
-    return 2 * (l1 + l2 + l3);
+    // + the two tile maps (raw / near), one byte per 32 x 32 tile and plane
+    const size_t tiles = (size_t)3 * S * ((H + 31) / 32) * ((W + 31) / 32);
+    return 2 * (l1 + l2 + l3) + 2 * ((tiles + 3) / 4) + 8;
+}
+
+static inline uint8_t* tile_maps(float* ws, int S, int H, int W, size_t* n_tiles) {
+    const size_t l1 = (size_t)3 * S * (H / 2) * (W / 2), l2 = l1 / 4, l3 = l2 / 4;
+    *n_tiles = (size_t)3 * S * ((H + 31) / 32) * ((W + 31) / 32);
+    return reinterpret_cast<uint8_t*>(ws + 2 * (l1 + l2 + l3));
 }
 
 extern "C" int mg_loss_fwd(const float* a1, const float* a4, const float* a8, const float* target, const float* w1,
@@ -426,12 +480,18 @@ extern "C" int mg_loss_fwd(const float* a1, const float* a4, const float* a8, co
     __half* sg0 = static_cast<__half*>(sg_f16);
     __half *sg1 = sg0 + n0, *sg2 = sg1 + n1;
     dim3 grid0(mg::ceil_div(W, 32), mg::ceil_div(H, 32), 3 * S);
-    MG_LAUNCH(loss_level0_kernel, grid0, dim3(16, 16), 0, stream, P, target, Wt, plane_scale, d1, sums, S, H, W);
+    size_t n_tiles;
+    uint8_t* t_raw = tile_maps(ws, S, H, W, &n_tiles);
+    uint8_t* t_near = t_raw + ((n_tiles + 3) / 4) * 4;
+    const int TY = (int)grid0.y, TX = (int)grid0.x;
+    MG_LAUNCH(loss_level0_kernel, grid0, dim3(16, 16), 0, stream, P, target, Wt, plane_scale, d1, sums, t_raw, S, H, W);
+    MG_LAUNCH(loss_tiles_near_kernel, small_grid(n_tiles), 256, 0, stream, (const uint8_t*)t_raw, t_near, 3 * S, TY, TX);
     MG_LAUNCH(loss_down_kernel, small_grid(n2), 256, 0, stream, d1, d2, 3 * S, H / 2, W / 2);
     MG_LAUNCH(loss_down_kernel, small_grid(n3), 256, 0, stream, d2, d3, 3 * S, H / 4, W / 4);
-    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n0 / 3), 3), 256, 0, stream, P, target, (const float*)nullptr, d1, Wt, plane_scale, sg0, sums, S, H, W, 0);
-    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n1 / 3), 3), 256, 0, stream, P, target, d1, d2, Wt, plane_scale, sg1, sums, S, H, W, 1);
-    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n2 / 3), 3), 256, 0, stream, P, target, d2, d3, Wt, plane_scale, sg2, sums, S, H, W, 2);
+    const uint8_t* nr = t_near;
+    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n0 / 3), 3), 256, 0, stream, P, target, (const float*)nullptr, d1, Wt, plane_scale, sg0, sums, nr, TY, TX, S, H, W, 0);
+    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n1 / 3), 3), 256, 0, stream, P, target, d1, d2, Wt, plane_scale, sg1, sums, nr, TY, TX, S, H, W, 1);
+    MG_LAUNCH(loss_lap_kernel, dim3(small_grid(n2 / 3), 3), 256, 0, stream, P, target, d2, d3, Wt, plane_scale, sg2, sums, nr, TY, TX, S, H, W, 2);
     MG_CHECK_LAUNCH("mg_loss_fwd");
     return MG_OK;
 }
@@ -450,12 +510,16 @@ extern "C" int mg_loss_bwd(const float* a1, const float* a4, const float* a8, co
     const __half* sg0 = static_cast<const __half*>(sg_f16);
     const __half *sg1 = sg0 + n0, *sg2 = sg1 + n1;
     // g_3 = -U^T (c_2 s_2);  g_2 = c_2 s_2 + (DG)^T g_3 - U^T (c_1 s_1);  g_1 = c_1 s_1 + (DG)^T g_2 - U^T (c_0 s_0)
-    MG_LAUNCH(loss_bwd_small_kernel, small_grid(n3), 256, 0, stream, (const __half*)nullptr, (const float*)nullptr, sg2, coef, g3, S,
-              H / 8, W / 8, 3);
-    MG_LAUNCH(loss_bwd_small_kernel, small_grid(n2), 256, 0, stream, sg2, (const float*)g3, sg1, coef, g2, S, H / 4, W / 4, 2);
-    MG_LAUNCH(loss_bwd_small_kernel, small_grid(n1), 256, 0, stream, sg1, (const float*)g2, sg0, coef, g1, S, H / 2, W / 2, 1);
     dim3 grid0(mg::ceil_div(W, 32), mg::ceil_div(H, 32), 3 * S);
-    MG_LAUNCH(loss_bwd_level0_kernel, grid0, dim3(32, 8), 0, stream, P, target, Wt, plane_scale, sg0, (const float*)g1, coef, G, S, H, W);
+    size_t n_tiles;
+    uint8_t* t_raw = tile_maps(ws, S, H, W, &n_tiles);
+    const uint8_t* nr = t_raw + ((n_tiles + 3) / 4) * 4;     // the `near` map left by the forward
+    const int TY = (int)grid0.y, TX = (int)grid0.x;
+    MG_LAUNCH(loss_bwd_small_kernel, small_grid(n3), 256, 0, stream, (const __half*)nullptr, (const float*)nullptr, sg2, coef, g3, nr,
+              TY, TX, S, H / 8, W / 8, 3);
+    MG_LAUNCH(loss_bwd_small_kernel, small_grid(n2), 256, 0, stream, sg2, (const float*)g3, sg1, coef, g2, nr, TY, TX, S, H / 4, W / 4, 2);
+    MG_LAUNCH(loss_bwd_small_kernel, small_grid(n1), 256, 0, stream, sg1, (const float*)g2, sg0, coef, g1, nr, TY, TX, S, H / 2, W / 2, 1);
+    MG_LAUNCH(loss_bwd_level0_kernel, grid0, dim3(32, 8), 0, stream, P, target, Wt, plane_scale, sg0, (const float*)g1, coef, G, nr, S, H, W);
     MG_CHECK_LAUNCH("mg_loss_bwd");
     return MG_OK;
 }

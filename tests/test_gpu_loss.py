@@ -51,3 +51,28 @@ def _check(ops, S, H, W, preds, tgt, ws, gs, name, plane_scale=None):
         for sl in (slice(0, 3), slice(-3, None)):
             assert float((a[:, sl] - b[:, sl]).abs().max()) < 2e-3 * float(b.abs().max()) + 1e-6
             assert float((a[:, :, sl] - b[:, :, sl]).abs().max()) < 2e-3 * float(b.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("S,H,W,band", [(6, 256, 256, 3.0), (4, 192, 320, 1.0), (3, 512, 512, 6.0)])
+def test_matte_loss_with_band_weights_skipped_tiles(S, H, W, band):
+    """The training configuration: the OS1 / OS4 weights are narrow bands (the refinement region), so most 32 x 32 tiles have
+    no weight within 32 pixels and are skipped by the forward / backward passes (tile maps of K12): sums and gradients must
+    still equal the dense evaluation, including tiles right next to the skipped ones."""
+    from maggie_b200 import ops
+    g = torch.Generator().manual_seed(S + H)
+    tgt = synth.soft_ellipse_alphas(1, S, H, W, edge_px=band)[0].cuda()
+    preds = [(tgt + 0.2 * torch.randn(S, H, W, generator=g).cuda()).clamp(0, 1) for _ in range(3)]
+    edge = ((tgt > 0.02) & (tgt < 0.98)).float()
+    ws = [edge.clone(), edge.clone(), torch.ones(S, H, W).cuda()]
+    ws[1][0] = 0                                   # a plane without any weight at the OS4 scale
+    ws[0][:, : H // 2] = 0                         # half of every OS1 plane empty: long borders between live and skipped tiles
+    assert float(ws[0].mean()) < 0.1
+    for k in range(3):
+        gs = torch.rand(3, 8, generator=g).cuda()
+        _check(ops, S, H, W, preds, tgt, ws, gs, f"band weights {k}")
+    # isolated single-pixel weights next to tile corners (reach of the adjoint pyramid across tile boundaries)
+    ws2 = [torch.zeros(S, H, W).cuda() for _ in range(2)] + [torch.ones(S, H, W).cuda()]
+    for (y, x) in ((31, 31), (32, 64), (95, 33), (H - 1, W - 1), (0, 0), (64, 127)):
+        ws2[0][:, y, x] = 1.0
+        ws2[1][:, min(y + 1, H - 1), x] = 1.0
+    _check(ops, S, H, W, preds, tgt, ws2, torch.rand(3, 8, generator=g).cuda(), "isolated weights")
