@@ -60,9 +60,15 @@ class _FFN(nn.Module):
 
     def forward(self, x):
         p, t = self.dropout.p, self.training
-        h = F.relu(ops.linear(x, self.linear1.weight, self.linear1.bias))
-        h = F.dropout(h, p, t)
-        h = F.dropout(ops.linear(h, self.linear2.weight, self.linear2.bias), p, t)
+        drop = (lambda h: F.dropout(h, p, t)) if (p > 0 and t) else (lambda h: h)
+        if x.is_cuda and x.numel() // x.shape[-1] >= 1024:
+            # site rows (inst_spec_layer on the OS8 sites): tcgen05 rows GEMM
+            h = drop(F.relu(ops.linear_rows(x, self.linear1.weight, self.linear1.bias)))
+            h = drop(ops.linear_rows(h, self.linear2.weight, self.linear2.bias))
+        else:
+            # instance tokens: fp32 library GEMMs on the master weights
+            h = drop(ops.small_linear(x, self.linear1.weight, self.linear1.bias, relu=True))
+            h = drop(ops.small_linear(h, self.linear2.weight, self.linear2.bias))
         return ops.layer_norm(x, self.norm, residual=h)
 
 
@@ -82,10 +88,11 @@ class _Attn(nn.Module):
         """tgt [B,L,E] (queries, residual stream), mem [B,S,E]; positional terms are added to Q and K only."""
         mha = getattr(self, self.attn_name)
         E = tgt.shape[-1]
-        w, b = mha.in_proj_weight, mha.in_proj_bias
-        q = ops.linear_rows(tgt if tgt_pos is None else tgt + tgt_pos, w[:E], b[:E])
-        k = ops.linear_rows(mem if mem_pos is None else mem + mem_pos, w[E:2 * E], b[E:2 * E])
-        v = ops.linear_rows(mem, w[2 * E:], b[2 * E:])
+        # q / k / v parts of the packed in_proj parameters as views; their gradients are re-assembled by ONE concatenation
+        (wq, wk, wv), (bq, bk, bv) = ops.split_rows(mha.in_proj_weight, 3), ops.split_rows(mha.in_proj_bias, 3)
+        q = ops.linear_rows(tgt, wq, bq, pos=tgt_pos)
+        k = ops.linear_rows(mem, wk, bk, pos=mem_pos)
+        v = ops.linear_rows(mem, wv, bv)
         o, stat = ops.attention(q, k, v, key_padding, guidance)
         o = ops.linear_rows(o, mha.out_proj.weight, mha.out_proj.bias)
         return ops.layer_norm(tgt, self.norm, residual=o), stat
@@ -148,8 +155,10 @@ class InstanceMatteDecoder(nn.Module):
         emb = self.id_embedding.weight
         x_pos = ops.id_embedding(id_pos.reshape(b, n_f, hw).permute(0, 2, 1).reshape(b, hw * n_f), emb, dt)   # [b,S,E]
         x = ops.linear_rows(x, self.feat_proj.layers[0].weight, self.feat_proj.layers[0].bias)
-        tok = self.query_feat.weight.to(dt)[None].expand(b, -1, -1)
-        tok_pos = emb[1:nq + 1].to(dt)[None].expand(b, -1, -1)
+        # the instance tokens (10 per sample) stay fp32 end to end: their layers read the fp32 master weights in place
+        tdt = torch.float32 if feat.is_cuda else dt
+        tok = self.query_feat.weight.to(tdt)[None].expand(b, -1, -1)
+        tok_pos = emb[1:nq + 1].to(tdt)[None].expand(b, -1, -1)
 
         valid = mask_os8.flatten(3).any(3).any(1)                                           # [b,n_i]
         if n_i < nq:
@@ -186,7 +195,7 @@ class InstanceMatteDecoder(nn.Module):
             x = self._smooth(prop.flatten(0, 1).contiguous(memory_format=torch.channels_last))
         else:
             x = out_feat = self._smooth(x)
-        tok = ops.linear(tok, self.final_mlp.layers[0].weight, self.final_mlp.layers[0].bias)
+        tok = ops.small_linear(tok, self.final_mlp.layers[0].weight, self.final_mlp.layers[0].bias)
         tok = F.layer_norm(tok.float(), (tok.shape[-1],), self.decoder_norm.weight, self.decoder_norm.bias,
                            self.decoder_norm.eps)                                           # [b,10,64] fp32
         logits = ops.token_logits(tok, x, n_f)

@@ -394,12 +394,51 @@ def linear(x, w, b=None):
     return F.linear(x, w.to(x.dtype), None if b is None else b.to(x.dtype))
 
 
-def linear_rows(x, w, b=None):
-    """Linear layer on [..., Cin] rows.  Large row counts (the pixel side of the attention: B*4096 rows) run on the
-    tcgen05 rows GEMM with native gradients (K9 with T = 1); the 10-token side stays a tiny torch matmul."""
+class _SplitRows(torch.autograd.Function):
+    """w [n * E, ...] -> n row chunks (views).  The backward is ONE concatenation instead of the zeros + copy + add chain
+    autograd builds for `w[:E]`, `w[E:2E]`, ... (the q / k / v slices of an in_proj matrix: ~8 launches per matrix)."""
+
+    @staticmethod
+    def forward(ctx, w, n):
+        E = w.shape[0] // n
+        ctx.meta = (n, E, tuple(w.shape[1:]), w.dtype, w.device)
+        return tuple(w.narrow(0, i * E, E) for i in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        n, E, rest, dt, dev = ctx.meta
+        if all(g is None for g in gs):
+            return None, None
+        parts = [g.to(dt) if g is not None else torch.zeros((E,) + rest, dtype=dt, device=dev) for g in gs]
+        return torch.cat(parts, 0), None
+
+
+def split_rows(w, n):
+    """The n equal row chunks of w as views (q / k / v parts of `in_proj_weight` / `in_proj_bias`)."""
+    return _SplitRows.apply(w, n)
+
+
+def small_linear(x, w, b=None, pos=None, relu=False):
+    """Linear layer on the TOKEN side (10 instance tokens per sample, a few hundred fp32 rows of <= 128 features):
+    y = act((x + pos) W^T + b).  A plain library GEMM (cuBLAS through torch) on the fp32 master weights - no casts, no
+    weight copies.  (A hand-written fp32 kernel with shared-memory-staged operands, one launch per direction, was measured
+    at 13 us against 7 us for add + addmm on the [80 x 128] x [128 x 128] layer and cost 0.45 ms per C2 step in an A/B
+    run: these 1-MFLOP GEMMs are pure launch latency, and the library's small-GEMM kernels win.)"""
+    if pos is not None:
+        x = x + pos
+    y = linear(x, w, b)
+    return F.relu(y) if relu else y
+
+
+def linear_rows(x, w, b=None, pos=None):
+    """Linear layer on [..., Cin] rows; `pos` (optional) is added to the input first (positional terms of Q / K).
+    Large row counts (the pixel side of the attention: B*4096 rows) run on the tcgen05 rows GEMM with native gradients
+    (K9 with T = 1); the 10-token side is a library GEMM on the fp32 master weights (`small_linear`)."""
     rows = x.numel() // x.shape[-1]
     if rows < 1024 or not x.is_cuda:
-        return linear(x, w, b)
+        return small_linear(x, w, b, pos=pos)
+    if pos is not None:
+        x = x + pos
     if x.dtype == torch.float32:      # fp32-accurate evaluation mode: split-operand tensor-core GEMM
         from . import dense
         return dense.linear_rows_x3(x, w, b)

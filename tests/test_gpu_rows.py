@@ -69,3 +69,18 @@ def test_token_logits_fwd_bwd(b, n_f, Q, h, w):
     assert y.shape == ref.shape and (y - ref).abs().max() < 1e-4 * max(1.0, float(ref.abs().max()))
     assert (tok.grad - tok2.grad).abs().max() < 1e-3 * max(1.0, float(tok2.grad.abs().max()))
     assert (x.grad.float() - x2.grad).abs().max() < 4e-3 * max(1.0, float(x2.grad.abs().max()))   # fp16 gradient
+
+
+def test_split_rows_gradient_is_one_concatenation():
+    """q / k / v chunks of a packed in_proj matrix as views; the gradient comes back as the full matrix."""
+    import torch.nn.functional as F
+    from maggie_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(3 * 64, 32, generator=g).cuda().requires_grad_(True)
+    x = torch.randn(10, 32, generator=g).cuda()
+    wq, wk, wv = ops.split_rows(w, 3)
+    assert wq.data_ptr() == w.data_ptr() and wk.data_ptr() == w[64:128].data_ptr()
+    (ops.small_linear(x, wq).sum() * 1.0 + ops.small_linear(x, wv, pos=x, relu=True).sum() * 2.0).backward()
+    w2 = w.detach().clone().requires_grad_(True)
+    (F.linear(x, w2[:64]).sum() + F.relu(F.linear(x + x, w2[128:])).sum() * 2.0).backward()
+    assert torch.allclose(w.grad, w2.grad, rtol=1e-5, atol=1e-6) and float(w.grad[64:128].abs().max()) == 0.0
