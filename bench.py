@@ -276,7 +276,7 @@ def kernel_probes(torch, dev, peaks):
     # ---- conv family: every layer of the C2 table, forward / data gradient / weight gradient, weight packs prepared outside
     # the timed region (in the step they come from the grouped K0 kernel).  Launches are accounted to the kernel
     # mg_conv_fprop / mg_conv_wgrad routed them to: K2 (generic), K2b / K4b (halo, <= 64 channels: HBM-bound, in bytes),
-    # K2h (mid-resolution 3x3 layers).
+    # K2t (mid-resolution 3x3 layers, transposed form; K2h is opt-in).
     orig_pack, memo = dense.pack_weight, {}
 
     def cached_pack(w, ci_pad=None):
@@ -286,8 +286,9 @@ def kernel_probes(torch, dev, peaks):
         return memo[key][0]
 
     dense.pack_weight = cached_pack
-    names = ["conv_tcgen05_kernel[fprop]", "conv_tcgen05_kernel[dgrad]", "conv_mid_tcgen05_kernel[fprop]",
-             "conv_mid_tcgen05_kernel[dgrad]", "wgrad_tcgen05_kernel", "conv_halo_tcgen05_kernel", "wgrad_halo_tcgen05_kernel"]
+    names = ["conv_tcgen05_kernel[fprop]", "conv_tcgen05_kernel[dgrad]", "conv_midt_tcgen05_kernel[fprop]",
+             "conv_midt_tcgen05_kernel[dgrad]", "conv_mid_tcgen05_kernel[fprop]", "conv_mid_tcgen05_kernel[dgrad]",
+             "wgrad_tcgen05_kernel", "conv_halo_tcgen05_kernel", "wgrad_halo_tcgen05_kernel"]
     tot = {k: [0.0, 0.0, 0] for k in names}
     try:
         for (hw, ci, co, k, s, d, tr, cnt) in C2_CONVS:
@@ -310,15 +311,16 @@ def kernel_probes(torch, dev, peaks):
 
             for kind, fn, nl in (("fprop", lambda i: g.fwd(xs[i], w), 1), ("dgrad", lambda i: g.dgrad(ys[i], w, x0.shape), 1),
                                  ("wgrad", lambda i: g.wgrad(ys[i], xs[i], w.shape, bank=Bank), 4 if tr else 1)):
-                h0, m0, w0 = L.mg_conv_halo_launches(), L.mg_conv_mid_launches(), L.mg_wgrad_halo_launches()
+                h0, m0, w0, t0 = (L.mg_conv_halo_launches(), L.mg_conv_mid_launches(), L.mg_wgrad_halo_launches(),
+                                  L.mg_conv_midt_launches())
                 fn(0)
                 halo = L.mg_conv_halo_launches() > h0 or L.mg_wgrad_halo_launches() > w0
-                mid = L.mg_conv_mid_launches() > m0
+                mid = "mid" if L.mg_conv_mid_launches() > m0 else ("midt" if L.mg_conv_midt_launches() > t0 else "")
                 t = burst(fn, ns)
                 if kind == "wgrad":
                     key = "wgrad_halo_tcgen05_kernel" if halo else "wgrad_tcgen05_kernel"
                 else:
-                    key = "conv_halo_tcgen05_kernel" if halo else (f"conv_mid_tcgen05_kernel[{kind}]" if mid else f"conv_tcgen05_kernel[{kind}]")
+                    key = "conv_halo_tcgen05_kernel" if halo else (f"conv_{mid}_tcgen05_kernel[{kind}]" if mid else f"conv_tcgen05_kernel[{kind}]")
                 tot[key][0] += (nbytes if halo else flops) * cnt
                 tot[key][1] += t * cnt
                 tot[key][2] += nl * cnt

@@ -173,8 +173,16 @@ unsigned long long mg_conv_halo_launches(void);
 /* Stride-1 layers with taps within +-1 pixel, Ci a multiple of 64 (>= 128), Co a multiple of 64 and width <= 64 (the 3x3
  * convolutions of the trunk at 64^2 / 32^2 / 16^2, of the dense decoder, and their data gradients) are routed to K2h, a
  * persistent kernel that keeps a halo patch of a whole row slab in shared memory, streams the weights through a ring and
- * accumulates up to five 128-pixel blocks per weight block (csrc/k2h_conv_mid.cu; MAGGIE_B200_NO_MID_CONV=1 disables it). */
+ * accumulates up to five 128-pixel blocks per weight block (csrc/k2h_conv_mid.cu).  OPT-IN since K2t (MAGGIE_B200_MID_CONV=h):
+ * measured slower than the generic kernel on every layer once K2 issued its MMAs warp-uniformly. */
 unsigned long long mg_conv_mid_launches(void);
+/* K2t (csrc/k2t_conv_mid_t.cu): the K2h layers whose Co is a multiple of 128 run in the TRANSPOSED form - weights as the
+ * M = 128 operand, the linear halo-patch pixels as the N operand (N = 128..256 per tcgen05.mma, the range where the
+ * instruction is paced by the tensor pipe instead of its shared-memory operand reads), BatchNorm sums as per-thread
+ * accumulations, one TMA store per item.  MAGGIE_B200_NO_MIDT_CONV=1 sends them back to K2h. */
+unsigned long long mg_conv_midt_launches(void);
+/* profiling aid: K2t launches write 8 globaltimer stamps per CTA into buf (device, >= 148 * 8 uint64; NULL = off) */
+void mg_conv_midt_trace(unsigned long long* buf);
 /* profiling aid: K2h launches write 8 globaltimer stamps per CTA into buf (device, >= 148 * 8 uint64; NULL = off) */
 void mg_conv_mid_trace(unsigned long long* buf);
 

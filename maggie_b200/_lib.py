@@ -38,6 +38,8 @@ SIGNATURES = {
     "mg_conv_wgrad": (c_int, [c_void_p, c_void_p]),
     "mg_conv_halo_launches": (c_ulonglong, []),
     "mg_conv_mid_launches": (c_ulonglong, []),
+    "mg_conv_midt_launches": (c_ulonglong, []),
+    "mg_conv_midt_trace": (None, [c_void_p]),
     "mg_conv_mid_trace": (None, [c_void_p]),
     "mg_wgrad_halo_launches": (c_ulonglong, []),
     "mg_attn_tq_workspace_floats": (c_size_t, [c_int, c_int, c_int]),

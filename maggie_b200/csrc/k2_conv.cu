@@ -271,6 +271,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 namespace mg {
 int conv_halo_launch(const mg_conv_desc* d, void* stream, bool* handled);     // k2b_conv_halo.cu
 int conv_mid_launch(const mg_conv_desc* d, void* stream, bool* handled);      // k2h_conv_mid.cu
+int conv_midt_launch(const mg_conv_desc* d, void* stream, bool* handled);     // k2t_conv_mid_t.cu
 }
 
 static int conv_launch_impl(const mg_conv_desc* d, const void* x_lo, const void* w_lo, void* stream) {
@@ -291,6 +292,12 @@ static int conv_launch_impl(const mg_conv_desc* d, const void* x_lo, const void*
         // high-resolution, low-channel stride-1 layers: halo-resident persistent kernel (K2b)
         bool handled = false;
         const int rc = mg::conv_halo_launch(d, stream, &handled);
+        if (rc != MG_OK || handled) return rc;
+    }
+    if (!hp) {
+        // the same layers with Co a multiple of 128: transposed form (weights as M, patch pixels as N <= 256), K2t
+        bool handled = false;
+        const int rc = mg::conv_midt_launch(d, stream, &handled);
         if (rc != MG_OK || handled) return rc;
     }
     if (!hp) {

@@ -330,9 +330,12 @@ conv_mid_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 std::atomic<unsigned long long> g_mid_launches{0};
 unsigned long long* g_mid_trace = nullptr;    // device buffer [148][8] set by mg_conv_mid_trace (profiling only)
 
+// Opt-in since K2t: after the warp-uniform MMA issue fix the generic kernel K2 (two co-resident CTAs per SM) is faster than
+// K2h on every mid-resolution layer (64^2 128->128: 14.0 vs 19.8 us, 64^2 256->128: 21.2 vs 32.0 us, CUDA-graph replay), and
+// K2t is faster than both where it applies.  MAGGIE_B200_MID_CONV=h routes the K2h-eligible layers K2t does not take here.
 bool mid_disabled() {
-    const char* e = std::getenv("MAGGIE_B200_NO_MID_CONV");
-    return e && e[0] == '1';
+    const char* e = std::getenv("MAGGIE_B200_MID_CONV");
+    return !(e && e[0] == 'h');
 }
 
 int env_int(const char* name, int dflt) {

@@ -1,5 +1,6 @@
-"""-m gpu: K2h (csrc/k2h_conv_mid.cu), the halo-patch / weight-streaming kernel that mg_conv_fprop routes the mid-resolution
-stride-1 3x3 layers to, against torch fp32 and against the generic kernel K2 it replaces."""
+"""-m gpu: K2h (csrc/k2h_conv_mid.cu) and K2t (csrc/k2t_conv_mid_t.cu, the transposed form for Co % 128 == 0), the
+halo-patch / weight-streaming kernels that mg_conv_fprop routes the mid-resolution stride-1 3x3 layers to, against torch
+fp32 and against the generic kernel K2 they replace."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -9,14 +10,24 @@ from maggie_b200 import _lib, dense
 pytestmark = pytest.mark.gpu
 
 
+def _mid_launches():
+    return _lib.lib().mg_conv_mid_launches() + _lib.lib().mg_conv_midt_launches()
+
+
 def _run(x, wp, taps, hw, monkeypatch, generic, **kw):
-    if generic:
-        monkeypatch.setenv("MAGGIE_B200_NO_MID_CONV", "1")
+    """generic: True = K2, False = default routing (K2t when eligible, else K2h), "h" = K2h."""
+    for k in ("MAGGIE_B200_MID_CONV", "MAGGIE_B200_NO_MIDT_CONV"):
+        monkeypatch.delenv(k, raising=False)
+    if generic is True:
+        monkeypatch.setenv("MAGGIE_B200_NO_MIDT_CONV", "1")
+    elif generic == "h":
+        monkeypatch.setenv("MAGGIE_B200_NO_MIDT_CONV", "1")
+        monkeypatch.setenv("MAGGIE_B200_MID_CONV", "h")    # K2h is opt-in (slower than K2 / K2t since round 2)
     else:
-        monkeypatch.delenv("MAGGIE_B200_NO_MID_CONV", raising=False)
-    m0 = _lib.lib().mg_conv_mid_launches()
+        monkeypatch.setenv("MAGGIE_B200_MID_CONV", "h")    # default routing + K2h for what K2t does not take
+    m0 = _mid_launches()
     y = dense.conv_launch(x, wp, taps, grid_hw=hw, **kw)
-    return y, _lib.lib().mg_conv_mid_launches() - m0
+    return y, _mid_launches() - m0
 
 
 @pytest.mark.parametrize("shape", [
@@ -24,14 +35,21 @@ def _run(x, wp, taps, hw, monkeypatch, generic, **kw):
     (8, 64, 64, 128, 128), (8, 32, 32, 256, 256), (8, 16, 16, 512, 512), (2, 64, 64, 256, 128), (3, 32, 32, 512, 256),
     (1, 24, 40, 128, 192), (2, 60, 52, 128, 64), (1, 8, 8, 128, 128), (5, 13, 17, 192, 128),
 ])
-def test_mid_conv_matches_torch_and_generic(shape, monkeypatch):
+@pytest.mark.parametrize("variant", [False, "h"])
+def test_mid_conv_matches_torch_and_generic(shape, variant, monkeypatch):
     N, H, W, Ci, Co = shape
     g = torch.Generator(device="cuda").manual_seed(N * H + Ci)
     x = torch.randn(N, H, W, Ci, device="cuda", generator=g).half()
     w = torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / (Ci * 9) ** 0.5
     wp, taps = dense.pack_weight(w, Ci), dense.conv_taps(3, 3, 1, 1, Ci)
-    y, used = _run(x, wp, taps, (H, W), monkeypatch, False)
-    assert used == 1, "layer was not routed to K2h"
+    t0 = _lib.lib().mg_conv_midt_launches()
+    y, used = _run(x, wp, taps, (H, W), monkeypatch, variant)
+    assert used == 1, "layer was not routed to K2h / K2t"
+    took_t = _lib.lib().mg_conv_midt_launches() - t0
+    if variant == "h" or Co % 128:
+        assert took_t == 0
+    elif shape in ((8, 64, 64, 128, 128), (8, 32, 32, 256, 256), (8, 16, 16, 512, 512), (5, 13, 17, 192, 128)):
+        assert took_t == 1, "K2t did not take a layer it is built for"
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.half().float(), padding=1).permute(0, 2, 3, 1)
     scale = float(ref.abs().max())
     assert float((y.float() - ref).abs().max()) < 2e-3 * scale      # fp16 output rounding
@@ -51,18 +69,37 @@ def test_mid_conv_epilogues_match_generic(monkeypatch):
     wp, taps = dense.pack_weight(w, Ci), dense.conv_taps(3, 3, 1, 1, Ci)
     # training forward: ReLU before the statistics (shortcut branches), statistics of the fp32 pre-images
     out = []
-    for generic in (False, True):
+    for generic in (False, "h", True):
         st = torch.zeros(dense.STAT_COPIES, 2, Co, device="cuda")
         y, used = _run(x, wp, taps, (H, W), monkeypatch, generic, stats=st, pre_act="relu")
-        assert used == (0 if generic else 1)
+        assert used == (0 if generic is True else 1)
         out.append((y.float(), st.sum(0)))
-    (y1, s1), (y0, s0) = out
-    assert float((y1 - y0).abs().max()) < 1e-3 * float(y0.abs().max())
-    assert float((s1 - s0).abs().max()) < 1e-4 * float(s0.abs().max())
+    (y1, s1), (y2, s2), (y0, s0) = out
+    for yy, ss in ((y1, s1), (y2, s2)):
+        assert float((yy - y0).abs().max()) < 1e-3 * float(y0.abs().max())
+        assert float((ss - s0).abs().max()) < 1e-4 * float(s0.abs().max())
     # eval forward: bias, affine, residual, LeakyReLU after the residual
     ys = [_run(x, wp, taps, (H, W), monkeypatch, generic, bias=bias, scale=sc, shift=sh, res=res, post_act="lrelu")[0].float()
-          for generic in (False, True)]
-    assert float((ys[0] - ys[1]).abs().max()) < 2e-3 * float(ys[1].abs().max())
+          for generic in (False, "h", True)]
+    assert float((ys[0] - ys[2]).abs().max()) < 2e-3 * float(ys[2].abs().max())
+    assert float((ys[1] - ys[2]).abs().max()) < 2e-3 * float(ys[2].abs().max())
+
+
+def test_midt_conv_concat_slice_and_two_items_per_cta(monkeypatch):
+    """K2t: output into a channel slice of a wider buffer (TMA store at a channel offset), more items than SMs (the
+    persistent loop re-uses the patch buffer as output staging), an image height the slab height does not divide."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, H, W, Ci, Co = 20, 30, 32, 128, 256
+    x = torch.randn(N, H, W, Ci, device="cuda", generator=g).half()
+    w = torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / (Ci * 9) ** 0.5
+    wp, taps = dense.pack_weight(w, Ci), dense.conv_taps(3, 3, 1, 1, Ci)
+    buf = torch.full((N, H, W, Co + 64), 7.0, device="cuda", dtype=torch.float16)
+    t0 = _lib.lib().mg_conv_midt_launches()
+    _run(x, wp, taps, (H, W), monkeypatch, False, out=buf, c_off=32)
+    assert _lib.lib().mg_conv_midt_launches() == t0 + 1
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.half().float(), padding=1).permute(0, 2, 3, 1)
+    assert float((buf[..., 32:32 + Co].float() - ref).abs().max()) < 2e-3 * float(ref.abs().max())
+    assert bool((buf[..., :32] == 7).all()) and bool((buf[..., 32 + Co:] == 7).all())
 
 
 def test_mid_conv_serves_the_data_gradient(monkeypatch):
@@ -72,9 +109,9 @@ def test_mid_conv_serves_the_data_gradient(monkeypatch):
     dy = torch.randn(N, H, W, Co, device="cuda", generator=g).half()
     w = torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / (Ci * 9) ** 0.5
     geom = dense.ConvGeom("conv", 3, 1, 1, 1)
-    monkeypatch.delenv("MAGGIE_B200_NO_MID_CONV", raising=False)
-    m0 = _lib.lib().mg_conv_mid_launches()
+    monkeypatch.delenv("MAGGIE_B200_NO_MIDT_CONV", raising=False)
+    m0 = _mid_launches()
     dx = geom.dgrad(dy, w, (N, H, W, Ci))
-    assert _lib.lib().mg_conv_mid_launches() == m0 + 1
+    assert _mid_launches() == m0 + 1
     ref = F.conv_transpose2d(dy.permute(0, 3, 1, 2).float(), w.half().float(), padding=1).permute(0, 2, 3, 1)
     assert float((dx.float() - ref).abs().max()) < 2e-3 * float(ref.abs().max())

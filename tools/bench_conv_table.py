@@ -55,9 +55,9 @@ def burst(fn, nsets, rounds=3):
     return e0.elapsed_time(e1) * 1e3 / (rounds * nsets)
 
 def route(fn):
-    h0, m0, w0 = L.mg_conv_halo_launches(), L.mg_conv_mid_launches(), L.mg_wgrad_halo_launches()
+    h0, m0, w0 = L.mg_conv_halo_launches(), L.mg_conv_mid_launches() + L.mg_conv_midt_launches(), L.mg_wgrad_halo_launches()
     fn(0)
-    return "h" if (L.mg_conv_halo_launches() > h0 or L.mg_wgrad_halo_launches() > w0) else ("m" if L.mg_conv_mid_launches() > m0 else " ")
+    return "h" if (L.mg_conv_halo_launches() > h0 or L.mg_wgrad_halo_launches() > w0) else ("m" if L.mg_conv_mid_launches() + L.mg_conv_midt_launches() > m0 else " ")
 
 tot = [0.0] * 6
 N = 8

@@ -23,7 +23,7 @@ def burst(fn, n=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / n
 shapes = [(64, 128, 128), (32, 256, 256), (16, 512, 512), (64, 256, 128), (32, 512, 256)]
-variants = [("generic", {"MAGGIE_B200_NO_MID_CONV": "1"}), ("mid", {}), ("mid ch32", {"MAGGIE_B200_MID_CH": "32"}),
+variants = [("generic", {"MAGGIE_B200_MID_CONV": "0"}), ("mid", {}), ("mid ch32", {"MAGGIE_B200_MID_CH": "32"}),
             ("mid blk4", {"MAGGIE_B200_MID_BLOCKS": "4"}), ("mid blk3", {"MAGGIE_B200_MID_BLOCKS": "3"})]
 for (hw, ci, co) in shapes:
     x = torch.randn(8, hw, hw, ci, device="cuda").half()
@@ -35,8 +35,10 @@ for (hw, ci, co) in shapes:
     ref = None
     row = [f"{hw}^2 {ci}->{co}:"]
     for name, env in variants:
-        for k in ("MAGGIE_B200_NO_MID_CONV", "MAGGIE_B200_MID_CH", "MAGGIE_B200_MID_BLOCKS"):
+        for k in ("MAGGIE_B200_MID_CONV", "MAGGIE_B200_MID_CH", "MAGGIE_B200_MID_BLOCKS"):
             os.environ.pop(k, None)
+        os.environ["MAGGIE_B200_NO_MIDT_CONV"] = "1"       # this tool compares K2h (opt-in) with the generic kernel
+        os.environ.setdefault("MAGGIE_B200_MID_CONV", "h")
         os.environ.update(env)
         m0 = _lib.lib().mg_conv_mid_launches()
         y = dense.conv_launch(x, wp, taps, grid_hw=(hw, hw))
@@ -54,8 +56,9 @@ for (hw, ci, co) in shapes:
 
 # ---- timeline of one K2h launch (globaltimer stamps per CTA, see mg_conv_mid_trace)
 import numpy as np
-for k in ("MAGGIE_B200_NO_MID_CONV", "MAGGIE_B200_MID_CH", "MAGGIE_B200_MID_BLOCKS"):
+for k in ("MAGGIE_B200_MID_CONV", "MAGGIE_B200_MID_CH", "MAGGIE_B200_MID_BLOCKS"):
     os.environ.pop(k, None)
+os.environ["MAGGIE_B200_MID_CONV"] = "h"
 names = ["entry", "pdl_wait done", "first patch", "first weights", "MMAs issued", "accum complete", "epilogue done", "exit"]
 for (hw, ci, co) in ((64, 128, 128), (32, 256, 256)):
     x = torch.randn(8, hw, hw, ci, device="cuda").half()
