@@ -4,6 +4,9 @@
 //   forward (eval) : mg_bn_finalize (running stats) -> scale/shift folded into the conv epilogue (no extra pass)
 //   backward       : mg_bn_bwd_reduce (sum dz, sum dz*xhat) -> mg_bn_bwd_apply (dx, optional d-residual)
 #include "common.cuh"
+#include "ptx.cuh"
+
+#include <cstdlib>
 
 namespace {
 
@@ -128,7 +131,7 @@ bn_bwd_reduce_kernel(const __half* __restrict__ dy, const __half* __restrict__ y
                      const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ sums,
                      size_t npix, int C, int act) {
     mg::pdl_prologue();
-    __shared__ float s_red[256 * 16];
+    __shared__ __align__(16) float s_red[256 * 16];
     const int G = C >> 3, lanes_per_g = 256 / G;  // G in {4..64} divides 256
     const int g = threadIdx.x % G, sub = threadIdx.x / G, c0 = g << 3;
     float m[8], is[8], a0[8], a1[8];
@@ -166,12 +169,17 @@ bn_bwd_reduce_kernel(const __half* __restrict__ dy, const __half* __restrict__ y
 #pragma unroll
     for (int i = 0; i < 8; ++i) s_red[threadIdx.x * 16 + i] = a0[i], s_red[threadIdx.x * 16 + 8 + i] = a1[i];
     __syncthreads();
-    // thread t < 16*G: channel group t/16, quantity t%16 -> sum over the lanes_per_g sub-rows
-    for (int t = threadIdx.x; t < 16 * G; t += 256) {
-        const int gg = t >> 4, k = t & 15;
-        float acc = 0.f;
-        for (int s = 0; s < lanes_per_g; ++s) acc += s_red[(s * G + gg) * 16 + k];
-        atomicAdd(sums + (k >> 3) * C + (gg << 3) + (k & 7), acc);
+    // thread t < 4*G: channel group t/4, four consecutive quantities -> sum over the lanes_per_g sub-rows, ONE 16-byte
+    // vector reduction (the kernel was bound by same-address atomics: 888 blocks x 2C scalar atomicAdds on 2C addresses
+    // took longer than streaming the three tensors out of L2)
+    for (int t = threadIdx.x; t < 4 * G; t += 256) {
+        const int gg = t >> 2, k4 = t & 3;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < lanes_per_g; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(&s_red[(s * G + gg) * 16 + 4 * k4]);
+            acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+        }
+        mg::ptx::red_add_v4(sums + (k4 >> 1) * C + (gg << 3) + 4 * (k4 & 1), acc.x, acc.y, acc.z, acc.w);
     }
 }
 
@@ -265,7 +273,8 @@ extern "C" int mg_bn_bwd_reduce(const void* dy, const void* y, const void* conv_
     const size_t npix = (size_t)N * H * W;
     if (npix == 0) return MG_OK;
     const int rows_per_block = 256 / (C / 8);
-    const int grid = (int)std::min<size_t>((npix + 2 * rows_per_block - 1) / (2 * rows_per_block), (size_t)mg::kNumSMs * 6);
+    static const int waves = [] { const char* e = std::getenv("MAGGIE_B200_BN_REDUCE_WAVES"); return e ? std::atoi(e) : 2; }();
+    const int grid = (int)std::min<size_t>((npix + 2 * rows_per_block - 1) / (2 * rows_per_block), (size_t)mg::kNumSMs * waves);
     MG_LAUNCH(bn_bwd_reduce_kernel, grid, 256, 0, stream, static_cast<const __half*>(dy), static_cast<const __half*>(y),
               static_cast<const __half*>(conv_out), mean, invstd, sums, npix, C, act);
     MG_CHECK_LAUNCH("mg_bn_bwd_reduce");

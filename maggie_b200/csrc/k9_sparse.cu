@@ -126,17 +126,19 @@ sparse_conv_kernel(const SArgs a) {
     if (warp < 4) {
         // ===== gather producers =====
         const int sub = tid % cpr, rr = tid / cpr, rstep = 128 / cpr;
-        if (a.stages == steps && a.kblocks == 1 && steps <= 9 && cpr <= 4) {
+        if (a.stages == steps && a.kblocks == 1 && steps <= 9) {
             // Every tap has its own stage: nothing is recycled, so ALL gathers of the tile are put in flight at once -
             // first every neighbour index of this thread's rows, then one 16-byte cp.async per (tap, row) straight into
             // the swizzled operand tile (zero-fill form for missing neighbours) - and the stages are handed to the MMA
             // thread in order as their copy groups land.  (The staged loop below serialises two dependent global-load
             // latencies per tap: 18 latencies per tile instead of 2.)
-            int idx[9][4];
+            // (64-channel rows, 8 chunks of 16 bytes: 8 rows per thread and tap - this path served 32-channel rows only
+            //  at first, and the 3x3 64-channel layers on the OS4 / OS8 site lists took 45-117 us in the staged loop)
+            int idx[9][8];
 #pragma unroll
             for (int t = 0; t < 9; ++t)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     const int p = tile0 + rr + i * rstep;
                     idx[t][i] = -1;
                     if (t < steps && i < cpr && p < a.No) idx[t][i] = a.table ? __ldg(a.table + (size_t)p * a.T + t) : p;
@@ -146,7 +148,7 @@ sparse_conv_kernel(const SArgs a) {
                 if (t < steps) {
                     const uint32_t tile = smem_u32(sA + (size_t)t * a_tile);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         if (i < cpr) {
                             const int r = rr + i * rstep;
                             const __half* srcp = idx[t][i] >= 0 ? a.src + (size_t)idx[t][i] * a.src_stride + sub * 8 : a.src;
@@ -392,12 +394,13 @@ sparse_wgrad_kernel(const SWArgs a) {
                                  swz_chunk(r, c % cpa, a.rowb_a) * 16), "l"(srcp), "r"(ok ? 16u : 0u) : "memory");
                 }
                 // B: gathered source rows, one tile per tap
-                if (cb_chunks <= 4) {
-                    // <= 4 (row, chunk) pairs per thread: fetch every neighbour index of the tile first (one latency),
-                    // then put every copy in flight
-                    int idx[4][9];
+                if (cb_chunks <= 8) {
+                    // <= 8 (row, chunk) pairs per thread: fetch every neighbour index of the tile first (one latency),
+                    // then put every copy in flight (64-channel rows: 8 pairs; they went through the loop below at first,
+                    // one index round trip per pair)
+                    int idx[8][9];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         const int e0 = tid + i * 128, r = e0 / cb_chunks, p = row0 + r;
 #pragma unroll
                         for (int tt = 0; tt < 9; ++tt) {
@@ -406,7 +409,7 @@ sparse_wgrad_kernel(const SWArgs a) {
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         const int e0 = tid + i * 128, r = e0 / cb_chunks, c = e0 - r * cb_chunks;
                         if (e0 < 128 * cb_chunks) {
 #pragma unroll
@@ -562,12 +565,12 @@ extern "C" int mg_sparse_conv(const mg_sparse_conv_desc* d, void* stream) {
     a.stages = std::min(4, std::max(2, steps));
     while (a.stages < steps && fixed_smem + (size_t)(a.stages + 1) * 128 * a.rowb <= 112 * 1024) ++a.stages;
     if (a.rowb == 128)   // 64-channel layers run on few sites (OS4 / OS8): latency matters there, not occupancy
-        while (a.stages < std::min(steps, 8) && fixed_smem + (size_t)(a.stages + 1) * 128 * a.rowb <= 216 * 1024) ++a.stages;
+        while (a.stages < std::min(steps, 9) && fixed_smem + (size_t)(a.stages + 1) * 128 * a.rowb <= 227 * 1024) ++a.stages;
     const size_t smem = fixed_smem + (size_t)a.stages * 128 * a.rowb;
-    MG_REQUIRE(smem <= 220 * 1024, "mg_sparse_conv: weight pack does not fit in shared memory (%zu B)", smem);
+    MG_REQUIRE(smem <= 227 * 1024, "mg_sparse_conv: weight pack does not fit in shared memory (%zu B)", smem);
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(sparse_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(sparse_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             mg::set_error("mg_sparse_conv: cannot raise dynamic shared memory limit");
             return MG_ERR_CUDA;
         }

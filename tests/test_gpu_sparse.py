@@ -174,3 +174,33 @@ def test_pointwise_rows_on_large_site_lists_persistent_vs_generic(ci, co, monkey
     assert _rel_l2(res[0][0], ref) < 2e-3
     for a, c, what in zip(res[0], res[1], ("y", "dsrc", "dw", "dbias")):
         assert _rel_l2(a, c) < 2e-3, f"{what}: persistent vs generic {_rel_l2(a, c)}"
+
+
+@pytest.mark.parametrize("mode,training", [("plain", False), ("bn_act", True)])
+def test_dense_rows_take_the_conv_kernels(mode, training, monkeypatch):
+    """Linear layers over contiguous dense rows (the pixel-side attention projections, 128 channels on 8 x 64 x 64 rows) are
+    routed to the 1x1 case of the dense conv / weight-gradient kernels: same results as the rulebook kernels."""
+    from maggie_b200 import _lib, ops, sparse
+    g = torch.Generator().manual_seed(11)
+    N, ci, co = 32768, 128, 128
+    src = (torch.randn(N, ci, generator=g) * 0.5).half().cuda()
+    w = (torch.randn(co, ci, generator=g) / ci ** 0.5).cuda()
+    b = torch.randn(co, generator=g).cuda()
+    gy = torch.randn(N, co, generator=g).half().cuda()
+    res = []
+    for dense_route in (True, False):
+        monkeypatch.setattr(sparse, "DENSE_ROWS", dense_route)
+        bn = torch.nn.BatchNorm1d(co).cuda() if mode != "plain" else None
+        s, ww, bb = (t.detach().clone().requires_grad_(True) for t in (src, w, b))
+        n0 = _lib.launch_count()
+        if mode == "plain":
+            y = ops.rows_conv(s, ww, bb)
+        else:
+            y = ops.rows_conv(s, ww, None, bn=bn, mode=mode, act="relu", training=training)
+        y.backward(gy)
+        res.append([y.detach().float(), s.grad.float(), ww.grad.float()] + ([bb.grad.float()] if mode == "plain" else [bn.weight.grad.float()]))
+    ref = src.float() @ w.t() + b
+    if mode == "plain":
+        assert _rel_l2(res[0][0], ref) < 2e-3
+    for a, c, what in zip(res[0], res[1], ("y", "dsrc", "dw", "dbias / dgamma")):
+        assert _rel_l2(a, c) < 2e-3, f"{what}: dense route vs rulebook kernel {_rel_l2(a, c)}"
