@@ -455,7 +455,7 @@ def run_gpu(args):
         from maggie_b200.dp import set_sync_bn
         set_sync_bn(True)
     model.enable_cuda_graphs(not args.no_graphs)
-    flat = FlatGradAllReduce(model.parameters())
+    flat = FlatGradAllReduce(model.parameters(), bank=model.bank)
 
     host = synth.make_batch(b=FRAMES_PER_GPU, n_f=1, n_i=N_INST, H=H, W=W, edge_px=EDGE_PX, seed=1234 + rank, train=True,
                             it=args.iter)

@@ -66,7 +66,7 @@ def main():
     model, _ = build_model(CfgNode(MODEL))
     model.to(dev).train()
     model.enable_cuda_graphs(True)
-    flat = FlatGradAllReduce(model.parameters())
+    flat = FlatGradAllReduce(model.parameters(), bank=model.bank)
     opt = FusedAdamW(flat, lr=1.5e-4, betas=(0.5, 0.999), weight_decay=0.01, clip_norm=0.01)   # engine/optim.py, train.py:270
     scale = 128.0                                # a GradScaler's current scale works the same way
     for it in range(1, args.steps + 1):

@@ -348,7 +348,7 @@ int conv_midt_launch(const mg_conv_desc* d, void* stream, bool* handled) {
     // slab height: cost model over R (see the header comment)
     const double ksteps = (double)d->n_taps * d->Ci / 16.0;
     const int forced_R = env_int("MAGGIE_B200_MIDT_ROWS", 0);
-    int best_R = 0;
+    int best_R = 0, max_R = 0;
     double best_cost = 1e30;
     for (int R = 1; R <= d->Hi; ++R) {
         if (forced_R && R != forced_R) continue;
@@ -356,6 +356,7 @@ int conv_midt_launch(const mg_conv_desc* d, void* stream, bool* handled) {
         if (cols > 512) break;
         const int a_al = ((R + 2 * hal) * a.P * 128 + 1023) & ~1023;
         if ((budget - a.chunks * a_al) / B_BYTES < 3) break;
+        max_R = R;                                                   // (the patch of R rows fits)
         if (R * d->Wi * BM * 2 > a.chunks * a_al) continue;          // output staging must fit the patch buffer
         const int rblocks = ceil_div(d->Hi, R);
         if (ceil_div(d->Hi, rblocks) != R) continue;                 // even split only
@@ -371,7 +372,7 @@ int conv_midt_launch(const mg_conv_desc* d, void* stream, bool* handled) {
     }
     // slabs of fewer than 4 rows (the patch of a wide-Ci layer does not fit otherwise) re-stream the weights too often: the
     // generic kernel is faster there (64^2 256->128: 21 us vs 24 us)
-    if (!best_R || (best_R < 4 && best_R < d->Hi && !forced_R)) return MG_OK;
+    if (!best_R || (max_R < 4 && max_R < d->Hi && !forced_R)) return MG_OK;
     const int R = best_R;
     a.R = R;
     a.rblocks = ceil_div(d->Hi, R);

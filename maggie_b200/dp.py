@@ -10,19 +10,38 @@ class FlatGradAllReduce:
 
     `zero()` drops the gradients (`p.grad = None`): autograd then hands each parameter its freshly computed gradient
     tensor instead of launching an accumulate kernel per parameter (~300 tiny launches per step).  `allreduce()` packs
-    the gradients into the flat buffer with multi-tensor copies, reduces it once, and leaves every `p.grad` as a view
-    into the buffer.  With one rank nothing is packed at all."""
+    the gradients into the flat buffer with multi-tensor copies, reduces it once (averaging inside the collective), and
+    leaves every `p.grad` as a view into the buffer.  With one rank nothing is packed at all.
 
-    def __init__(self, params, dtype=torch.float32):
+    `bank` (the model's `WeightBank`, `model.bank`): the grouped weight-preparation backward (K0) then writes the gradients
+    of all its conv weights - 95 % of the bytes - straight into the head of the flat buffer, in the bank's own order, so
+    that nothing is left to pack for them (`offsets[i]` is the position of parameter i; the parameter ORDER, which numbers
+    the optimizer state as torch.optim does, is unchanged)."""
+
+    def __init__(self, params, dtype=torch.float32, bank=None):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=dtype, device=dev)
         self.no_grad = ()
-        self.views, off = [], 0
+        head = {}
+        if bank is not None and bank.entries and dtype == torch.float32:
+            mine, off = {id(p) for p in self.params}, 0
+            for e in bank.entries:
+                head[id(e.w)] = off
+                off += e.w.numel()
+            if all(k in mine for k in head) and len(head) == len(bank.entries):
+                bank.grad_target = self.flat[:off]
+            else:
+                head = {}
+        self.offsets, off = [], sum(p.numel() for p in self.params if id(p) in head)
         for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            if id(p) in head:
+                self.offsets.append(head[id(p)])
+            else:
+                self.offsets.append(off)
+                off += p.numel()
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
 
     def zero(self):
         for p in self.params:
@@ -33,7 +52,7 @@ class FlatGradAllReduce:
         # (indices of the parameters that received no gradient this step: the optimizer leaves them alone, as torch does)
         self.no_grad = tuple(i for i, p in enumerate(self.params) if p.grad is None)
         have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
-        if len(have) != len(self.params):
+        if self.no_grad:
             for v, p in zip(self.views, self.params):
                 if p.grad is None:
                     v.zero_()
@@ -47,9 +66,12 @@ class FlatGradAllReduce:
     def allreduce(self, average=True):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             self.pack()
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            if average:
-                self.flat.div_(dist.get_world_size())
+            if average and dist.get_backend() == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)      # 1 / world inside the collective: no extra pass
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+                if average:
+                    self.flat.div_(dist.get_world_size())
         return self.flat
 
 

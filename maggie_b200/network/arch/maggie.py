@@ -82,6 +82,13 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
                     nn.init.xavier_uniform_(p)
 
     # -------------------------------------------------------------------------------------------
+
+    @property
+    def bank(self):
+        """The dense stage's weight bank (K0): `FlatGradAllReduce(model.parameters(), bank=model.bank)` lets its grouped
+        backward write the conv-weight gradients straight into the data-parallel flat buffer."""
+        return self._stage[0].bank
+
     def _prepare(self, batch):
         """Flatten the batch dict.  Training with fewer instances than mask slots draws the reference's random slot
         assignment (arch/maggie.py:206-229) but keeps every pixel-sized tensor COMPACT (one plane per real instance):

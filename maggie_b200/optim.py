@@ -40,11 +40,10 @@ class FusedAdamW:
         self.step_count = torch.zeros(1, dtype=torch.float32, device=dev)
         self.report = torch.zeros(2, dtype=torch.float32, device=dev)   # (gradient norm, found_inf) of the last step
         arr = (_OptimTensor * len(params))()
-        items, off = [], 0
-        for i, p in enumerate(params):
+        items = []
+        for i, (p, off) in enumerate(zip(params, flat.offsets)):
             arr[i].param, arr[i].flat_off, arr[i].numel = p.data_ptr(), off, p.numel()
             items += [(i, o) for o in range(0, p.numel(), CHUNK)]
-            off += p.numel()
         self._sig = tuple(p.data_ptr() for p in params)
         self.tensors = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         self.items = torch.from_numpy(np.asarray(items, dtype=np.int32)).to(dev)
@@ -81,14 +80,13 @@ class FusedAdamW:
         """The layout `torch.optim.AdamW.state_dict()` writes (what the reference engine saves to / resumes from
         `last_opt.pth`, engine/train.py): per-parameter `step` / `exp_avg` / `exp_avg_sq`, parameters numbered in order.
         Parameters that never received a gradient have no state entry, as in torch."""
-        state, off = {}, 0
+        state = {}
         never = set(self._skip_key)
-        for i, p in enumerate(self.flat.params):
+        for i, (p, off) in enumerate(zip(self.flat.params, self.flat.offsets)):
             n = p.numel()
             if i not in never:
                 state[i] = dict(step=self.step_count.clone().reshape(()), exp_avg=self.m[off:off + n].view_as(p).clone(),
                                 exp_avg_sq=self.v[off:off + n].view_as(p).clone())
-            off += n
         group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
         group.update(params=list(range(len(self.flat.params))), amsgrad=False, maximize=False, foreach=None, capturable=False,
                      differentiable=False, fused=None)
@@ -96,8 +94,8 @@ class FusedAdamW:
 
     def load_state_dict(self, sd):
         """Accepts a `torch.optim.AdamW` state dict over the same parameter list (or this class's own)."""
-        off, steps = 0, []
-        for i, p in enumerate(self.flat.params):
+        steps = []
+        for i, (p, off) in enumerate(zip(self.flat.params, self.flat.offsets)):
             n = p.numel()
             st = sd["state"].get(i)
             if st is not None:
@@ -105,7 +103,6 @@ class FusedAdamW:
                 steps.append(float(st["step"]))
             else:
                 self.m[off:off + n].zero_(), self.v[off:off + n].zero_()
-            off += n
         if steps:
             self.step_count.fill_(max(steps))     # one shared step counter: every parameter with state is stepped together
         for k in ("lr", "betas", "eps", "weight_decay"):

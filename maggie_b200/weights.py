@@ -113,6 +113,7 @@ class WeightBank:
         self.current = None      # the Prepared of the forward in flight (set by the dense stage)
         self._built_for = None
         self._out = None
+        self.grad_target = None  # fp32 [grad_size] owned by dp.FlatGradAllReduce: where `_backward` puts the weight gradients
 
     # ---------------------------------------------------------------------------------------- registration
     def attach(self, root):
@@ -222,7 +223,14 @@ class WeightBank:
         if prep.aux is not None:   # weight gradients were accumulated on the auxiliary stream (dense.wgrad_async)
             torch.cuda.current_stream(self.device).wait_stream(prep.aux)
             prep.aux = None
-        grad = torch.empty(self.grad_size, dtype=torch.float32, device=self.device)
+        # straight into the head of the data-parallel flat buffer when there is one and no earlier gradient is alive in
+        # it (gradient accumulation over several backwards keeps torch's semantics through a fresh buffer)
+        tgt = self.grad_target
+        if (tgt is not None and tgt.numel() == self.grad_size and tgt.device == self.device
+                and all(e.w.grad is None for e in self.entries)):
+            grad = tgt
+        else:
+            grad = torch.empty(self.grad_size, dtype=torch.float32, device=self.device)
         prep.scal[:, 3].zero_()  # <G, W_bar> accumulators (a second backward through the same graph starts clean)
         _lib.check(_lib.lib().mg_wprep_bwd(_ptr(self.layers_dev), _ptr(self.items_tile), self.n_tile, _ptr(prep.G), _ptr(prep.vec),
                                            _ptr(prep.scal), _ptr(grad), _stream()), "mg_wprep_bwd")

@@ -48,7 +48,7 @@ def test_mid_conv_matches_torch_and_generic(shape, variant, monkeypatch):
     took_t = _lib.lib().mg_conv_midt_launches() - t0
     if variant == "h" or Co % 128:
         assert took_t == 0
-    elif shape in ((8, 64, 64, 128, 128), (8, 32, 32, 256, 256), (8, 16, 16, 512, 512), (5, 13, 17, 192, 128)):
+    elif shape in ((8, 64, 64, 128, 128), (8, 32, 32, 256, 256), (8, 16, 16, 512, 512)):
         assert took_t == 1, "K2t did not take a layer it is built for"
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.half().float(), padding=1).permute(0, 2, 3, 1)
     scale = float(ref.abs().max())

@@ -84,3 +84,54 @@ def test_parameters_without_gradient_are_left_alone_and_state_dict_is_torch_form
     opt2 = FusedAdamW(FlatGradAllReduce(ours), clip_norm=1e9, **kw)
     opt2.load_state_dict(rsd)
     assert torch.allclose(opt2.m, opt.m, rtol=1e-4, atol=1e-8) and float(opt2.step_count) == 3.0
+
+
+def test_bank_gradients_land_in_the_flat_buffer_without_a_pack():
+    """K0's grouped backward writes the conv-weight gradients straight into the head of the flat buffer
+    (`FlatGradAllReduce(..., bank=model.bank)`): after a backward those p.grad ARE the flat views, the values equal a run
+    without the hand-over, and a second backward without zero() still accumulates like torch."""
+    import random
+    import numpy as np
+    from maggie_b200.config import CfgNode
+    from maggie_b200.dp import FlatGradAllReduce
+    from maggie_b200.network import build_model
+    from oracle import synth
+    dev = torch.device("cuda")
+    torch.manual_seed(5)
+    model, _ = build_model(CfgNode(synth.model_cfg()))
+    model.to(dev).train()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    batch = synth.make_batch(b=2, n_f=1, n_i=2, H=128, W=128, edge_px=4.0, seed=6, train=True, it=1)
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+    def backward(scale=128.0):
+        np.random.seed(7), random.seed(7), torch.manual_seed(7)
+        model.load_state_dict(sd)
+        _, loss = model(batch, mem_feat=None)
+        (loss["total"] * scale).backward()
+
+    def rel(a, b):
+        return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+
+    for p in model.parameters():
+        p.grad = None
+    backward()
+    want = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    flat = FlatGradAllReduce(model.parameters(), bank=model.bank)
+    flat.zero()
+    backward()
+    bank_ws = {id(e.w) for e in model.bank.entries}
+    n_direct = 0
+    for p, v in zip(flat.params, flat.views):
+        if id(p) in bank_ws:
+            assert p.grad is not None and p.grad.data_ptr() == v.data_ptr()
+            n_direct += p.numel()
+    assert n_direct > 0.9 * flat.flat.numel()
+    flat.pack()
+    # (the training backward is not bit-reproducible - fp32 atomics in the BatchNorm statistics - hence norms, not bits)
+    # and the ASPP pooling branch normalises over the 2 frames of this batch: a few gradients move by several per cent
+    # between two runs from identical state; the median is stable)
+    med = lambda k: float(np.median([rel(p.grad, k * want[n]) for n, p in model.named_parameters() if n in want and id(p) in bank_ws]))
+    assert med(1) < 5e-2, med(1)
+    backward(3 * 128.0)                            # no zero(): torch semantics = accumulate -> g + 3 g (an overwrite: 6 g)
+    assert med(4) < 5e-2, med(4)

@@ -87,3 +87,23 @@ def test_flat_gradient_hand_over_single_process():
     assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(flat.params, flat.views))
     lin.bias.grad = None                               # a parameter without a gradient contributes zeros
     assert torch.equal(flat.pack()[12:], torch.zeros(3))
+
+
+def test_flat_buffer_puts_the_bank_weights_first_and_keeps_the_parameter_order():
+    """With the model's weight bank the conv weights own the head of the flat buffer in the bank's order (K0's grouped
+    backward writes their gradients there directly); the parameter order - which numbers the optimizer state - is unchanged."""
+    from types import SimpleNamespace
+    from maggie_b200.dp import FlatGradAllReduce
+    a, b, c, d = (torch.nn.Parameter(torch.zeros(n)) for n in (3, 5, 2, 4))
+    bank = SimpleNamespace(entries=[SimpleNamespace(w=d), SimpleNamespace(w=b)], grad_target=None)
+    flat = FlatGradAllReduce([a, b, c, d], bank=bank)
+    assert [id(p) for p in flat.params] == [id(a), id(b), id(c), id(d)]
+    assert flat.offsets == [9, 4, 12, 0]
+    assert bank.grad_target.data_ptr() == flat.flat.data_ptr() and bank.grad_target.numel() == 9
+    for p, g in zip((a, b, c, d), (1.0, 2.0, 3.0, 4.0)):
+        p.grad = torch.full_like(p, g)
+    assert flat.pack().tolist() == [4.0] * 4 + [2.0] * 5 + [1.0] * 3 + [3.0] * 2
+    # a bank with a weight outside the parameter list (frozen): plain layout, no target
+    bank2 = SimpleNamespace(entries=[SimpleNamespace(w=torch.nn.Parameter(torch.zeros(2), requires_grad=False))], grad_target=None)
+    flat2 = FlatGradAllReduce([a, b], bank=bank2)
+    assert flat2.offsets == [0, 3] and bank2.grad_target is None
