@@ -12,6 +12,7 @@ batch of 8 frames x 512x512 x 3 instances per GPU (weak scaling), training mode,
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -525,6 +526,10 @@ def run_gpu(args):
     def timed(fn, n):
         """Mean over exactly n steps between two events (barrier + synchronize on both sides, max over ranks); the median
         of the per-step intervals (one event per step, read after the region) is kept in `last_median`."""
+        # (the cyclic garbage collector is parked for the timed region, as training loops do around their hot loop: a
+        #  generation-2 pass over the process's ~10^6 objects showed up as one 20-80 ms step at random positions)
+        gc.collect()
+        gc.disable()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = []
@@ -536,15 +541,22 @@ def run_gpu(args):
                 marks[-1].record()
         e1.record()
         barrier()
+        gc.enable()
         pts = [e0] + marks + [e1]
-        per = sorted(a.elapsed_time(b) for a, b in zip(pts, pts[1:]))
+        raw = [a.elapsed_time(b) for a, b in zip(pts, pts[1:])]
+        per = sorted(raw)
         last_median[0] = per[len(per) // 2]
+        if os.environ.get("MAGGIE_B200_BENCH_VERBOSE", "0") == "1":
+            print(f"[rank {rank}] per-step ms: " + " ".join(f"{t:.2f}" for t in raw), file=sys.stderr, flush=True)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n
 
-    for _ in range(max(args.warmup, 3)):
+    # multi-rank runs take a few more untimed steps: the first collectives after start-up (NCCL channel set-up, allocator
+    # growth on every rank) showed up as one 20-100 ms step inside the first timed steps of a 5-step warm-up
+    n_warm = max(args.warmup, 3) + (8 if world > 1 else 0)
+    for _ in range(n_warm):
         step(resident)
     torch.cuda.synchronize()
     sampler.mark()
@@ -640,7 +652,7 @@ def run_gpu(args):
     roof = dict(probes[top], kernel=top, peak_source=peaks["src"])
     line = {
         "metric": "frames_per_sec_fwd_bwd", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms, "ms_per_step_median": ms_median, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": n_warm, "ms_per_step": ms, "ms_per_step_median": ms_median, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": f"C2: {FRAMES_PER_GPU}x{H}x{W}x{N_INST}-inst train fwd+bwd per GPU (iter={args.iter}, edge {EDGE_PX}px)",
                    "frames_per_gpu": FRAMES_PER_GPU, "active_sites_os1_os2_os4_os8": counts,
