@@ -347,7 +347,7 @@ def kernel_probes(torch, dev, peaks):
     return out
 
 
-def other_configs(torch, dev):
+def other_configs(torch, dev, args_no_graphs=False):
     """The remaining BASELINE.json configs on one GPU, each a short measurement (CUDA events, inputs resident, 3 warm-up +
     median of >= 5): C1 = eval forward of one 256 x 256 image with one instance (both precisions); C4 = video model, one
     5-frame 480 x 832 clip with 2 instances, training step; C5 = 1024 x 1024 x 8 instances, training step at three widths
@@ -397,8 +397,9 @@ def other_configs(torch, dev):
             c1[prec] = {"ms": ms, "frames_per_sec": 1e3 / ms}
     model.set_precision("fp16")
     res["c1_eval_256_1inst"] = dict(c1, note="eval forward incl. the one host read of the status word; 'high' = fp32-accurate mode")
-    # C5 sweep
+    # C5 sweep (training modes replay the dense stage as CUDA graphs, as the headline run does)
     model.train()
+    model.enable_cuda_graphs(not args_no_graphs)
     sweep = []
     for edge in (3.0, 8.0, 24.0):
         b5 = to_dev(synth.make_batch(b=1, n_f=1, n_i=8, H=1024, W=1024, edge_px=edge, seed=77, train=True, it=1))
@@ -413,6 +414,7 @@ def other_configs(torch, dev):
     # C4
     vmodel, _ = build_model(CfgNode(synth.video_cfg()))
     vmodel.to(dev).train()
+    vmodel.enable_cuda_graphs(not args_no_graphs)
     b4 = to_dev(synth.make_batch(b=1, n_f=5, n_i=2, H=480, W=832, edge_px=6.0, seed=9, train=True, it=1))
     ms = med(lambda: train_step(vmodel, b4), n=5)
     res["c4_video_train_5x480x832_2inst"] = {"ms_per_clip": ms, "clips_per_sec": 1e3 / ms, "frames_per_sec": 5e3 / ms,
@@ -675,7 +677,7 @@ def run_gpu(args):
     if world == 1 and not args.no_extras:
         del model, flat
         torch.cuda.empty_cache()
-        line["other_configs"] = other_configs(torch, dev)
+        line["other_configs"] = other_configs(torch, dev, args.no_graphs)
     if world == 1 and not args.no_cpu_baseline:
         cstep, cframes = cpu_step_fn(2)
         cstep()

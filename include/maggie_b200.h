@@ -62,6 +62,33 @@ int mg_unknown_mask_select(const float* alpha, const float* alt, const int32_t* 
 int mg_fuse_stage(const float* src, const float* finer, const float* coarser, int slices, int H, int W,
                   const int32_t* widths, const uint8_t* and_mask, uint8_t* out_w_u8, float* out_alpha, void* stream);
 
+/* ---- K11: element-wise half of the video model (MaGGIe_Temp) --------------------------------------------------
+ * replaces: the gating arithmetic of ConvGRU.forward_single_frame (module/conv_gru.py:50-58: sigmoid / split / r*h /
+ *           torch.cat / tanh / blend, ~12 torch launches per step and direction) around the two native convolutions, and
+ *           the forward / backward alpha recurrences of bidirectional_fusion
+ *           (decoder/resnet_inst_matt_spconv_temp.py:122-142: 4 (n_f - 1) full-resolution blend passes).
+ * GRU tensors are NHWC fp16 rows [P = N*h*w][channels]; C = hidden channels (multiple of 8).
+ *   cat1 = [x | h] ([P][2C]),  rz = conv_ih(cat1) + bias ([P][2C], r then z),  cat2 = [x | sigmoid(r) * h],
+ *   c_pre = conv_hh(cat2) + bias ([P][C]),  h_new = (1 - z) h + z tanh(c_pre).
+ * Backward: gate2_bwd turns dh_new into drz[:, C:], dc_pre and dh_direct = dh_new (1 - z); gate1_bwd turns
+ *   dcat2 (data gradient of conv_hh) into drz[:, :C] and dpart = [dcat2[:, :C] | dh_direct + dcat2[:, C:] sigmoid(r)], which
+ *   the data gradient of conv_ih takes as its residual input: its output is [dx | dh]. */
+int mg_gru_concat2(const void* x, const void* h, void* cat1, size_t P, int C, void* stream);
+int mg_gru_gate1_fwd(const void* rz, const void* cat1, void* cat2, size_t P, int C, void* stream);
+int mg_gru_gate2_fwd(const void* rz, const void* c_pre, const void* cat1, void* h_new, size_t P, int C, void* stream);
+int mg_gru_gate2_bwd(const void* dh_new, const void* rz, const void* c_pre, const void* cat1, void* drz, void* dc_pre,
+                     void* dh_direct, size_t P, int C, void* stream);
+int mg_gru_gate1_bwd(const void* dcat2, const void* rz, const void* cat1, const void* dh_direct, void* drz, void* dpart,
+                     size_t P, int C, void* stream);
+/* fd / bd: fp32 logits [B][F][HW] of the forward / backward temporal-difference maps (plane 0 of fd and plane F-1 of bd
+ * are not read); preds / fused fp32 [B][F][n_i][HW]:  fp_0 = p_0, fp_i = fp_{i-1} (1 - s(fd_i)) + p_i s(fd_i);
+ * bp_{F-1} = p_{F-1}, bp_i = bp_{i+1} (1 - s(bd_i)) + p_i s(bd_i);  fused = [fp_0, (fp_i + bp_i) / 2 ..., bp_{F-1}].
+ * 2 <= F <= 8.  The backward recomputes both recurrences and returns the gradients w.r.t. preds and the logits. */
+int mg_temporal_fuse_fwd(const float* fd, const float* bd, const float* preds, float* fused, int B, int F, int n_i,
+                         size_t HW, void* stream);
+int mg_temporal_fuse_bwd(const float* fd, const float* bd, const float* preds, const float* dfused, float* dpreds,
+                         float* dfd, float* dbd, int B, int F, int n_i, size_t HW, void* stream);
+
 /* ---- K8b: active-site lists for the sparse refinement ---------------------------------------------
  * replaces: decoder/resnet_inst_matt_spconv.py:203-218 (torch.nonzero + spconv `dummy_downscale`, whose only
  *           live product is the OS1/OS2/OS4/OS8 index sets and the (in,out,tap) pair tables).

@@ -542,8 +542,10 @@ class ConvGeom:
         return conv2d_nhwc(x, w, stride=self.stride, padding=self.pad, dilation=self.dil, **epi)
 
     # ---- data gradient: dx [N,Hi,Wi,Ci_pad] from dy [N,Ho,Wo,Co]
-    def dgrad(self, dy, w, x_shape):
+    def dgrad(self, dy, w, x_shape, res=None):
+        """`res` (stride-1 convs only): NHWC fp16 tensor of the input's shape added in the epilogue (dx = conv^T(dy) + res)."""
         N, Hi, Wi, ci_pad = x_shape
+        assert res is None or (self.kind == "conv" and self.stride == 1)
         k, p, dl = self.k, self.pad, self.dil
         if self.kind == "convT":
             Ci, Co = wshape(w)[:2]
@@ -564,7 +566,7 @@ class ConvGeom:
             wp = pack_weight(wt, Co)      # [Ci_pad][k*k][Co]
         if self.stride == 1:
             taps = [(p - ky * dl, p - kx * dl, (ky * k + kx) * Co) for ky in range(k) for kx in range(k)]
-            return conv_launch(dy, wp, taps, grid_hw=(Hi, Wi))
+            return conv_launch(dy, wp, taps, grid_hw=(Hi, Wi), res=res)
         assert Hi % 2 == 0 and Wi % 2 == 0
         dx = torch.empty((N, Hi, Wi, ci_pad), dtype=torch.float16, device=dy.device)
         phases = []
@@ -823,3 +825,65 @@ def conv_bias(x, w, bias=None, *, padding=1):
     if x.dtype != torch.float16 or not x.permute(0, 2, 3, 1).is_contiguous():
         x = x.to(torch.float16).contiguous(memory_format=torch.channels_last)
     return _ConvBias.apply(x, w, bias, ConvGeom("conv", w.shape[-1], 1, padding, 1))
+
+
+# ================================================================================================ ConvGRU step (K11)
+class _GRUStep(torch.autograd.Function):
+    """One ConvGRU step (module/conv_gru.py:50-58), all native: concat -> conv_ih -> gate1 -> conv_hh -> gate2, and the
+    reverse chain in the backward (the data gradient of conv_ih adds the directly propagated parts in its epilogue and
+    returns [dx | dh] as one tensor).  x, h: NCHW-shaped channels-last fp16 [N, C, h, w]."""
+
+    @staticmethod
+    def forward(ctx, x, h, w_ih, b_ih, w_hh, b_hh):
+        L = _lib.lib()
+        xn, hn = x.permute(0, 2, 3, 1), h.permute(0, 2, 3, 1)
+        assert xn.is_contiguous() and hn.is_contiguous() and xn.dtype == hn.dtype == torch.float16
+        N, Hh, Ww, C = xn.shape
+        P = N * Hh * Ww
+        g = ConvGeom("conv", 3, 1, 1, 1)
+        wi, wh = w_ih.detach(), w_hh.detach()
+        cat1 = torch.empty((N, Hh, Ww, 2 * C), dtype=torch.float16, device=x.device)
+        _lib.check(L.mg_gru_concat2(_ptr(xn), _ptr(hn), _ptr(cat1), P, C, _stream()), "mg_gru_concat2")
+        rz = g.fwd(cat1, wi, bias=b_ih.detach().float().contiguous())
+        cat2 = torch.empty_like(cat1)
+        _lib.check(L.mg_gru_gate1_fwd(_ptr(rz), _ptr(cat1), _ptr(cat2), P, C, _stream()), "mg_gru_gate1_fwd")
+        cpre = g.fwd(cat2, wh, bias=b_hh.detach().float().contiguous())
+        hnew = torch.empty_like(xn)
+        _lib.check(L.mg_gru_gate2_fwd(_ptr(rz), _ptr(cpre), _ptr(cat1), _ptr(hnew), P, C, _stream()), "mg_gru_gate2_fwd")
+        ctx.save_for_backward(cat1, cat2, rz, cpre, wi, wh)
+        return hnew.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gh):
+        from . import ops
+        L = _lib.lib()
+        cat1, cat2, rz, cpre, wi, wh = ctx.saved_tensors
+        N, Hh, Ww, C2 = cat1.shape
+        C, P = C2 // 2, N * Hh * Ww
+        g = ConvGeom("conv", 3, 1, 1, 1)
+        dhn = gh.permute(0, 2, 3, 1)
+        if not dhn.is_contiguous() or dhn.dtype != torch.float16:
+            dhn = dhn.contiguous().to(torch.float16)
+        drz, dcpre, dhd = torch.empty_like(rz), torch.empty_like(cpre), torch.empty_like(cpre)
+        _lib.check(L.mg_gru_gate2_bwd(_ptr(dhn), _ptr(rz), _ptr(cpre), _ptr(cat1), _ptr(drz), _ptr(dcpre), _ptr(dhd), P, C,
+                                      _stream()), "mg_gru_gate2_bwd")
+        dcat2 = g.dgrad(dcpre, wh, cat2.shape)
+        dpart = torch.empty_like(cat1)
+        _lib.check(L.mg_gru_gate1_bwd(_ptr(dcat2), _ptr(rz), _ptr(cat1), _ptr(dhd), _ptr(drz), _ptr(dpart), P, C, _stream()),
+                   "mg_gru_gate1_bwd")
+        dcat1 = g.dgrad(drz, wi, cat1.shape, res=dpart)            # = [dx | dh]
+        dx = dcat1[..., :C].permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
+        dh = dcat1[..., C:].permute(0, 3, 1, 2) if ctx.needs_input_grad[1] else None
+        dwi = g.wgrad(drz, cat1, tuple(wi.shape)) if ctx.needs_input_grad[2] else None
+        dbi = ops.col_sum(drz.view(P, C2)) if ctx.needs_input_grad[3] else None
+        dwh = g.wgrad(dcpre, cat2, tuple(wh.shape)) if ctx.needs_input_grad[4] else None
+        dbh = ops.col_sum(dcpre.view(P, C)) if ctx.needs_input_grad[5] else None
+        return dx, dh, dwi, dbi, dwh, dbh
+
+
+def gru_step(x, h, w_ih, b_ih, w_hh, b_hh):
+    """x, h [N, C, h, w] channels-last fp16; w_ih [2C, 2C, 3, 3], w_hh [C, 2C, 3, 3] fp32 (reference layout)."""
+    _need_cuda(x, h, w_ih, w_hh)
+    cl = lambda t: t if (t.dtype == torch.float16 and t.permute(0, 2, 3, 1).is_contiguous()) else \
+        t.to(torch.float16).contiguous(memory_format=torch.channels_last)
+    return _GRUStep.apply(cl(x), cl(h), w_ih, b_ih, w_hh, b_hh)

@@ -462,12 +462,7 @@ class MaGGIeTempDecoder(MaGGIeDecoder):
     # -- ConvGRU -------------------------------------------------------------------------------------------
     def _gru_step(self, x, h):
         g = self.os8_temp_module
-        C = x.shape[1]
-        rz = torch.sigmoid(ops.conv_bias(torch.cat([x, h], 1), g.ih[0].weight, g.ih[0].bias).float())
-        r, z = rz[:, :C], rz[:, C:]
-        hf = h.float()
-        c = torch.tanh(ops.conv_bias(torch.cat([x, (r * hf).to(x.dtype)], 1), g.hh[0].weight, g.hh[0].bias).float())
-        return ((1 - z) * hf + z * c).to(x.dtype)
+        return ops.gru_step(x, h, g.ih[0].weight, g.ih[0].bias, g.hh[0].weight, g.hh[0].bias)
 
     def propagate(self, feat, prev_h=None):
         """feat [b, n_f, C, h, w] -> (bidirectionally propagated features, forward hidden states) (conv_gru.py:50-70)."""
@@ -501,23 +496,13 @@ class MaGGIeTempDecoder(MaGGIeDecoder):
     def bidirectional_fusion(self, feat, preds):
         n_f = feat.shape[1]
         cat = lambda a, c: torch.cat([feat[:, a], feat[:, c]], 1).contiguous(memory_format=torch.channels_last)
-        fd, fp = [], [preds[:, 0]]
-        for i in range(1, n_f):
-            d = self._diff(cat(i - 1, i))
-            fd.append(d)
-            s = torch.sigmoid(d)
-            fp.append(fp[-1] * (1 - s) + preds[:, i] * s)
+        fd = [self._diff(cat(i - 1, i)) for i in range(1, n_f)]          # frame i-1 -> i
+        # frame i -> i-1, in the reference's call order (every call advances the spectral-norm power iteration)
+        bd = [self._diff(cat(i, i - 1)) for i in range(n_f - 1, 0, -1)][::-1]
         fd = torch.stack([torch.zeros_like(fd[0])] + fd, 1)
-        bd, bp = [], [preds[:, n_f - 1]]
-        for i in range(n_f - 1, 0, -1):
-            d = self._diff(cat(i, i - 1))
-            bd.append(d)
-            s = torch.sigmoid(d)
-            bp.append(bp[-1] * (1 - s) + preds[:, i - 1] * s)
-        bp, bd = bp[::-1], bd[::-1]
         bd = torch.stack(bd + [torch.zeros_like(bd[-1])], 1)
-        fused = [fp[0]] + [(fp[i] + bp[i]) / 2 for i in range(1, n_f - 1)] + [bp[n_f - 1]]
-        return fd, bd, torch.stack(fused, 1)
+        # both alpha recurrences + their average in one pass (K11)
+        return fd, bd, ops.temporal_fuse(fd, bd, preds.float())
 
     @staticmethod
     def _gaussian_smoothing(x, sigma=3):

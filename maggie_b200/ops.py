@@ -390,6 +390,62 @@ def conv_bias(x, w, bias=None, *, padding=1):
     return y[:, :co] if y.shape[1] != co else y
 
 
+def gru_step(x, h, w_ih, b_ih, w_hh, b_hh):
+    """One ConvGRU step (module/conv_gru.py:50-58): rz = sigmoid(conv_ih([x | h])); c = tanh(conv_hh([x | r * h]));
+    h' = (1 - z) h + z c.  ROUTED: fp16 CUDA tensors -> K11 gate kernels around the native convs (one autograd node, no
+    torch.cat / sigmoid / tanh launches); anything else -> the torch composition."""
+    C = x.shape[1]
+    if x.is_cuda and x.dtype == torch.float16 and C % 8 == 0:
+        from . import dense
+        return dense.gru_step(x, h, w_ih, b_ih, w_hh, b_hh)
+    rz = torch.sigmoid(conv_bias(torch.cat([x, h], 1), w_ih, b_ih).float())
+    r, z = rz[:, :C], rz[:, C:]
+    hf = h.float()
+    c = torch.tanh(conv_bias(torch.cat([x, (r * hf).to(x.dtype)], 1), w_hh, b_hh).float())
+    return ((1 - z) * hf + z * c).to(x.dtype)
+
+
+class _TemporalFuse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fd, bd, preds):
+        B, n_f, n_i, H, W = preds.shape
+        fd, bd, preds = fd.contiguous(), bd.contiguous(), preds.contiguous()
+        fused = torch.empty_like(preds)
+        _lib.check(_lib.lib().mg_temporal_fuse_fwd(_ptr(fd), _ptr(bd), _ptr(preds), _ptr(fused), B, n_f, n_i, H * W, _stream()),
+                   "mg_temporal_fuse_fwd")
+        ctx.save_for_backward(fd, bd, preds)
+        return fused
+
+    @staticmethod
+    def backward(ctx, g):
+        fd, bd, preds = ctx.saved_tensors
+        B, n_f, n_i, H, W = preds.shape
+        g = g.contiguous().float()
+        dp, dfd, dbd = torch.empty_like(preds), torch.empty_like(fd), torch.empty_like(bd)
+        _lib.check(_lib.lib().mg_temporal_fuse_bwd(_ptr(fd), _ptr(bd), _ptr(preds), _ptr(g), _ptr(dp), _ptr(dfd), _ptr(dbd), B, n_f,
+                                                   n_i, H * W, _stream()), "mg_temporal_fuse_bwd")
+        return dfd, dbd, dp
+
+
+def temporal_fuse(fd, bd, preds):
+    """Bidirectional alpha fusion over the frames of a clip (decoder/resnet_inst_matt_spconv_temp.py:122-142).
+    fd, bd [B, n_f, 1, H, W] fp32 logits of the forward / backward temporal-difference maps (fd[:, 0] and bd[:, -1] are the
+    reference's zero planes and are not read); preds [B, n_f, n_i, H, W] fp32.  ROUTED: CUDA fp32 with n_f <= 8 -> K11 (one
+    pass forward, one backward); anything else -> the torch recurrences."""
+    n_f = preds.shape[1]
+    if preds.is_cuda and preds.dtype == fd.dtype == bd.dtype == torch.float32 and 2 <= n_f <= 8:
+        return _TemporalFuse.apply(fd, bd, preds)
+    sf, sb = torch.sigmoid(fd), torch.sigmoid(bd)
+    fp = [preds[:, 0]]
+    for i in range(1, n_f):
+        fp.append(fp[-1] * (1 - sf[:, i]) + preds[:, i] * sf[:, i])
+    bp = [preds[:, n_f - 1]]
+    for i in range(n_f - 2, -1, -1):
+        bp.append(bp[-1] * (1 - sb[:, i]) + preds[:, i] * sb[:, i])
+    bp = bp[::-1]
+    return torch.stack([fp[0]] + [(fp[i] + bp[i]) / 2 for i in range(1, n_f - 1)] + [bp[n_f - 1]], 1)
+
+
 def linear(x, w, b=None):
     return F.linear(x, w.to(x.dtype), None if b is None else b.to(x.dtype))
 
