@@ -76,6 +76,52 @@ wprep_u_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict
     if (lane == 0) vec[L.vec_off + width + row] = acc / (sqrtf(nn) + kEps);
 }
 
+// The tile bodies are instantiated for the tap counts of the model (1, 9, 16; 0 = run-time value): every index of the
+// re-layout loops is a quotient / remainder by `taps`-derived sizes, and with run-time divisors the kernels were bound by
+// integer-division instructions (wprep_pack 219 us for a 240 MB stream), not by memory.
+template <int TAPS>
+__device__ __forceinline__ void pack_tile(const mg_wprep_layer& L, const int4 it, const float inv_sigma, float (*s)[SROW],
+                                          __half* __restrict__ P, __half* __restrict__ D) {
+    const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
+    const int taps = TAPS ? TAPS : L.taps, width = d1 * taps, tid = threadIdx.x;
+    const int a0 = it.y, b0 = it.z, seg = TB * taps;
+    for (int i = tid; i < TA * seg; i += 256) {
+        const int a = i / seg, e = i - a * seg;
+        const int col = b0 * taps + e;
+        s[a][e] = (a0 + a < d0 && col < width) ? L.w[(size_t)(a0 + a) * width + col] : 0.f;
+    }
+    __syncthreads();
+    const float mul = inv_sigma * (L.fold ? 0.25f : 1.f);
+    const int to = TAPS > 1 ? TAPS : (L.fold ? 4 : taps), Co = L.Co, cip = L.ci_pad;   // (only 1x1 layers fold)
+    __half* Pl = P + L.p_off;
+    __half* Dl = D ? D + L.d_off : nullptr;
+    if (!L.transposed) {   // a = co, b = ci
+        for (int i = tid; i < TA * to * TB; i += 256) {             // P: ci fastest
+            const int b = i % TB, tp = (i / TB) % to, a = i / (TB * to);
+            const int co = a0 + a, ci = b0 + b;
+            if (co < Co && ci < cip) Pl[((size_t)co * to + tp) * cip + ci] = __float2half(s[a][b * taps + (L.fold ? 0 : tp)] * mul);
+        }
+        if (Dl)
+            for (int i = tid; i < TA * to * TB; i += 256) {         // D: co fastest
+                const int a = i % TA, tp = (i / TA) % to, b = i / (TA * to);
+                const int co = a0 + a, ci = b0 + b;
+                if (co < Co && ci < cip) Dl[((size_t)ci * to + tp) * Co + co] = __float2half(s[a][b * taps + (L.fold ? 0 : tp)] * mul);
+            }
+    } else {               // a = ci, b = co
+        for (int i = tid; i < TA * to * TB; i += 256) {             // P: ci fastest
+            const int a = i % TA, tp = (i / TA) % to, b = i / (TA * to);
+            const int ci = a0 + a, co = b0 + b;
+            if (co < Co && ci < cip) Pl[((size_t)co * to + tp) * cip + ci] = __float2half(s[a][b * taps + tp] * mul);
+        }
+        if (Dl)
+            for (int i = tid; i < TA * to * TB; i += 256) {         // D: co fastest
+                const int b = i % TB, tp = (i / TB) % to, a = i / (TB * to);
+                const int ci = a0 + a, co = b0 + b;
+                if (co < Co && ci < cip) Dl[((size_t)ci * to + tp) * Co + co] = __float2half(s[a][b * taps + tp] * mul);
+            }
+    }
+}
+
 // ---- C: sigma, in-place u / v update, fp16 packs -----------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 wprep_pack_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ vec,
@@ -108,48 +154,19 @@ wprep_pack_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restr
     } else if (it.w && tid == 0) {
         scal[it.x * 4 + 0] = 1.f, scal[it.x * 4 + 1] = 0.f, scal[it.x * 4 + 2] = 0.f, scal[it.x * 4 + 3] = 0.f;
     }
-    const int a0 = it.y, b0 = it.z, seg = TB * taps;
-    for (int i = tid; i < TA * seg; i += 256) {
-        const int a = i / seg, e = i - a * seg;
-        const int col = b0 * taps + e;
-        s[a][e] = (a0 + a < d0 && col < width) ? L.w[(size_t)(a0 + a) * width + col] : 0.f;
-    }
-    __syncthreads();
-    const float mul = inv_sigma * (L.fold ? 0.25f : 1.f);
-    const int to = L.fold ? 4 : taps, Co = L.Co, cip = L.ci_pad;
-    __half* Pl = P + L.p_off;
-    __half* Dl = D ? D + L.d_off : nullptr;
-    if (!L.transposed) {   // a = co, b = ci
-        for (int i = tid; i < TA * to * TB; i += 256) {             // P: ci fastest
-            const int b = i % TB, tp = (i / TB) % to, a = i / (TB * to);
-            const int co = a0 + a, ci = b0 + b;
-            if (co < Co && ci < cip) Pl[((size_t)co * to + tp) * cip + ci] = __float2half(s[a][b * taps + (L.fold ? 0 : tp)] * mul);
-        }
-        if (Dl)
-            for (int i = tid; i < TA * to * TB; i += 256) {         // D: co fastest
-                const int a = i % TA, tp = (i / TA) % to, b = i / (TA * to);
-                const int co = a0 + a, ci = b0 + b;
-                if (co < Co && ci < cip) Dl[((size_t)ci * to + tp) * Co + co] = __float2half(s[a][b * taps + (L.fold ? 0 : tp)] * mul);
-            }
-    } else {               // a = ci, b = co
-        for (int i = tid; i < TA * to * TB; i += 256) {             // P: ci fastest
-            const int a = i % TA, tp = (i / TA) % to, b = i / (TA * to);
-            const int ci = a0 + a, co = b0 + b;
-            if (co < Co && ci < cip) Pl[((size_t)co * to + tp) * cip + ci] = __float2half(s[a][b * taps + tp] * mul);
-        }
-        if (Dl)
-            for (int i = tid; i < TA * to * TB; i += 256) {         // D: co fastest
-                const int b = i % TB, tp = (i / TB) % to, a = i / (TB * to);
-                const int ci = a0 + a, co = b0 + b;
-                if (co < Co && ci < cip) Dl[((size_t)ci * to + tp) * Co + co] = __float2half(s[a][b * taps + tp] * mul);
-            }
+    switch (L.taps) {
+        case 1: pack_tile<1>(L, it, inv_sigma, s, P, D); break;
+        case 9: pack_tile<9>(L, it, inv_sigma, s, P, D); break;
+        case 16: pack_tile<16>(L, it, inv_sigma, s, P, D); break;
+        default: pack_tile<0>(L, it, inv_sigma, s, P, D); break;
     }
 }
 
 // Loads the tile of dL/dW (torch layout order) from the packed gradient G [Co][taps_out][ci_pad] into s[a][b*taps+tap].
+template <int TAPS>
 __device__ __forceinline__ void load_grad_tile(const mg_wprep_layer& L, const float* __restrict__ G, int a0, int b0,
                                                float (*s)[SROW]) {
-    const int taps = L.taps, to = L.fold ? 4 : taps, Co = L.Co, Ci = L.Ci, cip = L.ci_pad, tid = threadIdx.x;
+    const int taps = TAPS ? TAPS : L.taps, to = TAPS > 1 ? TAPS : (L.fold ? 4 : taps), Co = L.Co, Ci = L.Ci, cip = L.ci_pad, tid = threadIdx.x;
     const float* Gl = G + L.g_off;
     if (!L.transposed) {
         for (int i = tid; i < TA * taps * TB; i += 256) {
@@ -174,40 +191,27 @@ __device__ __forceinline__ void load_grad_tile(const mg_wprep_layer& L, const fl
     }
 }
 
-// ---- D: inner[layer] = <dL/dW, W_bar>  (spectral-norm layers only) -------------------------------------------------
-__global__ void __launch_bounds__(256)
-wprep_bwd_inner_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ G,
-                       float* __restrict__ scal) {
-    mg::pdl_prologue();
-    __shared__ float s[TA][SROW];
-    __shared__ float red[8];
-    const int4 it = items[blockIdx.x];
-    const mg_wprep_layer L = layers[it.x];
-    if (!L.u) return;
+template <int TAPS>
+__device__ __forceinline__ float inner_tile(const mg_wprep_layer& L, const int4 it, const float* __restrict__ G, float (*s)[SROW]) {
     const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
-    const int taps = L.taps, width = d1 * taps, seg = TB * taps;
-    load_grad_tile(L, G, it.y, it.z, s);
+    const int taps = TAPS ? TAPS : L.taps, width = d1 * taps, seg = TB * taps;
+    load_grad_tile<TAPS>(L, G, it.y, it.z, s);
     __syncthreads();
     float acc = 0.f;
     for (int i = threadIdx.x; i < TA * seg; i += 256) {
         const int a = i / seg, e = i - a * seg, col = it.z * taps + e;
         if (it.y + a < d0 && col < width) acc += s[a][e] * L.w[(size_t)(it.y + a) * width + col];
     }
-    acc = block_sum(acc, red);
-    if (threadIdx.x == 0 && acc != 0.f) atomicAdd(scal + it.x * 4 + 3, acc);
+    return acc;
 }
 
-// ---- E: dW_bar in the torch layout ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-wprep_bwd_final_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ G,
-                       const float* __restrict__ vec, const float* __restrict__ scal, float* __restrict__ grad) {
-    mg::pdl_prologue();
-    __shared__ float s[TA][SROW];
-    const int4 it = items[blockIdx.x];
-    const mg_wprep_layer L = layers[it.x];
+template <int TAPS>
+__device__ __forceinline__ void final_tile(const mg_wprep_layer& L, const int4 it, const float* __restrict__ G,
+                                           const float* __restrict__ vec, const float* __restrict__ scal, float* __restrict__ grad,
+                                           float (*s)[SROW]) {
     const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
-    const int taps = L.taps, width = d1 * taps, seg = TB * taps;
-    load_grad_tile(L, G, it.y, it.z, s);
+    const int taps = TAPS ? TAPS : L.taps, width = d1 * taps, seg = TB * taps;
+    load_grad_tile<TAPS>(L, G, it.y, it.z, s);
     __syncthreads();
     float* gl = grad + L.grad_off;
     if (L.u) {
@@ -225,6 +229,43 @@ wprep_bwd_final_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __
             const int a = i / seg, e = i - a * seg, col = it.z * taps + e;
             if (it.y + a < d0 && col < width) gl[(size_t)(it.y + a) * width + col] = s[a][e];
         }
+    }
+}
+
+// ---- D: inner[layer] = <dL/dW, W_bar>  (spectral-norm layers only) -------------------------------------------------
+__global__ void __launch_bounds__(256)
+wprep_bwd_inner_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ G,
+                       float* __restrict__ scal) {
+    mg::pdl_prologue();
+    __shared__ float s[TA][SROW];
+    __shared__ float red[8];
+    const int4 it = items[blockIdx.x];
+    const mg_wprep_layer L = layers[it.x];
+    if (!L.u) return;
+    float acc;
+    switch (L.taps) {
+        case 1: acc = inner_tile<1>(L, it, G, s); break;
+        case 9: acc = inner_tile<9>(L, it, G, s); break;
+        case 16: acc = inner_tile<16>(L, it, G, s); break;
+        default: acc = inner_tile<0>(L, it, G, s); break;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0 && acc != 0.f) atomicAdd(scal + it.x * 4 + 3, acc);
+}
+
+// ---- E: dW_bar in the torch layout ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wprep_bwd_final_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict__ items, const float* __restrict__ G,
+                       const float* __restrict__ vec, const float* __restrict__ scal, float* __restrict__ grad) {
+    mg::pdl_prologue();
+    __shared__ float s[TA][SROW];
+    const int4 it = items[blockIdx.x];
+    const mg_wprep_layer L = layers[it.x];
+    switch (L.taps) {
+        case 1: final_tile<1>(L, it, G, vec, scal, grad, s); break;
+        case 9: final_tile<9>(L, it, G, vec, scal, grad, s); break;
+        case 16: final_tile<16>(L, it, G, vec, scal, grad, s); break;
+        default: final_tile<0>(L, it, G, vec, scal, grad, s); break;
     }
 }
 
