@@ -84,7 +84,8 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // EPI: 0 / 1 / 2 = lean epilogue (pre-activation none / ReLU / LeakyReLU fixed at compile time: training forward and data
-// gradients), 3 = general (bias, eval BN affine, residual, post-activation).
+// gradients), 3 = general (bias, eval BN affine, residual, post-activation), 4 = bias only (Linear layers over dense rows:
+// the run-time switches of the general form tripled the instruction-bound epilogue, 6.7 -> 18 us on 32768 x 128 -> 128).
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_midt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
@@ -227,6 +228,8 @@ conv_midt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 if (a.bias) bias = __ldg(a.bias + co);
                 if (a.scale) sc = __ldg(a.scale + co), sh = __ldg(a.shift + co);
                 if (a.res) res_l = a.res + ((size_t)img * a.H + y0) * a.W * a.Co + co;
+            } else if constexpr (EPI == 4) {
+                bias = __ldg(a.bias + co);
             }
             float s_sum = 0.f, s_sq = 0.f;
             auto process = [&](const uint32_t (&r)[16], int g) {
@@ -245,6 +248,8 @@ conv_midt_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                                 v = fmaxf(v, 0.f);
                             } else if constexpr (EPI == 2) {
                                 v = v > 0.f ? v : 0.2f * v;
+                            } else if constexpr (EPI == 4) {
+                                v += bias;
                             }
                             s_sum += v, s_sq = fmaf(v, v, s_sq);
                             if constexpr (EPI == 3) {
@@ -309,6 +314,10 @@ bool midt_disabled() {
     const char* e = std::getenv("MAGGIE_B200_NO_MIDT_CONV");
     return e && e[0] == '1';
 }
+bool midt_1x1_disabled() {
+    const char* e = std::getenv("MAGGIE_B200_NO_MIDT_1X1");
+    return e && e[0] == '1';
+}
 int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : dflt;
@@ -327,11 +336,12 @@ int conv_midt_launch(const mg_conv_desc* d, void* stream, bool* handled) {
     if (midt_disabled()) return MG_OK;
     if (d->sy != 1 || d->sx != 1 || d->oys != 1 || d->oxs != 1 || d->oy0 != 0 || d->ox0 != 0 || d->res_up) return MG_OK;
     if (d->Hg != d->Hi || d->Wg != d->Wi || d->Ho != d->Hi || d->Wo != d->Wi || d->n_phases > 1) return MG_OK;
-    if (d->n_taps > 9 || d->n_taps < 4 || d->Ci % CH || d->Ci < 128 || d->Ci > CH * MAX_CHUNKS || d->Co % BM) return MG_OK;
+    if (d->n_taps > 9 || (d->n_taps < 4 && d->n_taps != 1) || d->Ci % CH || d->Ci < 128 || d->Ci > CH * MAX_CHUNKS || d->Co % BM) return MG_OK;
     if (d->Wi > 64 || d->Wi < 8 || d->Hi < 4) return MG_OK;
     int hal = 0;
     for (int t = 0; t < d->n_taps; ++t) hal = std::max(hal, std::max(std::abs(d->tap_dy[t]), std::abs(d->tap_dx[t])));
-    if (hal < 1 || hal > 2) return MG_OK;
+    if (hal > 2 || (hal == 0) != (d->n_taps == 1)) return MG_OK;   // 1x1 layers (no halo, P = W) or taps within +-2 pixels
+    if (d->n_taps == 1 && midt_1x1_disabled()) return MG_OK;
     if (d->res && (d->c_off != 0 || d->Cs != d->Co)) return MG_OK;
     if (d->Cs % 8 || d->c_off % 8) return MG_OK;
     EncodeTiledFn enc = get_encode();
@@ -429,13 +439,14 @@ int conv_midt_launch(const mg_conv_desc* d, void* stream, bool* handled) {
     }
     const size_t smem = (size_t)fixed + (size_t)a.chunks * a.a_al + (size_t)a.NB * B_BYTES;
     const bool lean = !d->bias && !d->scale && !d->res && !d->post_act;
-    const int epi = lean ? d->pre_act : 3;
+    const bool bias_only = d->bias && !d->scale && !d->res && !d->post_act && !d->pre_act;
+    const int epi = lean ? d->pre_act : (bias_only ? 4 : 3);
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TArgs);
-    static const KernelFn table[4] = {conv_midt_tcgen05_kernel<0>, conv_midt_tcgen05_kernel<1>, conv_midt_tcgen05_kernel<2>,
-                                      conv_midt_tcgen05_kernel<3>};
+    static const KernelFn table[5] = {conv_midt_tcgen05_kernel<0>, conv_midt_tcgen05_kernel<1>, conv_midt_tcgen05_kernel<2>,
+                                      conv_midt_tcgen05_kernel<3>, conv_midt_tcgen05_kernel<4>};
     static bool attr_set = false;
     if (!attr_set) {
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 5; ++j)
             if (cudaFuncSetAttribute(table[j], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
                 set_error("mg_conv_fprop: cannot raise dynamic shared memory limit (transposed mid kernel)");
                 return MG_ERR_CUDA;

@@ -1,9 +1,9 @@
 """Dev tool: two launches each (the second one is the warm one ncu keeps) of the kernels captured with `ncu --set full` for
-profiles/ (C2 shapes): K2b halo conv 512^2 32->32 (+ BN statistics), K2h mid conv 64^2 128->128 and 32^2 256->256,
-K2 generic conv 64^2 128->256 stride 2, K4 wgrad 64^2 128->128, K4b halo wgrad 512^2 32->32, K9b persistent sparse conv and
+profiles/ (C2 shapes): K2b halo conv 512^2 32->32 (+ BN statistics), K2t transposed mid conv 64^2 128->128 (+ BN statistics,
+and as a data gradient), 32^2 256->256 and 16^2 512->512, K2 generic conv 64^2 128->256 stride 2, K4 wgrad 64^2 128->128, K4b halo wgrad 512^2 32->32, K9b persistent sparse conv and
 K9c persistent sparse wgrad on the C2 OS1 site list, K8a unknown mask, K1 mask embedding.
 
-    ncu --set full --clock-control none --import-source on -k regex:'tcgen05|sparse_|unknown_mask|mask_embed_fwd' \\
+    ncu --set full --clock-control none --import-source on -k regex:'tcgen05|sparse_|unknown_mask|mask_embed_fwd|bn_' \\
         -o gpurun_out/r2_full python tools/ncu_kernels.py
     python tools/ncu_parse.py gpurun_out/r2_full.ncu-rep        # -> profiles/r2_ncu_full_kernels.csv, r2_ncu_traffic.json
 """
@@ -29,12 +29,20 @@ for rep in range(2):
     stats = dense.new_stats(32, dev)
     y = dense.conv_launch(x, dense.pack_weight(w, 32), dense.conv_taps(3, 3, 1, 1, 32), grid_hw=(512, 512), stats=stats)   # K2b
     g.wgrad(y, x, w.shape)                                                                                                 # K4b
-    for (hw, ci, co) in ((64, 128, 128), (32, 256, 256)):
+    for (hw, ci, co) in ((64, 128, 128), (32, 256, 256), (16, 512, 512)):
         x, w = mk(8, hw, hw, ci, co, 3)
-        y = g.fwd(x, w)                                                                                                    # K2h
+        st = dense.new_stats(co, dev)
+        y = dense.conv_launch(x, dense.pack_weight(w, ci), dense.conv_taps(3, 3, 1, 1, ci), grid_hw=(hw, hw), stats=st)    # K2t + BN sums
         if hw == 64:
-            g.dgrad(y, w, x.shape)                                                                                         # K2h (dgrad)
+            g.dgrad(y, w, x.shape)                                                                                         # K2t (dgrad)
             g.wgrad(y, x, w.shape)                                                                                         # K4
+            mean, inv, gam, sums = torch.zeros(co, device=dev), torch.ones(co, device=dev), torch.ones(co, device=dev), torch.zeros(2, co, device=dev)
+            from maggie_b200 import _lib
+            L, P, S = _lib.lib(), _lib.tensor_ptr, _lib.stream_ptr
+            yo, dx = torch.empty_like(y), torch.empty_like(y)
+            L.mg_bn_apply(P(y), P(gam), P(mean), None, 0, P(yo), 8, hw, hw, co, 1, S())                                    # K3
+            L.mg_bn_bwd_reduce(P(y), P(yo), P(y), P(mean), P(inv), P(sums), 8, hw, hw, co, 1, S())
+            L.mg_bn_bwd_apply(P(y), P(yo), P(y), P(mean), P(inv), P(gam), P(sums), P(dx), None, 8, hw, hw, co, 1, 0, None, S())
     x, w = mk(8, 64, 64, 128, 256, 3)
     dense.ConvGeom("conv", 3, 2, 1, 1).fwd(x, w)                                                                           # K2 (stride 2)
     T = ops.build_sites(ops.unknown_mask(al, [15] * 24).reshape(-1, 512, 512))

@@ -32,7 +32,7 @@ def num(v, unit):
 out_rows, traffic = [], {}
 for r in data:
     name = re.sub(r"\(.*$", "", r[col["Kernel Name"]])
-    name = re.sub(r"^void ", "", name).replace("(anonymous namespace)::", "")
+    name = re.sub(r"^void ", "", name).replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
     rec = {"kernel": name}
     for m, n in have:
         rec[n] = num(r[col[m]], units[col[m]])
