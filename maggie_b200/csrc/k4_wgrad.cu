@@ -8,7 +8,11 @@
 // (SBO = 8 rows = 1024 B between K groups, LBO = 128 rows = 16 KB between 64-channel atoms).  The shifted X box
 // uses the same hardware zero fill / element strides as the forward kernel.  M = 128 output channels (rows of a
 // narrower layer are zero-filled by TMA), N = up to 256 input channels, accumulators [128 x N] fp32 in TMEM.
-// Split-K over pixel tiles across CTAs; partial results are added to the fp32 dW pack with red.global.add.
+// Split-K over pixel tiles across CTAs; partial results are added to the fp32 dW pack with TMA reduce-add
+// (cp.reduce.async.bulk.tensor) from a swizzled staging tile.
+// (Measured and dropped: a halo-patch form - one X patch per dy group, the three dx taps read from shifted descriptor starts
+//  and sharing the dY tile, 3x fewer staged bytes per FLOP - was correct but not faster on any mid-resolution layer, with 8 x 16
+//  and with 4 x 16 pixel tiles: 64^2 128->128 16.2 vs 16.3 us, 32^2 256->256 24.2 vs 14.1 us.)
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
@@ -34,7 +38,8 @@ struct WArgs {
 // TMEM: taps_per_cta * BN columns).  A layer with <= 64 output channels has only one real 64-channel atom of dY; the
 // second atom of the M = 128 operand is a shared zero region reached through the descriptor's leading-byte offset.
 __global__ void __launch_bounds__(THREADS, 1)
-wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WArgs a) {
+wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                     const __grid_constant__ CUtensorMap tmDW, const WArgs a) {
     mg::pdl_launch();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -59,6 +64,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmDY);
         prefetch_tmap(&tmX);
+        prefetch_tmap(&tmDW);
         for (int s = 0; s < a.stages; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
@@ -132,19 +138,62 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
             const int co = co0 + q * 32 + lane;
             mbar_wait(tfull, 0);
             tc_fence_after();
-            for (int tt = 0; tt < nt; ++tt) {
-                float* drow = a.dw + (size_t)co * a.Ktot + a.tap_koff[t0 + tt] + ci0;
-                for (int c0 = 0; c0 < a.BN; c0 += 16) {
+            const int et = threadIdx.x - 64, arow = q * 32 + lane;            // epilogue thread index / accumulator lane = dW row
+            if (a.BN < 32) {
+                // 16-channel layers: plain vector reductions (a 32-column chunk does not exist)
+                for (int tt = 0; tt < nt; ++tt) {
+                    float* drow = a.dw + (size_t)co * a.Ktot + a.tap_koff[t0 + tt] + ci0;
                     uint32_t r[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tt * a.BN + c0, r);
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tt * a.BN, r);
                     tmem_ld_wait();
                     if (co < a.Co) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)   // Ci is a multiple of 16 and every offset of 4: aligned
-                            red_add_v4(drow + c0 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
-                                       __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                        for (int i = 0; i < 16; i += 4)
+                            red_add_v4(drow + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                       __uint_as_float(r[i + 3]));
                     }
                 }
+            } else {
+                // Split-K flush through TMA reduce-add.  (Per-thread red.global.add.v4 made every warp instruction 32 separate
+                // 16-byte L2 atomics - lane = dW row, rows Ktot floats apart: 1.8 M atomic transactions per 64^2 128->128
+                // launch.)  The [128 x 32] fp32 chunks of the accumulator go through a ring of four 128-byte-swizzled staging
+                // tiles (the stage buffers are free once the accumulators are complete) and leave as
+                // cp.reduce.async.bulk.tensor: one 128-byte line per dW row and chunk; rows beyond Co are clipped by the map.
+                // The CTAs of a (tap group, channel tile) start at different chunks and wrap around.
+                const int chunks_per_tap = a.BN >> 5, total = nt * chunks_per_tap;
+                const int rot = (int)((blockIdx.x * 5u) % (unsigned)total);
+                uint8_t* stg = sA;                                              // 4 x 16 KB, 1 KB aligned
+                for (int it = 0; it < total; ++it) {
+                    int g = it + rot;
+                    if (g >= total) g -= total;
+                    const int tt = g / chunks_per_tap, c0 = (g - tt * chunks_per_tap) << 5;
+                    const int buf = it & 3;
+                    if (it >= 4) {
+                        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");   // this buffer's last store was read
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tt * a.BN + c0, r0);
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tt * a.BN + c0 + 16, r1);
+                    tmem_ld_wait();
+                    const uint32_t row = smem_u32(stg + buf * 16384) + arow * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ (arow & 7)) << 4)), "r"(r0[4 * j]),
+                                     "r"(r0[4 * j + 1]), "r"(r0[4 * j + 2]), "r"(r0[4 * j + 3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((j + 4) ^ (arow & 7)) << 4)), "r"(r1[4 * j]),
+                                     "r"(r1[4 * j + 1]), "r"(r1[4 * j + 2]), "r"(r1[4 * j + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et == 0) {
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&tmDW)), "r"(smem_u32(stg + buf * 16384)),
+                                       "r"(a.tap_koff[t0 + tt] + ci0 + c0), "r"(co0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             }
         }
     }
@@ -200,6 +249,7 @@ extern "C" int mg_conv_wgrad(const mg_wgrad_desc* d, void* stream) {
     if (a.BN == 64) a.taps_per_cta = 1;                    // measured: 64-channel layers prefer 2 small CTAs per SM
     a.stages = a.taps_per_cta == 1 && a.BN <= 128 ? std::max(2, std::min(3, (int)((94 * 1024) / (a_bytes + b_tile))))
                                                   : std::max(2, std::min(4, (int)((190 * 1024) / (a_bytes + a.taps_per_cta * b_tile))));
+    while ((size_t)a.stages * (a_bytes + a.taps_per_cta * b_tile) < 64 * 1024) ++a.stages;   // the epilogue's staging ring lives there
     const size_t smem = 1024 + 256 + 128 * 128 + (size_t)a.stages * (a_bytes + a.taps_per_cta * b_tile);
     const int tap_groups = mg::ceil_div(d->n_taps, a.taps_per_cta);
     const int base_ctas = tap_groups * a.co_tiles * ci_tiles;
@@ -219,6 +269,20 @@ extern "C" int mg_conv_wgrad(const mg_wgrad_desc* d, void* stream) {
         mg::set_error("mg_conv_wgrad: cuTensorMapEncodeTiled(X) failed (%d)", (int)r);
         return MG_ERR_CUDA;
     }
+    CUtensorMap tmDW;
+    {
+        // dW pack [Co][Ktot] fp32: [128 rows x 32 floats] boxes, 128-byte swizzle (the reduce-add flush of the epilogue)
+        cuuint64_t dims[2] = {(cuuint64_t)d->Ktot, (cuuint64_t)d->Co};
+        cuuint64_t strides[1] = {(cuuint64_t)d->Ktot * 4};
+        cuuint32_t box[2] = {32, 128};
+        cuuint32_t estr[2] = {1, 1};
+        r = mg::get_encode()(&tmDW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d->dw, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            mg::set_error("mg_conv_wgrad: cuTensorMapEncodeTiled(dW) failed (%d)", (int)r);
+            return MG_ERR_CUDA;
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
@@ -228,7 +292,7 @@ extern "C" int mg_conv_wgrad(const mg_wgrad_desc* d, void* stream) {
         attr_set = true;
     }
     dim3 grid(splits, tap_groups, a.co_tiles * ci_tiles);
-    MG_LAUNCH(wgrad_tcgen05_kernel, grid, THREADS, smem, stream, tmDY, tmX, a);
+    MG_LAUNCH(wgrad_tcgen05_kernel, grid, THREADS, smem, stream, tmDY, tmX, tmDW, a);
     MG_CHECK_LAUNCH("mg_conv_wgrad");
     return MG_OK;
 }

@@ -161,3 +161,20 @@ def test_halo_wgrad_matches_torch_and_generic_kernel(N, H, W, Co, monkeypatch):
         outs.append(got)
     # same products, different summation order (split-K partition): tiny differences only
     assert float((outs[0] - outs[2]).abs().max()) <= 1e-3 * float(ref.abs().max()) + 1e-3
+
+
+# ---- K4: split-K flush through TMA reduce-add (rows beyond Co clipped, several channel tiles / tap groups) ---------------
+@pytest.mark.parametrize("N,H,W,Ci,Co", [(8, 64, 64, 128, 128), (2, 32, 32, 256, 256), (1, 16, 16, 512, 512), (2, 128, 128, 64, 64),
+                                         (1, 24, 40, 128, 192), (3, 13, 17, 128, 64), (2, 64, 64, 256, 128), (1, 20, 52, 64, 32),
+                                         (1, 40, 24, 16, 48)])
+def test_wgrad_reduce_flush_matches_torch(N, H, W, Ci, Co):
+    from maggie_b200 import dense
+    g = torch.Generator().manual_seed(H + W + Co + Ci)
+    x = torch.randn(N, H, W, Ci, generator=g).half().cuda()
+    dy = (torch.randn(N, H, W, Co, generator=g) * 0.1).half().cuda()
+    taps = dense.conv_taps(3, 3, 1, 1, Ci)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Co, Ci, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
+    dw = torch.full((Co, 9 * Ci), 0.5, device="cuda")                  # accumulates INTO the buffer
+    dense.wgrad_launch(dy, x, taps, dw, grid_hw=(H, W))
+    got = (dw - 0.5).view(Co, 3, 3, Ci).permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-3
