@@ -386,8 +386,9 @@ def other_configs(torch, dev, args_no_graphs=False):
         _, loss = m(batch, mem_feat=None)
         (loss["total"] * LOSS_SCALE).backward()
 
-    # C1
+    # C1 (evaluation forwards replay the dense stage as a CUDA graph too)
     model.eval()
+    model.enable_cuda_graphs(not args_no_graphs)
     b1 = to_dev(synth.make_batch(b=1, n_f=1, n_i=1, H=256, W=256, edge_px=6.0))
     c1 = {}
     with torch.no_grad():

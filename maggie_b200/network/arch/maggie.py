@@ -134,11 +134,51 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         return self
 
     def enable_cuda_graphs(self, on=True):
-        """Replay the dense stage (encoder, ASPP, dense decoder blocks, attention; forward AND backward) as CUDA graphs.
-        Training mode only; one graph pair per input shape.  The sparse stage stays eager (its shapes follow the
-        number of active sites)."""
+        """Replay the dense stage (encoder, ASPP, dense decoder blocks, attention) as CUDA graphs: forward AND backward in
+        training mode, the forward alone under `torch.no_grad()` in evaluation mode; one graph (pair) per input shape.
+        The sparse stage stays eager (its shapes follow the number of active sites).  The warm-up passes a capture needs
+        do not count: the stage's running statistics and spectral-norm vectors are restored after the capture, so the
+        first replay starts from the state an eager run would have started from."""
         self._use_graphs = bool(on)
         return self
+
+    @staticmethod
+    def _volatile_state(stage):
+        """The tensors a forward of the stage updates in place: BatchNorm running statistics / counters, spectral-norm u, v."""
+        keep = ("running_mean", "running_var", "num_batches_tracked", "weight_u", "weight_v")
+        return {k: v for k, v in stage.state_dict(keep_vars=True).items() if k.endswith(keep)}
+
+    def _eval_graph(self, stage, args):
+        """Capture (once per shape / precision) and replay the evaluation forward of the dense stage."""
+        key = ("eval", getattr(self.encoder, "precision", "fp16")) + tuple((tuple(a.shape), a.dtype) for a in args)
+        entry = self._graphs.get(key)
+        if entry is None:
+            from ... import _lib
+            static_in = tuple(a.clone() for a in args)
+            vol = self._volatile_state(stage)
+            saved = {k: v.detach().clone() for k, v in vol.items()}
+            cur = torch.cuda.current_stream(args[0].device)
+            side = torch.cuda.Stream(device=args[0].device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    stage(*static_in)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(args[0].device)
+            before = _lib.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = stage(*static_in)
+            with torch.no_grad():
+                for k, v in vol.items():
+                    v.copy_(saved[k])
+            entry = self._graphs[key] = (g, static_in, static_out, _lib.launch_count() - before)
+        g, static_in, static_out, n = entry
+        for dst, src in zip(static_in, args):
+            dst.copy_(src)
+        g.replay()
+        self.replayed_native_launches += n
+        return tuple(o.clone() if torch.is_tensor(o) else o for o in static_out) if isinstance(static_out, tuple) else static_out
 
     def _dense(self, x, masks, slot_ids, mask_os8, gt_os8, mem_feat=None):
         stage = self._stage[0]
@@ -149,6 +189,8 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
                 gt_os8.float() if gt_os8 is not None else mask_os8.float())
         if mem_feat is not None:
             args = args + (mem_feat,)
+        if self._use_graphs and not self.training and not torch.is_grad_enabled() and x.is_cuda:
+            return self._eval_graph(stage, args)
         if not (self._use_graphs and self.training and torch.is_grad_enabled()) or dense.sync_bn_needs_eager(self, x.device):
             return stage(*args)      # (the collective fallback of the BatchNorm statistics exchange cannot be captured)
         key = tuple((tuple(a.shape), a.dtype) for a in args)
@@ -156,9 +198,15 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         if entry is None:
             from ... import _lib
             sample = tuple(a.clone() for a in args)
+            vol = self._volatile_state(stage)
+            saved = {k: v.detach().clone() for k, v in vol.items()}
             before = _lib.launch_count()
             fn = torch.cuda.make_graphed_callables(stage, sample, num_warmup_iters=3, allow_unused_input=True)
-            # 3 warm-up iterations + 1 capture, each one forward + backward of the stage
+            # 3 warm-up iterations + 1 capture, each one forward + backward of the stage; their in-place updates of the
+            # running statistics / power-iteration vectors are undone (the first batch must count once, not five times)
+            with torch.no_grad():
+                for k, v in vol.items():
+                    v.copy_(saved[k])
             entry = self._graphs[key] = (fn, (_lib.launch_count() - before) // 4)
         self.replayed_native_launches += entry[1]
         return entry[0](*args)

@@ -178,6 +178,46 @@ def test_cuda_graph_dense_stage_matches_eager():
     assert float(rel.median()) < 2e-2, float(rel.median())
 
 
+def test_eval_graph_replay_is_bit_identical_to_eager_and_keeps_the_state_in_step():
+    """Evaluation forward with the dense stage replayed as a CUDA graph: identical bits to the eager run on every call,
+    and the state the forward advances (spectral-norm power iteration) evolves identically - the warm-up passes of the
+    capture do not count."""
+    batch = _to_dev(synth.make_batch(b=1, n_f=1, n_i=2, H=128, W=128, edge_px=4.0, seed=5))
+    outs, us = [], []
+    for graphs in (False, True):
+        m = _model(False)
+        m.enable_cuda_graphs(graphs)
+        with torch.no_grad():
+            seq = [m(batch, mem_feat=None) for _ in range(3)]        # graphs: capture + first replay, then two replays
+        outs.append([{k: v.float().clone() for k, v in o.items()} for o in seq])
+        us.append(m.state_dict()["encoder.conv1.module.weight_u"].clone())
+    for a, b in zip(*outs):
+        for k in ("alpha_os8", "refined_masks", "detail_mask"):
+            assert torch.equal(a[k], b[k]), k
+    assert torch.equal(us[0], us[1])
+    # the three forwards really differ (the power iteration moves the weights): the comparison above is not vacuous
+    assert not torch.equal(outs[0][0]["alpha_os8"], outs[0][2]["alpha_os8"])
+
+
+def test_training_graph_capture_does_not_count_its_warmup_passes():
+    """BatchNorm running statistics after ONE graph-replayed training step equal those after one eager step."""
+    batch = _to_dev(synth.make_batch(b=2, n_f=1, n_i=2, H=128, W=128, edge_px=4.0, seed=3, train=True, it=1))
+    stats = []
+    for graphs in (False, True):
+        m = _model(True)
+        m.enable_cuda_graphs(graphs)
+        G.seed_all()
+        _, loss = m(batch, mem_feat=None)
+        (loss["total"] * 64.0).backward()
+        sd = m.state_dict()
+        stats.append((sd["encoder.bn1.running_mean"].clone(), sd["encoder.bn1.num_batches_tracked"].clone(),
+                      sd["encoder.conv1.module.weight_u"].clone()))
+    (rm0, n0, u0), (rm1, n1, u1) = stats
+    assert int(n0) == int(n1) == 1
+    assert torch.allclose(rm0, rm1, rtol=1e-3, atol=1e-5)
+    assert torch.allclose(u0, u1, rtol=1e-4, atol=1e-6)
+
+
 # ---- video model (MaGGIe_Temp, BASELINE config C4) -------------------------------------------------------------
 def _video_model(training):
     m, _ = build_model(CfgNode(synth.video_cfg()))
