@@ -85,7 +85,9 @@ sparse_conv_kernel(const SArgs a) {
     uint8_t* sA = sB + (size_t)steps * b_tile;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)a.stages * a_tile);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
-    float* s_stage = reinterpret_cast<float*>(tmem_slot + 4);
+    // the epilogue's transposition / partial-sum buffers alias the first operand stages (free once the accumulator is
+    // complete): the 64 -> 64 3x3 layers then fit nine stages and take the all-gathers-in-flight path
+    float* s_stage = reinterpret_cast<float*>(sA);
     float* s_part = s_stage + 4 * 32 * 17;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
@@ -561,7 +563,7 @@ extern "C" int mg_sparse_conv(const mg_sparse_conv_desc* d, void* stream) {
     const int b_tile = ((a.Cout * a.rowb + 1023) / 1024) * 1024;
     // Stage recycling costs a tcgen05.commit -> mbarrier -> producer round trip (~1.3 us measured in K2b): give every
     // tap its own stage whenever two CTAs still fit per SM, so that the gathers of a tile never wait for the MMAs.
-    const size_t fixed_smem = 1024 + (size_t)steps * b_tile + 256 + 4 * 32 * 17 * 4 + 4 * 2 * a.Cout * 4;
+    const size_t fixed_smem = 1024 + (size_t)steps * b_tile + 256;   // (epilogue scratch aliases the first operand stages)
     a.stages = std::min(4, std::max(2, steps));
     while (a.stages < steps && fixed_smem + (size_t)(a.stages + 1) * 128 * a.rowb <= 112 * 1024) ++a.stages;
     if (a.rowb == 128)   // 64-channel layers run on few sites (OS4 / OS8): latency matters there, not occupancy
