@@ -145,10 +145,13 @@ __global__ void __launch_bounds__(256)
 loss_down_kernel(const float* __restrict__ din, float* __restrict__ dout, int n_img, int h, int w) {
     mg::pdl_prologue();
     const int ho = h >> 1, wo = w >> 1;
-    const size_t total = (size_t)n_img * ho * wo;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int ox = (int)(i % wo), oy = (int)((i / wo) % ho);
-        const float* src = din + (i / ((size_t)wo * ho)) * h * w;
+    // (32-bit index arithmetic: every plane set of the path is < 2^31 elements (checked by the launcher), and the 64-bit
+    //  quotients / remainders by run-time sizes were a large share of these per-pixel kernels' instructions)
+    const unsigned total = (unsigned)n_img * ho * wo, uwo = wo, uho = ho;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned q = i / uwo;
+        const int ox = (int)(i - q * uwo), oy = (int)(q % uho);
+        const float* src = din + (size_t)(q / uho) * h * w;
         float v = 0.f;
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky) {
@@ -196,8 +199,9 @@ loss_lap_kernel(Ptr3 P, const float* __restrict__ T, const float* __restrict__ d
     const int scale = blockIdx.y;                                   // one scale per grid row: partial sums never mix
     const size_t per_scale = (size_t)S * h * w, base = scale * per_scale;
     float acc[2] = {0.f, 0.f};
-    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < per_scale; r += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(r % w), y = (int)((r / w) % h), sl = (int)(r / ((size_t)w * h));
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < (unsigned)per_scale; r += gridDim.x * blockDim.x) {
+        const unsigned qy = r / (unsigned)w, qs = qy / (unsigned)h;
+        const int x = (int)(r - qy * (unsigned)w), y = (int)(qy - qs * (unsigned)h), sl = (int)qs;
         if (!tile_near(near, (size_t)scale * S + sl, y, x, level, TY, TX)) {
             sg[base + r] = __float2half(0.f);   // nothing to add, nothing read; (the adjoint's taps may reach into this tile)
             continue;
@@ -325,10 +329,10 @@ loss_bwd_small_kernel(const __half* __restrict__ sg_k, const float* __restrict__
                       int S, int h, int w, int level) {
     mg::pdl_prologue();
     const size_t per_scale = (size_t)S * h * w, total = 3 * per_scale;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int scale = (int)(i / per_scale);
-        const int x = (int)(i % w), y = (int)((i / w) % h);
-        const size_t img = i / ((size_t)w * h);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
+        const int scale = (int)(i / (unsigned)per_scale);
+        const unsigned qy = i / (unsigned)w, img = qy / (unsigned)h;
+        const int x = (int)(i - qy * (unsigned)w), y = (int)(qy - img * (unsigned)h);
         if (!tile_near(near, img, y, x, level, TY, TX)) {     // exactly zero there (see loss_tiles_near_kernel)
             g_out[i] = 0.f;
             continue;
@@ -474,6 +478,7 @@ extern "C" int mg_loss_fwd(const float* a1, const float* a4, const float* a8, co
     MG_REQUIRE(a1 && a4 && a8 && target && w1 && w4 && w8 && ws && sg_f16 && sums, "mg_loss_fwd: null pointer");
     MG_REQUIRE(S > 0 && H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16, "mg_loss_fwd: H, W must be multiples of 8, >= 16");
     MG_REQUIRE(3 * S <= 65535, "mg_loss_fwd: too many slices");
+    MG_REQUIRE((size_t)3 * S * H * W < ((size_t)1 << 31), "mg_loss_fwd: 3 * S * H * W must stay below 2^31 (32-bit pixel indices)");
     Ptr3 P{{a1, a4, a8}}, Wt{{w1, w4, w8}};
     const size_t n0 = (size_t)3 * S * H * W, n1 = n0 / 4, n2 = n1 / 4, n3 = n2 / 4;
     float *d1 = ws, *d2 = d1 + n1, *d3 = d2 + n2;
@@ -502,6 +507,7 @@ extern "C" int mg_loss_bwd(const float* a1, const float* a4, const float* a8, co
                            const float* coef, float* g1_out, float* g4_out, float* g8_out, void* stream) {
     MG_REQUIRE(a1 && a4 && a8 && target && w1 && w4 && w8 && ws && sg_f16 && coef && g1_out && g4_out && g8_out,
                "mg_loss_bwd: null pointer");
+    MG_REQUIRE((size_t)3 * S * H * W < ((size_t)1 << 31), "mg_loss_bwd: 3 * S * H * W must stay below 2^31 (32-bit pixel indices)");
     Ptr3 P{{a1, a4, a8}}, Wt{{w1, w4, w8}};
     MPtr3 G{{g1_out, g4_out, g8_out}};
     const size_t n0 = (size_t)3 * S * H * W, n1 = n0 / 4, n2 = n1 / 4, n3 = n2 / 4;
