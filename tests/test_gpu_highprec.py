@@ -152,6 +152,17 @@ def _stage_errors(case, z, precision):
     for k in ("alpha_os8", "alpha_os4", "alpha_os1", "refined_masks"):
         err[k] = (float(np.abs(out[k].float().cpu().numpy() - z["out/" + k]).max()), 1.0)
     err["detail_mask_agree"] = (float((out["detail_mask"].cpu().numpy() == z["out/detail_mask"]).mean()), 1.0)
+    # The refinement region is a THRESHOLD of alpha_os8 (1/255 < a < 254/255, then dilated): a pixel whose alpha_os8 sits within
+    # the fp32 noise of a threshold flips the detail mask there, the refined alpha at a flipped site is a different function
+    # (OS8 value vs OS1 logit), and the 3x3 rulebook convs carry the difference a few pixels further.  Errors of the refined
+    # outputs are therefore reported away from such flips (6 pixels; measured: 4 suffice) together with the number of flips.
+    dis = torch.from_numpy((out["detail_mask"].cpu().numpy() != z["out/detail_mask"]).astype(np.float32))
+    sh = dis.shape
+    near = torch.nn.functional.max_pool2d(dis.reshape(-1, 1, *sh[-2:]), 13, 1, 6).reshape(sh).numpy() > 0
+    err["flipped_px"] = (float(dis.sum()), float(dis.numel()))
+    for k in ("alpha_os4", "alpha_os1", "refined_masks"):
+        e = np.abs(out[k].float().cpu().numpy() - z["out/" + k])
+        err[k + "_away_from_flips"] = (float(e[~near].max()), 1.0)
     return err
 
 
@@ -168,6 +179,12 @@ def test_high_precision_eval_meets_the_north_star_tolerance(case, golden):
     for k in ("aspp", "os8_feat", "os8_logits", "queries"):
         assert hi[k][0] <= 2e-4 * max(1.0, hi[k][1]), (k, hi[k])
     assert hi["detail_mask_agree"][0] >= 0.9999
+    # every alpha the model returns - OS4, OS1 and the fused result - meets the tolerance away from the (<= 8 per case:
+    # measured 2 / 8 / 1) threshold flips of the detail mask; measured 3.7e-4 .. 4.5e-4
+    assert hi["flipped_px"][0] <= 16 and hi["flipped_px"][0] <= 1e-4 * hi["flipped_px"][1]
+    for k in ("alpha_os4", "alpha_os1", "refined_masks"):
+        assert hi[k + "_away_from_flips"][0] <= ALPHA_TOL, (k, hi[k + "_away_from_flips"])
+        assert hi[k + "_away_from_flips"][0] <= 1.25 * 4.5e-4, (k, hi[k + "_away_from_flips"])
     # and the mode is what makes the difference: fp16 storage is at least 10x further away on the same case
     assert lo["alpha_os8"][0] > 10 * hi["alpha_os8"][0]
     assert _lib.launch_count() > 0
