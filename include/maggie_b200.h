@@ -62,6 +62,16 @@ int mg_unknown_mask_select(const float* alpha, const float* alt, const int32_t* 
 int mg_fuse_stage(const float* src, const float* finer, const float* coarser, int slices, int H, int W,
                   const int32_t* widths, const uint8_t* and_mask, uint8_t* out_w_u8, float* out_alpha, void* stream);
 
+/* ---- K18: transition ("trimap") ground truth of the loaders ---------------------------------------------------
+ * replaces: gen_transition_gt (dataloader/utils.py:15-35, called by dataloader/him.py:187-193 and vim.py:199: cv2.dilate /
+ *           cv2.erode of every instance alpha with MORPH_ELLIPSE (k, k), `iterations` times, on the CPU):
+ *           trans = (dilate(alpha) - erode(alpha) > 0) | ((alpha > 127) != (mask == 255)), uint8 {0,1}.
+ * alpha_u8 [planes, H, W]; mask_u8 NULL or [planes, H / mask_div, W / mask_div] (mask_div 1 or 8: the loader's down-scaled
+ * masks, repeated 8 x 8 as `torch.repeat_interleave` does); tmp_u8: 4 * planes * H * W bytes of scratch (may be NULL for one
+ * iteration); k_size 1..31.  Bit-exact against OpenCV (tests/test_io_host.py pins the oracle, tests/test_gpu_io.py the kernel). */
+int mg_transition_gt(const void* alpha_u8, const void* mask_u8, int mask_div, int planes, int H, int W, int k_size,
+                     int iterations, void* tmp_u8, void* trans_u8, void* stream);
+
 /* ---- K11: element-wise half of the video model (MaGGIe_Temp) --------------------------------------------------
  * replaces: the gating arithmetic of ConvGRU.forward_single_frame (module/conv_gru.py:50-58: sigmoid / split / r*h /
  *           torch.cat / tanh / blend, ~12 torch launches per step and direction) around the two native convolutions, and

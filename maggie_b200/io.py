@@ -93,3 +93,42 @@ def finalize_alpha(alpha, transform_info=(), lo=1.0 / 255.0, hi=254.0 / 255.0):
                    "mg_alpha_finalize")
         cur = nxt
     return cur.reshape(*lead, *cur.shape[-2:])
+
+
+def transition_gt(alphas, masks=None, k_size=25, iterations=1, temporal=False):
+    """`gen_transition_gt` / `gen_transition_temporal_gt` of the loaders (dataloader/utils.py:15-60) on the GPU (K18).
+    alphas uint8 [n, H, W] (one plane per instance, or per frame for the temporal form); masks uint8 [n, H, W] or
+    [n, H/8, W/8] or None -> uint8 {0,1} [n, H, W].  temporal: planes i >= 1 are additionally zeroed where
+    alphas[i] - alphas[i-1] <= 1/255 (the reference compares the raw uint8 tensors: a non-positive difference), before the
+    mask disagreement is OR-ed in."""
+    _lib.need_cuda(alphas, masks)
+    if alphas.dtype != torch.uint8 or alphas.dim() != 3:
+        raise ValueError("transition_gt: alphas must be uint8 [n, H, W]")
+    n, H, W = alphas.shape
+    div = 1
+    if masks is not None:
+        if masks.dtype != torch.uint8 or masks.dim() != 3 or masks.shape[0] != n:
+            raise ValueError("transition_gt: masks must be uint8 [n, h, w]")
+        if tuple(masks.shape[1:]) == (H, W):
+            div = 1
+        elif tuple(masks.shape[1:]) == (H // 8, W // 8) and H % 8 == 0 and W % 8 == 0:
+            div = 8
+        else:
+            raise ValueError("transition_gt: masks must be full size or 1/8 size")
+    a = alphas.contiguous()
+    out = torch.empty_like(a)
+    tmp = torch.empty(4 * a.numel(), dtype=torch.uint8, device=a.device) if iterations > 1 else None
+    p = _lib.tensor_ptr
+    run = lambda m, o: _lib.check(_lib.lib().mg_transition_gt(p(a), p(m), div, n, H, W, int(k_size), int(iterations), p(tmp), p(o),
+                                                              _lib.stream_ptr()), "mg_transition_gt")
+    if not temporal:
+        run(masks.contiguous() if masks is not None else None, out)
+        return out
+    run(None, out)
+    if n > 1:
+        sparse = (a[1:].float() - a[:-1].float()) > 1.0 / 255.0
+        out[1:] = out[1:] * sparse.to(torch.uint8)
+    if masks is not None:
+        up = masks if div == 1 else masks.repeat_interleave(8, -1).repeat_interleave(8, -2)
+        out = torch.where((a > 127) != (up == 255), torch.ones_like(out), out)
+    return out

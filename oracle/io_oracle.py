@@ -46,3 +46,40 @@ def finalize_alpha(img, transform_info):
     out[out <= 1.0 / 255.0] = 0.0
     out[out >= 254.0 / 255.0] = 1.0
     return out, pre
+
+
+def _morph(x, k, iterations, dilate):
+    """Grey-level dilation / erosion of a uint8 [H, W] plane by cv2's MORPH_ELLIPSE (k, k), anchor (k // 2, k // 2), pixels outside
+    the image ignored (cv2's default morphology border), `iterations` times.  numpy restatement, pinned against cv2 itself in
+    tests/test_io_host.py."""
+    from .unknown import ellipse_spans
+    H, W = x.shape
+    a = k // 2
+    spans = ellipse_spans(k)
+    neutral = 0 if dilate else 255
+    cur = x.astype(np.uint8)
+    for _ in range(iterations):
+        pad = np.full((H + 2 * k, W + 2 * k), neutral, np.uint8)
+        pad[k:k + H, k:k + W] = cur
+        out = np.full((H, W), neutral, np.uint8)
+        for i, (j1, j2) in enumerate(spans):
+            for j in range(j1, j2):
+                win = pad[k + i - a:k + i - a + H, k + j - a:k + j - a + W]
+                out = np.maximum(out, win) if dilate else np.minimum(out, win)
+        cur = out
+    return cur
+
+
+def transition_gt(alphas, masks=None, k_size=25, iterations=1):
+    """dataloader/utils.py:15-35 on uint8 numpy planes [n, H, W] (masks [n, H, W] or [n, H/8, W/8]) -> uint8 {0,1} [n, H, W]."""
+    out = []
+    for x in alphas:
+        d = _morph(x, k_size, iterations, True).astype(np.int32)
+        e = _morph(x, k_size, iterations, False).astype(np.int32)
+        out.append(((d - e) > 0).astype(np.uint8))
+    out = np.stack(out)
+    if masks is not None:
+        if masks.shape[-1] != alphas.shape[-1]:
+            masks = np.repeat(np.repeat(masks, 8, axis=-1), 8, axis=-2)
+        out[(alphas > 127) != (masks == 255)] = 1
+    return out
