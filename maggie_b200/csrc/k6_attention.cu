@@ -18,7 +18,8 @@ namespace {
 constexpr int E = 128;        // attention width (atten_dim of both live configs)
 constexpr int TM = 128;       // many-side rows per CTA
 constexpr int MAXF = 16;      // few-side rows
-constexpr int ROWP = E + 8;   // padded tile row (halfs) -> 2-way instead of 32-way bank conflicts
+constexpr int ROWP = E + 8;   // padded tile row (halfs): 272 B = 17 x 16 B, conflict-free for 16-byte loads by consecutive threads
+constexpr int PF = 20;        // pitch (floats) of the key-major probability / score-gradient rows of the backward kernels
 
 __device__ __forceinline__ void load_tile(__half (*dst)[ROWP], const __half* __restrict__ src, int rows_valid) {
     // 128 rows x 128 halfs, coalesced 16-byte pieces
@@ -30,15 +31,23 @@ __device__ __forceinline__ void load_tile(__half (*dst)[ROWP], const __half* __r
     }
 }
 
+// Row . q over E = 128 dims.  16-byte shared-memory loads: the padded row pitch (272 B = 17 x 16 B) makes the 128-bit row loads
+// of consecutive threads conflict-free (the 4-byte loads of the first version were 4-way conflicted: pitch 68 words), and the
+// broadcast reads of q go four floats at a time.  Two accumulators break the dependent FMA chain.
 __device__ __forceinline__ float dot_row(const __half* row, const float* q) {
-    float acc = 0.f;
-#pragma unroll 8
-    for (int e = 0; e < E; e += 2) {
-        const float2 k2 = __half22float2(*reinterpret_cast<const __half2*>(row + e));
-        acc = fmaf(k2.x, q[e], acc);
-        acc = fmaf(k2.y, q[e + 1], acc);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+    for (int e = 0; e < E; e += 8) {
+        const uint4 kk = *reinterpret_cast<const uint4*>(row + e);
+        const float4 q0 = *reinterpret_cast<const float4*>(q + e), q1 = *reinterpret_cast<const float4*>(q + e + 4);
+        const float2 k0 = __half22float2(*reinterpret_cast<const __half2*>(&kk.x)), k1 = __half22float2(*reinterpret_cast<const __half2*>(&kk.y));
+        const float2 k2 = __half22float2(*reinterpret_cast<const __half2*>(&kk.z)), k3 = __half22float2(*reinterpret_cast<const __half2*>(&kk.w));
+        a0 = fmaf(k0.x, q0.x, a0), a1 = fmaf(k0.y, q0.y, a1);
+        a0 = fmaf(k1.x, q0.z, a0), a1 = fmaf(k1.y, q0.w, a1);
+        a0 = fmaf(k2.x, q1.x, a0), a1 = fmaf(k2.y, q1.y, a1);
+        a0 = fmaf(k3.x, q1.z, a0), a1 = fmaf(k3.y, q1.w, a1);
     }
-    return acc;
+    return a0 + a1;
 }
 
 // ---- fp32 many side (evaluation at fp32-level accuracy, forward only): rows of E floats, padded to E + 4 -------------
@@ -130,20 +139,49 @@ attn_tq_partial_kernel(const float* __restrict__ Q, const T* __restrict__ K, con
     }
 }
 
-// grid (F, B), 128 threads: merge the key splits.
+// grid (F, B), 128 threads: merge the key splits.  The per-split scalars are staged in shared memory with ONE round of
+// loads (the first version walked the splits serially, two dependent global-load latencies per split: 25 us for a kernel
+// that moves 160 KB), and the partial outputs are read eight at a time.
 __global__ void __launch_bounds__(128)
 attn_tq_merge_kernel(const float* __restrict__ pm, const float* __restrict__ pl, const float* __restrict__ po,
                      const float* __restrict__ pstat, int F, int nsplit, float* __restrict__ O, float* __restrict__ stat,
                      float* __restrict__ M, float* __restrict__ L, int accurate) {
     mg::pdl_prologue();
+    constexpr int MAXS = 256;                        // splits staged per pass (S <= 32768 keys per sample)
+    __shared__ float s_m[MAXS], s_w[MAXS];
+    __shared__ float s_red[4];
     const int f = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     float m = -INFINITY;
-    for (int s = 0; s < nsplit; ++s) m = fmaxf(m, pm[((size_t)b * nsplit + s) * F + f]);
+    for (int s = t; s < nsplit; s += 128) m = fmaxf(m, pm[((size_t)b * nsplit + s) * F + f]);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((t & 31) == 0) s_red[t >> 5] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
     float l = 0.f, st = 0.f, acc = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-        const size_t o = ((size_t)b * nsplit + s) * F + f;
-        const float w = pm[o] > -INFINITY ? (accurate ? expf(pm[o] - m) : __expf(pm[o] - m)) : 0.f;
-        l += w * pl[o], st += w * pstat[o], acc += w * po[o * E + t];
+    for (int s0 = 0; s0 < nsplit; s0 += MAXS) {
+        const int ns = min(MAXS, nsplit - s0);
+        __syncthreads();
+        for (int s = t; s < ns; s += 128) {
+            const float v = pm[((size_t)b * nsplit + s0 + s) * F + f];
+            s_m[s] = v;
+            s_w[s] = v > -INFINITY ? (accurate ? expf(v - m) : __expf(v - m)) : 0.f;
+        }
+        __syncthreads();
+        // l and stat: every thread accumulates the same sums from shared weights (the loads of pl / pstat are independent)
+        for (int s = 0; s < ns; ++s) {
+            const size_t o = ((size_t)b * nsplit + s0 + s) * F + f;
+            l = fmaf(s_w[s], __ldg(pl + o), l), st = fmaf(s_w[s], __ldg(pstat + o), st);
+        }
+        int s = 0;
+        for (; s + 8 <= ns; s += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(po + (((size_t)b * nsplit + s0 + s + j) * F + f) * E + t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(s_w[s + j], v[j], acc);
+        }
+        for (; s < ns; ++s) acc = fmaf(s_w[s], __ldg(po + (((size_t)b * nsplit + s0 + s) * F + f) * E + t), acc);
     }
     // a fully masked row (l == 0) yields NaN exactly like softmax over an all -inf row in the reference
     O[((size_t)b * F + f) * E + t] = acc / l;
@@ -164,21 +202,29 @@ attn_tq_bwd_kernel(const float* __restrict__ Q, const __half* __restrict__ K, co
     __half (*sV)[ROWP] = sK + TM;
     float* sQ = reinterpret_cast<float*>(sV + TM);   // [MAXF][E]
     float* sdO = sQ + MAXF * E;                       // [MAXF][E]
-    float* sP = sdO + MAXF * E;                       // [MAXF][TM]
-    float* sdS = sP + MAXF * TM;                      // [MAXF][TM]
-    float* sD = sdS + MAXF * TM;                      // [MAXF]: sum_k P dP
+    float* sP = sdO + MAXF * E;                       // [TM][PF]
+    float* sdS = sP + TM * PF;                        // [TM][PF]
+    float* sD = sdS + TM * PF;                        // [MAXF]: sum_k P dP
     const int b = blockIdx.y, split = blockIdx.x, t = threadIdx.x;
     const int s0 = split * TM, rows = min(TM, S - s0);
     load_tile(sK, K + ((size_t)b * S + s0) * E, rows);
     load_tile(sV, V + ((size_t)b * S + s0) * E, rows);
     for (int i = t; i < F * E; i += 128) sQ[i] = Q[(size_t)b * F * E + i], sdO[i] = dO[(size_t)b * F * E + i];
     __syncthreads();
-    if (t < F) {
+    // D[f] = dO[f] . O[f] (+ the statistic's term): one warp per query, coalesced reads of O (ten threads walking O with 128
+    // dependent global loads each held the whole CTA back)
+    for (int f = t >> 5; f < F; f += 4) {
+        const int lane = t & 31;
         float d = 0.f;
-        for (int e = 0; e < E; ++e) d = fmaf(sdO[t * E + e], O[((size_t)b * F + t) * E + e], d);
-        sD[t] = d + (dstat ? dstat[(size_t)b * F + t] * stat[(size_t)b * F + t] : 0.f);
+#pragma unroll
+        for (int j = 0; j < E / 32; ++j) d = fmaf(sdO[f * E + lane + 32 * j], __ldg(O + ((size_t)b * F + f) * E + lane + 32 * j), d);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) sD[f] = d + (dstat ? dstat[(size_t)b * F + f] * stat[(size_t)b * F + f] : 0.f);
     }
     __syncthreads();
+    // sP / sdS are KEY-major ([TM][PF], PF = 20 floats: 16-byte aligned rows): the channel phase below reads all queries of
+    // a key with broadcast 16-byte loads
     const bool live = t < rows && !(key_pad && key_pad[(size_t)b * S + s0 + t]);
     for (int f = 0; f < F; ++f) {
         float p = 0.f, ds = 0.f;
@@ -189,24 +235,40 @@ attn_tq_bwd_kernel(const float* __restrict__ Q, const __half* __restrict__ K, co
             if (dstat && guid && guid[((size_t)b * F + f) * S + s0 + t]) dp += dstat[(size_t)b * F + f];
             ds = p * (dp - sD[f]);
         }
-        sP[f * TM + t] = p, sdS[f * TM + t] = ds;
+        sP[t * PF + f] = p, sdS[t * PF + f] = ds;
     }
     __syncthreads();
-    // thread = channel e: dV[k][e], dK[k][e] rows and dQ[f][e]
+    // thread = channel e: dV[k][e], dK[k][e] rows and dQ[f][e] in ONE pass over the keys; the query-side factors of this
+    // channel live in registers
+    float rdO[MAXF], rQ[MAXF], aq[MAXF];
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f) rdO[f] = f < F ? sdO[f * E + t] : 0.f, rQ[f] = f < F ? sQ[f * E + t] : 0.f, aq[f] = 0.f;
     for (int k = 0; k < rows; ++k) {
+        float pv[MAXF], dv[MAXF];
+#pragma unroll
+        for (int j = 0; j < MAXF / 4; ++j) {
+            if (4 * j < F) {
+                const float4 a4 = *reinterpret_cast<const float4*>(sP + k * PF + 4 * j), b4 = *reinterpret_cast<const float4*>(sdS + k * PF + 4 * j);
+                pv[4 * j] = a4.x, pv[4 * j + 1] = a4.y, pv[4 * j + 2] = a4.z, pv[4 * j + 3] = a4.w;
+                dv[4 * j] = b4.x, dv[4 * j + 1] = b4.y, dv[4 * j + 2] = b4.z, dv[4 * j + 3] = b4.w;
+            }
+        }
+        const float kv = __half2float(sK[k][t]);
         float av = 0.f, ak = 0.f;
-        for (int f = 0; f < F; ++f) {
-            av = fmaf(sP[f * TM + k], sdO[f * E + t], av);
-            ak = fmaf(sdS[f * TM + k], sQ[f * E + t], ak);
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) {
+            if (f < F) {
+                av = fmaf(pv[f], rdO[f], av);
+                ak = fmaf(dv[f], rQ[f], ak);
+                aq[f] = fmaf(dv[f], kv, aq[f]);
+            }
         }
         dV[((size_t)b * S + s0 + k) * E + t] = __float2half(av);
         dK[((size_t)b * S + s0 + k) * E + t] = __float2half(ak * scale);
     }
-    for (int f = 0; f < F; ++f) {
-        float aq = 0.f;
-        for (int k = 0; k < rows; ++k) aq = fmaf(sdS[f * TM + k], __half2float(sK[k][t]), aq);
-        atomicAdd(dQ + ((size_t)b * F + f) * E + t, aq * scale);
-    }
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f)
+        if (f < F) atomicAdd(dQ + ((size_t)b * F + f) * E + t, aq[f] * scale);
 }
 
 // ================================================================================================ fq forward / backward
@@ -305,7 +367,7 @@ attn_fq_bwd_kernel(const __half* __restrict__ Q, const float* __restrict__ K, co
 size_t tq_smem() { return 2 * TM * ROWP * 2 + (MAXF * E + MAXF * TM + 8) * 4; }
 size_t tq_smem_f32() { return 2 * TM * ROWF * 4 + (MAXF * E + MAXF * TM + 8) * 4; }
 size_t fq_smem_f32() { return TM * ROWF * 4 + (2 * MAXF * E + TM * (MAXF + 1)) * 4; }
-size_t tq_bwd_smem() { return 2 * TM * ROWP * 2 + (2 * MAXF * E + 2 * MAXF * TM + MAXF) * 4; }
+size_t tq_bwd_smem() { return 2 * TM * ROWP * 2 + (2 * MAXF * E + 2 * TM * PF + MAXF) * 4; }
 size_t fq_smem() { return TM * ROWP * 2 + (2 * MAXF * E + TM * (MAXF + 1)) * 4; }
 size_t fq_bwd_smem() { return 2 * TM * ROWP * 2 + (2 * MAXF * E + 2 * TM * (MAXF + 1)) * 4; }
 
