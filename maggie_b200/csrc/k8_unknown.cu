@@ -8,9 +8,11 @@
 // HBM-bound: reads 4 B/px once (+ halo rows, mostly L2 hits), writes 1 B/px.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
-constexpr int TH = 64;          // output rows per CTA
+constexpr int TH_DEFAULT = 64;  // output rows per CTA (run-time `th`: see unknown_mask())
 constexpr int MAXK = 29;        // largest ellipse the reference can draw (utils.py:27)
 constexpr int THREADS = 256;
 
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(THREADS)
 unknown_mask_kernel(const float* __restrict__ alpha, const float* __restrict__ alt, const int32_t* __restrict__ use_alt,
                     int H, int W, const int32_t* __restrict__ widths, const uint8_t* __restrict__ and_mask,
                     uint8_t* __restrict__ out_u8, uint32_t* __restrict__ out_bits, const float* __restrict__ blend_x,
-                    const float* __restrict__ blend_y, float* __restrict__ blend_out) {
+                    const float* __restrict__ blend_y, float* __restrict__ blend_out, int TH) {
     mg::pdl_prologue();
     if (alt && use_alt && *use_alt != 0) alpha = alt;
     extern __shared__ uint32_t sbits[];  // [TH + MAXK - 1][Wd + 2]
@@ -188,10 +190,16 @@ static int unknown_mask(const float* alpha, const float* alt, const int32_t* use
     if (slices == 0) return MG_OK;
     MG_REQUIRE(slices <= 65535, "mg_unknown_mask: too many slices (%d)", slices);
     const int Wd = (W + 31) / 32;
+    // rows per CTA: enough CTAs to keep several resident per SM (the threshold phase and the dilation phase of ONE CTA do
+    // not overlap; co-resident CTAs make them overlap), at the price of re-reading the k - 1 halo rows more often (L2 hits)
+    static const int th_env = [] { const char* e = std::getenv("MAGGIE_B200_UNKNOWN_TH"); return e ? std::atoi(e) : 0; }();
+    int TH = th_env > 0 ? th_env : TH_DEFAULT;
+    if (th_env <= 0)
+        while (TH > 16 && (long long)mg::ceil_div(H, TH) * slices < 5LL * mg::kNumSMs) TH >>= 1;   // measured: 24 planes 36.9 -> 18.4 us, 80 planes 55.9 -> 47.4 us
     const size_t smem = (size_t)(TH + MAXK - 1) * (Wd + 2) * sizeof(uint32_t);
     dim3 grid(mg::ceil_div(H, TH), slices);
     MG_LAUNCH(unknown_mask_kernel, grid, THREADS, smem, stream, alpha, alt, use_alt, H, W, widths, and_mask, out_u8, out_bits,
-              blend_x, blend_y, blend_out);
+              blend_x, blend_y, blend_out, TH);
     MG_CHECK_LAUNCH("mg_unknown_mask");
     return MG_OK;
 }
