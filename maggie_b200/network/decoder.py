@@ -214,7 +214,9 @@ def _scatter_slots(t, slots, n_slots):
 
 def _draw_widths(n, k_size, is_train):
     """Ellipse sizes for compute_unknown: same numpy draws, in the same order, as utils/utils.py:45-50."""
-    return [int(np.random.randint(1, k_size)) for _ in range(n)] if is_train else [k_size // 2] * n
+    # (one vectorised draw: the legacy RandomState yields the same stream as n scalar calls - tests/test_ops_host.py - at
+    #  13 us instead of 370 us for the 80 slots of a C2 step, five times per step)
+    return np.random.randint(1, k_size, size=n).tolist() if is_train else [k_size // 2] * n
 
 
 class MaGGIeDecoder(nn.Module):

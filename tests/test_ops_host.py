@@ -107,3 +107,19 @@ def test_flat_buffer_puts_the_bank_weights_first_and_keeps_the_parameter_order()
     bank2 = SimpleNamespace(entries=[SimpleNamespace(w=torch.nn.Parameter(torch.zeros(2), requires_grad=False))], grad_target=None)
     flat2 = FlatGradAllReduce([a, b], bank=bank2)
     assert flat2.offsets == [0, 3] and bank2.grad_target is None
+
+
+def test_ellipse_width_draws_consume_the_random_stream_like_the_reference():
+    """`_draw_widths` draws all slots with one vectorised call; the reference (utils/utils.py:45-50) draws them one by one:
+    same values, same generator state afterwards."""
+    import numpy as np
+    from maggie_b200.network.decoder import _draw_widths
+    for k in (15, 27, 30):
+        np.random.seed(11)
+        want = [int(np.random.randint(1, k)) for _ in range(80)]
+        after_want = np.random.randint(0, 1 << 30)
+        np.random.seed(11)
+        got = _draw_widths(80, k, True)
+        after_got = np.random.randint(0, 1 << 30)
+        assert got == want and after_got == after_want and all(isinstance(v, int) for v in got)
+    assert _draw_widths(4, 30, False) == [15] * 4
