@@ -22,7 +22,13 @@ LARGE = {
     "c2_train_8x512_3inst_iter1": (dict(b=8, n_f=1, n_i=3, H=512, W=512, edge_px=6.0, seed=2002, train=True, it=1), True, 4),
     # BASELINE config C5: 1024 x 1024 x 8 instances (evaluation)
     "c5_eval_1024_8inst": (dict(b=1, n_f=1, n_i=8, H=1024, W=1024, edge_px=8.0, seed=2003), False, 8),
+    # BASELINE config C4 (video model MaGGIe_Temp): the 3-frame evaluation window and a 5-frame training clip at 480 x 832
+    "c4_video_eval_3x480x832_2inst": (dict(b=1, n_f=3, n_i=2, H=480, W=832, edge_px=6.0, seed=2004), False, 4),
+    # (the reference's LapLoss.upsample mixes up H and W - loss.py:138 - so its training runs on square crops only: the training
+    #  clip is 5 x 384 x 384, about the pixel count of 480 x 832 / 2.7)
+    "c4_video_train_5x384_2inst_iter1": (dict(b=1, n_f=5, n_i=2, H=384, W=384, edge_px=6.0, seed=2005, train=True, it=1), True, 4),
 }
+VIDEO = {"c4_video_eval_3x480x832_2inst", "c4_video_train_5x384_2inst_iter1"}
 CURVE = "curve_b8_128_2inst_20steps"
 # the published recipe's update rule (configs/maggie_image.yaml: AdamW lr 1.5e-4, betas (0.9, 0.999); engine/train.py:274 clips
 # the global gradient norm at 0.01).  (A first version used lr 1e-3 / clip 0.1: at that step size the 8-sample BatchNorm
@@ -30,9 +36,9 @@ CURVE = "curve_b8_128_2inst_20steps"
 CURVE_STEPS, CURVE_LR, CURVE_CLIP, CURVE_BATCHES = 20, 1.5e-4, 0.01, 4
 
 
-def _reference(training):
+def _reference(training, video=False):
     net = ref_shims.import_reference_network()
-    model, _ = net.build_model(ref_shims.CfgNode(synth.model_cfg()))
+    model, _ = net.build_model(ref_shims.CfgNode(synth.video_cfg() if video else synth.model_cfg()))
     model.load_state_dict(synth.synth_state_dict(model.state_dict()), strict=True)
     model.train(training)
     model.decoder.inst_spec_layer.dropout.p = 0.0
@@ -41,7 +47,7 @@ def _reference(training):
 
 def run_large(case):
     kw, training, sub = LARGE[case]
-    model = _reference(training)
+    model = _reference(training, case in VIDEO)
     batch = synth.make_batch(**kw)
     stages = {}
     model.decoder.refine_OS8.register_forward_hook(
@@ -63,8 +69,11 @@ def run_large(case):
     z["stage/os8_logits"] = stages["os8_logits"].float().numpy()
     z["stage/queries"] = stages["queries"].float().numpy()
     z["sub"] = np.int64(sub)
-    for k in ("alpha_os8", "refined_masks"):
-        z["out_sub/" + k] = out[k].detach().float().numpy()[..., ::sub, ::sub].copy()
+    for k in ("alpha_os8", "refined_masks", "temp_alpha", "diff_pred_forward", "diff_pred_backward"):
+        if k in out:
+            z["out_sub/" + k] = out[k].detach().float().numpy()[..., ::sub, ::sub].copy()
+    if "mem_feat" in out and torch.is_tensor(out["mem_feat"]):
+        z["out_sub/mem_feat"] = out["mem_feat"].detach().float().numpy()[..., ::4, ::4].copy()
     dm = out["detail_mask"].detach().numpy() != 0
     z["out_bits/detail_mask"] = np.packbits(dm.reshape(-1))
     z["out_shape/detail_mask"] = np.array(dm.shape, np.int64)
