@@ -91,7 +91,7 @@ def cpu_step_fn(frames=2):
 
     from oracle import maggie_oracle as O
     from oracle import make_golden as G
-    from oracle import synth
+    import synthdata as synth
 
     torch.set_num_threads(os.cpu_count())
     import numpy as np
@@ -124,7 +124,7 @@ def cpu_c1_eval_ms():
 
     from oracle import maggie_oracle as O
     from oracle import make_golden as G
-    from oracle import synth
+    import synthdata as synth
 
     z = np.load(os.path.join(G.GOLDEN_DIR, "state_shapes.npz"))
     tmpl = {k: torch.zeros(tuple(z[k]), dtype=torch.long if k.endswith("num_batches_tracked") else torch.float32)
@@ -203,7 +203,7 @@ def kernel_probes(torch, dev, peaks):
     C2 layer table (forward, data gradient, weight gradient); achieved = sum of algorithmic FLOPs (or bytes) / sum of
     average launch durations x launches per step."""
     from maggie_b200 import _lib, dense, ops, sparse
-    from oracle import synth
+    import synthdata as synth
 
     L = _lib.lib()
     traffic = _traffic_table()
@@ -357,7 +357,7 @@ def other_configs(torch, dev, args_no_graphs=False):
 
     from maggie_b200.config import CfgNode
     from maggie_b200.network import build_model
-    from oracle import synth
+    import synthdata as synth
 
     def med(fn, n=5, warm=3):
         for _ in range(warm):
@@ -438,7 +438,7 @@ def run_gpu(args):
     from maggie_b200.config import CfgNode
     from maggie_b200.dp import FlatGradAllReduce
     from maggie_b200.network import build_model
-    from oracle import synth  # synthetic inputs only (test infrastructure used as a data generator)
+    import synthdata as synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

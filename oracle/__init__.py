@@ -2,9 +2,9 @@
 
 CPU restatements of the MaGGIe hot path (reference: hmchuong/MaGGIe, `maggie/network`), used as the
 checker in `tests/`, in `__graft_entry__.smoke()` and as the `cpu_baseline` / `--impl reference` arm of
-`bench.py`.  Nothing under `maggie_b200/` may import this package.  (`oracle/synth.py`, the deterministic input / weight
-generator, is additionally used as the data source of `bench.py`'s GPU arm and of the developer scripts under `tools/`,
-which are measurement helpers and never part of the product path.)
+`bench.py`.  Nothing under `maggie_b200/` may import this package.  (The deterministic input / weight generator is the
+repo-root `synthdata.py`, re-exported as `oracle/synth.py`; the GPU arm of `bench.py` and the scripts under `tools/` import
+`synthdata` directly, so nothing on the measured GPU path imports this package.)
 
 Pinning status: the reference ships no tests or golden vectors, so the oracle is pinned
 against outputs of the *unmodified reference itself*, imported in the build container from

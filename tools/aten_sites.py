@@ -15,7 +15,7 @@ from torch.utils._python_dispatch import TorchDispatchMode
 
 from maggie_b200.config import CfgNode
 from maggie_b200.network import build_model
-from oracle import synth
+import synthdata as synth
 
 SKIP = {"aten::view", "aten::_unsafe_view", "aten::permute", "aten::reshape", "aten::detach", "aten::alias", "aten::expand",
         "aten::slice.Tensor", "aten::select.int", "aten::transpose.int", "aten::t", "aten::unsqueeze", "aten::squeeze.dim",

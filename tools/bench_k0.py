@@ -6,7 +6,7 @@ import torch
 from maggie_b200 import ops
 from maggie_b200.config import CfgNode
 from maggie_b200.network import build_model
-from oracle import synth
+import synthdata as synth
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model, _ = build_model(CfgNode(synth.model_cfg()))

@@ -7,7 +7,8 @@ import ops_ref
 from maggie_b200 import ops
 from maggie_b200.config import CfgNode
 from maggie_b200.network import build_model
-from oracle import make_golden as G, synth
+from oracle import make_golden as G
+import synthdata as synth
 
 def run(case, mode):
     kw, training = G.CASES[case]

@@ -6,7 +6,8 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 from maggie_b200.config import CfgNode
 from maggie_b200.network import build_model
-from oracle import make_golden as G, synth
+from oracle import make_golden as G
+import synthdata as synth
 
 for case in [c for c in G.CASES if c.startswith("eval")]:
     kw, _ = G.CASES[case]

@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from maggie_b200.config import CfgNode
 from maggie_b200.network import build_model
-from oracle import make_golden as G, synth
+from oracle import make_golden as G
+import synthdata as synth
 case = sys.argv[1] if len(sys.argv) > 1 else "eval_128_3inst_maskos8"
 kw, _ = G.CASES[case]
 m, _ = build_model(CfgNode(synth.model_cfg()))

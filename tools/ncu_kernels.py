@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from maggie_b200 import dense, ops, sparse
-from oracle import synth
+import synthdata as synth
 
 dev = torch.device("cuda")
 torch.manual_seed(0)

@@ -19,7 +19,7 @@ from maggie_b200 import ops
 from maggie_b200.config import CfgNode
 from maggie_b200.network import build_model
 from oracle import make_golden as G
-from oracle import synth
+import synthdata as synth
 
 q16 = lambda t: t.half().float()
 

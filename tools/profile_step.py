@@ -6,7 +6,7 @@ from torch.profiler import profile, ProfilerActivity
 from maggie_b200.config import CfgNode
 from maggie_b200.network import build_model
 from maggie_b200.dp import FlatGradAllReduce
-from oracle import synth
+import synthdata as synth
 
 dev = torch.device("cuda:0")
 torch.manual_seed(1234)

@@ -6,7 +6,7 @@ import numpy as np, torch
 from maggie_b200 import sparse, _lib
 from maggie_b200.config import CfgNode
 from maggie_b200.network import build_model
-from oracle import synth
+import synthdata as synth
 
 dev = torch.device("cuda:0")
 torch.manual_seed(1234)
