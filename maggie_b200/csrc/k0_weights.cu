@@ -79,12 +79,82 @@ wprep_u_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict
 // The tile bodies are instantiated for the tap counts of the model (1, 9, 16; 0 = run-time value): every index of the
 // re-layout loops is a quotient / remainder by `taps`-derived sizes, and with run-time divisors the kernels were bound by
 // integer-division instructions (wprep_pack 219 us for a 240 MB stream), not by memory.
+// A full tile (no fold) of a layer whose rows are 16-byte aligned takes the vector forms below: 16-byte loads of the master
+// weights / packed gradients and 16-byte stores of eight fp16 pack entries (or four fp32 gradients) per thread.  With one
+// scalar access and its index arithmetic per element the kernels were bound by instruction issue, not by memory.
+__device__ __forceinline__ bool full_tile(const mg_wprep_layer& L, const int4 it, int taps) {
+    const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
+    return !L.fold && it.y + TA <= d0 && it.z + TB <= d1 && ((d1 * taps) & 3) == 0 && (L.ci_pad & 7) == 0 && (L.Co & 7) == 0 &&
+           (reinterpret_cast<uintptr_t>(L.w) & 15) == 0;
+}
+
+// s[a][e] <- W[a0 + a][b0 * taps + e], e < TB * taps, 16 bytes per load
+__device__ __forceinline__ void load_w_tile_v4(const mg_wprep_layer& L, int a0, int b0, int taps, int width, float (*s)[SROW]) {
+    const int seg4 = (TB * taps) >> 2;
+    for (int i = threadIdx.x; i < TA * seg4; i += 256) {
+        const int a = i / seg4, q = i - a * seg4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(L.w + (size_t)(a0 + a) * width + (size_t)b0 * taps) + q);
+        float* d = &s[a][4 * q];
+        d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
+    }
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], float mul) {
+    uint4 o;
+    __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[2 * j] * mul, f[2 * j + 1] * mul);
+    return o;
+}
+
+// dst[((b0 + b) * to + tp) * ld + a0 + 8h .. +8] = s[8h + j][b * taps + tp]      ("a" is the contiguous index of dst)
+template <int TAPS>
+__device__ __forceinline__ void store_a_fastest(__half* __restrict__ dst, int ld, int a0, int b0, int taps, float mul,
+                                                float (*s)[SROW]) {
+    constexpr int HG = TA / 8;
+    for (int i = threadIdx.x; i < TB * taps * HG; i += 256) {
+        const int h = i % HG, tp = (i / HG) % taps, b = i / (HG * taps);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = s[8 * h + j][b * taps + tp];
+        *reinterpret_cast<uint4*>(dst + ((size_t)(b0 + b) * taps + tp) * ld + a0 + 8 * h) = pack8(f, mul);
+    }
+}
+
+// dst[((a0 + a) * to + tp) * ld + b0 + 8g .. +8] = s[a][(8g + j) * taps + tp]    ("b" is the contiguous index of dst)
+template <int TAPS>
+__device__ __forceinline__ void store_b_fastest(__half* __restrict__ dst, int ld, int a0, int b0, int taps, float mul,
+                                                float (*s)[SROW]) {
+    constexpr int BG = TB / 8;
+    for (int i = threadIdx.x; i < TA * taps * BG; i += 256) {
+        const int g = i % BG, tp = (i / BG) % taps, a = i / (BG * taps);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = s[a][(8 * g + j) * taps + tp];
+        *reinterpret_cast<uint4*>(dst + ((size_t)(a0 + a) * taps + tp) * ld + b0 + 8 * g) = pack8(f, mul);
+    }
+}
+
 template <int TAPS>
 __device__ __forceinline__ void pack_tile(const mg_wprep_layer& L, const int4 it, const float inv_sigma, float (*s)[SROW],
                                           __half* __restrict__ P, __half* __restrict__ D) {
     const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
     const int taps = TAPS ? TAPS : L.taps, width = d1 * taps, tid = threadIdx.x;
     const int a0 = it.y, b0 = it.z, seg = TB * taps;
+    if (full_tile(L, it, taps)) {
+        load_w_tile_v4(L, a0, b0, taps, width, s);
+        __syncthreads();
+        __half* Pl = P + L.p_off;
+        __half* Dl = D ? D + L.d_off : nullptr;
+        if (!L.transposed) {   // a = co, b = ci:  P [co][tap][ci_pad],  D [ci][tap][Co]
+            store_b_fastest<TAPS>(Pl, L.ci_pad, a0, b0, taps, inv_sigma, s);
+            if (Dl) store_a_fastest<TAPS>(Dl, L.Co, a0, b0, taps, inv_sigma, s);
+        } else {               // a = ci, b = co
+            store_a_fastest<TAPS>(Pl, L.ci_pad, a0, b0, taps, inv_sigma, s);
+            if (Dl) store_b_fastest<TAPS>(Dl, L.Co, a0, b0, taps, inv_sigma, s);
+        }
+        return;
+    }
     for (int i = tid; i < TA * seg; i += 256) {
         const int a = i / seg, e = i - a * seg;
         const int col = b0 * taps + e;
@@ -168,6 +238,26 @@ __device__ __forceinline__ void load_grad_tile(const mg_wprep_layer& L, const fl
                                                float (*s)[SROW]) {
     const int taps = TAPS ? TAPS : L.taps, to = TAPS > 1 ? TAPS : (L.fold ? 4 : taps), Co = L.Co, Ci = L.Ci, cip = L.ci_pad, tid = threadIdx.x;
     const float* Gl = G + L.g_off;
+    if (full_tile(L, make_int4(0, a0, b0, 0), taps) && (reinterpret_cast<uintptr_t>(Gl) & 15) == 0) {
+        if (!L.transposed) {   // G [co = a0 + a][tap][ci = b0 + b]: b contiguous
+            constexpr int Q = TB / 4;
+            for (int i = tid; i < TA * taps * Q; i += 256) {
+                const int q = i % Q, tp = (i / Q) % taps, a = i / (Q * taps);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(Gl + ((size_t)(a0 + a) * taps + tp) * cip + b0) + q);
+                float* d = &s[a][(4 * q) * taps + tp];
+                d[0] = v.x, d[taps] = v.y, d[2 * taps] = v.z, d[3 * taps] = v.w;
+            }
+        } else {               // G [co = b0 + b][tap][ci = a0 + a]: a contiguous
+            constexpr int Q = TA / 4;
+            for (int i = tid; i < TB * taps * Q; i += 256) {
+                const int q = i % Q, tp = (i / Q) % taps, b = i / (Q * taps);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(Gl + ((size_t)(b0 + b) * taps + tp) * cip + a0) + q);
+                const int e = b * taps + tp;
+                s[4 * q][e] = v.x, s[4 * q + 1][e] = v.y, s[4 * q + 2][e] = v.z, s[4 * q + 3][e] = v.w;
+            }
+        }
+        return;
+    }
     if (!L.transposed) {
         for (int i = tid; i < TA * taps * TB; i += 256) {
             const int b = i % TB, tp = (i / TB) % taps, a = i / (TB * taps);
@@ -198,6 +288,16 @@ __device__ __forceinline__ float inner_tile(const mg_wprep_layer& L, const int4 
     load_grad_tile<TAPS>(L, G, it.y, it.z, s);
     __syncthreads();
     float acc = 0.f;
+    if (full_tile(L, it, taps)) {
+        const int seg4 = seg >> 2;
+        for (int i = threadIdx.x; i < TA * seg4; i += 256) {
+            const int a = i / seg4, q = i - a * seg4;
+            const float4 w = __ldg(reinterpret_cast<const float4*>(L.w + (size_t)(it.y + a) * width + (size_t)it.z * taps) + q);
+            const float* g = &s[a][4 * q];
+            acc += g[0] * w.x + g[1] * w.y + g[2] * w.z + g[3] * w.w;
+        }
+        return acc;
+    }
     for (int i = threadIdx.x; i < TA * seg; i += 256) {
         const int a = i / seg, e = i - a * seg, col = it.z * taps + e;
         if (it.y + a < d0 && col < width) acc += s[a][e] * L.w[(size_t)(it.y + a) * width + col];
@@ -214,6 +314,28 @@ __device__ __forceinline__ void final_tile(const mg_wprep_layer& L, const int4 i
     load_grad_tile<TAPS>(L, G, it.y, it.z, s);
     __syncthreads();
     float* gl = grad + L.grad_off;
+    if (full_tile(L, it, taps) && (reinterpret_cast<uintptr_t>(gl) & 15) == 0) {
+        float inv_sigma = 1.f, k = 0.f;
+        const float* vr = vec + L.vec_off;
+        const float* t = vr + width;
+        if (L.u) {
+            const float sigma = scal[it.x * 4 + 0], ivn = scal[it.x * 4 + 1], itn = scal[it.x * 4 + 2], inner = scal[it.x * 4 + 3];
+            inv_sigma = 1.f / sigma, k = inner * inv_sigma * ivn * itn;
+        }
+        const int seg4 = seg >> 2;
+        for (int i = threadIdx.x; i < TA * seg4; i += 256) {
+            const int a = i / seg4, q = i - a * seg4, col = it.z * taps + 4 * q;
+            const float* g = &s[a][4 * q];
+            float4 o = make_float4(g[0], g[1], g[2], g[3]);
+            if (L.u) {
+                const float kt = k * t[it.y + a];
+                o.x = (o.x - kt * vr[col]) * inv_sigma, o.y = (o.y - kt * vr[col + 1]) * inv_sigma;
+                o.z = (o.z - kt * vr[col + 2]) * inv_sigma, o.w = (o.w - kt * vr[col + 3]) * inv_sigma;
+            }
+            *reinterpret_cast<float4*>(gl + (size_t)(it.y + a) * width + col) = o;
+        }
+        return;
+    }
     if (L.u) {
         const float sigma = scal[it.x * 4 + 0], ivn = scal[it.x * 4 + 1], itn = scal[it.x * 4 + 2], inner = scal[it.x * 4 + 3];
         const float inv_sigma = 1.f / sigma, k = inner * inv_sigma * ivn * itn;
