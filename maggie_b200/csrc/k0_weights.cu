@@ -40,7 +40,34 @@ wprep_vt_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restric
     const int4 it = items[blockIdx.x];
     const mg_wprep_layer L = layers[it.x];
     const int d0 = L.transposed ? L.Ci : L.Co, d1 = L.transposed ? L.Co : L.Ci;
-    const int width = d1 * L.taps, cx = threadIdx.x & 63, rg = threadIdx.x >> 6, col = it.z + cx;
+    const int width = d1 * L.taps;
+    if ((width & 3) == 0 && (reinterpret_cast<uintptr_t>(L.w) & 15) == 0 && (reinterpret_cast<uintptr_t>(vec + L.vec_off) & 15) == 0) {
+        // 16 threads x 4 columns, 16 row groups: 16-byte loads, the same fixed summation order on every run
+        __shared__ float4 s_p4[16][16];
+        const int c4 = threadIdx.x & 15, rg = threadIdx.x >> 4, col = it.z + 4 * c4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < width) {
+#pragma unroll 4
+            for (int r = rg; r < d0; r += 16) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(L.w + (size_t)r * width + col));
+                const float u = __ldg(L.u + r);
+                acc.x += w.x * u, acc.y += w.y * u, acc.z += w.z * u, acc.w += w.w * u;
+            }
+        }
+        s_p4[rg][c4] = acc;
+        __syncthreads();
+        if (rg == 0 && col < width) {
+            float4 t = s_p4[0][c4];
+#pragma unroll
+            for (int g = 1; g < 16; ++g) {
+                const float4 q = s_p4[g][c4];
+                t.x += q.x, t.y += q.y, t.z += q.z, t.w += q.w;
+            }
+            *reinterpret_cast<float4*>(vec + L.vec_off + col) = t;
+        }
+        return;
+    }
+    const int cx = threadIdx.x & 63, rg = threadIdx.x >> 6, col = it.z + cx;
     float acc = 0.f;
     if (col < width) {
 #pragma unroll 4
@@ -63,6 +90,15 @@ wprep_u_kernel(const mg_wprep_layer* __restrict__ layers, const int4* __restrict
     const float* vr = vec + L.vec_off;
     const float* wr = L.w + (size_t)row * width;
     float acc = 0.f, nn = 0.f;
+    if ((width & 3) == 0 && ((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(vr)) & 15) == 0) {
+#pragma unroll 2
+        for (int j = lane; j < (width >> 2); j += 32) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wr) + j);
+            const float4 x = *(reinterpret_cast<const float4*>(vr) + j);
+            acc += (w.x * x.x + w.y * x.y) + (w.z * x.z + w.w * x.w);
+            nn += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+        }
+    } else
     for (int j = lane; j < width; j += 32) {
         const float x = vr[j];
         acc += wr[j] * x;

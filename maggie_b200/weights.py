@@ -169,7 +169,7 @@ class WeightBank:
             if e.u is not None:
                 vt += [(i, 0, c, 0) for c in range(0, width, 64)]   # one CTA per 64 columns, all rows (deterministic)
                 uu += [(i, r, 0, 0) for r in range(0, d0, 8)]
-                vec += width + d0
+                vec = _align(vec + width + d0, 4)   # 16-byte aligned per-layer vectors (float4 paths of K0)
             ra, rb = (e.ci_pad, e.Co) if e.transposed else (e.Co, e.ci_pad)
             first = 1
             for a in range(0, ra, 16):

@@ -13,7 +13,7 @@ torch.manual_seed(1234)
 model, _ = build_model(CfgNode(synth.model_cfg()))
 model.to(dev).train()
 model.enable_cuda_graphs(os.environ.get("GRAPHS", "0") == "1")
-flat = FlatGradAllReduce(model.parameters())
+flat = FlatGradAllReduce(model.parameters(), bank=model.bank)
 b = int(os.environ.get("B", "8"))
 batch = synth.make_batch(b=b, n_f=1, n_i=3, H=512, W=512, edge_px=6.0, train=True, it=1)
 batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
