@@ -295,27 +295,55 @@ __device__ __forceinline__ float bwd_level_value(const __half* __restrict__ sg_k
                                                  int w) {
     float v = 0.f;
     if (sg_k) v = c_k * __half2float(sg_k[(img * h + y) * w + x]);
+    // Interior pixels (all but a 3-pixel frame) take the closed forms of taps_DGt / taps_Ut unrolled in registers, in the
+    // same summation order (a zero third tap for odd indices adds exactly 0): the generic tap lists are run-time sized
+    // arrays, i.e. local memory and divergent loops in every thread of these per-pixel kernels.
     if (g_k1) {
         const int hc = h >> 1, wc = w >> 1;
-        Taps ty, tx;
-        taps_DGt(y, h, ty);
-        taps_DGt(x, w, tx);
-        for (int a = 0; a < ty.n; ++a) {
-            float r = 0.f;
-            for (int b = 0; b < tx.n; ++b) r += tx.wt[b] * __ldg(g_k1 + (img * hc + ty.idx[a]) * wc + tx.idx[b]);
-            v += ty.wt[a] * r;
+        if (y >= 3 && y + 3 < h && x >= 3 && x + 3 < w) {
+            const int oy = y & 1, ox = x & 1;
+            const float* gp = g_k1 + (img * hc + (y >> 1) - 1 + oy) * wc + (x >> 1) - 1 + ox;
+            const float wy[3] = {oy ? 0.25f : 0.0625f, oy ? 0.25f : 0.375f, oy ? 0.f : 0.0625f};
+            const float wx[3] = {ox ? 0.25f : 0.0625f, ox ? 0.25f : 0.375f, ox ? 0.f : 0.0625f};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float r = 0.f;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) r += wx[b] * __ldg(gp + a * wc + b);
+                v += wy[a] * r;
+            }
+        } else {
+            Taps ty, tx;
+            taps_DGt(y, h, ty);
+            taps_DGt(x, w, tx);
+            for (int a = 0; a < ty.n; ++a) {
+                float r = 0.f;
+                for (int b = 0; b < tx.n; ++b) r += tx.wt[b] * __ldg(g_k1 + (img * hc + ty.idx[a]) * wc + tx.idx[b]);
+                v += ty.wt[a] * r;
+            }
         }
     }
     if (sg_km1) {
         const int hf = h << 1, wf = w << 1;
-        Taps ty, tx;
-        taps_Ut(y, hf, ty);
-        taps_Ut(x, wf, tx);
         float u = 0.f;
-        for (int a = 0; a < ty.n; ++a) {
-            float r = 0.f;
-            for (int b = 0; b < tx.n; ++b) r += tx.wt[b] * __half2float(sg_km1[(img * hf + ty.idx[a]) * wf + tx.idx[b]]);
-            u += ty.wt[a] * r;
+        if (y >= 2 && 2 * y + 2 < hf - 1 && x >= 2 && 2 * x + 2 < wf - 1) {
+            const __half* sp = sg_km1 + (img * hf + 2 * y + 2) * wf + 2 * x + 2;
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                float r = 0.f;
+#pragma unroll
+                for (int b = 0; b < 5; ++b) r += 2.f * gk(b) * __half2float(sp[-(a * wf) - b]);
+                u += 2.f * gk(a) * r;
+            }
+        } else {
+            Taps ty, tx;
+            taps_Ut(y, hf, ty);
+            taps_Ut(x, wf, tx);
+            for (int a = 0; a < ty.n; ++a) {
+                float r = 0.f;
+                for (int b = 0; b < tx.n; ++b) r += tx.wt[b] * __half2float(sg_km1[(img * hf + ty.idx[a]) * wf + tx.idx[b]]);
+                u += ty.wt[a] * r;
+            }
         }
         v -= c_km1 * u;
     }
