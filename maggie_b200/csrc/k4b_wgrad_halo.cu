@@ -1,5 +1,7 @@
-// K4b: weight gradient of the high-resolution 32-channel 3x3 stride-1 layers (512^2 / 256^2: HBM-bound, 2 x 134 MB per
-// layer at 512^2), persistent and halo-resident like K2b.
+// K4b: weight gradient of the high-resolution 32- and 64-channel 3x3 stride-1 layers (512^2 / 256^2 x 32, 128^2 x 64:
+// HBM-bound, 2 x 134 MB per layer at 512^2), persistent and halo-resident like K2b.  With 64 input channels the
+// [128 x 9 * 64] accumulator would not fit the 512 TMEM columns: the CTAs then form two populations, each loading and
+// accumulating 32 of the channels (the X patch is still read once, the dY tile twice).
 //
 //   dW[co][(dy,dx)][ci] = sum over pixels p   dY[p][co] * X[p + (dy,dx)][ci]
 //
@@ -34,7 +36,8 @@ std::atomic<unsigned long long> g_wgrad_halo_launches{0};
 struct WHArgs {
     int H, W, Co, R, strips, rblocks, n_tiles, mode;
     int x_bytes, y_bytes;
-    float* dw;                 // [Co][9*32]
+    int halves, Ci;            // 64 input channels: two CTA populations, each with the [128 x 288] accumulator of 32 of them
+    float* dw;                 // [Co][9*Ci]
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -69,18 +72,19 @@ wgrad_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
     mg::pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_img = a.rblocks * a.strips;
-    const bool any = blockIdx.x < a.n_tiles;
+    const int half = blockIdx.x % a.halves, tile0 = blockIdx.x / a.halves, tile_step = gridDim.x / a.halves;
+    const bool any = tile0 < a.n_tiles;
 
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < a.n_tiles; tile += tile_step, ++it) {
                 const int buf = it & 1, ph = (it >> 1) & 1;
                 const int img = tile / tiles_img, rem = tile - img * tiles_img;
                 const int rb = rem / a.strips, st = rem - rb * a.strips;
                 mbar_wait(empty + 8 * buf, ph ^ 1);
                 mbar_expect_tx(full + 8 * buf, a.x_bytes + a.y_bytes);
-                tma_load_4d(smem_u32(sX + buf * x_al), &tmX, full + 8 * buf, 0, st * WS - 1, rb * a.R - 1, img);
+                tma_load_4d(smem_u32(sX + buf * x_al), &tmX, full + 8 * buf, half * 32, st * WS - 1, rb * a.R - 1, img);
                 tma_load_4d(smem_u32(sY + buf * y_al), &tmDY, full + 8 * buf, 0, st * WS, rb * a.R, img);
             }
         }
@@ -91,7 +95,7 @@ wgrad_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
         const uint32_t zbase = smem_u32(sZ), sX_u = smem_u32(sX), sY_u = smem_u32(sY);
         int buf = 0, ph = 0;
         bool first = true;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < a.n_tiles; tile += tile_step) {
             mbar_wait(full + 8 * buf, ph);
             tc_fence_after();
             const uint32_t xbase = sX_u + buf * x_al, ybase = sY_u + buf * y_al;
@@ -128,7 +132,7 @@ wgrad_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
         }
         if (any && elect_one()) mma_commit(tfull);
     } else if (any) {
-        // final epilogue: accumulator row = output channel (TMEM lane), 288 columns = (dy, dx, ci)
+        // final epilogue: accumulator row = output channel (TMEM lane), 288 columns = (dy, dx, ci of this CTA's 32 channels)
         const int q = warp & 3, co = q * 32 + lane;
         mbar_wait(tfull, 0);
         tc_fence_after();
@@ -138,7 +142,7 @@ wgrad_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid
                 tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
                 tmem_ld_wait();
                 if (co < a.Co) {
-                    float* drow = a.dw + (size_t)co * 288 + c0;
+                    float* drow = a.dw + (size_t)co * (9 * a.Ci) + (c0 >> 5) * a.Ci + half * 32 + (c0 & 31);
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
                         red_add_v4(drow + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
@@ -163,18 +167,19 @@ int wgrad_halo_launch(const mg_wgrad_desc* d, void* stream, bool* handled) {
     *handled = false;
     const char* e = std::getenv("MAGGIE_B200_NO_HALO_CONV");
     if (e && e[0] == '1') return MG_OK;
-    if (d->n_taps != 9 || d->Ci != 32 || d->Co > 64 || d->Co % 8 || d->Ktot != 288) return MG_OK;
+    if (d->n_taps != 9 || (d->Ci != 32 && d->Ci != 64) || d->Co > 64 || d->Co % 8 || d->Ktot != 9 * d->Ci) return MG_OK;
     if (d->sy != 1 || d->sx != 1 || d->ays != 1 || d->axs != 1 || d->ay0 != 0 || d->ax0 != 0) return MG_OK;
     if (d->Hy != d->Hi || d->Wy != d->Wi || d->Hg != d->Hi || d->Wg != d->Wi || d->Wi % WS || d->Hi < 2) return MG_OK;
     for (int t = 0; t < 9; ++t)
-        if (d->tap_dy[t] != t / 3 - 1 || d->tap_dx[t] != t % 3 - 1 || d->tap_koff[t] != t * 32) return MG_OK;
+        if (d->tap_dy[t] != t / 3 - 1 || d->tap_dx[t] != t % 3 - 1 || d->tap_koff[t] != t * d->Ci) return MG_OK;
     if (!get_encode()) return MG_OK;
     WHArgs a;
     a.H = d->Hi, a.W = d->Wi, a.Co = d->Co, a.dw = d->dw;
     a.R = 2;
     a.strips = d->Wi / WS, a.rblocks = ceil_div(d->Hi, a.R);
     a.n_tiles = d->N * a.rblocks * a.strips;
-    if (a.n_tiles < 2 * kNumSMs) return MG_OK;
+    a.halves = d->Ci / 32, a.Ci = d->Ci;
+    if (a.n_tiles * a.halves < 2 * kNumSMs) return MG_OK;
     a.x_bytes = (a.R + 2) * P * XROW, a.y_bytes = a.R * 128 * YROW;
     {
         const char* m = std::getenv("MAGGIE_B200_WGRAD_HALO_MODE");
@@ -193,7 +198,8 @@ int wgrad_halo_launch(const mg_wgrad_desc* d, void* stream, bool* handled) {
         }
         attr_set = true;
     }
-    MG_LAUNCH(wgrad_halo_tcgen05_kernel, std::min(a.n_tiles, kNumSMs), THREADS, smem, stream, tmDY, tmX, a);
+    MG_LAUNCH(wgrad_halo_tcgen05_kernel, std::min(a.n_tiles * a.halves, kNumSMs / a.halves * a.halves), THREADS, smem, stream, tmDY,
+              tmX, a);
     MG_CHECK_LAUNCH("mg_conv_wgrad(halo)");
     g_wgrad_halo_launches.fetch_add(1, std::memory_order_relaxed);
     *handled = true;

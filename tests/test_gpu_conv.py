@@ -141,22 +141,28 @@ def test_halo_conv_data_gradient_path():
     _close(dx, ref, "halo dgrad")
 
 
-# ---- K4b: halo-resident persistent weight gradient of the high-resolution 32-channel 3x3 layers --------------------
-@pytest.mark.parametrize("N,H,W,Co", [(2, 256, 256, 32), (1, 512, 256, 64), (3, 130, 128, 32), (2, 256, 384, 16)])
-def test_halo_wgrad_matches_torch_and_generic_kernel(N, H, W, Co, monkeypatch):
-    from maggie_b200 import dense
-    g = torch.Generator().manual_seed(H + W + Co)
-    x = torch.randn(N, H, W, 32, generator=g).half().cuda()
+# ---- K4b: halo-resident persistent weight gradient of the high-resolution 32- / 64-channel 3x3 layers --------------
+@pytest.mark.parametrize("N,H,W,Co,Ci", [(2, 256, 256, 32, 32), (1, 512, 256, 64, 32), (3, 130, 128, 32, 32), (2, 256, 384, 16, 32),
+                                         (8, 128, 128, 64, 64), (2, 256, 128, 32, 64), (3, 130, 128, 48, 64)])
+def test_halo_wgrad_matches_torch_and_generic_kernel(N, H, W, Co, Ci, monkeypatch):
+    """Ci = 64: two CTA populations, each accumulating 32 of the input channels (the [128 x 9*64] tile exceeds TMEM)."""
+    from maggie_b200 import _lib, dense
+    g = torch.Generator().manual_seed(H + W + Co + Ci)
+    x = torch.randn(N, H, W, Ci, generator=g).half().cuda()
     dy = (torch.randn(N, H, W, Co, generator=g) * 0.1).half().cuda()
-    taps = dense.conv_taps(3, 3, 1, 1, 32)
-    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Co, 32, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
+    taps = dense.conv_taps(3, 3, 1, 1, Ci)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Co, Ci, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
     outs = []
     for mode in ("halo", "halo_one_tap_per_mma", "generic"):
         monkeypatch.setenv("MAGGIE_B200_NO_HALO_CONV", "1" if mode == "generic" else "0")
         monkeypatch.setenv("MAGGIE_B200_WGRAD_HALO_MODE", "1" if mode == "halo_one_tap_per_mma" else "0")
-        dw = torch.zeros(Co, 9 * 32, device="cuda")
+        dw = torch.zeros(Co, 9 * Ci, device="cuda")
+        before = _lib.lib().mg_wgrad_halo_launches()
         dense.wgrad_launch(dy, x, taps, dw, grid_hw=(H, W))
-        got = dw.view(Co, 3, 3, 32).permute(0, 3, 1, 2)
+        # (persistent kernel: taken when there are at least two work items per SM)
+        routed = mode != "generic" and N * ((H + 1) // 2) * (W // 128) * (Ci // 32) >= 2 * 148
+        assert _lib.lib().mg_wgrad_halo_launches() == before + routed, "routing"
+        got = dw.view(Co, 3, 3, Ci).permute(0, 3, 1, 2)
         assert float((got - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-3, mode
         outs.append(got)
     # same products, different summation order (split-K partition): tiny differences only
