@@ -1,6 +1,6 @@
 """Dev tool: two launches each (the second one is the warm one ncu keeps) of the kernels captured with `ncu --set full` for
 profiles/ (C2 shapes): K2b halo conv 512^2 32->32 (+ BN statistics), K2t transposed mid conv 64^2 128->128 (+ BN statistics,
-and as a data gradient), 32^2 256->256 and 16^2 512->512, K2 generic conv 64^2 128->256 stride 2, K4 wgrad 64^2 128->128, K4b halo wgrad 512^2 32->32, K9b persistent sparse conv and
+and as a data gradient), 32^2 256->256 and 16^2 512->512, K2 generic conv 64^2 128->256 stride 2, K4 wgrad 64^2 128->128, K4b halo wgrad 512^2 32->32 and 128^2 64->64, K9b persistent sparse conv and
 K9c persistent sparse wgrad on the C2 OS1 site list, K8a unknown mask, K1 mask embedding.
 
     ncu --set full --clock-control none --import-source on -k regex:'tcgen05|sparse_|unknown_mask|mask_embed_fwd|bn_' \\
@@ -29,6 +29,8 @@ for rep in range(2):
     stats = dense.new_stats(32, dev)
     y = dense.conv_launch(x, dense.pack_weight(w, 32), dense.conv_taps(3, 3, 1, 1, 32), grid_hw=(512, 512), stats=stats)   # K2b
     g.wgrad(y, x, w.shape)                                                                                                 # K4b
+    x, w = mk(8, 128, 128, 64, 64, 3)
+    g.wgrad(torch.randn(8, 128, 128, 64, device=dev).half(), x, w.shape)                                                   # K4b, 64 channels in two halves
     for (hw, ci, co) in ((64, 128, 128), (32, 256, 256), (16, 512, 512)):
         x, w = mk(8, hw, hw, ci, co, 3)
         st = dense.new_stats(co, dev)
