@@ -176,7 +176,7 @@ int mg_wprep_bwd(const mg_wprep_layer* layers, const int32_t* items_tile, int n_
  * per-channel sum (row 0) and sum of squares (row 1) of the stored values' fp32 pre-images, spread over the
  * copies to keep atomics uncontended (mg_bn_finalize adds the copies up).                                  */
 #define MG_CONV_MAX_TAPS 16
-#define MG_CONV_STAT_COPIES 64
+#define MG_CONV_STAT_COPIES 16
 typedef struct mg_conv_desc {
     const void* x; int32_t N, Hi, Wi, Ci;
     const void* w; int32_t Co, Ktot;
@@ -260,6 +260,12 @@ int mg_bn_finalize(const float* stats, float count, const float* gamma, const fl
                    float* save_invstd, int C, const float* count_dev, void* stream);
 int mg_bn_apply(const void* x, const float* scale, const float* shift, const void* res, int res_up, void* y, int N,
                 int H, int W, int C, int act, void* stream);
+/* Training forward in one launch (local statistics): sums the MG_CONV_STAT_COPIES copies, derives scale / shift, updates the
+ * running statistics (optional) and applies y = act(x*scale + shift (+ res)); out4 = float [4][C]: scale, shift, mean, 1/std
+ * (saved for the backward).  Same arithmetic as mg_bn_finalize followed by mg_bn_apply.  C % 8 == 0, C <= 512.            */
+int mg_bn_train_apply(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, float momentum, float eps, float* out4, const void* x, const void* res, int res_up,
+                      void* y, int N, int H, int W, int C, int act, void* stream);
 int mg_bn_bwd_reduce(const void* dy, const void* y, const void* conv_out, const float* mean, const float* invstd,
                      float* sums, int N, int H, int W, int C, int act, void* stream);
 int mg_bn_bwd_apply(const void* dy, const void* y, const void* conv_out, const float* mean, const float* invstd,

@@ -1,7 +1,7 @@
 // K15: SyncBatchNorm-equivalent statistics exchange INSIDE the BatchNorm kernel chain, over peer memory (NVLink / NVSwitch)
 // instead of one NCCL all-reduce per layer and direction (engine/train.py:160-161, 71 BatchNorms x 2).
 //
-//   forward : conv epilogue (64 statistic copies) -> [K15: reduce copies, push to peers, wait, sum] -> mg_bn_finalize
+//   forward : conv epilogue (MG_CONV_STAT_COPIES statistic copies) -> [K15: reduce copies, push to peers, wait, sum] -> mg_bn_finalize
 //   backward: mg_bn_bwd_reduce ([2][C] sums)      -> [K15: push to peers, wait, sum]                -> mg_bn_bwd_apply
 //
 // Every rank owns one exchange WINDOW (device memory exported with CUDA IPC and mapped by all peers):

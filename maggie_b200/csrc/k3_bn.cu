@@ -1,6 +1,7 @@
 // K3: BatchNorm around the conv kernel, NHWC fp16 activations, fp32 statistics.  All HBM-bound streaming
 // kernels (one 16-byte vector = 8 channels per thread access).
-//   forward (train): conv epilogue -> per-channel sum/sumsq copies -> mg_bn_finalize -> mg_bn_apply
+//   forward (train): conv epilogue -> per-channel sum/sumsq copies -> mg_bn_train_apply (finalize + apply in one launch;
+//                    mg_bn_finalize -> mg_bn_apply when the statistics are exchanged across ranks first)
 //   forward (eval) : mg_bn_finalize (running stats) -> scale/shift folded into the conv epilogue (no extra pass)
 //   backward       : mg_bn_bwd_reduce (sum dz, sum dz*xhat) -> mg_bn_bwd_apply (dx, optional d-residual)
 #include "common.cuh"
@@ -12,7 +13,7 @@ namespace {
 
 constexpr int STAT_COPIES = MG_CONV_STAT_COPIES;
 
-// block = 8 copy-groups x 32 channels: the 64 statistic copies are summed by 8 threads per channel (coalesced over the
+// block = 8 copy-groups x 32 channels: the statistic copies are summed by 8 threads per channel (coalesced over the
 // channels) and combined through shared memory - the kernel is pure latency, so the serial chain is kept short.
 __global__ void __launch_bounds__(256)
 bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ count_dev,
@@ -84,7 +85,10 @@ struct H8 {
     }
 };
 
-// y = act(x*scale + shift (+ res)), vectorised over 8 channels.
+// y = act(x*scale + shift (+ res)), vectorised over 8 channels; s_ss = [scale | shift] in shared memory.
+__device__ __forceinline__ void bn_apply_body(const float* s_ss, const __half* __restrict__ x, const __half* __restrict__ res,
+                                              int res_up, __half* __restrict__ y, size_t npix, int C, int H, int W, int act);
+
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                 const __half* __restrict__ res, int res_up, __half* __restrict__ y, size_t npix, int C, int H, int W, int act) {
@@ -92,6 +96,59 @@ bn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ scale, c
     extern __shared__ float s_ss[];  // [2][C]
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_ss[i] = scale[i], s_ss[C + i] = shift[i];
     __syncthreads();
+    bn_apply_body(s_ss, x, res, res_up, y, npix, C, H, W, act);
+}
+
+// Training forward in ONE launch after the conv: every CTA adds up the statistic copies of the conv epilogue itself
+// (2 C sums of STAT_COPIES values: a few loads per thread from L2) and derives scale / shift, then streams its share of
+// the tensor; CTA 0 also publishes scale, shift, mean, 1/std for the backward and updates the running statistics.  Same
+// arithmetic, same summation order as bn_finalize_kernel + bn_apply_kernel (which remain for exchanged statistics and
+// for evaluation): a separate finalize launch cost more than the work it did, 71 times per step.
+__global__ void __launch_bounds__(256)
+bn_train_apply_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps, float* __restrict__ out4,
+                      const __half* __restrict__ x, const __half* __restrict__ res, int res_up, __half* __restrict__ y, size_t npix,
+                      int C, int H, int W, int act) {
+    mg::pdl_prologue();
+    extern __shared__ float s_ss[];  // [2][C]: first the sums (sum | sum of squares), then scale | shift
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float part[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            float p = 0.f;
+#pragma unroll
+            for (int k = g; k < STAT_COPIES; k += 8) p += __ldg(stats + (size_t)k * 2 * C + i);
+            part[g] = p;
+        }
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += part[g];
+        s_ss[i] = t;
+    }
+    __syncthreads();
+    float sc[2], sh[2];   // C <= 512: at most two channels per thread
+    for (int c = threadIdx.x, j = 0; c < C; c += blockDim.x, ++j) {
+        const float mean = s_ss[c] / count;
+        const float var = fmaxf(s_ss[C + c] / count - mean * mean, 0.f);
+        const float invstd = rsqrtf(var + eps);
+        const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+        sc[j] = g * invstd, sh[j] = b - mean * g * invstd;
+        if (blockIdx.x == 0) {
+            if (rmean) {
+                rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+                rvar[c] = (1.f - momentum) * rvar[c] + momentum * var * (count > 1.f ? count / (count - 1.f) : 1.f);
+            }
+            out4[c] = sc[j], out4[C + c] = sh[j], out4[2 * C + c] = mean, out4[3 * C + c] = invstd;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x, j = 0; c < C; c += blockDim.x, ++j) s_ss[c] = sc[j], s_ss[C + c] = sh[j];
+    __syncthreads();
+    bn_apply_body(s_ss, x, res, res_up, y, npix, C, H, W, act);
+}
+
+__device__ __forceinline__ void bn_apply_body(const float* s_ss, const __half* __restrict__ x, const __half* __restrict__ res,
+                                              int res_up, __half* __restrict__ y, size_t npix, int C, int H, int W, int act) {
     const int G = C >> 3, gs = (G & (G - 1)) == 0 ? __ffs(G) - 1 : -1;   // (a 64-bit division per 16-byte item otherwise)
     const size_t total = npix * G;
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
@@ -263,6 +320,21 @@ extern "C" int mg_bn_apply(const void* x, const float* scale, const float* shift
               static_cast<const __half*>(x), scale, shift, static_cast<const __half*>(res), res_up,
               static_cast<__half*>(y), npix, C, H, W, act);
     MG_CHECK_LAUNCH("mg_bn_apply");
+    return MG_OK;
+}
+
+extern "C" int mg_bn_train_apply(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
+                                 float* running_var, float momentum, float eps, float* out4, const void* x, const void* res,
+                                 int res_up, void* y, int N, int H, int W, int C, int act, void* stream) {
+    MG_REQUIRE(stats && out4 && x && y, "mg_bn_train_apply: null pointer");
+    MG_REQUIRE(C % 8 == 0 && C <= 512, "mg_bn_train_apply: C must be a multiple of 8, at most 512 (got %d)", C);
+    MG_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "mg_bn_train_apply: running_mean/running_var go together");
+    const size_t npix = (size_t)N * H * W;
+    MG_REQUIRE(npix > 0, "mg_bn_train_apply: empty tensor");
+    MG_LAUNCH(bn_train_apply_kernel, stream_grid(npix * (C / 8)), 256, 2 * C * sizeof(float), stream, stats, count, gamma, beta,
+              running_mean, running_var, momentum, eps, out4, static_cast<const __half*>(x), static_cast<const __half*>(res), res_up,
+              static_cast<__half*>(y), npix, C, H, W, act);
+    MG_CHECK_LAUNCH("mg_bn_train_apply");
     return MG_OK;
 }
 

@@ -24,7 +24,8 @@ def wshape(w):
     return tuple(w.shape)
 
 MAX_TAPS = 16
-STAT_COPIES = 64
+STAT_COPIES = 16
+FUSED_BN_APPLY = os.environ.get("MAGGIE_B200_NO_FUSED_BN_APPLY", "0") != "1"   # K3: finalize + apply in one launch (training)
 
 
 class ConvDesc(ctypes.Structure):
@@ -648,15 +649,26 @@ class _ConvBNAct(torch.autograd.Function):
         stats = new_stats(Co, x.device)
         r = geom.fwd(xn, wd, stats=stats) if not act_first else geom.fwd(xn, wd, stats=stats, pre_act=act)
         N, Ho, Wo, _ = r.shape
-        scale, shift, mean, invstd, *cnt = bn_finalize(stats, N * Ho * Wo, bn, True, group)
-        ctx.sync = (group, cnt[0]) if group is not None else None    # (group, global element count on the device)
         y = torch.empty_like(r)
         rn = None
         if res is not None:
             rn = res.permute(0, 2, 3, 1)
             assert rn.is_contiguous() and rn.dtype == torch.float16
-        _lib.check(_lib.lib().mg_bn_apply(_ptr(r), _ptr(scale), _ptr(shift), _ptr(rn), int(res_up), _ptr(y), N, Ho, Wo, Co,
-                                          0 if act_first else ACT[act], _stream()), "mg_bn_apply")
+        if group is None and FUSED_BN_APPLY and Co <= 512:
+            # local statistics: finalize + apply in ONE launch (every CTA adds up the statistic copies itself)
+            bump_counter(bn.num_batches_tracked)
+            out4 = torch.empty((4, Co), dtype=torch.float32, device=x.device)
+            _lib.check(_lib.lib().mg_bn_train_apply(_ptr(stats), float(N * Ho * Wo), _ptr(bn.weight), _ptr(bn.bias),
+                                                    _ptr(bn.running_mean), _ptr(bn.running_var), float(bn.momentum), float(bn.eps),
+                                                    _ptr(out4), _ptr(r), _ptr(rn), int(res_up), _ptr(y), N, Ho, Wo, Co,
+                                                    0 if act_first else ACT[act], _stream()), "mg_bn_train_apply")
+            mean, invstd = out4[2], out4[3]
+            ctx.sync = None
+        else:
+            scale, shift, mean, invstd, *cnt = bn_finalize(stats, N * Ho * Wo, bn, True, group)
+            ctx.sync = (group, cnt[0]) if group is not None else None    # (group, global element count on the device)
+            _lib.check(_lib.lib().mg_bn_apply(_ptr(r), _ptr(scale), _ptr(shift), _ptr(rn), int(res_up), _ptr(y), N, Ho, Wo, Co,
+                                              0 if act_first else ACT[act], _stream()), "mg_bn_apply")
         ctx.save_for_backward(xn, None if handle is not None else wd, r, y, mean, invstd, gamma.detach())
         ctx.handle = handle
         ctx.sums = zeros_f32(2 * Co, x.device).view(2, Co) if _SCOPES else None  # zeroed now, filled by the backward

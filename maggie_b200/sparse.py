@@ -6,7 +6,7 @@ from ctypes import c_int32, c_void_p
 
 import torch
 
-from . import _lib, packs
+from . import _lib, dense, packs
 from .dense import ACT, bn_finalize, exchange_sums, new_stats, sync_group, zeros_f32
 
 _need_cuda, _ptr, _stream = _lib.need_cuda, _lib.tensor_ptr, _lib.stream_ptr
@@ -172,11 +172,22 @@ class _RowsConv(torch.autograd.Function):
         group = sync_group(bn)   # SyncBatchNorm-equivalent: statistics over the active sites of all ranks (dense.py)
         stats = new_stats(co, src.device)
         r = sparse_conv_launch(src, wp, T, ci, co, table=table, bias=b32, stats=stats, pre_act=1 if mode == "act_bn" else 0)
-        scale, shift, mean, invstd, *cnt = bn_finalize(stats, max(No, 1) if group is None else No, bn, True, group)
-        ctx.sync = (group, cnt[0]) if group is not None else None
         y = torch.empty_like(r)
-        _lib.check(_lib.lib().mg_bn_apply(_ptr(r), _ptr(scale), _ptr(shift), None, 0, _ptr(y), No, 1, 1, co,
-                                          0 if mode == "act_bn" else ACT[act], _stream()), "mg_bn_apply")
+        if group is None and dense.FUSED_BN_APPLY and No > 0 and co <= 512:
+            # local statistics: finalize + apply in one launch (dense.py, _ConvBNAct)
+            dense.bump_counter(bn.num_batches_tracked)
+            out4 = torch.empty((4, co), dtype=torch.float32, device=src.device)
+            _lib.check(_lib.lib().mg_bn_train_apply(_ptr(stats), float(No), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean),
+                                                    _ptr(bn.running_var), float(bn.momentum), float(bn.eps), _ptr(out4), _ptr(r),
+                                                    None, 0, _ptr(y), No, 1, 1, co, 0 if mode == "act_bn" else ACT[act],
+                                                    _stream()), "mg_bn_train_apply")
+            mean, invstd = out4[2], out4[3]
+            ctx.sync = None
+        else:
+            scale, shift, mean, invstd, *cnt = bn_finalize(stats, max(No, 1) if group is None else No, bn, True, group)
+            ctx.sync = (group, cnt[0]) if group is not None else None
+            _lib.check(_lib.lib().mg_bn_apply(_ptr(r), _ptr(scale), _ptr(shift), None, 0, _ptr(y), No, 1, 1, co,
+                                              0 if mode == "act_bn" else ACT[act], _stream()), "mg_bn_apply")
         ctx.save_for_backward(src, wd, table, table_t, r, y, mean, invstd, gamma.detach())
         ctx.sums = zeros_f32(2 * co, src.device).view(2, co)  # zeroed now (scope pool), filled by the backward
         return y
