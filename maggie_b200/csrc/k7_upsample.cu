@@ -123,34 +123,39 @@ upsample_tanh_bwd_kernel(const float* __restrict__ logits, const float* __restri
         }
         s_v[ly_][lx_] = v;
     }
+    // separable bilinear weights of the tile's coarse pixels over their 2S-wide windows, once per block (the same
+    // src_index arithmetic; 0 outside the image): the window sums below are then two table reads and one FMA per tap
+    __shared__ float s_wy[TC][2 * S], s_wx[TC][2 * S];
+    for (int i = threadIdx.x; i < 2 * TC * 2 * S; i += 256) {
+        const int which = i / (TC * 2 * S), j = i - which * (TC * 2 * S), c = j / (2 * S), r = j - c * (2 * S);
+        const int cc = (which ? cx0 : cy0) + c, n = which ? w : h, N = which ? W : H;
+        const int f = S * cc - S / 2 + r;
+        float wt = 0.f;
+        if (f >= 0 && f < N) {
+            int i0, i1;
+            float l;
+            src_index(f, rs, n, i0, i1, l);
+            wt = (i0 == cc ? 1.f - l : 0.f) + (i1 == cc ? l : 0.f);
+        }
+        (which ? s_wx : s_wy)[c][r] = wt;
+    }
     __syncthreads();
     // 256 threads = TC*TC coarse pixels x PARTS row groups of the 2S-row window
     constexpr int PARTS = 256 / (TC * TC);
     const int c = threadIdx.x / PARTS, part = threadIdx.x - c * PARTS;
-    const int cy = cy0 + c / TC, cx = cx0 + c % TC;
+    const int cyl = c / TC, cxl = c % TC;
+    const int cy = cy0 + cyl, cx = cx0 + cxl;
     float acc = 0.f;
     if (cy < h && cx < w) {
         // fine rows that can touch coarse row cy: [S*cy - S/2, S*cy + 3S/2), split over the PARTS threads of this pixel
         constexpr int ROWS = 2 * S / PARTS > 0 ? 2 * S / PARTS : 1;
         for (int ry = part * ROWS; ry < (part + 1) * ROWS && ry < 2 * S; ++ry) {
-            const int y = S * cy - S / 2 + ry;
-            if (y < 0 || y >= H) continue;
-            int y0, y1;
-            float ly;
-            src_index(y, rs, h, y0, y1, ly);
-            const float wy = (y0 == cy ? 1.f - ly : 0.f) + (y1 == cy ? ly : 0.f);
+            const float wy = s_wy[cyl][ry];
             if (wy == 0.f) continue;
+            const float* row = &s_v[S * cyl + ry][S * cxl];
             float racc = 0.f;
-#pragma unroll 4
-            for (int rx = 0; rx < 2 * S; ++rx) {
-                const int x = S * cx - S / 2 + rx;
-                if (x < 0 || x >= W) continue;
-                int x0, x1;
-                float lx;
-                src_index(x, rs, w, x0, x1, lx);
-                const float wx = (x0 == cx ? 1.f - lx : 0.f) + (x1 == cx ? lx : 0.f);
-                racc += wx * s_v[y - fy0][x - fx0];
-            }
+#pragma unroll
+            for (int rx = 0; rx < 2 * S; ++rx) racc += s_wx[cxl][rx] * row[rx];
             acc += wy * racc;
         }
     }
