@@ -142,6 +142,11 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
         self._use_graphs = bool(on)
         return self
 
+    def _graph_flags(self):
+        """What a captured graph bakes in besides the input shapes: the statistics-exchange setting (`set_sync_bn`, or
+        BatchNorm containers converted to `nn.SyncBatchNorm` after a capture) and the stream / kernel-chain switches."""
+        return (dense._SYNC_EPOCH, type(self.encoder.bn1).__name__, dense.SIDE_BRANCHES, dense.AUX_WGRAD, dense.FUSED_BN_APPLY)
+
     @staticmethod
     def _volatile_state(stage):
         """The tensors a forward of the stage updates in place: BatchNorm running statistics / counters, spectral-norm u, v."""
@@ -150,7 +155,7 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
 
     def _eval_graph(self, stage, args):
         """Capture (once per shape / precision) and replay the evaluation forward of the dense stage."""
-        key = ("eval", getattr(self.encoder, "precision", "fp16")) + tuple((tuple(a.shape), a.dtype) for a in args)
+        key = ("eval", getattr(self.encoder, "precision", "fp16")) + self._graph_flags() + tuple((tuple(a.shape), a.dtype) for a in args)
         entry = self._graphs.get(key)
         if entry is None:
             from ... import _lib
@@ -193,7 +198,7 @@ class MaGGIe(nn.Module, PyTorchModelHubMixin):
             return self._eval_graph(stage, args)
         if not (self._use_graphs and self.training and torch.is_grad_enabled()) or dense.sync_bn_needs_eager(self, x.device):
             return stage(*args)      # (the collective fallback of the BatchNorm statistics exchange cannot be captured)
-        key = tuple((tuple(a.shape), a.dtype) for a in args)
+        key = self._graph_flags() + tuple((tuple(a.shape), a.dtype) for a in args)
         entry = self._graphs.get(key)
         if entry is None:
             from ... import _lib
