@@ -35,3 +35,42 @@ def test_every_kernel_file_is_named_in_design_md():
     files = sorted(f for f in os.listdir(os.path.join(ROOT, "maggie_b200", "csrc")) if f.endswith(".cu") and f != "lib.cu")
     missing = [f for f in files if f not in doc]
     assert not missing, f"kernel files not described in DESIGN.md: {missing}"
+
+
+def _oracle_imports(path):
+    """(enclosing function or None, line) of every import of the `oracle` package in a Python file."""
+    import ast
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    owner = {}
+    for fn in ast.walk(tree):
+        if isinstance(fn, (ast.FunctionDef, ast.AsyncFunctionDef)):
+            for n in ast.walk(fn):
+                owner.setdefault(id(n), fn.name)
+    hits = []
+    for n in ast.walk(tree):
+        mods = []
+        if isinstance(n, ast.ImportFrom):
+            mods = [n.module or ""]
+        elif isinstance(n, ast.Import):
+            mods = [a.name for a in n.names]
+        if any(m == "oracle" or m.startswith("oracle.") for m in mods):
+            hits.append((owner.get(id(n)), n.lineno))
+    return hits
+
+
+def test_the_oracle_is_test_infrastructure_only():
+    """Nothing under maggie_b200/ imports oracle/; bench.py only in its two CPU-arm functions; tools/ and examples/ only
+    the golden scripts' seeding helper (developer tools that compare against the reference), never oracle compute on a
+    measured path."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "maggie_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert not _oracle_imports(os.path.join(dirpath, f)), f"{f} imports the oracle"
+    owners = {o for o, _ in _oracle_imports(os.path.join(ROOT, "bench.py"))}
+    assert owners <= {"cpu_step_fn", "cpu_c1_eval_ms"}, owners
+    assert not _oracle_imports(os.path.join(ROOT, "synthdata.py"))
+    ex = os.path.join(ROOT, "examples")
+    for f in os.listdir(ex) if os.path.isdir(ex) else []:
+        if f.endswith(".py"):
+            assert not _oracle_imports(os.path.join(ex, f)), f"examples/{f} imports the oracle"
